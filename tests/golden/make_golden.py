@@ -1,0 +1,104 @@
+"""Generate golden fixtures from the LIVE reference (Gymnasium v1.4.0).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONPATH=/root/reference python tests/golden/make_golden.py
+
+Every fixture is produced by the reference's own ``gymnasium.make_vec(..., vectorization_mode="sync")``
+(``gymnasium/envs/registration.py:833``, ``gymnasium/vector/sync_vector_env.py``) stepping the reference's
+``CartPoleEnv`` / ``FrozenLakeEnv``; nothing from this repo is involved.  Action tapes are drawn from a
+numpy Generator seeded per fixture and stored next to the outputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+import gymnasium as gym
+from gymnasium.vector import AutoresetMode
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def rollout(envs, seed, actions, options=None, state_attr=None):
+    obs0, info0 = envs.reset(seed=seed, options=options)
+    T = actions.shape[0]
+    obs = np.zeros((T + 1,) + obs0.shape, dtype=obs0.dtype)
+    obs[0] = obs0
+    rew = np.zeros((T, envs.num_envs), np.float64)
+    term = np.zeros((T, envs.num_envs), bool)
+    trunc = np.zeros((T, envs.num_envs), bool)
+    extras = {}
+    states = []
+    if state_attr:
+        states.append(np.stack([np.asarray(s, dtype=np.float64) for s in envs.get_attr(state_attr)]))
+    for t in range(T):
+        o, r, te, tr, info = envs.step(actions[t])
+        obs[t + 1], rew[t], term[t], trunc[t] = o, r, te, tr
+        for k, v in info.items():
+            if k in ("final_obs", "_final_obs", "final_info", "_final_info"):
+                continue
+            extras.setdefault(k, np.zeros((T,) + v.shape, dtype=np.float64 if not k.startswith("_") else bool))
+            extras[k][t] = v
+        if state_attr:
+            states.append(np.stack([np.asarray(s, dtype=np.float64) for s in envs.get_attr(state_attr)]))
+    out = dict(obs=obs, reward=rew, terminated=term, truncated=trunc, actions=actions, seed=np.int64(seed))
+    for k, v in extras.items():
+        out["info_" + k] = v
+    if state_attr:
+        out["state"] = np.stack(states)
+    return out
+
+
+def cartpole(name, n, T, seed, max_episode_steps=None, policy="random", options=None, mode=AutoresetMode.NEXT_STEP,
+             **kw):
+    mk = dict(max_episode_steps=max_episode_steps) if max_episode_steps else {}
+    envs = gym.make_vec("CartPole-v1", num_envs=n, vectorization_mode="sync",
+                        vector_kwargs={"autoreset_mode": mode}, **mk, **kw)
+    rng = np.random.default_rng(1000 + seed)
+    actions = rng.integers(0, 2, size=(T, n)).astype(np.int64)
+    if policy == "balance":
+        # closed-loop tape: second half of the lanes follow theta+theta_dot sign so they reach the time limit
+        e2 = gym.make_vec("CartPole-v1", num_envs=n, vectorization_mode="sync",
+                          vector_kwargs={"autoreset_mode": mode}, **mk, **kw)
+        o, _ = e2.reset(seed=seed, options=options)
+        for t in range(T):
+            a = actions[t]
+            a[n // 2:] = (o[n // 2:, 2] + 0.5 * o[n // 2:, 3] > 0).astype(np.int64)
+            o, *_ = e2.step(a)
+        e2.close()
+    out = rollout(envs, seed, actions, options=options, state_attr="state")
+    out["max_episode_steps"] = np.int64(max_episode_steps or 500)
+    envs.close()
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")}, "term", out["terminated"].sum(), "trunc",
+          out["truncated"].sum())
+
+
+def frozenlake(name, n, T, seed, mode=AutoresetMode.NEXT_STEP, **kw):
+    envs = gym.make_vec("FrozenLake-v1", num_envs=n, vectorization_mode="sync",
+                        vector_kwargs={"autoreset_mode": mode}, **kw)
+    rng = np.random.default_rng(2000 + seed)
+    actions = rng.integers(0, 4, size=(T, n)).astype(np.int64)
+    out = rollout(envs, seed, actions)
+    out["max_episode_steps"] = np.int64(envs.envs[0].spec.max_episode_steps if "max_episode_steps" not in kw else kw["max_episode_steps"])
+    envs.close()
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")}, "term", out["terminated"].sum(), "trunc",
+          out["truncated"].sum(), "reward", out["reward"].sum())
+
+
+if __name__ == "__main__":
+    assert "reference" in gym.__file__ or "_ref" in gym.__file__, gym.__file__
+    print("reference:", gym.__version__, gym.__file__, "numpy", np.__version__)
+    cartpole("cartpole_n8_s42_T300.npz", 8, 300, 42)
+    cartpole("cartpole_n16_s7_T400_limit60_balance.npz", 16, 400, 7, max_episode_steps=60, policy="balance")
+    cartpole("cartpole_n4_s123_bounds.npz", 4, 60, 123, options={"low": -0.1, "high": 0.1})
+    cartpole("cartpole_n4_s5_sutton.npz", 4, 120, 5, sutton_barto_reward=True)
+    cartpole("cartpole_n6_s11_samestep.npz", 6, 200, 11, max_episode_steps=40, policy="balance", mode=AutoresetMode.SAME_STEP)
+    cartpole("cartpole_n3_s2p40.npz", 3, 50, 2**40 + 12345)
+    frozenlake("frozenlake8x8_n16_s0_T400.npz", 16, 400, 0, map_name="8x8")
+    frozenlake("frozenlake4x4_n8_s3_T300.npz", 8, 300, 3)
+    frozenlake("frozenlake8x8_n8_s9_noslip.npz", 8, 150, 9, map_name="8x8", is_slippery=False)
+    frozenlake("frozenlake8x8_n8_s21_limit25.npz", 8, 200, 21, map_name="8x8", max_episode_steps=25)
+    frozenlake("frozenlake8x8_n6_s4_samestep.npz", 6, 300, 4, map_name="8x8", mode=AutoresetMode.SAME_STEP)

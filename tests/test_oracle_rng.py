@@ -1,0 +1,28 @@
+"""Pins oracle/np_rng.py against numpy itself (the reference's RNG: gymnasium/utils/seeding.py:39-41)."""
+import numpy as np
+import pytest
+
+from oracle.np_rng import PCG64, seed_sequence_state
+
+SEEDS = [0, 1, 42, 123, 65535, 2**32 - 1, 2**32, 2**40 + 17, 2**63 - 1, 2**64 - 1, 2**64 + 5, 2**100 + 3]
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_seed_sequence_matches_numpy(seed):
+    assert list(np.random.SeedSequence(seed).generate_state(8)) == seed_sequence_state(seed)
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_pcg64_stream_matches_numpy(seed):
+    g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+    p = PCG64(seed)
+    assert list(g.uniform(-0.05, 0.05, size=4)) == [p.uniform(-0.05, 0.05) for _ in range(4)]
+    assert list(g.random(64)) == [p.next_double() for _ in range(64)]
+    assert list(g.uniform(-1.0, 1.0, size=3)) == [p.uniform(-1.0, 1.0) for _ in range(3)]
+
+
+def test_known_answer_seed42():
+    # env 0 of the doctest at gymnasium/vector/vector_env.py:157 (float64 values behind the float32 literals)
+    p = PCG64(42)
+    got = [p.uniform(-0.05, 0.05) for _ in range(4)]
+    assert got == [0.027395604855596334, -0.006112156024794771, 0.03585979199113824, 0.019736802905936393]
