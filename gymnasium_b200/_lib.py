@@ -1,0 +1,117 @@
+"""ctypes binding of libb200env.so (the C-ABI declared in include/b200env.h).
+
+There is NO CPU fallback: if the shared library is missing, fails to load, or there is no CUDA device, the engine
+raises.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C gymnasium_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200env.so")
+
+# enums (include/b200env.h)
+AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP, AUTORESET_DISABLED = 0, 1, 2
+RNG_NUMPY, RNG_PHILOX = 0, 1
+ACT_I64, ACT_I32, ACT_U8, ACT_F32, ACT_F64 = 0, 1, 2, 3, 4
+
+c_void_p, c_i32, c_i64, c_u64, c_double = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+
+
+class Batch(C.Structure):
+    """``b2e_batch``."""
+
+    _fields_ = [
+        ("n", c_i64),
+        ("env_offset", c_i64),
+        ("max_episode_steps", c_i32),
+        ("autoreset_mode", c_i32),
+        ("rng_mode", c_i32),
+        ("action_dtype", c_i32),
+        ("philox_seed", c_u64),
+        ("call_counter", c_u64),
+    ]
+
+
+class CartPoleCfg(C.Structure):
+    """``b2e_cartpole_cfg``."""
+
+    _fields_ = [("reset_low", c_double), ("reset_high", c_double), ("sutton_barto_reward", c_i32), ("_pad", c_i32)]
+
+
+class FrozenLakeCfg(C.Structure):
+    """``b2e_frozenlake_cfg``."""
+
+    _fields_ = [
+        ("n_states", c_i32),
+        ("n_actions", c_i32),
+        ("table", c_void_p),
+        ("isd_cum", c_void_p),
+        ("cum3", c_double * 3),
+        ("p3", c_double * 3),
+        ("rewards", c_double * 3),
+    ]
+
+
+P = c_void_p
+_BP = C.POINTER(Batch)
+
+# symbol -> (restype, argtypes); every symbol include/b200env.h declares must be listed here (tests check both ways)
+SIGNATURES = {
+    "b2e_version": (C.c_int, []),
+    "b2e_last_error": (C.c_char_p, []),
+    "b2e_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_size_t)]),
+    "b2e_rng_seed": (C.c_int, [_BP, c_u64, P, P, P, P]),
+    "b2e_rng_random": (C.c_int, [_BP, P, c_i32, P, P]),
+    "b2e_cartpole_reset": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P]),
+    "b2e_cartpole_step": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P, P, P, P, P]),
+    "b2e_cartpole_rollout": (C.c_int, [_BP, C.POINTER(CartPoleCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),
+    "b2e_frozenlake_reset": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P]),
+    "b2e_frozenlake_step": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P, P, P, P, P, P]),
+    "b2e_frozenlake_rollout": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),
+}
+
+
+class B200EnvError(RuntimeError):
+    """A libb200env call returned non-zero."""
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libb200env.so once; raises if it is not built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is not built. Run `make -C gymnasium_b200/csrc` (needs nvcc, targets sm_100a). "
+            "gymnasium_b200 has no CPU fallback."
+        )
+    import torch  # noqa: F401  -- loads the CUDA runtime (libcudart.so.12) this library links against dynamically
+
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b2e_version() != 1:
+        raise ImportError(f"libb200env.so ABI version {lib.b2e_version()} != 1; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().b2e_last_error().decode(errors="replace")
+        raise B200EnvError(f"{what} failed with status {status}: {msg}")
+
+
+def device_info(device: int = 0) -> dict:
+    lib = load()
+    sm, maj, mnr, l2 = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+    check(lib.b2e_device_info(device, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(l2)), "b2e_device_info")
+    return {"sm_count": sm.value, "cc": (maj.value, mnr.value), "l2_bytes": l2.value}

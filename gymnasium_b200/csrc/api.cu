@@ -1,0 +1,109 @@
+// api.cu -- library-wide C-ABI entry points (version, errors, device query) and the numpy-parity RNG seeding kernel.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace b2e {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_batch(const b2e_batch* b, const char* fn) {
+  if (!b) {
+    set_error("%s: batch descriptor is NULL", fn);
+    return B2E_EINVAL;
+  }
+  if (b->n < 0 || b->env_offset < 0) {
+    set_error("%s: n=%lld env_offset=%lld must be >= 0", fn, (long long)b->n, (long long)b->env_offset);
+    return B2E_EINVAL;
+  }
+  if (b->autoreset_mode < 0 || b->autoreset_mode > 2 || b->rng_mode < 0 || b->rng_mode > 1) {
+    set_error("%s: bad autoreset_mode=%d or rng_mode=%d", fn, b->autoreset_mode, b->rng_mode);
+    return B2E_EINVAL;
+  }
+  return 0;
+}
+
+int cuda_status(cudaError_t e, const char* fn) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: CUDA error %d (%s)", fn, (int)e, cudaGetErrorString(e));
+  return (int)e;
+}
+
+namespace {
+
+// SyncVectorEnv.reset seeds sub-env i with seed+i (sync_vector_env.py:205-208); Env.reset(seed) builds
+// Generator(PCG64(SeedSequence(seed))) (gymnasium/utils/seeding.py:39-41).
+__global__ void __launch_bounds__(kBlock) rng_seed_kernel(int64_t n, int64_t env_offset, uint64_t base_seed,
+                                                          const uint64_t* __restrict__ seeds,
+                                                          const uint8_t* __restrict__ mask, uint64_t* __restrict__ rng) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask != nullptr && mask[i] == 0) return;
+  const uint64_t seed = seeds ? seeds[i] : base_seed + (uint64_t)(env_offset + i);
+  pcg64_store_all(rng, n, i, pcg64_from_seed(seed));
+}
+
+__global__ void __launch_bounds__(kBlock) rng_random_kernel(int64_t n, uint64_t* __restrict__ rng, int k,
+                                                            double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Pcg64 g = pcg64_load(rng, n, i);
+  for (int j = 0; j < k; ++j) out[i * k + j] = g.next_double();
+  pcg64_store_state(rng, i, g);
+}
+
+}  // namespace
+}  // namespace b2e
+
+using namespace b2e;
+
+extern "C" int b2e_version(void) { return B2E_VERSION; }
+
+extern "C" const char* b2e_last_error(void) { return g_err; }
+
+extern "C" int b2e_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) {
+    set_error("b2e_device_info: no CUDA device %d (count=%d, %s)", device, count, cudaGetErrorString(e));
+    return B2E_ENODEV;
+  }
+  cudaDeviceProp p;
+  if (int s = cuda_status(cudaGetDeviceProperties(&p, device), "b2e_device_info")) return s;
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (l2_bytes) *l2_bytes = (size_t)p.l2CacheSize;
+  return 0;
+}
+
+extern "C" int b2e_rng_seed(const b2e_batch* b, uint64_t base_seed, const uint64_t* seeds, const uint8_t* mask,
+                            uint64_t* rng, void* stream) {
+  if (int e = check_batch(b, "b2e_rng_seed")) return e;
+  if (!rng) {
+    set_error("b2e_rng_seed: rng is NULL");
+    return B2E_EINVAL;
+  }
+  if (b->n == 0) return 0;
+  rng_seed_kernel<<<grid_for(b->n), kBlock, 0, (cudaStream_t)stream>>>(b->n, b->env_offset, base_seed, seeds, mask, rng);
+  return cuda_status(cudaGetLastError(), "b2e_rng_seed");
+}
+
+extern "C" int b2e_rng_random(const b2e_batch* b, uint64_t* rng, int32_t k, double* out, void* stream) {
+  if (int e = check_batch(b, "b2e_rng_random")) return e;
+  if (!rng || !out || k < 0) {
+    set_error("b2e_rng_random: null pointer or k < 0");
+    return B2E_EINVAL;
+  }
+  if (b->n == 0 || k == 0) return 0;
+  rng_random_kernel<<<grid_for(b->n), kBlock, 0, (cudaStream_t)stream>>>(b->n, rng, k, out);
+  return cuda_status(cudaGetLastError(), "b2e_rng_random");
+}

@@ -1,0 +1,348 @@
+"""``B200VectorEnv`` -- the VectorEnv the engine exposes to Gymnasium.
+
+Host-side mirror of ``gymnasium.vector.SyncVectorEnv`` (gymnasium/vector/sync_vector_env.py:76-403) for the
+step()/reset() path: same constructor-visible attributes (``num_envs``, batched and single spaces,
+``metadata["autoreset_mode"]``), same ``reset(seed=..., options=...)`` / ``step(actions)`` signatures, dtypes, seeding
+convention (sub-env i gets ``seed + i``, :205-208) and error behaviour (:196-231), but every sub-env lives in a
+struct-of-arrays batch in HBM and one CUDA launch (libb200env.so, include/b200env.h) advances all of them.
+
+Returned arrays are torch tensors on the env's CUDA device (``output="torch"``, default) or host numpy arrays
+(``output="numpy"``, one device->host copy per call).  There is no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import secrets
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._api import AutoresetMode, VectorEnv, batch_space
+
+_MODE = {
+    AutoresetMode.NEXT_STEP: _lib.AUTORESET_NEXT_STEP,
+    AutoresetMode.SAME_STEP: _lib.AUTORESET_SAME_STEP,
+    AutoresetMode.DISABLED: _lib.AUTORESET_DISABLED,
+}
+_ACT_DTYPES = {torch.int64: _lib.ACT_I64, torch.int32: _lib.ACT_I32, torch.uint8: _lib.ACT_U8,
+               torch.float32: _lib.ACT_F32, torch.float64: _lib.ACT_F64}
+_U64 = (1 << 64) - 1
+
+
+def _as_autoreset_mode(mode) -> AutoresetMode:
+    if isinstance(mode, AutoresetMode):
+        return mode
+    for m in AutoresetMode:  # accept the enum of the *other* namespace (compat vs gymnasium) and plain strings
+        if getattr(mode, "value", mode) == m.value:
+            return m
+    raise ValueError(f"Unexpected autoreset mode, {mode}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+class B200VectorEnv(VectorEnv):
+    """Family-independent host logic; subclasses provide the spaces, device state and the two kernel calls."""
+
+    metadata: dict[str, Any] = {"render_modes": [], "autoreset_mode": AutoresetMode.NEXT_STEP}
+    discrete_actions = True  # Box-action families override
+
+    def __init__(
+        self,
+        num_envs: int,
+        single_observation_space,
+        single_action_space,
+        *,
+        max_episode_steps: int | None,
+        autoreset_mode=AutoresetMode.NEXT_STEP,
+        device: str | int | torch.device | None = None,
+        rng: str = "numpy",
+        env_offset: int = 0,
+        output: str = "torch",
+        copy: bool = True,
+        render_mode: str | None = None,
+    ):
+        if render_mode is not None:
+            raise ValueError("gymnasium_b200 environments do not render (render_mode must be None)")
+        if int(num_envs) <= 0:
+            raise ValueError(f"num_envs must be positive, got {num_envs}")
+        if rng not in ("numpy", "philox"):
+            raise ValueError(f"rng must be 'numpy' (bit-exact PCG64 streams) or 'philox' (stateless), got {rng!r}")
+        if output not in ("torch", "numpy"):
+            raise ValueError(f"output must be 'torch' or 'numpy', got {output!r}")
+        self.num_envs = int(num_envs)
+        self.single_observation_space = single_observation_space
+        self.single_action_space = single_action_space
+        self.observation_space = batch_space(single_observation_space, self.num_envs)
+        self.action_space = batch_space(single_action_space, self.num_envs)
+        self.autoreset_mode = _as_autoreset_mode(autoreset_mode)
+        self.metadata = {**type(self).metadata, "autoreset_mode": self.autoreset_mode}
+        self.max_episode_steps = None if max_episode_steps is None else int(max_episode_steps)
+        self.render_mode = None
+        self.rng_mode = rng
+        self.env_offset = int(env_offset)
+        self.output = output
+        self.copy = bool(copy)
+
+        # ---- device + library: no fallback -------------------------------------------------------------------
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "gymnasium_b200 needs a CUDA device (B200, sm_100a): torch.cuda.is_available() is False and the "
+                "engine has no CPU fallback. Use gymnasium.vector.SyncVectorEnv on CPU-only hosts."
+            )
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError(f"device must be a CUDA device, got {dev}")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+
+        n = self.num_envs
+        self._batch = _lib.Batch(
+            n=n,
+            env_offset=self.env_offset,
+            max_episode_steps=self.max_episode_steps if self.max_episode_steps is not None else 0,
+            autoreset_mode=_MODE[self.autoreset_mode],
+            rng_mode=_lib.RNG_NUMPY if rng == "numpy" else _lib.RNG_PHILOX,
+            action_dtype=_lib.ACT_I64,
+            philox_seed=0,
+            call_counter=0,
+        )
+        self._ctrl = torch.zeros(n, dtype=torch.int32, device=dev)
+        # numpy-parity streams: uint64 [2][n][2] = PCG64 state then increment (stored as int64 bit patterns)
+        self._rng = torch.zeros((2, n, 2), dtype=torch.int64, device=dev) if rng == "numpy" else None
+        self._seeded = False
+        self._base_seed: int | None = None
+        self._seed_list: list[int] | None = None
+        self._has_reset = False
+        self._pinned_actions: torch.Tensor | None = None
+        self._out: dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------------------
+    # hooks for families
+    def _alloc_outputs(self) -> dict[str, torch.Tensor]:
+        raise NotImplementedError
+
+    def _reset_kernel(self, mask: torch.Tensor | None, options: dict | None, out: dict[str, torch.Tensor]) -> None:
+        raise NotImplementedError
+
+    def _step_kernel(self, actions: torch.Tensor, out: dict[str, torch.Tensor]) -> None:
+        raise NotImplementedError
+
+    def _reset_info(self, out, mask) -> dict:
+        return {}
+
+    def _step_info(self, out) -> dict:
+        return {}
+
+    # ------------------------------------------------------------------------------------------------------------
+    @property
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _outputs(self) -> dict[str, torch.Tensor]:
+        if self.copy or not self._out:
+            self._out = self._alloc_outputs()  # fresh tensors from the caching allocator; kernels write in place
+        return self._out
+
+    def _deliver(self, t):
+        if self.output == "numpy":
+            if isinstance(t, dict):
+                return {k: self._deliver(v) for k, v in t.items()}
+            return t.cpu().numpy() if isinstance(t, torch.Tensor) else t
+        return t
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _seed_streams(self, seed, mask: torch.Tensor | None) -> None:
+        """SyncVectorEnv.reset seeding (sync_vector_env.py:203-212): int -> seed+i; list -> per env; None -> keep."""
+        n = self.num_envs
+        seeds_dev = None
+        base = 0
+        if seed is None:
+            if self._seeded:
+                return  # Env.reset(seed=None) keeps the stream (gymnasium/core.py:157-159)
+            base = secrets.randbits(62)  # lazy self-seeding (core.py:226-235); kept for np_random_seed
+            self._base_seed, self._seed_list = base, None
+        elif isinstance(seed, (int, np.integer)):
+            base = int(seed)
+            if base < 0:
+                raise ValueError(f"Seed must be a non-negative integer, got {base}")  # seeding.py:28-34
+            if base + self.env_offset + n - 1 > _U64:
+                raise ValueError("gymnasium_b200 supports seeds below 2**64")
+            if mask is None or self._base_seed is None:
+                self._base_seed, self._seed_list = base, None
+        else:
+            seed = list(seed)
+            if len(seed) != n:
+                raise ValueError(
+                    f"If seeds are passed as a list the length must match num_envs={n} but got length={len(seed)}."
+                )
+            if any(s is None for s in seed):
+                # per-env None: those lanes keep their stream (or get fresh entropy if never seeded)
+                keep = torch.tensor([s is not None for s in seed], dtype=torch.bool)
+                fill = [secrets.randbits(62) if (s is None and not self._seeded) else (0 if s is None else int(s))
+                        for s in seed]
+                lane_mask = keep if self._seeded else torch.ones(n, dtype=torch.bool)
+                lane_mask = lane_mask.to(self.device)
+                mask = lane_mask if mask is None else (mask & lane_mask)
+                seed = fill
+            if any(int(s) < 0 or int(s) > _U64 for s in seed):
+                raise ValueError("gymnasium_b200 supports seeds in [0, 2**64)")
+            arr = np.array([int(s) for s in seed], dtype=np.uint64).view(np.int64)
+            seeds_dev = torch.from_numpy(arr).to(self.device)
+            self._seed_list, self._base_seed = [int(s) for s in seed], None
+        if self.rng_mode == "numpy":
+            mask_u8 = None if mask is None else mask.view(torch.uint8)
+            _lib.check(
+                self._lib.b2e_rng_seed(C.byref(self._batch), base & _U64, ptr(seeds_dev), ptr(mask_u8),
+                                       ptr(self._rng), self._stream),
+                "b2e_rng_seed",
+            )
+        else:
+            self._batch.philox_seed = (base if seeds_dev is None else int(seed[0])) & _U64
+        self._seeded = True
+
+    def _parse_reset_mask(self, options: dict | None):
+        """Validation and messages of sync_vector_env.py:214-231 (torch bool tensors are accepted too)."""
+        if options is None or "reset_mask" not in options:
+            return options, None
+        options = dict(options)
+        reset_mask = options.pop("reset_mask")
+        n = self.num_envs
+        if isinstance(reset_mask, torch.Tensor):
+            if tuple(reset_mask.shape) != (n,):
+                raise ValueError(f"`options['reset_mask']` must have shape `({n},)`, got {tuple(reset_mask.shape)}")
+            if reset_mask.dtype != torch.bool:
+                raise TypeError(f"`options['reset_mask']` must have `dtype=np.bool_`, got {reset_mask.dtype}")
+            mask = reset_mask.to(self.device)
+            if not bool(mask.any()):
+                raise ValueError(
+                    f"`options['reset_mask']` must contain a boolean array with at least one True value, got reset_mask={reset_mask}"
+                )
+            return options, mask.contiguous()
+        if not isinstance(reset_mask, np.ndarray):
+            raise TypeError(f"`options['reset_mask']` must be a numpy array, got {type(reset_mask)}")
+        if reset_mask.shape != (n,):
+            raise ValueError(f"`options['reset_mask']` must have shape `({n},)`, got {reset_mask.shape}")
+        if reset_mask.dtype != np.bool_:
+            raise TypeError(f"`options['reset_mask']` must have `dtype=np.bool_`, got {reset_mask.dtype}")
+        if not np.any(reset_mask):
+            raise ValueError(
+                f"`options['reset_mask']` must contain a boolean array with at least one True value, got reset_mask={reset_mask}"
+            )
+        return options, torch.from_numpy(np.ascontiguousarray(reset_mask)).to(self.device)
+
+    def reset(self, *, seed: int | list[int | None] | None = None, options: dict[str, Any] | None = None):
+        """SyncVectorEnv.reset (gymnasium/vector/sync_vector_env.py:187-264) on device."""
+        options, mask = self._parse_reset_mask(options)
+        with torch.cuda.device(self.device):
+            self._seed_streams(seed, mask)
+            out = self._outputs()
+            self._reset_kernel(mask, options, out)
+            self._batch.call_counter += 1
+        self._has_reset = True
+        return self._deliver(out["obs"]), self._deliver(self._reset_info(out, mask))
+
+    def _prepare_actions(self, actions) -> torch.Tensor:
+        """One conversion to a contiguous device tensor; wrong count -> ValueError, scalar -> TypeError
+        (tests/vector/test_vector_env.py:330-364)."""
+        n = self.num_envs
+        if isinstance(actions, torch.Tensor):
+            t = actions
+        else:
+            if np.ndim(actions) == 0:
+                raise TypeError(f"actions must be an iterable of length num_envs={n}, got a scalar {actions!r}")
+            a = np.ascontiguousarray(actions)
+            if a.dtype == object or a.dtype.kind not in "iuf" + "b":
+                raise TypeError(f"unsupported action array dtype {a.dtype}")
+            if a.dtype == np.bool_:
+                a = a.astype(np.uint8)
+            if self.discrete_actions and a.dtype.kind == "f":
+                raise TypeError(f"discrete actions must be integers, got dtype {a.dtype}")
+            if self.discrete_actions and a.dtype not in (np.int64, np.int32, np.uint8):
+                a = a.astype(np.int64)
+            t = torch.from_numpy(a)
+        if t.dim() == 0:
+            raise TypeError(f"actions must have a leading dimension of num_envs={n}, got a scalar tensor")
+        if t.shape[0] != n:
+            raise ValueError(f"expected {n} actions (one per sub-environment), got {t.shape[0]}")
+        if self.discrete_actions:
+            if t.dim() != 1:
+                raise ValueError(f"discrete actions must have shape ({n},), got {tuple(t.shape)}")
+            if t.dtype not in (torch.int64, torch.int32, torch.uint8):
+                t = t.to(torch.int64)
+        if t.device != self.device:
+            if t.device.type == "cpu":
+                if self._pinned_actions is None or self._pinned_actions.shape != t.shape or self._pinned_actions.dtype != t.dtype:
+                    self._pinned_actions = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                self._pinned_actions.copy_(t)
+                t = self._pinned_actions.to(self.device, non_blocking=True)
+            else:
+                t = t.to(self.device)
+        return t.contiguous()
+
+    def step(self, actions):
+        """SyncVectorEnv.step (gymnasium/vector/sync_vector_env.py:266-337) as one fused launch."""
+        if not self._has_reset:
+            # OrderEnforcing.step (gymnasium/wrappers/common.py:393-397) raises ResetNeeded per sub-env
+            from . import errors
+
+            raise errors.ResetNeeded("Cannot call env.step() before calling env.reset()")
+        with torch.cuda.device(self.device):
+            t = self._prepare_actions(actions)
+            out = self._outputs()
+            self._batch.action_dtype = _ACT_DTYPES[t.dtype]
+            self._step_kernel(t, out)
+            self._batch.call_counter += 1
+        info = self._step_info(out)
+        return (
+            self._deliver(out["obs"]),
+            self._deliver(out["reward"]),
+            self._deliver(out["terminated"]),
+            self._deliver(out["truncated"]),
+            self._deliver(info),
+        )
+
+    # ------------------------------------------------------------------------------------------------------------
+    @property
+    def np_random_seed(self) -> tuple[int, ...]:
+        """Seeds of the sub-envs, as SyncVectorEnv.np_random_seed (sync_vector_env.py:177-180)."""
+        if not self._seeded:
+            with torch.cuda.device(self.device):
+                self._seed_streams(None, None)
+        if self._seed_list is not None:
+            return tuple(self._seed_list)
+        return tuple(self._base_seed + self.env_offset + i for i in range(self.num_envs))
+
+    @property
+    def np_random(self):
+        raise AttributeError(
+            "B200VectorEnv keeps its per-env PCG64 streams on the device; read `rng_state()` for the raw "
+            "(state, inc) words (they equal numpy's bit_generator.state for the same seed)."
+        )
+
+    def rng_state(self) -> np.ndarray | None:
+        """uint64 [2][n][2] host copy of the PCG64 (state, inc) words; None in philox mode."""
+        if self._rng is None:
+            return None
+        return self._rng.cpu().numpy().view(np.uint64)
+
+    def elapsed_steps(self) -> torch.Tensor:
+        """TimeLimit counters (gymnasium/wrappers/common.py:108) as an int32 device tensor."""
+        return self._ctrl & 0x7FFFFFFF
+
+    def close_extras(self, **kwargs):
+        self._out = {}
+        self._rng = None
+        self._ctrl = None
+
+    # SyncVectorEnv.call/get_attr/set_attr (sync_vector_env.py:343-398): there are no sub-env objects here
+    def get_attr(self, name: str):
+        if hasattr(self, name):
+            v = getattr(self, name)
+            return tuple(v for _ in range(self.num_envs)) if not isinstance(v, (torch.Tensor, tuple)) else v
+        raise AttributeError(f"{type(self).__name__} has no per-env attribute {name!r}")

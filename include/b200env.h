@@ -1,0 +1,141 @@
+/* b200env.h -- C-ABI of libb200env.so, the B200-native vector-env step engine.
+ *
+ * Drop-in boundary for Gymnasium's vectorised step()/reset() hot path.  Gymnasium (v1.4.0) is pure Python; the
+ * interfaces these entry points replace are (paths relative to the reference tree):
+ *   - SyncVectorEnv.reset / .step          gymnasium/vector/sync_vector_env.py:187-264, :266-337
+ *   - AsyncVectorEnv.step_async/step_wait  gymnasium/vector/async_vector_env.py:440-521 (+ worker loop :773-904)
+ *   - TimeLimit.step / .reset              gymnasium/wrappers/common.py:116-151
+ *   - seeding.np_random                    gymnasium/utils/seeding.py:10-42
+ *   - per-family dynamics, cited at each declaration below.
+ * The reference-side binding is a ctypes stub inside a VectorEnv subclass registered as a spec's
+ * `vector_entry_point` (gymnasium/envs/registration.py:933-963); see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B2E_E* code for an argument error, or a positive cudaError_t;
+ *     b2e_last_error() returns a thread-local message for the last non-zero return.
+ *   - all array pointers are DEVICE pointers owned by the caller (torch allocates them); nothing is allocated,
+ *     freed or synchronised inside a call; kernels are enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - shapes are given per argument; "n" is the number of envs in this shard (b2e_batch.n).
+ *   - bool outputs are 1 byte (0/1), i.e. torch.bool / numpy.bool_ storage.
+ */
+#ifndef B200ENV_H_
+#define B200ENV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2E_VERSION 1
+
+/* error codes */
+#define B2E_EINVAL (-1)  /* bad argument (null pointer, bad enum, n < 0) */
+#define B2E_ENODEV (-2)  /* no CUDA device / wrong architecture */
+
+/* autoreset modes: gymnasium/vector/vector_env.py:34-39 */
+#define B2E_AUTORESET_NEXT_STEP 0
+#define B2E_AUTORESET_SAME_STEP 1
+#define B2E_AUTORESET_DISABLED 2
+
+/* rng modes */
+#define B2E_RNG_NUMPY 0  /* per-env numpy Generator(PCG64(SeedSequence(seed+i))) streams, bit-exact */
+#define B2E_RNG_PHILOX 1 /* stateless Philox4x32-10 keyed by (seed, global env index, call counter) */
+
+/* action dtypes */
+#define B2E_ACT_I64 0
+#define B2E_ACT_I32 1
+#define B2E_ACT_U8 2
+#define B2E_ACT_F32 3
+#define B2E_ACT_F64 4
+
+/* Batch descriptor shared by every family (passed by pointer, host memory). */
+typedef struct b2e_batch {
+  int64_t n;                 /* envs in this shard */
+  int64_t env_offset;        /* global index of this shard's env 0 (multi-GPU sharding; seeds are seed+offset+i) */
+  int32_t max_episode_steps; /* TimeLimit; <= 0 disables truncation */
+  int32_t autoreset_mode;    /* B2E_AUTORESET_* */
+  int32_t rng_mode;          /* B2E_RNG_* */
+  int32_t action_dtype;      /* B2E_ACT_* */
+  uint64_t philox_seed;      /* B2E_RNG_PHILOX only */
+  uint64_t call_counter;     /* B2E_RNG_PHILOX only: index of this reset/step call (the caller increments it) */
+} b2e_batch;
+
+int b2e_version(void);
+const char* b2e_last_error(void);
+/* sm_count / cc may be NULL. Returns B2E_ENODEV when no device. */
+int b2e_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+
+/* ---- RNG: gymnasium/utils/seeding.py:39-41 -> numpy SeedSequence -> PCG64 ---------------------------------------
+ * rng   : uint64 [2][n][2]  = {state(lo,hi)}[n] then {inc(lo,hi)}[n]
+ * seeds : uint64 [n] device, or NULL => seed_i = base_seed + env_offset + i  (SyncVectorEnv.reset seed+i, :205-208)
+ * mask  : uint8 [n] device or NULL (all) -- only masked lanes are re-seeded
+ */
+int b2e_rng_seed(const b2e_batch* b, uint64_t base_seed, const uint64_t* seeds, const uint8_t* mask, uint64_t* rng,
+                 void* stream);
+/* Debug/test helper: draw k doubles per env (Generator.random()) into out[n][k], advancing the streams. */
+int b2e_rng_random(const b2e_batch* b, uint64_t* rng, int32_t k, double* out, void* stream);
+
+/* ---- CartPole-v1: gymnasium/envs/classic_control/cartpole.py:164-247 ---------------------------------------------
+ * state  : float64 [4][n]  (x, x_dot, theta, theta_dot) struct-of-arrays
+ * ctrl   : int32 [n]       bits 0..30 elapsed steps (TimeLimit), bit 31 = autoreset pending (NEXT_STEP)
+ * obs    : float32 [n][4]
+ */
+typedef struct b2e_cartpole_cfg {
+  double reset_low, reset_high; /* cartpole.py:236-241 (+ options low/high, classic_control/utils.py:17-46) */
+  int32_t sutton_barto_reward;  /* cartpole.py:205-220 */
+  int32_t _pad;
+} b2e_cartpole_cfg;
+
+/* CartPoleEnv.reset for lanes with mask!=0 (NULL = all); clears elapsed/autoreset; writes obs for those lanes. */
+int b2e_cartpole_reset(const b2e_batch* b, const b2e_cartpole_cfg* cfg, const uint8_t* mask, double* state,
+                       int32_t* ctrl, uint64_t* rng, float* obs, void* stream);
+/* One fused step + time-limit + autoreset over the batch.
+ * actions: [n] of b->action_dtype in {I64,I32,U8}; reward float64 [n]; terminated/truncated uint8 [n];
+ * final_obs float32 [n][4] is written for done lanes in SAME_STEP mode only (may be NULL otherwise). */
+int b2e_cartpole_step(const b2e_batch* b, const b2e_cartpole_cfg* cfg, const void* actions, double* state,
+                      int32_t* ctrl, uint64_t* rng, float* obs, double* reward, uint8_t* terminated,
+                      uint8_t* truncated, float* final_obs, void* stream);
+/* K fused steps in one launch, state kept in registers, trajectory streamed to HBM.
+ * actions: [K][n] of b->action_dtype, or NULL => uniform random actions from Philox(philox_seed, env, call_counter+k),
+ *          written to actions_out uint8 [K][n] when that is non-NULL.
+ * obs float32 [K][n][4]; reward float32 [K][n]; terminated/truncated uint8 [K][n]. NEXT_STEP autoreset only. */
+int b2e_cartpole_rollout(const b2e_batch* b, const b2e_cartpole_cfg* cfg, int32_t K, const void* actions,
+                         uint8_t* actions_out, double* state, int32_t* ctrl, uint64_t* rng, float* obs, float* reward,
+                         uint8_t* terminated, uint8_t* truncated, void* stream);
+
+/* ---- FrozenLake-v1: gymnasium/envs/toy_text/frozen_lake.py:232-348, toy_text/utils.py:4-8 -----------------------
+ * Transition table (device, immutable, built by the host from the map exactly as frozen_lake.py:256-300):
+ *   table  : uint32 [nS*nA*3]  entry = next_state | done<<16 | reward_class<<17 (0..2 -> rewards[class], 3 -> 0.0) | n_out<<20
+ *            n_out is 3 for a slippery row (outcomes ordered (a-1)%4, a, (a+1)%4) or 1 (terminal tile / not slippery)
+ *   cum3/p3: cumulative (numpy cumsum order) and plain probabilities of the three outcomes of a slippery row;
+ *            a one-outcome row has p = 1.0
+ *   isd_cum: float64 [nS] device, cumulative initial-state distribution
+ * pstate : int32 [n]  current state;  ctrl as for CartPole
+ * obs    : int64 [n];  prob float64 [n] (info["prob"], 1.0 on reset calls)
+ */
+typedef struct b2e_frozenlake_cfg {
+  int32_t n_states, n_actions;
+  const uint32_t* table;
+  const double* isd_cum;
+  double cum3[3];
+  double p3[3];
+  double rewards[3];
+} b2e_frozenlake_cfg;
+
+int b2e_frozenlake_reset(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, const uint8_t* mask, int32_t* pstate,
+                         int32_t* ctrl, uint64_t* rng, int64_t* obs, double* prob, void* stream);
+int b2e_frozenlake_step(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, const void* actions, int32_t* pstate,
+                        int32_t* ctrl, uint64_t* rng, int64_t* obs, double* reward, uint8_t* terminated,
+                        uint8_t* truncated, double* prob, int64_t* final_obs, double* final_prob, void* stream);
+/* K fused steps; actions [K][n] or NULL (Philox random, written to actions_out when non-NULL).
+ * obs uint8/int64 per obs_i64 flag: obs [K][n]; reward float32 [K][n]; flags uint8 [K][n]. */
+int b2e_frozenlake_rollout(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, int32_t K, const void* actions,
+                           uint8_t* actions_out, int32_t* pstate, int32_t* ctrl, uint64_t* rng, int64_t* obs,
+                           float* reward, uint8_t* terminated, uint8_t* truncated, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ENV_H_ */

@@ -1,0 +1,310 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C-ABI / B200VectorEnv, against
+(1) golden fixtures from the live reference, (2) the numpy oracle on seeded inputs, (3) size-independent properties at
+BASELINE.json's full sizes.  Tolerances: integer/bool/RNG bit-exact; CartPole float32 observations rtol=atol=1e-5
+(the reference's own `data_equivalence`, gymnasium/utils/env_checker.py:34-75)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import fixture_kwargs, fixture_options, golden, golden_files, have_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="needs a CUDA device")]
+
+RTOL = ATOL = 1e-5
+
+
+def make(env_id, n, **kw):
+    import gymnasium_b200
+
+    kw.setdefault("output", "numpy")
+    return gymnasium_b200.make_vec(env_id, num_envs=n, **kw)
+
+
+def replay(env, seed, actions, options=None):
+    obs, info = env.reset(seed=seed, options=options)
+    out = dict(obs=[obs], reward=[], terminated=[], truncated=[], info=[info])
+    for a in actions:
+        o, r, te, tr, info = env.step(a)
+        out["obs"].append(o); out["reward"].append(r); out["terminated"].append(te); out["truncated"].append(tr)
+        out["info"].append(info)
+    return {k: (np.stack(v) if k != "info" else v) for k, v in out.items()}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# RNG
+@pytest.mark.parametrize("base", [0, 42, 2**32 - 2, 2**40 + 12345, 2**63 + 11])
+def test_rng_streams_bit_exact_with_numpy(base):
+    import torch
+    from gymnasium_b200 import _lib
+
+    lib = _lib.load()
+    n, k = 257, 9
+    b = _lib.Batch(n=n, env_offset=3)
+    rng = torch.zeros((2, n, 2), dtype=torch.int64, device="cuda")
+    out = torch.zeros((n, k), dtype=torch.float64, device="cuda")
+    _lib.check(lib.b2e_rng_seed(C.byref(b), base, None, None, rng.data_ptr(), None))
+    state = rng.cpu().numpy().view(np.uint64)
+    _lib.check(lib.b2e_rng_random(C.byref(b), rng.data_ptr(), k, out.data_ptr(), None))
+    got = out.cpu().numpy()
+    for i in [0, 1, 2, 100, 256]:
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(base + 3 + i)))
+        st = g.bit_generator.state["state"]
+        assert int(state[0, i, 0]) | (int(state[0, i, 1]) << 64) == st["state"]
+        assert int(state[1, i, 0]) | (int(state[1, i, 1]) << 64) == st["inc"]
+        np.testing.assert_array_equal(got[i], g.random(k))
+    # explicit seed list + mask
+    seeds = np.array([7, 2**64 - 1, 5, 2**33], dtype=np.uint64)
+    b = _lib.Batch(n=4)
+    rng = torch.zeros((2, 4, 2), dtype=torch.int64, device="cuda")
+    mask = torch.tensor([1, 1, 0, 1], dtype=torch.uint8, device="cuda")
+    sd = torch.from_numpy(seeds.view(np.int64)).cuda()
+    _lib.check(lib.b2e_rng_seed(C.byref(b), 0, sd.data_ptr(), mask.data_ptr(), rng.data_ptr(), None))
+    out = torch.zeros((4, 3), dtype=torch.float64, device="cuda")
+    st_before = rng.clone()
+    _lib.check(lib.b2e_rng_random(C.byref(b), rng.data_ptr(), 3, out.data_ptr(), None))
+    for i in [0, 1, 3]:
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(seeds[i]))))
+        np.testing.assert_array_equal(out[i].cpu().numpy(), g.random(3))
+    assert (st_before[:, 2] == 0).all()  # masked-out lane untouched by seeding
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CartPole
+@pytest.mark.parametrize("name", golden_files("cartpole"))
+def test_cartpole_matches_reference_golden(name):
+    g = golden(name)
+    n = g["actions"].shape[1]
+    env = make("CartPole-v1", n, max_episode_steps=int(g["max_episode_steps"]), **fixture_kwargs(name))
+    out = replay(env, int(g["seed"]), g["actions"], fixture_options(name))
+    np.testing.assert_array_equal(out["obs"][0], g["obs"][0])  # reset draws: exact fp64 RNG math
+    np.testing.assert_array_equal(out["terminated"], g["terminated"])
+    np.testing.assert_array_equal(out["truncated"], g["truncated"])
+    np.testing.assert_array_equal(out["reward"], g["reward"])
+    assert out["reward"].dtype == np.float64 and out["obs"].dtype == np.float32
+    np.testing.assert_allclose(out["obs"], g["obs"], rtol=RTOL, atol=ATOL)
+    # in practice far tighter than the contract: sin/cos are the only non-identical ops
+    assert np.max(np.abs(out["obs"].astype(np.float64) - g["obs"])) < 1e-6
+
+
+def test_cartpole_state_fp64_vs_reference():
+    g = golden("cartpole_n8_s42_T300.npz")
+    env = make("CartPole-v1", 8)
+    env.reset(seed=42)
+    np.testing.assert_array_equal(env.state.cpu().numpy(), g["state"][0])
+    worst = 0.0
+    for t, a in enumerate(g["actions"]):
+        env.step(a)
+        worst = max(worst, np.max(np.abs(env.state.cpu().numpy() - g["state"][t + 1])))
+    assert worst < 1e-11, worst
+
+
+@pytest.mark.parametrize("rng_dtype", [np.int64, np.int32, np.uint8])
+def test_cartpole_vs_oracle_4096(rng_dtype):
+    from oracle.cartpole import OracleCartPole
+
+    n, T, seed = 4096, 260, 1234
+    acts = np.random.default_rng(5).integers(0, 2, size=(T, n)).astype(rng_dtype)
+    env = make("CartPole-v1", n, max_episode_steps=100)
+    ora = OracleCartPole(n, max_episode_steps=100)
+    o1, _ = env.reset(seed=seed)
+    o2, _ = ora.reset(seed=seed)
+    np.testing.assert_array_equal(o1, o2)
+    n_done = n_trunc = 0
+    for t in range(T):
+        a1 = env.step(acts[t])
+        a2 = ora.step(acts[t].astype(np.int64))
+        np.testing.assert_allclose(a1[0], a2[0], rtol=RTOL, atol=ATOL)
+        for k in (1, 2, 3):
+            np.testing.assert_array_equal(a1[k], a2[k])
+        n_done += a2[2].sum(); n_trunc += a2[3].sum()
+    assert n_done > n and n_trunc > 0  # every lane reset at least once on average; the time limit was exercised
+
+
+def test_cartpole_rollout_equals_step_loop_full_size():
+    """Property at BASELINE size (N=65536): K fused steps == K step() calls, bit for bit (same device arithmetic)."""
+    import torch
+
+    n, K = 65536, 64
+    acts = torch.randint(0, 2, (K, n), dtype=torch.int64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    a = make("CartPole-v1", n, output="torch")
+    b = make("CartPole-v1", n, output="torch")
+    a.reset(seed=99); b.reset(seed=99)
+    traj = a.rollout(K, actions=acts)
+    for k in range(K):
+        o, r, te, tr, _ = b.step(acts[k])
+        assert torch.equal(o, traj["obs"][k]) and torch.equal(te, traj["terminated"][k])
+        assert torch.equal(tr, traj["truncated"][k]) and torch.equal(r.float(), traj["reward"][k])
+    assert torch.equal(a.state, b.state) and torch.equal(a._ctrl, b._ctrl) and torch.equal(a._rng, b._rng)
+    done = traj["terminated"] | traj["truncated"]
+    assert 0.03 < done.float().mean().item() < 0.06  # ~1/22.8 of random-action steps end an episode
+    # rows after a done are resets: reward 0 and |obs| <= 0.05
+    after = done[:-1]
+    assert (traj["reward"][1:][after] == 0).all() and (traj["obs"][1:][after].abs() <= 0.05).all()
+
+
+def test_cartpole_sharding_is_invariant():
+    """Shards with env_offset reproduce the matching slice of one big batch (seeds are global: seed + offset + i)."""
+    n, T = 1024, 40
+    acts = np.random.default_rng(3).integers(0, 2, size=(T, n))
+    whole = make("CartPole-v1", n)
+    parts = [make("CartPole-v1", n // 4, env_offset=r * (n // 4)) for r in range(4)]
+    ow, _ = whole.reset(seed=17)
+    op = np.concatenate([p.reset(seed=17)[0] for p in parts])
+    np.testing.assert_array_equal(ow, op)
+    for t in range(T):
+        w = whole.step(acts[t])
+        ps = [p.step(acts[t, r * (n // 4):(r + 1) * (n // 4)]) for r, p in enumerate(parts)]
+        for k in range(4):
+            np.testing.assert_array_equal(w[k], np.concatenate([x[k] for x in ps]))
+
+
+def test_cartpole_random_rollout_philox_statistics():
+    import torch
+
+    n, K = 65536, 200
+    env = make("CartPole-v1", n, output="torch", rng="philox")
+    env.reset(seed=5)
+    traj = env.rollout(K, return_actions=True)
+    assert abs(traj["actions"].float().mean().item() - 0.5) < 0.002
+    done = (traj["terminated"] | traj["truncated"])
+    ep_len = (K * n) / max(done.sum().item(), 1)
+    assert 20.0 < ep_len < 26.0, ep_len  # mean random-policy episode ~22.8 steps + 1 reset call
+    env2 = make("CartPole-v1", n, output="torch", rng="philox")
+    env2.reset(seed=5)
+    t2 = env2.rollout(K, return_actions=True)
+    assert all(torch.equal(traj[k], t2[k]) for k in traj)  # deterministic
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FrozenLake
+@pytest.mark.parametrize("name", golden_files("frozenlake"))
+def test_frozenlake_matches_reference_golden_bit_exact(name):
+    g = golden(name)
+    n = g["actions"].shape[1]
+    env = make("FrozenLake-v1", n, max_episode_steps=int(g["max_episode_steps"]), **fixture_kwargs(name))
+    out = replay(env, int(g["seed"]), g["actions"])
+    assert out["obs"].dtype == np.int64
+    np.testing.assert_array_equal(out["obs"], g["obs"])
+    np.testing.assert_array_equal(out["reward"], g["reward"])
+    np.testing.assert_array_equal(out["terminated"], g["terminated"])
+    np.testing.assert_array_equal(out["truncated"], g["truncated"])
+    for t, info in enumerate(out["info"][1:]):
+        ref = g["info_prob"][t]
+        assert ((ref == info["prob"]) | (ref == np.floor(info["prob"]))).all()
+        np.testing.assert_array_equal(info["_prob"], g["info__prob"][t])
+
+
+def test_frozenlake_vs_oracle_2048():
+    from oracle.frozenlake import OracleFrozenLake
+
+    n, T, seed = 2048, 230, 77
+    acts = np.random.default_rng(8).integers(0, 4, size=(T, n))
+    env = make("FrozenLake-v1", n, map_name="8x8", max_episode_steps=100)
+    ora = OracleFrozenLake(n, map_name="8x8", max_episode_steps=100)
+    np.testing.assert_array_equal(env.reset(seed=seed)[0], ora.reset(seed=seed)[0])
+    for t in range(T):
+        a1, a2 = env.step(acts[t]), ora.step(acts[t])
+        for k in range(4):
+            np.testing.assert_array_equal(a1[k], a2[k])
+        np.testing.assert_array_equal(a1[4]["prob"], a2[4]["prob"])
+
+
+def test_frozenlake_rollout_equals_step_loop_full_size():
+    """Property at BASELINE size (N=1,048,576, 8x8): fused rollout == step loop bit-exact; states stay on the map."""
+    import torch
+
+    n, K = 1 << 20, 24
+    acts = torch.randint(0, 4, (K, n), dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    a = make("FrozenLake-v1", n, map_name="8x8", output="torch", copy=False)
+    b = make("FrozenLake-v1", n, map_name="8x8", output="torch", copy=False)
+    a.reset(seed=3); b.reset(seed=3)
+    traj = a.rollout(K, actions=acts)
+    for k in range(K):
+        o, r, te, tr, info = b.step(acts[k])
+        assert torch.equal(o, traj["obs"][k]) and torch.equal(te, traj["terminated"][k])
+        assert torch.equal(tr, traj["truncated"][k]) and torch.equal(r.float(), traj["reward"][k])
+    assert torch.equal(a._pstate, b._pstate) and torch.equal(a._rng, b._rng) and torch.equal(a._ctrl, b._ctrl)
+    assert int(traj["obs"].min()) >= 0 and int(traj["obs"].max()) < 64
+    holes = torch.tensor([19, 29, 35, 41, 42, 46, 49, 52, 54, 59], device="cuda")
+    term_obs = traj["obs"][traj["terminated"]]
+    assert torch.isin(term_obs, torch.cat([holes, torch.tensor([63], device="cuda")])).all()
+    assert (traj["reward"][traj["terminated"] & (traj["obs"] == 63)] == 1).all()
+
+
+def test_frozenlake_numpy_stream_consumption():
+    """One draw per call on every path: after T calls env i's PCG64 state equals numpy's after T+1 draws."""
+    n, T = 64, 37
+    env = make("FrozenLake-v1", n, map_name="8x8")
+    env.reset(seed=1000)
+    for t in range(T):
+        env.step(np.full(n, t % 4))
+    st = env.rng_state()
+    for i in [0, 5, 63]:
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(1000 + i)))
+        g.random(T + 1)
+        assert int(st[0, i, 0]) | (int(st[0, i, 1]) << 64) == g.bit_generator.state["state"]["state"]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# API behaviour shared with SyncVectorEnv
+def test_api_errors_and_reset_mask():
+    import torch
+    from gymnasium_b200 import errors
+
+    env = make("CartPole-v1", 3)
+    with pytest.raises(errors.ResetNeeded):
+        env.step([0, 1, 0])
+    env.reset(seed=0)
+    with pytest.raises(ValueError):
+        env.step([0, 1])
+    with pytest.raises(TypeError):
+        env.step(1)
+    with pytest.raises(TypeError):
+        env.reset(options={"reset_mask": [True, False, False]})
+    with pytest.raises(ValueError):
+        env.reset(options={"reset_mask": np.array([True, False])})
+    with pytest.raises(TypeError):
+        env.reset(options={"reset_mask": np.array([1, 0, 0])})
+    with pytest.raises(ValueError):
+        env.reset(options={"reset_mask": np.zeros(3, dtype=bool)})
+    with pytest.raises(ValueError):
+        env.reset(seed=[1, 2])
+    assert env.np_random_seed == (0, 1, 2)
+    assert env.metadata["autoreset_mode"].value == "NextStep"
+    assert env.observation_space.shape == (3, 4) and env.action_space.shape == (3,)
+    # partial reset (DISABLED mode workflow, tests/vector/test_autoreset_mode.py:105-260)
+    from oracle.cartpole import OracleCartPole
+
+    env = make("CartPole-v1", 4, autoreset_mode="Disabled", max_episode_steps=15)
+    ora = OracleCartPole(4, max_episode_steps=15, autoreset_mode="Disabled")
+    np.testing.assert_array_equal(env.reset(seed=11)[0], ora.reset(seed=11)[0])
+    rs = np.random.default_rng(0)
+    for t in range(80):
+        a = rs.integers(0, 2, 4)
+        x, y = env.step(a), ora.step(a)
+        np.testing.assert_allclose(x[0], y[0], rtol=RTOL, atol=ATOL)
+        for k in (1, 2, 3):
+            np.testing.assert_array_equal(x[k], y[k])
+        done = y[2] | y[3]
+        if done.any():
+            o1, _ = env.reset(options={"reset_mask": done.copy()})
+            o2, _ = ora.reset(options={"reset_mask": done.copy()})
+            np.testing.assert_allclose(o1, o2, rtol=RTOL, atol=ATOL)
+    env.close()
+    assert env.closed
+
+
+def test_torch_outputs_and_devices():
+    import torch
+
+    env = make("CartPole-v1", 8, output="torch")
+    obs, info = env.reset(seed=1)
+    assert obs.is_cuda and obs.dtype == torch.float32 and info == {}
+    o, r, te, tr, info = env.step(torch.ones(8, dtype=torch.int64, device="cuda"))
+    assert o.is_cuda and r.dtype == torch.float64 and te.dtype == torch.bool and tr.dtype == torch.bool
+    o2, *_ = env.step(np.zeros(8, dtype=np.int64))
+    assert o2.data_ptr() != o.data_ptr()  # copy=True hands out fresh tensors, like SyncVectorEnv(copy=True)
+    fl = make("FrozenLake-v1", 8, map_name="8x8", output="torch")
+    obs, info = fl.reset(seed=1)
+    assert obs.dtype == torch.int64 and info["prob"].dtype == torch.float64 and bool(info["_prob"].all())

@@ -1,0 +1,95 @@
+"""CPU-only checks (no compute on a GPU): the C-ABI library loads and exports exactly what include/b200env.h declares,
+host-side logic (table packing, option parsing, registration), and the no-fallback rule."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, have_cuda
+
+import gymnasium_b200
+from gymnasium_b200 import _lib
+from gymnasium_b200.envs.cartpole import _parse_reset_bounds
+from gymnasium_b200.envs.frozen_lake import MAPS, pack_transition_table
+from oracle.frozenlake import build_table
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200env.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2e_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = header_symbols()
+    assert declared, "no symbols parsed from include/b200env.h"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200env.h but not exported by libb200env.so"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES and the header disagree"
+    assert lib.b2e_version() == 1
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+
+    assert C.sizeof(_lib.Batch) == 48
+    assert C.sizeof(_lib.CartPoleCfg) == 24
+    assert C.sizeof(_lib.FrozenLakeCfg) == 8 + 16 + 72
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    assert lib.b2e_rng_seed(None, 0, None, None, None, None) == -1
+    assert b"NULL" in lib.b2e_last_error()
+    b = _lib.Batch(n=-3)
+    import ctypes as C
+
+    assert lib.b2e_cartpole_step(C.byref(b), None, None, None, None, None, None, None, None, None, None, None) == -1
+    assert b"n=-3" in lib.b2e_last_error()
+
+
+@pytest.mark.skipif(have_cuda(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gymnasium_b200.make_vec("CartPole-v1", num_envs=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gymnasium_b200.make_vec("FrozenLake-v1", num_envs=4, map_name="8x8")
+
+
+@pytest.mark.parametrize("map_name", ["4x4", "8x8"])
+@pytest.mark.parametrize("slippery", [True, False])
+def test_packed_table_equals_reference_P(map_name, slippery):
+    sched = (1, 0, 0) if slippery else (5, -2, 3)
+    table, cum3, p3, isd_cum, nS, shape = pack_transition_table(MAPS[map_name], slippery, 1.0 / 3.0, sched)
+    P, isd = build_table(MAPS[map_name], slippery, 1.0 / 3.0, sched)
+    table = table.reshape(nS, 4, 3)
+    np.testing.assert_array_equal(np.cumsum(isd), isd_cum)
+    rewards = list(sched) + [0]
+    for s in range(nS):
+        for a in range(4):
+            tr = P[s][a]
+            n_out = int(table[s, a, 0] >> 20)
+            assert n_out == len(tr)
+            for k, (p, s2, r, d) in enumerate(tr):
+                e = int(table[s, a, k])
+                assert (e & 0xFFFF) == s2 and bool((e >> 16) & 1) == d and rewards[(e >> 17) & 3] == r
+                assert (p3[k] if n_out == 3 else 1.0) == p
+    assert list(cum3) == list(np.cumsum([t[0] for t in P[0][1]])) if slippery else True
+
+
+def test_reset_bounds_parsing():
+    assert _parse_reset_bounds(None, -0.05, 0.05) == (-0.05, 0.05)
+    assert _parse_reset_bounds({"low": -0.1, "high": 0.1}, -0.05, 0.05) == (-0.1, 0.1)
+    assert _parse_reset_bounds({"high": 0.2}, -0.05, 0.05) == (-0.05, 0.2)
+    with pytest.raises(ValueError):
+        _parse_reset_bounds({"low": 0.2, "high": 0.1}, -0.05, 0.05)
+    with pytest.raises(ValueError):
+        _parse_reset_bounds({"low": "abc"}, -0.05, 0.05)
+
+
+def test_registry_ids():
+    assert set(gymnasium_b200.registration.ENVS) >= {"CartPole-v1", "FrozenLake-v1", "FrozenLake8x8-v1"}
+    with pytest.raises(KeyError):
+        gymnasium_b200.make_vec("NoSuchEnv-v0", 2)
