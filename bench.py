@@ -1,0 +1,552 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the fused step+autoreset hot path on B200 (contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
+  python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU vectorisers on the host cores
+
+A "step" is ONE vectorised step() over ONE batch of --num-envs (65536) CartPole-v1 envs = one launch of
+cartpole_step_kernel.  Workload = BASELINE.json configs[1]: "CartPole-v1 65536 envs on 1 B200, fused step+auto-reset
+kernel", random actions, NEXT_STEP autoreset, TimeLimit 500, numpy-parity PCG64 streams (seed + i).
+
+Timed region (value): inputs resident in HBM.  To keep every launch HBM-cold the bench rotates over a RING of independent
+65536-env batches whose total footprint is > 2x the L2 (so a batch's state has been evicted before it is stepped again),
+launched as CUDA graphs, timed with CUDA events on the launch stream, max over ranks.
+e2e: the public API (`gymnasium_b200.make_vec(...).step(host_actions)` -> host numpy arrays) with the pinned
+host->device action copy and the device->host result copy inside every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env steps/sec at N=65536 random-action, 1/2/4/8 B200 vs CPU AsyncVectorEnv"
+UNIT = "env-steps/s"
+# algorithmic HBM bytes per env-step of cartpole_step_kernel: read state 4xf64 + ctrl i32 +
+# action i64, write state + ctrl + obs 4xf32 + reward f64 + terminated u8 + truncated u8
+CARTPOLE_STEP_BYTES = (32 + 4 + 8) + (32 + 4 + 16 + 8 + 1 + 1)
+FROZENLAKE_STEP_BYTES = (16 + 16 + 4 + 4 + 8) + (16 + 4 + 4 + 8 + 8 + 1 + 1 + 8)  # rng state+inc, s, ctrl, act | outs
+ROLLOUT_STEP_BYTES = 16 + 4 + 1 + 1  # obs f32x4 + reward f32 + flags per env-step streamed by the fused-K kernel
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_ncu_traffic(kernel_key):
+    """dram bytes per launch from the committed ncu capture (profiles/ncu_summary.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel_key, {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock + clock-event reasons through NVML in a background thread while the timed regions run."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index, period=0.02):
+        self.samples, self.windows, self.period, self._stop = [], [], period, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _one(self):
+        nv = self.nv
+        mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.samples.append((time.perf_counter(), mhz, reasons))
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._one()
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+        return self
+
+    def window(self):
+        s = self
+
+        class W:
+            def __enter__(self_w):
+                self_w.t0 = time.perf_counter()
+
+            def __exit__(self_w, *a):
+                s.windows.append((self_w.t0, time.perf_counter()))
+                if s.ok:
+                    try:
+                        s._one()
+                    except Exception:
+                        pass
+
+        return W()
+
+    def stop(self):
+        self._stop.set()
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        self.t.join(timeout=1)
+        inside = [(m, r) for (t, m, r) in self.samples if any(a - 0.005 <= t <= b + 0.005 for a, b in self.windows)]
+        if not inside:
+            inside = [(m, r) for (_, m, r) in self.samples]
+        bits = 0
+        for _, r in inside:
+            bits |= r
+        return {"sm_mhz": statistics.median([m for m, _ in inside]) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(v for k, v in self.REASONS.items() if bits & k), "samples": len(inside)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the path on this host's cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref, "gymnasium")) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    import numpy as np
+
+    cores = os.cpu_count() or 1
+    budget = float(args.ref_budget)
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "gpu_launches": 0}
+    try:
+        import gymnasium as gym
+        from gymnasium.utils.performance import benchmark_vector_step
+
+        have_ref = True
+    except Exception as e:  # noqa: BLE001
+        have_ref, why = False, repr(e)
+
+    alternatives = {}
+    if have_ref:
+        import warnings
+
+        warnings.filterwarnings("ignore")
+        C = max(2, min(cores, 256))
+        envs = gym.make_vec(args.env, num_envs=C, vectorization_mode="async", **env_kwargs(args.env))
+        envs.action_space.seed(0)
+        envs.reset(seed=0)
+        t0 = time.perf_counter()
+        for _ in range(max(args.warmup, 3)):
+            envs.step(envs.action_space.sample())
+        t_call = (time.perf_counter() - t0) / max(args.warmup, 3)
+        calls_per_step = max(1, int(budget / max(args.steps * t_call, 1e-9)))
+        calls_per_step = min(calls_per_step, 200)
+        done_prev = np.zeros(C, dtype=bool)
+        counted = 0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for _ in range(calls_per_step):
+                _, _, te, tr, _ = envs.step(envs.action_space.sample())
+                counted += C - int(done_prev.sum())  # gymnasium/utils/performance.py:88-90
+                done_prev = te | tr
+        dt = time.perf_counter() - t0
+        envs.close()
+        total = args.steps * calls_per_step * C
+        value = total / dt
+        sample = (f"AsyncVectorEnv({args.env}) num_envs={C} (one process per env; 65536 processes is not runnable), "
+                  f"{calls_per_step} vector calls per bench step, host action sampling included")
+        kind = "reference"
+        line["value_excluding_reset_calls"] = counted / dt
+        if not args.no_extras:
+            for mode, n, kw in [("sync", 4, {}), ("vector_entry_point", args.num_envs, {})]:
+                if mode == "vector_entry_point" and not args.env.startswith("CartPole"):
+                    continue
+                try:
+                    e = gym.make_vec(args.env, num_envs=n, vectorization_mode=mode, **env_kwargs(args.env))
+                    alternatives[f"{mode}_n{n}"] = benchmark_vector_step(e, target_duration=3, seed=0)
+                    e.close()
+                except Exception as ex:  # noqa: BLE001
+                    alternatives[f"{mode}_n{n}"] = f"failed: {ex!r}"
+    else:
+        # oracle port (numpy restatement), one core
+        from oracle.cartpole import OracleCartPole
+        from oracle.frozenlake import OracleFrozenLake
+
+        n = args.num_envs if args.env.startswith("CartPole") else 4096
+        env = OracleCartPole(n) if args.env.startswith("CartPole") else OracleFrozenLake(n, map_name="8x8")
+        nact = 2 if args.env.startswith("CartPole") else 4
+        rs = np.random.default_rng(0)
+        env.reset(seed=0)
+        t0 = time.perf_counter()
+        for _ in range(max(args.warmup, 3)):
+            env.step(rs.integers(0, nact, n))
+        t_call = (time.perf_counter() - t0) / max(args.warmup, 3)
+        steps = max(1, min(args.steps, int(budget / t_call)))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            env.step(rs.integers(0, nact, n))
+        dt = time.perf_counter() - t0
+        total, value = steps * n, steps * n / dt
+        sample = f"oracle numpy port, N={n}, {steps} vector steps (gymnasium not importable: {why})"
+        kind, cores = "port", 1
+    line.update({
+        "value": value, "ms_per_step": dt / args.steps * 1e3,
+        "config": {"workload": f"{args.env} reference CPU vectoriser, bounded sample: {sample}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores if kind == "reference" else 1, "kind": kind,
+                         "sample": sample, "alternatives": alternatives},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    })
+    print(json.dumps(line))
+    return 0
+
+
+def env_kwargs(env_id):
+    return {"map_name": "8x8"} if env_id.startswith("FrozenLake") else {}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import gymnasium_b200
+    from gymnasium_b200 import _lib
+    from gymnasium_b200.distributed import BatchGather, env_rank_world
+
+    rank, local_rank, world = env_rank_world()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    info = _lib.device_info(local_rank)
+    hbm_peak, peak_src = load_peaks()
+    n = args.num_envs
+    is_cartpole = args.env.startswith("CartPole")
+    nact = 2 if is_cartpole else 4
+    step_bytes = CARTPOLE_STEP_BYTES if is_cartpole else FROZENLAKE_STEP_BYTES
+    kw = env_kwargs(args.env)
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- ring of independent batches, total footprint > 2 x L2 ------------------------------------------------------
+    foot = n * (step_bytes + 32)  # + the PCG64 words each batch also owns
+    ring = args.ring or max(2, math.ceil(2.0 * info["l2_bytes"] / foot))
+    T = 8  # distinct action vectors per batch
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    envs, acts = [], []
+    for j in range(ring):
+        e = gymnasium_b200.make_vec(args.env, num_envs=n, device=dev, copy=False, env_offset=(rank * ring + j) * n, **kw)
+        e.reset(seed=0)
+        envs.append(e)
+        acts.append(torch.randint(0, nact, (T, n), device=dev, dtype=torch.int64, generator=gen))
+    torch.cuda.synchronize()
+
+    def launch(k):  # one bench step = one fused step launch on the next batch of the ring
+        j = k % ring
+        envs[j].step(acts[j][(k // ring) % T])
+
+    def capture(count, start=0):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for k in range(start, start + count):
+                launch(k)
+        return g
+
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):  # warm every code path once before capture
+        for k in range(ring):
+            launch(k)
+    torch.cuda.synchronize()
+    G = ring * T
+    K, W = args.steps, args.warmup
+    g_main = capture(min(K, G)) if K > 0 else None
+    g_tail = capture(K % G) if (K > G and K % G) else None
+    g_warm = capture(max(1, min(W, G)))
+
+    def run_steps(count, gm, gt):
+        if count <= G:
+            gm.replay()
+        else:
+            for _ in range(count // G):
+                gm.replay()
+            if gt is not None:
+                gt.replay()
+
+    # warm-up (>= W launches), then the timed region
+    for _ in range(max(1, math.ceil(W / max(1, min(W, G))))):
+        g_warm.replay()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx = sampler.window() if sampler else None
+    if ctx:
+        ctx.__enter__()
+    sync_all()
+    e0.record()
+    run_steps(K, g_main, g_tail)
+    e1.record()
+    sync_all()
+    if ctx:
+        ctx.__exit__()
+    elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    value = world * K * n / elapsed
+    kernel_s = elapsed / K
+    achieved = step_bytes * n / kernel_s / 1e9
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        extras = run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, envs[0], acts[0])
+
+    # ---- end to end through the public API ----------------------------------------------------------------------------
+    del g_main, g_tail, g_warm
+    e2e_env = gymnasium_b200.make_vec(args.env, num_envs=n, device=dev, copy=False, env_offset=rank * n,
+                                      output="numpy" if world == 1 else "torch", **kw)
+    e2e_env.reset(seed=0)
+    host_actions = np.random.default_rng(rank).integers(0, nact, size=(16, n)).astype(np.int64)
+    gather = BatchGather(world * n, world, rank, dst=0) if world > 1 else None
+    pinned = {}
+
+    def e2e_step(k):
+        out = e2e_env.step(host_actions[k % 16])
+        if gather is None:
+            return out  # numpy arrays on the host (pinned H2D of actions + D2H of obs/reward/flags inside step())
+        o, r, te, tr, _ = out
+        full = gather(obs=o, reward=r, terminated=te, truncated=tr)  # NCCL gather of the shard outputs to rank 0
+        if rank == 0:
+            for key, t in full.items():
+                if key not in pinned:
+                    pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                pinned[key].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pinned
+
+    Ke = max(1, min(K, args.e2e_steps))
+    for k in range(max(3, min(W, 20))):
+        e2e_step(k)
+    ctx = sampler.window() if sampler else None
+    if ctx:
+        ctx.__enter__()
+    sync_all()
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        e2e_step(k)
+    sync_all()
+    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
+    if ctx:
+        ctx.__exit__()
+    e2e_value = world * Ke * n / e2e_elapsed
+    out_bytes = n * ((16 + 8 + 1 + 1) if is_cartpole else (8 + 8 + 1 + 1 + 8 + 1))
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": out_bytes,
+           "steps": Ke, "ms_per_step": e2e_elapsed / Ke * 1e3,
+           "path": "gymnasium_b200.make_vec(...).step(numpy int64 actions) -> numpy arrays"
+                   + ("" if world == 1 else " + NCCL gather of every shard's outputs to rank 0 + D2H of the gathered batch")}
+
+    clocks = sampler.stop() if sampler else None
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_subprocess(args)
+
+    if rank == 0:
+        kname = "cartpole_step_kernel<int64>" if is_cartpole else "frozenlake_step_kernel<int64>"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if is_cartpole else "int32+f64", "data": "synthetic",
+            "config": {
+                "workload": f"{args.env} {n} envs per GPU, fused step+auto-reset kernel, random actions, NEXT_STEP "
+                            f"autoreset, TimeLimit, numpy-parity PCG64 streams",
+                "num_envs_per_gpu": n, "parallelism": f"env-shards x{world} (no data-path collective)",
+                "l2_policy": f"inputs larger than L2: ring of {ring} independent {n}-env batches "
+                             f"({ring * foot / 1e6:.0f} MB > 2 x {info['l2_bytes'] / 1e6:.0f} MB L2), round-robin",
+                "launch": "CUDA graphs of one step launch per batch, CUDA-event timing on the launch stream",
+                "counting": "calls x N (reset calls included); see value_excluding_reset_calls",
+            },
+            "value_excluding_reset_calls": value * (1 - extras.get("reset_call_fraction", 0.0)) if extras else None,
+            "gpu_launches": K,
+            "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": step_bytes, "avg_launch_us": kernel_s * 1e6,
+                         "traffic": load_ncu_traffic(kname)},
+            "e2e": e2e,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "device": torch.cuda.get_device_name(dev),
+        }
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0):
+    """Supporting measurements (rank 0): the same kernel at a DRAM-sized batch, the fused-K rollout kernel, the
+    L2-resident single-batch rate, FrozenLake at its BASELINE size, and the reset-call fraction."""
+    out = {}
+    is_cartpole = args.env.startswith("CartPole")
+    nact = 2 if is_cartpole else 4
+    kw = env_kwargs(args.env)
+
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with sampler.window():
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / iters
+
+    step_bytes = CARTPOLE_STEP_BYTES if is_cartpole else FROZENLAKE_STEP_BYTES
+    # (1) L2-resident: one batch stepped back to back (what a single training loop sees)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for t in range(64):
+            env0.step(acts0[t % acts0.shape[0]])
+    t = timed(g.replay, 50) / 64
+    out["l2_resident"] = {"steps_per_s": args.num_envs / t, "us_per_launch": t * 1e6,
+                          "note": "single 65536-env batch, state stays in L2 (not HBM-cold)"}
+    del g
+    # (2) same step kernel, DRAM-sized batch: kernel quality away from the launch-latency floor
+    big = 1 << 24
+    e = gymnasium_b200.make_vec(args.env, num_envs=big, device=dev, copy=False, **kw)
+    e.reset(seed=0)
+    a = torch.randint(0, nact, (big,), device=dev, dtype=torch.int64)
+    t = timed(lambda: e.step(a), 20)
+    bw = step_bytes * big / t / 1e9
+    out["roofline_large_batch"] = {"kernel": "same step kernel, N=16,777,216 (1.7 GB footprint)", "achieved": bw,
+                                   "peak": hbm_peak, "unit": "GB/s", "frac": bw / hbm_peak,
+                                   "steps_per_s": big / t, "us_per_launch": t * 1e6}
+    # (3) reset-call fraction (reference counting rule, performance.py:88-90)
+    _, _, te, tr, _ = e.step(a)
+    frac = float((e._ctrl < 0).float().mean().item())
+    out["reset_call_fraction"] = frac
+    del e, a
+    torch.cuda.empty_cache()
+    # (4) fused K-step rollout kernel with on-device Philox actions, trajectory streamed to HBM
+    Kf = 64
+    e = gymnasium_b200.make_vec(args.env, num_envs=args.num_envs, device=dev, **kw)
+    e.reset(seed=0)
+    t = timed(lambda: e.rollout(Kf), 30)
+    rb = (ROLLOUT_STEP_BYTES if is_cartpole else 8 + 4 + 1 + 1)
+    out["rollout_fused"] = {"K": Kf, "steps_per_s": args.num_envs * Kf / t, "us_per_env_batch_step": t / Kf * 1e6,
+                            "hbm_write_GBs": rb * args.num_envs * Kf / t / 1e9,
+                            "frac_of_hbm_peak": rb * args.num_envs * Kf / t / 1e9 / hbm_peak,
+                            "bytes_per_env_step": rb, "gpu_launches": 1,
+                            "note": f"{Kf} steps per launch, state in registers, [K,N] trajectory written once"}
+    del e
+    # (5) the other BASELINE single-GPU config: FrozenLake-v1 8x8, 1,048,576 envs
+    if is_cartpole:
+        nfl = 1 << 20
+        ringf = 4  # 4 x 103 MB > 2 x L2
+        fls = []
+        for j in range(ringf):
+            f = gymnasium_b200.make_vec("FrozenLake-v1", num_envs=nfl, map_name="8x8", device=dev, copy=False,
+                                        env_offset=j * nfl)
+            f.reset(seed=0)
+            fls.append((f, torch.randint(0, 4, (nfl,), device=dev, dtype=torch.int64)))
+        k = [0]
+
+        def fstep():
+            f, a = fls[k[0] % ringf]
+            f.step(a)
+            k[0] += 1
+
+        t = timed(fstep, 40, warm=8)
+        bw = FROZENLAKE_STEP_BYTES * nfl / t / 1e9
+        out["frozenlake_8x8_1M"] = {"steps_per_s": nfl / t, "us_per_launch": t * 1e6, "achieved_GBs": bw,
+                                    "frac_of_hbm_peak": bw / hbm_peak,
+                                    "algorithmic_bytes_per_env_step": FROZENLAKE_STEP_BYTES,
+                                    "l2_policy": f"ring of {ringf} batches of 1,048,576 envs (inputs larger than L2)"}
+    return out
+
+
+def cpu_baseline_subprocess(args):
+    """Times the reference arm in a fresh process (AsyncVectorEnv forks workers; keep that away from the CUDA context)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "20", "--warmup", "3",
+           "--env", args.env, "--num-envs", str(args.num_envs), "--ref-budget", "12"]
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+            env.pop(k, None)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        for ln in reversed(p.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (p.stderr or p.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--env", default="CartPole-v1", choices=["CartPole-v1", "FrozenLake-v1"])
+    ap.add_argument("--num-envs", type=int, default=65536)
+    ap.add_argument("--ring", type=int, default=0, help="batches in the L2-defeating ring (0 = auto: > 2 x L2)")
+    ap.add_argument("--e2e-steps", type=int, default=2000)
+    ap.add_argument("--ref-budget", type=float, default=20.0, help="seconds of CPU work for the reference arm")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

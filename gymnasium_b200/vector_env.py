@@ -121,6 +121,7 @@ class B200VectorEnv(VectorEnv):
         self._has_reset = False
         self._pinned_actions: torch.Tensor | None = None
         self._out: dict[str, torch.Tensor] = {}
+        self._pinned_out: dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------------------------
     # hooks for families
@@ -149,12 +150,47 @@ class B200VectorEnv(VectorEnv):
             self._out = self._alloc_outputs()  # fresh tensors from the caching allocator; kernels write in place
         return self._out
 
-    def _deliver(self, t):
-        if self.output == "numpy":
-            if isinstance(t, dict):
-                return {k: self._deliver(v) for k, v in t.items()}
-            return t.cpu().numpy() if isinstance(t, torch.Tensor) else t
-        return t
+    def _deliver(self, tree):
+        """output="torch": hand back the device tensors.  output="numpy": one batch of async device->host copies into
+        cached pinned buffers, one stream synchronise, numpy arrays out (fresh copies when ``copy=True``)."""
+        if self.output != "numpy":
+            return tree
+        leaves: list[tuple[str, torch.Tensor]] = []
+
+        def walk(x, path):
+            if isinstance(x, torch.Tensor):
+                leaves.append((path, x))
+            elif isinstance(x, dict):
+                for k, v in x.items():
+                    walk(v, f"{path}/{k}")
+            elif isinstance(x, (tuple, list)):
+                for j, v in enumerate(x):
+                    walk(v, f"{path}/{j}")
+
+        walk(tree, "")
+        host = {}
+        for path, t in leaves:
+            buf = self._pinned_out.get(path)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                self._pinned_out[path] = buf
+            buf.copy_(t, non_blocking=True)
+            host[path] = buf
+        torch.cuda.current_stream(self.device).synchronize()
+
+        def build(x, path):
+            if isinstance(x, torch.Tensor):
+                a = host[path].numpy()
+                return a.copy() if self.copy else a
+            if isinstance(x, dict):
+                return {k: build(v, f"{path}/{k}") for k, v in x.items()}
+            if isinstance(x, tuple):
+                return tuple(build(v, f"{path}/{j}") for j, v in enumerate(x))
+            if isinstance(x, list):
+                return [build(v, f"{path}/{j}") for j, v in enumerate(x)]
+            return x
+
+        return build(tree, "")
 
     # ------------------------------------------------------------------------------------------------------------
     def _seed_streams(self, seed, mask: torch.Tensor | None) -> None:
@@ -245,7 +281,7 @@ class B200VectorEnv(VectorEnv):
             self._reset_kernel(mask, options, out)
             self._batch.call_counter += 1
         self._has_reset = True
-        return self._deliver(out["obs"]), self._deliver(self._reset_info(out, mask))
+        return self._deliver((out["obs"], self._reset_info(out, mask)))
 
     def _prepare_actions(self, actions) -> torch.Tensor:
         """One conversion to a contiguous device tensor; wrong count -> ValueError, scalar -> TypeError
@@ -298,14 +334,7 @@ class B200VectorEnv(VectorEnv):
             self._batch.action_dtype = _ACT_DTYPES[t.dtype]
             self._step_kernel(t, out)
             self._batch.call_counter += 1
-        info = self._step_info(out)
-        return (
-            self._deliver(out["obs"]),
-            self._deliver(out["reward"]),
-            self._deliver(out["terminated"]),
-            self._deliver(out["truncated"]),
-            self._deliver(info),
-        )
+        return self._deliver((out["obs"], out["reward"], out["terminated"], out["truncated"], self._step_info(out)))
 
     # ------------------------------------------------------------------------------------------------------------
     @property
