@@ -6,7 +6,11 @@ gymnasium/vector/vector_env.py:374-377) and is created by ``gymnasium.make_vec``
 """
 from __future__ import annotations
 
+import os as _os
+
 try:
+    if _os.environ.get("B200ENV_FORCE_COMPAT"):
+        raise ImportError("B200ENV_FORCE_COMPAT is set")
     import gymnasium as _gym
     from gymnasium.spaces import Box, Discrete, MultiDiscrete
     from gymnasium.vector import AutoresetMode, VectorEnv

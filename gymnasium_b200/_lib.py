@@ -68,6 +68,7 @@ SIGNATURES = {
     "b2e_cartpole_reset": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P]),
     "b2e_cartpole_step": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P, P, P, P, P]),
     "b2e_cartpole_rollout": (C.c_int, [_BP, C.POINTER(CartPoleCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),
+    "b2e_selftest_math": (C.c_int, [c_i64, c_u64, P, P]),
     "b2e_frozenlake_reset": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P]),
     "b2e_frozenlake_step": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P, P, P, P, P, P]),
     "b2e_frozenlake_rollout": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),

@@ -43,18 +43,56 @@ struct State4 {
   double x, xd, th, thd;
 };
 
-// cartpole.py:169-189, literal op order
+// x / total_mass, correctly rounded, without the generic division sequence: q0 = x * RN(1/d), then two
+// residual-correction FMAs (Markstein).  Bit-identical to __ddiv_rn(x, kTotalMass) on every input the self-test sweeps
+// (b2e_selftest_math, tests/test_gpu_parity.py); ~5 FP64 issue slots instead of ~25.
+__device__ __forceinline__ double div_total_mass(double x) {
+  constexpr double d = kTotalMass, r = 1.0 / kTotalMass;
+  double q = __dmul_rn(x, r);
+  q = __fma_rn(__fma_rn(-q, d, x), r, q);
+  return __fma_rn(__fma_rn(-q, d, x), r, q);
+}
+
+// sin/cos for |x| < 0.3 (every non-terminated CartPole angle: |theta| <= 12 deg = 0.2094): the classic fdlibm kernel
+// polynomials (k_sin.c / k_cos.c coefficients), no range reduction, < 1 ulp; larger arguments (custom reset bounds,
+// DISABLED-mode steps past termination) take libdevice's sincos.
+__device__ __forceinline__ void sincos_pole(double x, double* sn, double* cs) {
+  if (fabs(x) < 0.3) {
+    constexpr double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                     S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                     S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    constexpr double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                     C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                     C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double z = __dmul_rn(x, x);
+    double r = __fma_rn(z, S6, S5);
+    r = __fma_rn(z, r, S4);
+    r = __fma_rn(z, r, S3);
+    r = __fma_rn(z, r, S2);
+    *sn = __fma_rn(__dmul_rn(z, x), __fma_rn(z, r, S1), x);
+    double q = __fma_rn(z, C6, C5);
+    q = __fma_rn(z, q, C4);
+    q = __fma_rn(z, q, C3);
+    q = __fma_rn(z, q, C2);
+    q = __fma_rn(z, q, C1);
+    q = __dmul_rn(z, q);
+    *cs = __dsub_rn(1.0, __fma_rn(-z, q, __dmul_rn(0.5, z)));
+  } else {
+    sincos(x, sn, cs);
+  }
+}
+
+// cartpole.py:169-189, literal op order (each rounding the reference makes is made here, none is fused)
 __device__ __forceinline__ State4 euler_step(State4 s, int action) {
   const double force = action == 1 ? kForceMag : -kForceMag;
   double sinth, costh;
-  sincos(s.th, &sinth, &costh);
+  sincos_pole(s.th, &sinth, &costh);
   const double temp =
-      __ddiv_rn(__dadd_rn(force, __dmul_rn(__dmul_rn(kPoleMassLength, __dmul_rn(s.thd, s.thd)), sinth)), kTotalMass);
-  const double denom = __dmul_rn(
-      kLength, __dsub_rn(4.0 / 3.0, __ddiv_rn(__dmul_rn(kMassPole, __dmul_rn(costh, costh)), kTotalMass)));
+      div_total_mass(__dadd_rn(force, __dmul_rn(__dmul_rn(kPoleMassLength, __dmul_rn(s.thd, s.thd)), sinth)));
+  const double denom =
+      __dmul_rn(kLength, __dsub_rn(4.0 / 3.0, div_total_mass(__dmul_rn(kMassPole, __dmul_rn(costh, costh)))));
   const double thacc = __ddiv_rn(__dsub_rn(__dmul_rn(kGravity, sinth), __dmul_rn(costh, temp)), denom);
-  const double xacc =
-      __dsub_rn(temp, __ddiv_rn(__dmul_rn(__dmul_rn(kPoleMassLength, thacc), costh), kTotalMass));
+  const double xacc = __dsub_rn(temp, div_total_mass(__dmul_rn(__dmul_rn(kPoleMassLength, thacc), costh)));
   State4 o;
   o.x = __dadd_rn(s.x, __dmul_rn(kTau, s.xd));
   o.xd = __dadd_rn(s.xd, __dmul_rn(kTau, xacc));
@@ -103,6 +141,7 @@ __device__ __forceinline__ State4 sample_reset(const A& a, int64_t i, uint64_t c
 }
 
 __global__ void __launch_bounds__(kBlock) cartpole_reset_kernel(const CartPoleArgs a) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   if (a.mask != nullptr && a.mask[i] == 0) return;
@@ -112,28 +151,33 @@ __global__ void __launch_bounds__(kBlock) cartpole_reset_kernel(const CartPoleAr
   reinterpret_cast<float4*>(a.obs)[i] = to_obs(s);
 }
 
+constexpr int kStepBlock = 128;  // N=65536 -> 512 CTAs: 3-4 per SM instead of 1-2, the tail is shorter
+
 template <typename ActT>
-__global__ void __launch_bounds__(kBlock) cartpole_step_kernel(const CartPoleArgs a) {
+__global__ void __launch_bounds__(kStepBlock) cartpole_step_kernel(const CartPoleArgs a) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
+  // every load is issued before the first use so one DRAM round trip covers them all
   const int32_t c = a.ctrl[i];
+  const State4 s0 = load_state(a.state, a.n, i);
+  const int action = load_action<ActT>(a.actions, i);
   if (a.mode == B2E_AUTORESET_NEXT_STEP && ctrl_pending(c)) {
     // sync_vector_env.py:279-284: the call after a done is the reset; reward 0, flags False, action ignored
     const State4 s = sample_reset(a, i, a.call_counter);
     store_state(a.state, a.n, i, s);
     a.ctrl[i] = 0;
-    reinterpret_cast<float4*>(a.obs)[i] = to_obs(s);
-    a.reward[i] = 0.0;
+    __stcs(reinterpret_cast<float4*>(a.obs) + i, to_obs(s));
+    __stcs(a.reward + i, 0.0);
     a.term[i] = 0;
     a.trunc[i] = 0;
     return;
   }
-  const int action = load_action<ActT>(a.actions, i);
-  State4 s = euler_step(load_state(a.state, a.n, i), action);
+  State4 s = euler_step(s0, action);
   const bool term = is_terminated(s);
   const int32_t elapsed = ctrl_elapsed(c) + 1;
   const bool trunc = a.max_steps > 0 && elapsed >= a.max_steps;  // wrappers/common.py:130-133
-  a.reward[i] = a.sutton ? (term ? -1.0 : 0.0) : 1.0;             // cartpole.py:205-211
+  __stcs(a.reward + i, a.sutton ? (term ? -1.0 : 0.0) : 1.0);    // cartpole.py:205-211
   a.term[i] = term;
   a.trunc[i] = trunc;
   int32_t cn = elapsed;
@@ -148,7 +192,7 @@ __global__ void __launch_bounds__(kBlock) cartpole_step_kernel(const CartPoleArg
   }
   store_state(a.state, a.n, i, s);
   a.ctrl[i] = cn;
-  reinterpret_cast<float4*>(a.obs)[i] = to_obs(s);
+  __stcs(reinterpret_cast<float4*>(a.obs) + i, to_obs(s));
 }
 
 struct RolloutArgs {
@@ -161,6 +205,7 @@ struct RolloutArgs {
 // K fused steps: state in registers, [K][n] trajectory streamed out with coalesced stores.
 template <typename ActT, bool kRandom>
 __global__ void __launch_bounds__(kBlock) cartpole_rollout_kernel(const RolloutArgs r) {
+  pdl_prologue();
   const CartPoleArgs& a = r.a;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
@@ -208,6 +253,26 @@ __global__ void __launch_bounds__(kBlock) cartpole_rollout_kernel(const RolloutA
   a.ctrl[i] = c;
 }
 
+// self-test of the two fast paths against the generic device routines on pseudo-random inputs in the ranges the
+// CartPole step feeds them: counts[0] = div_total_mass != __ddiv_rn, counts[1] = |sin| or |cos| off by > 1 ulp
+__global__ void __launch_bounds__(kBlock) cartpole_selftest_kernel(int64_t n, uint64_t seed, unsigned long long* counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 r = philox_block(seed, (uint64_t)i, 0, 7u), r2 = philox_block(seed, (uint64_t)i, 1, 7u);
+  // numerators: mantissa uniform, exponent uniform over 2^-40 .. 2^8, both signs
+  const double mant = 1.0 + u53_to_double(r.x, r.y);
+  const double x = ldexp(mant, (int)(r.z % 49u) - 40) * ((r.w & 1u) ? -1.0 : 1.0);
+  if (div_total_mass(x) != __ddiv_rn(x, kTotalMass)) atomicAdd(counts + 0, 1ull);
+  const double th = (u53_to_double(r2.x, r2.y) * 2.0 - 1.0) * 0.2999;
+  double s0, c0, s1, c1;
+  sincos_pole(th, &s0, &c0);
+  sincos(th, &s1, &c1);
+  const long long ds = llabs(__double_as_longlong(s0) - __double_as_longlong(s1));
+  const long long dc = llabs(__double_as_longlong(c0) - __double_as_longlong(c1));
+  if (ds > 1 || dc > 1) atomicAdd(counts + 1, 1ull);
+  if (ds == 1 || dc == 1) atomicAdd(counts + 2, 1ull);
+}
+
 CartPoleArgs make_args(const b2e_batch* b, const b2e_cartpole_cfg* cfg) {
   CartPoleArgs a{};
   a.n = b->n;
@@ -228,6 +293,17 @@ CartPoleArgs make_args(const b2e_batch* b, const b2e_cartpole_cfg* cfg) {
 
 using namespace b2e;
 
+extern "C" int b2e_selftest_math(int64_t n, uint64_t seed, uint64_t* counts, void* stream) {
+  if (n < 0 || !counts) {
+    set_error("b2e_selftest_math: bad arguments");
+    return B2E_EINVAL;
+  }
+  if (n == 0) return 0;
+  cartpole_selftest_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(n, seed,
+                                                                            (unsigned long long*)counts);
+  return cuda_status(cudaGetLastError(), "b2e_selftest_math");
+}
+
 extern "C" int b2e_cartpole_reset(const b2e_batch* b, const b2e_cartpole_cfg* cfg, const uint8_t* mask, double* state,
                                   int32_t* ctrl, uint64_t* rng, float* obs, void* stream) {
   if (int e = check_batch(b, "b2e_cartpole_reset")) return e;
@@ -242,8 +318,8 @@ extern "C" int b2e_cartpole_reset(const b2e_batch* b, const b2e_cartpole_cfg* cf
   a.ctrl = ctrl;
   a.rng = rng;
   a.obs = obs;
-  cartpole_reset_kernel<<<grid_for(b->n), kBlock, 0, (cudaStream_t)stream>>>(a);
-  return cuda_status(cudaGetLastError(), "b2e_cartpole_reset");
+  return cuda_status(launch_pdl(cartpole_reset_kernel, grid_for(b->n), kBlock, 0, (cudaStream_t)stream, a),
+                     "b2e_cartpole_reset");
 }
 
 extern "C" int b2e_cartpole_step(const b2e_batch* b, const b2e_cartpole_cfg* cfg, const void* actions, double* state,
@@ -266,15 +342,16 @@ extern "C" int b2e_cartpole_step(const b2e_batch* b, const b2e_cartpole_cfg* cfg
   a.term = terminated;
   a.trunc = truncated;
   a.final_obs = final_obs;
-  const unsigned grid = grid_for(b->n);
+  const unsigned grid = grid_for(b->n, kStepBlock);
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
   switch (b->action_dtype) {
-    case B2E_ACT_I64: cartpole_step_kernel<int64_t><<<grid, kBlock, 0, st>>>(a); break;
-    case B2E_ACT_I32: cartpole_step_kernel<int32_t><<<grid, kBlock, 0, st>>>(a); break;
-    case B2E_ACT_U8: cartpole_step_kernel<uint8_t><<<grid, kBlock, 0, st>>>(a); break;
+    case B2E_ACT_I64: e = launch_pdl(cartpole_step_kernel<int64_t>, grid, kStepBlock, 0, st, a); break;
+    case B2E_ACT_I32: e = launch_pdl(cartpole_step_kernel<int32_t>, grid, kStepBlock, 0, st, a); break;
+    case B2E_ACT_U8: e = launch_pdl(cartpole_step_kernel<uint8_t>, grid, kStepBlock, 0, st, a); break;
     default: set_error("b2e_cartpole_step: action_dtype %d is not a discrete dtype", b->action_dtype); return B2E_EINVAL;
   }
-  return cuda_status(cudaGetLastError(), "b2e_cartpole_step");
+  return cuda_status(e, "b2e_cartpole_step");
 }
 
 extern "C" int b2e_cartpole_rollout(const b2e_batch* b, const b2e_cartpole_cfg* cfg, int32_t K, const void* actions,
@@ -305,15 +382,16 @@ extern "C" int b2e_cartpole_rollout(const b2e_batch* b, const b2e_cartpole_cfg* 
   r.reward32 = reward;
   const unsigned grid = grid_for(b->n);
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
   if (!actions) {
-    cartpole_rollout_kernel<uint8_t, true><<<grid, kBlock, 0, st>>>(r);
+    e = launch_pdl(cartpole_rollout_kernel<uint8_t, true>, grid, kBlock, 0, st, r);
   } else {
     switch (b->action_dtype) {
-      case B2E_ACT_I64: cartpole_rollout_kernel<int64_t, false><<<grid, kBlock, 0, st>>>(r); break;
-      case B2E_ACT_I32: cartpole_rollout_kernel<int32_t, false><<<grid, kBlock, 0, st>>>(r); break;
-      case B2E_ACT_U8: cartpole_rollout_kernel<uint8_t, false><<<grid, kBlock, 0, st>>>(r); break;
+      case B2E_ACT_I64: e = launch_pdl(cartpole_rollout_kernel<int64_t, false>, grid, kBlock, 0, st, r); break;
+      case B2E_ACT_I32: e = launch_pdl(cartpole_rollout_kernel<int32_t, false>, grid, kBlock, 0, st, r); break;
+      case B2E_ACT_U8: e = launch_pdl(cartpole_rollout_kernel<uint8_t, false>, grid, kBlock, 0, st, r); break;
       default: set_error("b2e_cartpole_rollout: bad action_dtype %d", b->action_dtype); return B2E_EINVAL;
     }
   }
-  return cuda_status(cudaGetLastError(), "b2e_cartpole_rollout");
+  return cuda_status(e, "b2e_cartpole_rollout");
 }

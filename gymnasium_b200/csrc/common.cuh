@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/b200env.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -26,6 +28,31 @@ int cuda_status(cudaError_t e, const char* fn);
 
 constexpr int kBlock = 256;  // 8 warps; every kernel here is 1 thread/env (or grid-stride), register-light
 inline unsigned grid_for(int64_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+
+// Programmatic dependent launch (sm_90+): every step kernel is launched with the programmatic-stream-serialization
+// attribute, triggers its dependents at once and waits for its predecessor before its first global access, so the
+// launch latency of step k+1 overlaps the execution of step k in a chain of tiny dependent launches (also inside
+// captured CUDA graphs).  The wait returns only when the previous grid has completed and flushed: semantics unchanged.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // control word: bits 0..30 = TimeLimit elapsed steps, bit 31 = autoreset pending (NEXT_STEP)

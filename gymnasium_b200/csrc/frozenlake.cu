@@ -90,6 +90,7 @@ __device__ __forceinline__ double philox_u(const LakeArgs& a, int64_t i, uint64_
 }
 
 __global__ void __launch_bounds__(kBlock) frozenlake_reset_kernel(const LakeArgs a) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   if (a.mask != nullptr && a.mask[i] == 0) return;
@@ -110,36 +111,34 @@ __global__ void __launch_bounds__(kBlock) frozenlake_reset_kernel(const LakeArgs
 
 template <typename ActT>
 __global__ void __launch_bounds__(kBlock) frozenlake_step_kernel(const LakeArgs a) {
+  pdl_prologue();
   const uint32_t* t = stage_table(a);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    // all loads first (one DRAM round trip), then the arithmetic
     const int32_t c = a.ctrl[i];
-    // exactly one draw per call on every path (step: frozen_lake.py:326, reset: :343)
-    double u;
+    const int s_cur = a.pstate[i];
+    int action = load_action<ActT>(a.actions, i);
     Pcg64 g;
-    if (a.rng_mode == B2E_RNG_NUMPY) {
-      g = pcg64_load(a.rng, a.n, i);
-      u = g.next_double();
-    } else {
-      u = philox_u(a, i, a.call_counter, 1u);
-    }
+    if (a.rng_mode == B2E_RNG_NUMPY) g = pcg64_load(a.rng, a.n, i);
+    // exactly one draw per call on every path (step: frozen_lake.py:326, reset: :343)
+    const double u = a.rng_mode == B2E_RNG_NUMPY ? g.next_double() : philox_u(a, i, a.call_counter, 1u);
     if (a.mode == B2E_AUTORESET_NEXT_STEP && ctrl_pending(c)) {
       const int s = sample_initial_state(a, u);
       if (a.rng_mode == B2E_RNG_NUMPY) pcg64_store_state(a.rng, i, g);
       a.pstate[i] = s;
       a.ctrl[i] = 0;
-      a.obs[i] = s;
-      a.reward[i] = 0.0;
+      __stcs(a.obs + i, (int64_t)s);
+      __stcs(a.reward + i, 0.0);
       a.term[i] = 0;
       a.trunc[i] = 0;
-      a.prob_out[i] = 1.0;
+      __stcs(a.prob_out + i, 1.0);
       continue;
     }
-    int action = load_action<ActT>(a.actions, i);
     action = min(max(action, 0), a.n_actions - 1);  // the reference would KeyError; clamp, never read out of bounds
-    StepOut o = transition(a, t, a.pstate[i], action, u);
+    StepOut o = transition(a, t, s_cur, action, u);
     const int32_t elapsed = ctrl_elapsed(c) + 1;
     const bool trunc = a.max_steps > 0 && elapsed >= a.max_steps;
-    a.reward[i] = o.reward;
+    __stcs(a.reward + i, o.reward);
     a.term[i] = o.done;
     a.trunc[i] = trunc;
     int32_t cn = elapsed;
@@ -158,14 +157,15 @@ __global__ void __launch_bounds__(kBlock) frozenlake_step_kernel(const LakeArgs 
     if (a.rng_mode == B2E_RNG_NUMPY) pcg64_store_state(a.rng, i, g);
     a.pstate[i] = o.s;
     a.ctrl[i] = cn;
-    a.obs[i] = o.s;
-    a.prob_out[i] = o.p;
+    __stcs(a.obs + i, (int64_t)o.s);
+    __stcs(a.prob_out + i, o.p);
   }
 }
 
 // K fused steps, state + RNG in registers, [K][n] trajectory streamed out
 template <typename ActT, bool kRandom>
 __global__ void __launch_bounds__(kBlock) frozenlake_rollout_kernel(const LakeArgs a) {
+  pdl_prologue();
   const uint32_t* t = stage_table(a);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     int32_t c = a.ctrl[i];
@@ -294,8 +294,8 @@ extern "C" int b2e_frozenlake_reset(const b2e_batch* b, const b2e_frozenlake_cfg
   a.rng = rng;
   a.obs = obs;
   a.prob_out = prob;
-  frozenlake_reset_kernel<<<grid_for(b->n), kBlock, 0, (cudaStream_t)stream>>>(a);
-  return cuda_status(cudaGetLastError(), "b2e_frozenlake_reset");
+  return cuda_status(launch_pdl(frozenlake_reset_kernel, grid_for(b->n), kBlock, 0, (cudaStream_t)stream, a),
+                     "b2e_frozenlake_reset");
 }
 
 extern "C" int b2e_frozenlake_step(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, const void* actions,
@@ -325,11 +325,12 @@ extern "C" int b2e_frozenlake_step(const b2e_batch* b, const b2e_frozenlake_cfg*
   const size_t smem = table_smem_bytes(a);
   const unsigned grid = persistent_grid(b->n);
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t ce = cudaSuccess;
   if (int e = launch_by_dtype(b->action_dtype, "b2e_frozenlake_step", [&](auto tag) {
-        frozenlake_step_kernel<decltype(tag)><<<grid, kBlock, smem, st>>>(a);
+        ce = launch_pdl(frozenlake_step_kernel<decltype(tag)>, grid, kBlock, smem, st, a);
       }))
     return e;
-  return cuda_status(cudaGetLastError(), "b2e_frozenlake_step");
+  return cuda_status(ce, "b2e_frozenlake_step");
 }
 
 extern "C" int b2e_frozenlake_rollout(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, int32_t K,
@@ -361,12 +362,13 @@ extern "C" int b2e_frozenlake_rollout(const b2e_batch* b, const b2e_frozenlake_c
   const size_t smem = table_smem_bytes(a);
   const unsigned grid = persistent_grid(b->n);
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t ce = cudaSuccess;
   if (!actions) {
-    frozenlake_rollout_kernel<uint8_t, true><<<grid, kBlock, smem, st>>>(a);
+    ce = launch_pdl(frozenlake_rollout_kernel<uint8_t, true>, grid, kBlock, smem, st, a);
   } else if (int e = launch_by_dtype(b->action_dtype, "b2e_frozenlake_rollout", [&](auto tag) {
-               frozenlake_rollout_kernel<decltype(tag), false><<<grid, kBlock, smem, st>>>(a);
+               ce = launch_pdl(frozenlake_rollout_kernel<decltype(tag), false>, grid, kBlock, smem, st, a);
              })) {
     return e;
   }
-  return cuda_status(cudaGetLastError(), "b2e_frozenlake_rollout");
+  return cuda_status(ce, "b2e_frozenlake_rollout");
 }

@@ -105,6 +105,10 @@ int b2e_cartpole_rollout(const b2e_batch* b, const b2e_cartpole_cfg* cfg, int32_
                          uint8_t* actions_out, double* state, int32_t* ctrl, uint64_t* rng, float* obs, float* reward,
                          uint8_t* terminated, uint8_t* truncated, void* stream);
 
+/* Device self-test of the CartPole fast math paths on n pseudo-random inputs: counts uint64 [3] (device, caller-zeroed)
+ * receives {const-division results != IEEE division, sin/cos more than 1 ulp from libdevice, exactly 1 ulp}. */
+int b2e_selftest_math(int64_t n, uint64_t seed, uint64_t* counts, void* stream);
+
 /* ---- FrozenLake-v1: gymnasium/envs/toy_text/frozen_lake.py:232-348, toy_text/utils.py:4-8 -----------------------
  * Transition table (device, immutable, built by the host from the map exactly as frozen_lake.py:256-300):
  *   table  : uint32 [nS*nA*3]  entry = next_state | done<<16 | reward_class<<17 (0..2 -> rewards[class], 3 -> 0.0) | n_out<<20

@@ -9,10 +9,7 @@ from conftest import ROOT, have_cuda
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="needs a CUDA device")]
 
-_REF = os.path.join(ROOT, "baseline", "_ref")
-if os.path.isdir(os.path.join(_REF, "gymnasium")) and _REF not in sys.path:
-    sys.path.insert(0, _REF)
-gym = pytest.importorskip("gymnasium")
+gym = pytest.importorskip("gymnasium")  # conftest.py puts baseline/_ref on sys.path when it exists
 
 
 def test_make_vec_through_the_registry():
@@ -57,3 +54,24 @@ def test_install_routes_stock_ids():
                 np.testing.assert_array_equal(x[k], y[k])
     finally:
         gymnasium_b200.uninstall()
+
+
+def test_compat_mode_without_gymnasium():
+    """The engine also runs on a box without the host framework (stand-in VectorEnv/spaces, gymnasium_b200/_compat.py)."""
+    import subprocess
+
+    code = (
+        "import sys, numpy as np\n"
+        "import gymnasium_b200\n"
+        "assert not gymnasium_b200.HAVE_GYMNASIUM and 'gymnasium' not in sys.modules\n"
+        "e = gymnasium_b200.make_vec('CartPole-v1', num_envs=3, output='numpy')\n"
+        "o, _ = e.reset(seed=42)\n"
+        "assert abs(float(o[0, 0]) - 0.0273956) < 1e-7, o\n"
+        "o, r, te, tr, _ = e.step(np.array([1, 0, 1]))\n"
+        "assert abs(float(o[0, 1]) - 0.18847767) < 1e-6 and r.dtype == np.float64\n"
+        "assert e.action_space.shape == (3,) and e.observation_space.shape == (3, 4)\n"
+        "print('compat ok')\n"
+    )
+    env = dict(os.environ, B200ENV_FORCE_COMPAT="1", PYTHONPATH=ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0 and "compat ok" in p.stdout, p.stderr[-2000:]

@@ -69,6 +69,23 @@ def test_rng_streams_bit_exact_with_numpy(base):
     assert (st_before[:, 2] == 0).all()  # masked-out lane untouched by seeding
 
 
+def test_fast_math_paths_match_ieee_division_and_libdevice():
+    """div_total_mass (reciprocal + 2 residual FMAs) must equal IEEE division bit for bit; the short sin/cos kernels must
+    stay within 1 ulp of libdevice on the whole non-terminated angle range (2^28 samples each)."""
+    import torch
+    from gymnasium_b200 import _lib
+
+    lib = _lib.load()
+    counts = torch.zeros(3, dtype=torch.int64, device="cuda")
+    n = 1 << 28
+    for seed in (1, 2):
+        _lib.check(lib.b2e_selftest_math(n, seed, counts.data_ptr(), None))
+    c = counts.cpu().tolist()
+    assert c[0] == 0, f"{c[0]} constant-division results differ from __ddiv_rn"
+    assert c[1] == 0, f"{c[1]} sin/cos results are more than 1 ulp from libdevice"
+    assert c[2] < 0.25 * 2 * n, c  # 1-ulp disagreements with libdevice are the minority
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # CartPole
 @pytest.mark.parametrize("name", golden_files("cartpole"))
