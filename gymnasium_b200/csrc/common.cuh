@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <utility>
 
@@ -46,11 +47,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
+  static const bool pdl = getenv("B2E_NO_PDL") == nullptr;  // debugging switch: plain stream order
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

@@ -57,15 +57,14 @@ class CartPoleVectorEnv(B200VectorEnv):
 
     # -- buffers -------------------------------------------------------------------------------------------------
     def _alloc_outputs(self):
-        n, dev = self.num_envs, self.device
-        out = {
-            "obs": torch.empty((n, 4), dtype=torch.float32, device=dev),
-            "reward": torch.empty(n, dtype=torch.float64, device=dev),
-            "terminated": torch.empty(n, dtype=torch.bool, device=dev),
-            "truncated": torch.empty(n, dtype=torch.bool, device=dev),
-        }
+        n = self.num_envs
+        layout = {"obs": ((n, 4), torch.float32), "reward": ((n,), torch.float64),
+                  "terminated": ((n,), torch.bool), "truncated": ((n,), torch.bool)}
         if self.autoreset_mode == AutoresetMode.SAME_STEP:
-            out["final_obs"] = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+            layout["final_obs"] = ((n, 4), torch.float32)
+        out = self._alloc_packed(layout)
+        if "final_obs" in out:
+            out["final_obs"].zero_()
         return out
 
     @property

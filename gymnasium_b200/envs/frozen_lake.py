@@ -116,17 +116,16 @@ class FrozenLakeVectorEnv(B200VectorEnv):
         self._pstate = torch.zeros(self.num_envs, dtype=torch.int32, device=dev)
 
     def _alloc_outputs(self):
-        n, dev = self.num_envs, self.device
-        out = {
-            "obs": torch.empty(n, dtype=torch.int64, device=dev),
-            "reward": torch.empty(n, dtype=torch.float64, device=dev),
-            "terminated": torch.empty(n, dtype=torch.bool, device=dev),
-            "truncated": torch.empty(n, dtype=torch.bool, device=dev),
-            "prob": torch.empty(n, dtype=torch.float64, device=dev),
-        }
+        n = self.num_envs
+        layout = {"obs": ((n,), torch.int64), "reward": ((n,), torch.float64), "prob": ((n,), torch.float64),
+                  "terminated": ((n,), torch.bool), "truncated": ((n,), torch.bool)}
         if self.autoreset_mode == AutoresetMode.SAME_STEP:
-            out["final_obs"] = torch.zeros(n, dtype=torch.int64, device=dev)
-            out["final_prob"] = torch.zeros(n, dtype=torch.float64, device=dev)
+            layout["final_obs"] = ((n,), torch.int64)
+            layout["final_prob"] = ((n,), torch.float64)
+        out = self._alloc_packed(layout)
+        if "final_obs" in out:
+            out["final_obs"].zero_()
+            out["final_prob"].zero_()
         return out
 
     def _reset_kernel(self, mask, options, out):
@@ -144,7 +143,10 @@ class FrozenLakeVectorEnv(B200VectorEnv):
         self._last_obs = out["obs"]
 
     def _reset_info(self, out, mask):
-        m = torch.ones(self.num_envs, dtype=torch.bool, device=self.device) if mask is None else mask.clone()
+        if isinstance(out["prob"], np.ndarray):
+            m = np.ones(self.num_envs, dtype=np.bool_) if mask is None else mask.copy()
+        else:
+            m = torch.ones(self.num_envs, dtype=torch.bool, device=self.device) if mask is None else mask.clone()
         return {"prob": out["prob"], "_prob": m}
 
     def _step_kernel(self, actions, out):
@@ -158,9 +160,14 @@ class FrozenLakeVectorEnv(B200VectorEnv):
         self._last_obs = out["obs"]
 
     def _step_info(self, out):
-        if not hasattr(self, "_all_true"):
-            self._all_true = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
-        info = {"prob": out["prob"], "_prob": self._all_true}
+        host = isinstance(out["prob"], np.ndarray)
+        if host:
+            all_true = np.ones(self.num_envs, dtype=np.bool_)
+        else:
+            if not hasattr(self, "_all_true"):
+                self._all_true = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+            all_true = self._all_true
+        info = {"prob": out["prob"], "_prob": all_true}
         if self.autoreset_mode == AutoresetMode.SAME_STEP:
             done = out["terminated"] | out["truncated"]
             info.update({"final_obs": out["final_obs"], "_final_obs": done,

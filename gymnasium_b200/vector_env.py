@@ -121,7 +121,10 @@ class B200VectorEnv(VectorEnv):
         self._has_reset = False
         self._pinned_actions: torch.Tensor | None = None
         self._out: dict[str, torch.Tensor] = {}
-        self._pinned_out: dict[str, torch.Tensor] = {}
+        self._pinned_wire: torch.Tensor | None = None
+        self._pinned_np: np.ndarray | None = None
+        self._pinned_actions_np: np.ndarray | None = None
+        self._h2d_event: torch.cuda.Event | None = None
 
     # ------------------------------------------------------------------------------------------------------------
     # hooks for families
@@ -150,47 +153,39 @@ class B200VectorEnv(VectorEnv):
             self._out = self._alloc_outputs()  # fresh tensors from the caching allocator; kernels write in place
         return self._out
 
-    def _deliver(self, tree):
-        """output="torch": hand back the device tensors.  output="numpy": one batch of async device->host copies into
-        cached pinned buffers, one stream synchronise, numpy arrays out (fresh copies when ``copy=True``)."""
-        if self.output != "numpy":
-            return tree
-        leaves: list[tuple[str, torch.Tensor]] = []
+    def _alloc_packed(self, layout: dict[str, tuple[tuple, torch.dtype]]) -> dict[str, torch.Tensor]:
+        """Allocates the per-call outputs as typed views of ONE contiguous byte buffer (widest dtype first, so every
+        view is naturally aligned).  Kernels write through the views; ``output="numpy"`` then needs a single
+        device->host copy for the whole step result."""
+        items = sorted(layout.items(), key=lambda kv: -torch.empty((), dtype=kv[1][1]).element_size())
+        sizes = [(k, shape, dt, int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()) for k, (shape, dt) in items]
+        offsets, total = {}, 0
+        for k, shape, dt, nbytes in sizes:
+            total = (total + 15) // 16 * 16
+            offsets[k] = total
+            total += nbytes
+        wire = torch.empty(total, dtype=torch.uint8, device=self.device)
+        out = {"_wire": wire}
+        for k, shape, dt, nbytes in sizes:
+            raw = wire[offsets[k]:offsets[k] + nbytes]
+            out[k] = (raw.view(torch.bool) if dt == torch.bool else raw.view(dt)).view(shape)
+        self._wire_layout = [(k, shape, dt, offsets[k], nbytes) for k, shape, dt, nbytes in sizes]
+        return out
 
-        def walk(x, path):
-            if isinstance(x, torch.Tensor):
-                leaves.append((path, x))
-            elif isinstance(x, dict):
-                for k, v in x.items():
-                    walk(v, f"{path}/{k}")
-            elif isinstance(x, (tuple, list)):
-                for j, v in enumerate(x):
-                    walk(v, f"{path}/{j}")
-
-        walk(tree, "")
-        host = {}
-        for path, t in leaves:
-            buf = self._pinned_out.get(path)
-            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                self._pinned_out[path] = buf
-            buf.copy_(t, non_blocking=True)
-            host[path] = buf
+    def _to_host(self, out: dict[str, torch.Tensor]) -> dict[str, np.ndarray]:
+        """One async D2H copy of the packed outputs into a cached pinned buffer + one stream sync -> numpy views."""
+        wire = out["_wire"]
+        if self._pinned_wire is None or self._pinned_wire.numel() != wire.numel():
+            self._pinned_wire = torch.empty(wire.numel(), dtype=torch.uint8, pin_memory=True)
+            self._pinned_np = self._pinned_wire.numpy()
+        self._pinned_wire.copy_(wire, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-
-        def build(x, path):
-            if isinstance(x, torch.Tensor):
-                a = host[path].numpy()
-                return a.copy() if self.copy else a
-            if isinstance(x, dict):
-                return {k: build(v, f"{path}/{k}") for k, v in x.items()}
-            if isinstance(x, tuple):
-                return tuple(build(v, f"{path}/{j}") for j, v in enumerate(x))
-            if isinstance(x, list):
-                return [build(v, f"{path}/{j}") for j, v in enumerate(x)]
-            return x
-
-        return build(tree, "")
+        host = {}
+        for k, shape, dt, off, nbytes in self._wire_layout:
+            npdt = np.bool_ if dt == torch.bool else torch.empty((), dtype=dt).numpy().dtype
+            a = self._pinned_np[off:off + nbytes].view(npdt).reshape(shape)
+            host[k] = a.copy() if self.copy else a
+        return host
 
     # ------------------------------------------------------------------------------------------------------------
     def _seed_streams(self, seed, mask: torch.Tensor | None) -> None:
@@ -281,19 +276,25 @@ class B200VectorEnv(VectorEnv):
             self._reset_kernel(mask, options, out)
             self._batch.call_counter += 1
         self._has_reset = True
-        return self._deliver((out["obs"], self._reset_info(out, mask)))
+        if self.output == "numpy":
+            host = self._to_host(out)
+            m = None if mask is None else mask.cpu().numpy()
+            return host["obs"], self._reset_info(host, m)
+        return out["obs"], self._reset_info(out, mask)
 
     def _prepare_actions(self, actions) -> torch.Tensor:
         """One conversion to a contiguous device tensor; wrong count -> ValueError, scalar -> TypeError
         (tests/vector/test_vector_env.py:330-364)."""
         n = self.num_envs
+        if isinstance(actions, torch.Tensor) and actions.device.type == "cpu":
+            actions = actions.numpy()
         if isinstance(actions, torch.Tensor):
             t = actions
         else:
             if np.ndim(actions) == 0:
                 raise TypeError(f"actions must be an iterable of length num_envs={n}, got a scalar {actions!r}")
             a = np.ascontiguousarray(actions)
-            if a.dtype == object or a.dtype.kind not in "iuf" + "b":
+            if a.dtype == object or a.dtype.kind not in "iufb":
                 raise TypeError(f"unsupported action array dtype {a.dtype}")
             if a.dtype == np.bool_:
                 a = a.astype(np.uint8)
@@ -301,7 +302,23 @@ class B200VectorEnv(VectorEnv):
                 raise TypeError(f"discrete actions must be integers, got dtype {a.dtype}")
             if self.discrete_actions and a.dtype not in (np.int64, np.int32, np.uint8):
                 a = a.astype(np.int64)
-            t = torch.from_numpy(a)
+            if a.shape[0] != n:
+                raise ValueError(f"expected {n} actions (one per sub-environment), got {a.shape[0]}")
+            if self.discrete_actions and a.ndim != 1:
+                raise ValueError(f"discrete actions must have shape ({n},), got {a.shape}")
+            # stage through a cached pinned buffer with a plain single-threaded memcpy, then one async H2D copy
+            pa = self._pinned_actions
+            if pa is None or tuple(pa.shape) != a.shape or self._pinned_actions_np.dtype != a.dtype:
+                pa = self._pinned_actions = torch.from_numpy(np.empty(a.shape, dtype=a.dtype)).pin_memory()
+                self._pinned_actions_np = pa.numpy()
+            if self._h2d_event is not None:
+                self._h2d_event.synchronize()  # the previous step's DMA out of this buffer must have finished
+            np.copyto(self._pinned_actions_np, a)
+            t = pa.to(self.device, non_blocking=True)
+            if self._h2d_event is None:
+                self._h2d_event = torch.cuda.Event()
+            self._h2d_event.record(torch.cuda.current_stream(self.device))
+            return t
         if t.dim() == 0:
             raise TypeError(f"actions must have a leading dimension of num_envs={n}, got a scalar tensor")
         if t.shape[0] != n:
@@ -312,13 +329,7 @@ class B200VectorEnv(VectorEnv):
             if t.dtype not in (torch.int64, torch.int32, torch.uint8):
                 t = t.to(torch.int64)
         if t.device != self.device:
-            if t.device.type == "cpu":
-                if self._pinned_actions is None or self._pinned_actions.shape != t.shape or self._pinned_actions.dtype != t.dtype:
-                    self._pinned_actions = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                self._pinned_actions.copy_(t)
-                t = self._pinned_actions.to(self.device, non_blocking=True)
-            else:
-                t = t.to(self.device)
+            t = t.to(self.device)
         return t.contiguous()
 
     def step(self, actions):
@@ -334,7 +345,9 @@ class B200VectorEnv(VectorEnv):
             self._batch.action_dtype = _ACT_DTYPES[t.dtype]
             self._step_kernel(t, out)
             self._batch.call_counter += 1
-        return self._deliver((out["obs"], out["reward"], out["terminated"], out["truncated"], self._step_info(out)))
+        if self.output == "numpy":
+            out = self._to_host(out)
+        return out["obs"], out["reward"], out["terminated"], out["truncated"], self._step_info(out)
 
     # ------------------------------------------------------------------------------------------------------------
     @property
