@@ -151,17 +151,8 @@ __global__ void __launch_bounds__(kBlock) cartpole_reset_kernel(const CartPoleAr
   reinterpret_cast<float4*>(a.obs)[i] = to_obs(s);
 }
 
-constexpr int kStepBlock = 128;  // N=65536 -> 512 CTAs: 3-4 per SM instead of 1-2, the tail is shorter
-
-template <typename ActT>
-__global__ void __launch_bounds__(kStepBlock) cartpole_step_kernel(const CartPoleArgs a) {
-  pdl_prologue();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  // every load is issued before the first use so one DRAM round trip covers them all
-  const int32_t c = a.ctrl[i];
-  const State4 s0 = load_state(a.state, a.n, i);
-  const int action = load_action<ActT>(a.actions, i);
+// one env's step given its preloaded inputs
+__device__ __forceinline__ void step_env(const CartPoleArgs& a, int64_t i, int32_t c, const State4& s0, int action) {
   if (a.mode == B2E_AUTORESET_NEXT_STEP && ctrl_pending(c)) {
     // sync_vector_env.py:279-284: the call after a done is the reset; reward 0, flags False, action ignored
     const State4 s = sample_reset(a, i, a.call_counter);
@@ -193,6 +184,60 @@ __global__ void __launch_bounds__(kStepBlock) cartpole_step_kernel(const CartPol
   store_state(a.state, a.n, i, s);
   a.ctrl[i] = cn;
   __stcs(reinterpret_cast<float4*>(a.obs) + i, to_obs(s));
+}
+
+// EPT envs per thread (strided by the thread count so every access stays coalesced): all loads of all EPT envs are
+// issued before the first use -> one memory round trip, and EPT independent FP64 dependency chains per thread.
+template <typename ActT, int EPT>
+__global__ void __launch_bounds__(256) cartpole_step_kernel(const CartPoleArgs a) {
+  pdl_prologue();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int32_t c[EPT];
+  State4 s0[EPT];
+  int act[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int64_t i = t + e * stride;
+    if (i < a.n) {
+      c[e] = a.ctrl[i];
+      s0[e] = load_state(a.state, a.n, i);
+      act[e] = load_action<ActT>(a.actions, i);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int64_t i = t + e * stride;
+    if (i < a.n) step_env(a, i, c[e], s0[e], act[e]);
+  }
+}
+
+// launch geometry (tunable through B2E_STEP_BLOCK / B2E_STEP_EPT for experiments)
+struct StepGeom {
+  int block, ept;
+};
+inline StepGeom step_geom() {
+  static const StepGeom g = [] {
+    StepGeom r{128, 1};
+    if (const char* s = getenv("B2E_STEP_BLOCK")) r.block = atoi(s);
+    if (const char* s = getenv("B2E_STEP_EPT")) r.ept = atoi(s);
+    if (r.block != 64 && r.block != 128 && r.block != 256) r.block = 128;
+    if (r.ept != 1 && r.ept != 2 && r.ept != 4) r.ept = 1;
+    return r;
+  }();
+  return g;
+}
+
+template <typename ActT>
+cudaError_t launch_step(const CartPoleArgs& a, cudaStream_t st) {
+  const StepGeom g = step_geom();
+  const int64_t threads = (a.n + g.ept - 1) / g.ept;
+  const unsigned grid = grid_for(threads, g.block);
+  switch (g.ept) {
+    case 4: return launch_pdl(cartpole_step_kernel<ActT, 4>, grid, g.block, 0, st, a);
+    case 2: return launch_pdl(cartpole_step_kernel<ActT, 2>, grid, g.block, 0, st, a);
+    default: return launch_pdl(cartpole_step_kernel<ActT, 1>, grid, g.block, 0, st, a);
+  }
 }
 
 struct RolloutArgs {
@@ -342,13 +387,12 @@ extern "C" int b2e_cartpole_step(const b2e_batch* b, const b2e_cartpole_cfg* cfg
   a.term = terminated;
   a.trunc = truncated;
   a.final_obs = final_obs;
-  const unsigned grid = grid_for(b->n, kStepBlock);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   switch (b->action_dtype) {
-    case B2E_ACT_I64: e = launch_pdl(cartpole_step_kernel<int64_t>, grid, kStepBlock, 0, st, a); break;
-    case B2E_ACT_I32: e = launch_pdl(cartpole_step_kernel<int32_t>, grid, kStepBlock, 0, st, a); break;
-    case B2E_ACT_U8: e = launch_pdl(cartpole_step_kernel<uint8_t>, grid, kStepBlock, 0, st, a); break;
+    case B2E_ACT_I64: e = launch_step<int64_t>(a, st); break;
+    case B2E_ACT_I32: e = launch_step<int32_t>(a, st); break;
+    case B2E_ACT_U8: e = launch_step<uint8_t>(a, st); break;
     default: set_error("b2e_cartpole_step: action_dtype %d is not a discrete dtype", b->action_dtype); return B2E_EINVAL;
   }
   return cuda_status(e, "b2e_cartpole_step");

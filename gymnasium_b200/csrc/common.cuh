@@ -47,7 +47,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  static const bool pdl = getenv("B2E_NO_PDL") == nullptr;  // debugging switch: plain stream order
+  static const bool pdl = getenv("B2E_PDL") != nullptr;  // opt-in: measured slower at N >= 65536
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
