@@ -339,6 +339,9 @@ def run_b200(args):
     kernel_s = elapsed / K
     achieved = step_bytes * n / kernel_s / 1e9
 
+    # reference counting rule (performance.py:88-90): NEXT_STEP reset calls are not env steps
+    import torch as _t
+    reset_frac = float(_t.stack([(e._ctrl < 0).float().mean() for e in envs]).mean().item())
     extras = {}
     if not args.no_extras and rank == 0:
         extras = run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, envs[0], acts[0])
@@ -407,7 +410,7 @@ def run_b200(args):
                 "launch": "CUDA graphs of one step launch per batch, CUDA-event timing on the launch stream",
                 "counting": "calls x N (reset calls included); see value_excluding_reset_calls",
             },
-            "value_excluding_reset_calls": value * (1 - extras.get("reset_call_fraction", 0.0)) if extras else None,
+            "value_excluding_reset_calls": value * (1 - reset_frac), "reset_call_fraction": reset_frac,
             "gpu_launches": K,
             "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "peak_source": peak_src,
@@ -466,10 +469,6 @@ def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0)
     out["roofline_large_batch"] = {"kernel": "same step kernel, N=16,777,216 (1.7 GB footprint)", "achieved": bw,
                                    "peak": hbm_peak, "unit": "GB/s", "frac": bw / hbm_peak,
                                    "steps_per_s": big / t, "us_per_launch": t * 1e6}
-    # (3) reset-call fraction (reference counting rule, performance.py:88-90)
-    _, _, te, tr, _ = e.step(a)
-    frac = float((e._ctrl < 0).float().mean().item())
-    out["reset_call_fraction"] = frac
     del e, a
     torch.cuda.empty_cache()
     # (4) fused K-step rollout kernel with on-device Philox actions, trajectory streamed to HBM

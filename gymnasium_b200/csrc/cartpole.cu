@@ -186,58 +186,26 @@ __device__ __forceinline__ void step_env(const CartPoleArgs& a, int64_t i, int32
   __stcs(reinterpret_cast<float4*>(a.obs) + i, to_obs(s));
 }
 
-// EPT envs per thread (strided by the thread count so every access stays coalesced): all loads of all EPT envs are
-// issued before the first use -> one memory round trip, and EPT independent FP64 dependency chains per thread.
-template <typename ActT, int EPT>
-__global__ void __launch_bounds__(256) cartpole_step_kernel(const CartPoleArgs a) {
-  pdl_prologue();
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int32_t c[EPT];
-  State4 s0[EPT];
-  int act[EPT];
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    const int64_t i = t + e * stride;
-    if (i < a.n) {
-      c[e] = a.ctrl[i];
-      s0[e] = load_state(a.state, a.n, i);
-      act[e] = load_action<ActT>(a.actions, i);
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    const int64_t i = t + e * stride;
-    if (i < a.n) step_env(a, i, c[e], s0[e], act[e]);
-  }
-}
+// One thread per env, 128-thread CTAs.  All loads are issued before the first use (one memory round trip).  Launch
+// geometry was swept on a B200 at N=65536 / 262144 (graph-chained launches, us per launch): block 64/128/256 x 1/2/4
+// envs per thread -> 128 x 1 is fastest (3.30 / 6.50 us; 2 envs/thread 4.10 / 7.00; 4 envs/thread 6.3 / 8.1), and
+// programmatic dependent launch made N >= 65536 slower (4.07 vs 3.27 us), so it is opt-in (B2E_PDL=1).
+constexpr int kStepBlock = 128;
 
-// launch geometry (tunable through B2E_STEP_BLOCK / B2E_STEP_EPT for experiments)
-struct StepGeom {
-  int block, ept;
-};
-inline StepGeom step_geom() {
-  static const StepGeom g = [] {
-    StepGeom r{128, 1};
-    if (const char* s = getenv("B2E_STEP_BLOCK")) r.block = atoi(s);
-    if (const char* s = getenv("B2E_STEP_EPT")) r.ept = atoi(s);
-    if (r.block != 64 && r.block != 128 && r.block != 256) r.block = 128;
-    if (r.ept != 1 && r.ept != 2 && r.ept != 4) r.ept = 1;
-    return r;
-  }();
-  return g;
+template <typename ActT>
+__global__ void __launch_bounds__(kStepBlock) cartpole_step_kernel(const CartPoleArgs a) {
+  pdl_prologue();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const int32_t c = a.ctrl[i];
+  const State4 s0 = load_state(a.state, a.n, i);
+  const int action = load_action<ActT>(a.actions, i);
+  step_env(a, i, c, s0, action);
 }
 
 template <typename ActT>
 cudaError_t launch_step(const CartPoleArgs& a, cudaStream_t st) {
-  const StepGeom g = step_geom();
-  const int64_t threads = (a.n + g.ept - 1) / g.ept;
-  const unsigned grid = grid_for(threads, g.block);
-  switch (g.ept) {
-    case 4: return launch_pdl(cartpole_step_kernel<ActT, 4>, grid, g.block, 0, st, a);
-    case 2: return launch_pdl(cartpole_step_kernel<ActT, 2>, grid, g.block, 0, st, a);
-    default: return launch_pdl(cartpole_step_kernel<ActT, 1>, grid, g.block, 0, st, a);
-  }
+  return launch_pdl(cartpole_step_kernel<ActT>, grid_for(a.n, kStepBlock), kStepBlock, 0, st, a);
 }
 
 struct RolloutArgs {

@@ -30,10 +30,11 @@ int cuda_status(cudaError_t e, const char* fn);
 constexpr int kBlock = 256;  // 8 warps; every kernel here is 1 thread/env (or grid-stride), register-light
 inline unsigned grid_for(int64_t n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
 
-// Programmatic dependent launch (sm_90+): every step kernel is launched with the programmatic-stream-serialization
-// attribute, triggers its dependents at once and waits for its predecessor before its first global access, so the
-// launch latency of step k+1 overlaps the execution of step k in a chain of tiny dependent launches (also inside
-// captured CUDA graphs).  The wait returns only when the previous grid has completed and flushed: semantics unchanged.
+// Programmatic dependent launch (sm_90+), opt-in with B2E_PDL=1: the kernel is launched with the programmatic-stream-
+// serialization attribute, triggers its dependents at once and waits for its predecessor before its first global
+// access, so the launch latency of step k+1 can overlap the execution of step k (also inside captured CUDA graphs).
+// Without the attribute the two griddepcontrol instructions are no-ops.  Measured on B200 (scripts/floor.py): helps
+// chains of tiny launches (N <= 4096: 2.05 vs 2.21 us) but hurts at N >= 65536 (4.07 vs 3.27 us), hence opt-in.
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");

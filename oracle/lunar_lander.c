@@ -1,0 +1,1214 @@
+/* oracle/lunar_lander.c -- CPU oracle for LunarLander-v3: a plain-C restatement of the Box2D 2.3.x subset that
+ * gymnasium/envs/box2d/lunar_lander.py drives, plus the environment logic itself.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): never linked into or called by gymnasium_b200/.
+ *
+ * PARITY UNPINNED.  The arithmetic of this env lives in the third-party wheel `box2d ==2.3.10` (pybox2d, SWIG over
+ * Box2D C++ 2.3.x; pyproject.toml:38-43 of the reference).  That wheel is not vendored in /root/reference, not
+ * installed in this image and not installable (no network, no swig), and the reference holds no golden vectors for
+ * this env.  This file therefore restates Box2D's published algorithm from its documented structure
+ * (b2World::Step -> b2ContactManager::Collide -> b2Island::Solve -> b2ContactSolver / b2RevoluteJoint, b2CollideEdge-
+ * AndPolygon, b2PolygonShape::ComputeMass, b2DynamicTree fat AABBs) and anchors on the reference's own call sites:
+ *   reset      gymnasium/envs/box2d/lunar_lander.py:321-447
+ *   step       lunar_lander.py:471-665 (world.Step(1/50, 180, 60) at :619)
+ *   contacts   lunar_lander.py:58-76 (ContactDetector Begin/EndContact)
+ * The only behavioural pin the reference offers for this boundary is the heuristic landing test
+ * (tests/envs/test_env_implementation.py:12-16 with the policy at lunar_lander.py:791-842); tests/test_oracle_lunar.py
+ * runs it against this file.
+ * Known deviation: b2World::SolveTOI (continuous collision vs the static terrain) is NOT restated; the discrete
+ * solver alone runs.  It matters only on the frames of a high-speed first impact, which end the episode anyway when
+ * the lander hull is involved (game_over).
+ *
+ * All Box2D arithmetic is float32 with one rounding per operation (compile with -ffp-contract=off); the Python-side
+ * glue (dispersion, impulses, observation scaling, shaping reward) is float64 as in the reference.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * numpy Generator(PCG64(SeedSequence(seed))) -- gymnasium/utils/seeding.py:39-41 (see oracle/np_rng.py for the pinned
+ * Python restatement; this is the same algorithm in C) */
+typedef unsigned __int128 u128;
+typedef struct { u128 state, inc; int seeded; } pcg64_t;
+
+static void pcg64_seed(pcg64_t* g, uint64_t seed) {
+  const uint32_t INIT_A = 0x43b0d7e5u, MULT_A = 0x931e8875u, INIT_B = 0x8b51f9ddu, MULT_B = 0x58f38dedu;
+  const uint32_t MIX_L = 0xca01f9ddu, MIX_R = 0x4973f715u;
+  uint32_t hc = INIT_A, pool[4], words[4] = {(uint32_t)seed, (uint32_t)(seed >> 32), 0, 0};
+  for (int i = 0; i < 4; ++i) { uint32_t v = words[i] ^ hc; hc *= MULT_A; v *= hc; v ^= v >> 16; pool[i] = v; }
+  for (int s = 0; s < 4; ++s)
+    for (int d = 0; d < 4; ++d)
+      if (s != d) {
+        uint32_t v = pool[s] ^ hc; hc *= MULT_A; v *= hc; v ^= v >> 16;
+        uint32_t r = MIX_L * pool[d] - MIX_R * v; r ^= r >> 16; pool[d] = r;
+      }
+  uint32_t out[8], hb = INIT_B;
+  for (int i = 0; i < 8; ++i) { uint32_t v = pool[i & 3] ^ hb; hb *= MULT_B; v *= hb; v ^= v >> 16; out[i] = v; }
+  uint64_t w[4];
+  for (int k = 0; k < 4; ++k) w[k] = out[2 * k] | ((uint64_t)out[2 * k + 1] << 32);
+  const u128 mult = ((u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+  u128 initstate = ((u128)w[0] << 64) | w[1], initseq = ((u128)w[2] << 64) | w[3];
+  g->inc = (initseq << 1) | 1;
+  g->state = 0;
+  g->state = g->state * mult + g->inc;
+  g->state += initstate;
+  g->state = g->state * mult + g->inc;
+  g->seeded = 1;
+}
+static double pcg64_double(pcg64_t* g) {
+  const u128 mult = ((u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+  g->state = g->state * mult + g->inc;
+  uint64_t hi = (uint64_t)(g->state >> 64), lo = (uint64_t)g->state, x = hi ^ lo;
+  unsigned rot = (unsigned)(hi >> 58);
+  x = (x >> rot) | (x << ((64 - rot) & 63));
+  return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+static double pcg64_uniform(pcg64_t* g, double lo, double hi) { return lo + (hi - lo) * pcg64_double(g); }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * b2Math */
+typedef struct { float x, y; } v2;
+typedef struct { float s, c; } rot_t;
+typedef struct { v2 p; rot_t q; } xf_t;
+typedef struct { v2 lo, hi; } aabb_t;
+
+static inline v2 V(float x, float y) { v2 r = {x, y}; return r; }
+static inline v2 vadd(v2 a, v2 b) { return V(a.x + b.x, a.y + b.y); }
+static inline v2 vsub(v2 a, v2 b) { return V(a.x - b.x, a.y - b.y); }
+static inline v2 vneg(v2 a) { return V(-a.x, -a.y); }
+static inline v2 vscale(float s, v2 a) { return V(s * a.x, s * a.y); }
+static inline float vdot(v2 a, v2 b) { return a.x * b.x + a.y * b.y; }
+static inline float vcross(v2 a, v2 b) { return a.x * b.y - a.y * b.x; }
+static inline v2 vcross_vs(v2 a, float s) { return V(s * a.y, -s * a.x); } /* b2Cross(vec, s) */
+static inline v2 vcross_sv(float s, v2 a) { return V(-s * a.y, s * a.x); } /* b2Cross(s, vec) */
+static inline float vlen(v2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
+static inline v2 vmin(v2 a, v2 b) { return V(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y); }
+static inline v2 vmax(v2 a, v2 b) { return V(a.x > b.x ? a.x : b.x, a.y > b.y ? a.y : b.y); }
+static inline float fclamp(float a, float lo, float hi) { return fmaxf(lo, fminf(a, hi)); }
+/* b2Rot::Set: sinf/cosf.  Evaluated as the correctly rounded float of the double result so that the CUDA engine,
+ * which does the same, agrees bit for bit (glibc's sinf/cosf are correctly rounded too). */
+static inline rot_t rot_set(float a) { rot_t r = {(float)sin((double)a), (float)cos((double)a)}; return r; }
+static inline v2 rmul(rot_t q, v2 v) { return V(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
+static inline v2 rmulT(rot_t q, v2 v) { return V(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
+static inline v2 xmul(xf_t T, v2 v) { return V((T.q.c * v.x - T.q.s * v.y) + T.p.x, (T.q.s * v.x + T.q.c * v.y) + T.p.y); }
+static inline v2 xmulT(xf_t T, v2 v) {
+  float px = v.x - T.p.x, py = v.y - T.p.y;
+  return V(T.q.c * px + T.q.s * py, -T.q.s * px + T.q.c * py);
+}
+/* b2Vec2::Normalize */
+static inline float vnormalize(v2* a) {
+  float len = vlen(*a);
+  if (len < 1.19209290e-7f) return 0.0f;
+  float inv = 1.0f / len;
+  a->x *= inv; a->y *= inv;
+  return len;
+}
+
+/* b2Settings.h */
+#define B2_PI 3.14159265359f
+#define LINEAR_SLOP 0.005f
+#define ANGULAR_SLOP (2.0f / 180.0f * B2_PI)
+#define POLYGON_RADIUS (2.0f * LINEAR_SLOP)
+#define AABB_EXTENSION 0.1f
+#define AABB_MULTIPLIER 2.0f
+#define VELOCITY_THRESHOLD 1.0f
+#define MAX_LINEAR_CORRECTION 0.2f
+#define MAX_ANGULAR_CORRECTION (8.0f / 180.0f * B2_PI)
+#define MAX_TRANSLATION 2.0f
+#define MAX_ROTATION (0.5f * B2_PI)
+#define BAUMGARTE 0.2f
+#define TIME_TO_SLEEP 0.5f
+#define LINEAR_SLEEP_TOL 0.01f
+#define ANGULAR_SLEEP_TOL (2.0f / 180.0f * B2_PI)
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * scene: body 0 = moon (static, 11 edge fixtures), 1 = lander, 2 = legs[0] (i=-1), 3 = legs[1] (i=+1) */
+#define NBODY 4
+#define NEDGE 11  /* fixture 0: base edge (0,0)-(W,0); 1..10: terrain */
+#define NDYN 3
+#define NPAIR (NDYN * NEDGE)
+#define MAXV 8
+
+typedef struct {
+  int count;
+  v2 v[MAXV], n[MAXV], centroid;
+} poly_t;
+
+typedef struct {
+  int dynamic;
+  xf_t xf;
+  v2 local_center, c0, c;
+  float a0, a;
+  v2 vel;
+  float w;
+  v2 force;
+  float torque, mass, inv_mass, I, inv_I, sleep_time;
+  int awake;
+} body_t;
+
+typedef struct { uint8_t indexA, indexB, typeA, typeB; } cid_t; /* b2ContactFeature */
+static inline uint32_t cid_key(cid_t c) { return c.indexA | (c.indexB << 8) | (c.typeA << 16) | ((uint32_t)c.typeB << 24); }
+
+typedef struct { v2 local_point; float normal_impulse, tangent_impulse; cid_t id; } mpoint_t;
+typedef struct { mpoint_t points[2]; v2 local_normal, local_point; int type /*1 faceA, 2 faceB*/, count; } manifold_t;
+
+typedef struct {
+  int exists, touching;
+  long seq;          /* creation order: lists are walked most-recent-first like Box2D's intrusive lists */
+  float friction;
+  manifold_t m;
+} contact_t;
+
+typedef struct {
+  int bodyB;                 /* bodyA is the lander (1) */
+  v2 local_anchor_a, local_anchor_b;
+  float reference_angle, lower, upper, max_motor_torque, motor_speed;
+  float imp_x, imp_y, imp_z, motor_impulse;
+  int limit_state;           /* 0 inactive, 1 lower, 2 upper, 3 equal */
+  /* solver temp */
+  v2 rA, rB, lcA, lcB;
+  float m[3][3];             /* m_mass columns ex, ey, ez: m[col][row] */
+  float motor_mass, mA, mB, iA, iB;
+} joint_t;
+
+typedef struct {
+  body_t b[NBODY];
+  poly_t poly[NDYN];          /* lander, leg0, leg1 (body-local) */
+  v2 edge_v1[NEDGE], edge_v2[NEDGE];
+  float edge_friction[NEDGE], poly_friction[NDYN];
+  aabb_t edge_fat[NEDGE], poly_fat[NDYN];
+  contact_t contact[NPAIR];   /* index = dyn * NEDGE + edge */
+  long seq;
+  joint_t joint[2];           /* joint[k] connects lander and legs[k] */
+  float inv_dt0;
+  int new_fixture;
+  /* env */
+  int game_over, leg_contact[2], has_prev_shaping;
+  double prev_shaping, helipad_y;
+  float gravity;
+  pcg64_t rng;
+} lander_t;
+
+/* --- b2PolygonShape::Set (hull) + ComputeCentroid ------------------------------------------------------------- */
+static v2 compute_centroid(const v2* vs, int count) {
+  v2 c = V(0, 0), pRef = V(0, 0);
+  float area = 0.0f;
+  const float inv3 = 1.0f / 3.0f;
+  for (int i = 0; i < count; ++i) {
+    v2 p1 = pRef, p2 = vs[i], p3 = i + 1 < count ? vs[i + 1] : vs[0];
+    v2 e1 = vsub(p2, p1), e2 = vsub(p3, p1);
+    float D = vcross(e1, e2), tri = 0.5f * D;
+    area += tri;
+    c = vadd(c, vscale(tri * inv3, vadd(vadd(p1, p2), p3)));
+  }
+  return vscale(1.0f / area, c);
+}
+static void poly_set(poly_t* p, const v2* in, int n) {
+  v2 ps[MAXV];
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) { /* weld close points */
+    int unique = 1;
+    for (int j = 0; j < cnt; ++j) {
+      v2 d = vsub(in[i], ps[j]);
+      if (vdot(d, d) < (0.5f * LINEAR_SLOP) * (0.5f * LINEAR_SLOP)) { unique = 0; break; }
+    }
+    if (unique) ps[cnt++] = in[i];
+  }
+  int i0 = 0;
+  float x0 = ps[0].x;
+  for (int i = 1; i < cnt; ++i) {
+    float x = ps[i].x;
+    if (x > x0 || (x == x0 && ps[i].y < ps[i0].y)) { i0 = i; x0 = x; }
+  }
+  int hull[MAXV], m = 0, ih = i0;
+  for (;;) {
+    hull[m] = ih;
+    int ie = 0;
+    for (int j = 1; j < cnt; ++j) {
+      if (ie == ih) { ie = j; continue; }
+      v2 r = vsub(ps[ie], ps[hull[m]]), v = vsub(ps[j], ps[hull[m]]);
+      float c = vcross(r, v);
+      if (c < 0.0f) ie = j;
+      if (c == 0.0f && vdot(v, v) > vdot(r, r)) ie = j;
+    }
+    ++m;
+    ih = ie;
+    if (ie == i0) break;
+  }
+  p->count = m;
+  for (int i = 0; i < m; ++i) p->v[i] = ps[hull[i]];
+  for (int i = 0; i < m; ++i) {
+    int i2 = i + 1 < m ? i + 1 : 0;
+    v2 e = vsub(p->v[i2], p->v[i]);
+    p->n[i] = vcross_vs(e, 1.0f);
+    vnormalize(&p->n[i]);
+  }
+  p->centroid = compute_centroid(p->v, m);
+}
+static void poly_set_box(poly_t* p, float hx, float hy) {
+  p->count = 4;
+  p->v[0] = V(-hx, -hy); p->v[1] = V(hx, -hy); p->v[2] = V(hx, hy); p->v[3] = V(-hx, hy);
+  p->n[0] = V(0, -1); p->n[1] = V(1, 0); p->n[2] = V(0, 1); p->n[3] = V(-1, 0);
+  p->centroid = V(0, 0);
+}
+/* b2PolygonShape::ComputeMass */
+static void poly_mass(const poly_t* p, float density, float* mass, v2* center_out, float* I_out) {
+  v2 center = V(0, 0), s = V(0, 0);
+  float area = 0.0f, I = 0.0f;
+  for (int i = 0; i < p->count; ++i) s = vadd(s, p->v[i]);
+  s = vscale(1.0f / (float)p->count, s);
+  const float inv3 = 1.0f / 3.0f;
+  for (int i = 0; i < p->count; ++i) {
+    v2 e1 = vsub(p->v[i], s), e2 = vsub(i + 1 < p->count ? p->v[i + 1] : p->v[0], s);
+    float D = vcross(e1, e2), tri = 0.5f * D;
+    area += tri;
+    center = vadd(center, vscale(tri * inv3, vadd(e1, e2)));
+    float ex1 = e1.x, ey1 = e1.y, ex2 = e2.x, ey2 = e2.y;
+    float intx2 = ex1 * ex1 + ex2 * ex1 + ex2 * ex2, inty2 = ey1 * ey1 + ey2 * ey1 + ey2 * ey2;
+    I += (0.25f * inv3 * D) * (intx2 + inty2);
+  }
+  *mass = density * area;
+  center = vscale(1.0f / area, center);
+  *center_out = vadd(center, s);
+  *I_out = density * I;
+  *I_out += *mass * (vdot(*center_out, *center_out) - vdot(center, center));
+}
+
+/* b2Body::ResetMassData for a one-fixture body, then the sweep set-up b2Body does at creation */
+static void body_init_dynamic(body_t* b, const poly_t* p, float density, v2 pos, float angle) {
+  memset(b, 0, sizeof(*b));
+  b->dynamic = 1;
+  b->awake = 1;
+  b->xf.p = pos;
+  b->xf.q = rot_set(angle);
+  b->c0 = b->c = pos;
+  b->a0 = b->a = angle;
+  float mass, I;
+  v2 center;
+  poly_mass(p, density, &mass, &center, &I);
+  b->mass = mass;
+  b->inv_mass = 1.0f / mass;
+  v2 lc = vscale(b->inv_mass, vscale(mass, center)); /* localCenter = sum(mass_i * center_i) * invMass */
+  I -= mass * vdot(lc, lc);
+  b->I = I;
+  b->inv_I = 1.0f / I;
+  b->local_center = lc;
+  b->c0 = b->c = xmul(b->xf, lc);
+}
+static void sync_transform(body_t* b) {
+  b->xf.q = rot_set(b->a);
+  b->xf.p = vsub(b->c, rmul(b->xf.q, b->local_center));
+}
+static void set_awake(body_t* b, int flag) {
+  if (flag) {
+    if (!b->awake) { b->awake = 1; b->sleep_time = 0.0f; }
+  } else {
+    b->awake = 0; b->sleep_time = 0.0f; b->vel = V(0, 0); b->w = 0.0f; b->force = V(0, 0); b->torque = 0.0f;
+  }
+}
+
+/* --- AABBs / broad phase ---------------------------------------------------------------------------------------- */
+static aabb_t poly_aabb(const poly_t* p, xf_t xf) {
+  v2 lo = xmul(xf, p->v[0]), hi = lo;
+  for (int i = 1; i < p->count; ++i) { v2 v = xmul(xf, p->v[i]); lo = vmin(lo, v); hi = vmax(hi, v); }
+  aabb_t r = {V(lo.x - POLYGON_RADIUS, lo.y - POLYGON_RADIUS), V(hi.x + POLYGON_RADIUS, hi.y + POLYGON_RADIUS)};
+  return r;
+}
+static aabb_t fatten(aabb_t a) {
+  aabb_t r = {V(a.lo.x - AABB_EXTENSION, a.lo.y - AABB_EXTENSION), V(a.hi.x + AABB_EXTENSION, a.hi.y + AABB_EXTENSION)};
+  return r;
+}
+static int aabb_contains(aabb_t a, aabb_t b) {
+  return a.lo.x <= b.lo.x && a.lo.y <= b.lo.y && b.hi.x <= a.hi.x && b.hi.y <= a.hi.y;
+}
+static int aabb_overlap(aabb_t a, aabb_t b) {
+  v2 d1 = vsub(b.lo, a.hi), d2 = vsub(a.lo, b.hi);
+  if (d1.x > 0.0f || d1.y > 0.0f) return 0;
+  if (d2.x > 0.0f || d2.y > 0.0f) return 0;
+  return 1;
+}
+
+/* --- b2CollideEdgeAndPolygon (b2EPCollider, plain edge without ghost vertices) ---------------------------------- */
+typedef struct { v2 v; cid_t id; } clipv_t;
+static int clip_segment(clipv_t out[2], const clipv_t in[2], v2 normal, float offset, int vertexIndexA) {
+  int n = 0;
+  float d0 = vdot(normal, in[0].v) - offset, d1 = vdot(normal, in[1].v) - offset;
+  if (d0 <= 0.0f) out[n++] = in[0];
+  if (d1 <= 0.0f) out[n++] = in[1];
+  if (d0 * d1 < 0.0f) {
+    float interp = d0 / (d0 - d1);
+    out[n].v = vadd(in[0].v, vscale(interp, vsub(in[1].v, in[0].v)));
+    out[n].id.indexA = (uint8_t)vertexIndexA;
+    out[n].id.indexB = in[0].id.indexB;
+    out[n].id.typeA = 0; /* e_vertex */
+    out[n].id.typeB = 1; /* e_face */
+    ++n;
+  }
+  return n;
+}
+static void collide_edge_polygon(manifold_t* mf, v2 ev1, v2 ev2, const poly_t* pb, xf_t xfB) {
+  /* xfA is the identity (the moon sits at the origin): m_xf = b2MulT(xfA, xfB) = xfB */
+  const xf_t xf = xfB;
+  const v2 centroidB = xmul(xf, pb->centroid);
+  v2 edge1 = vsub(ev2, ev1);
+  vnormalize(&edge1);
+  const v2 normal1 = V(edge1.y, -edge1.x);
+  const float offset1 = vdot(normal1, vsub(centroidB, ev1));
+  const int front = offset1 >= 0.0f;
+  v2 normal, lower, upper;
+  if (front) { normal = normal1; lower = vneg(normal1); upper = vneg(normal1); }
+  else { normal = vneg(normal1); lower = normal1; upper = normal1; }
+  v2 pv[MAXV], pn[MAXV];
+  const int count = pb->count;
+  for (int i = 0; i < count; ++i) { pv[i] = xmul(xf, pb->v[i]); pn[i] = rmul(xf.q, pb->n[i]); }
+  const float radius = 2.0f * POLYGON_RADIUS;
+  mf->count = 0;
+  /* ComputeEdgeSeparation */
+  float edge_sep = 3.402823466e+38f;
+  for (int i = 0; i < count; ++i) { float s = vdot(normal, vsub(pv[i], ev1)); if (s < edge_sep) edge_sep = s; }
+  if (edge_sep > radius) return;
+  /* ComputePolygonSeparation */
+  int ptype = 0 /*unknown*/, pindex = -1;
+  float psep = -3.402823466e+38f;
+  const v2 perp = V(-normal.y, normal.x);
+  for (int i = 0; i < count; ++i) {
+    v2 n = vneg(pn[i]);
+    float s1 = vdot(n, vsub(pv[i], ev1)), s2 = vdot(n, vsub(pv[i], ev2)), s = s1 < s2 ? s1 : s2;
+    if (s > radius) { ptype = 2; pindex = i; psep = s; break; }
+    if (vdot(n, perp) >= 0.0f) { if (vdot(vsub(n, upper), normal) < -ANGULAR_SLOP) continue; }
+    else { if (vdot(vsub(n, lower), normal) < -ANGULAR_SLOP) continue; }
+    if (s > psep) { ptype = 2; pindex = i; psep = s; }
+  }
+  if (ptype != 0 && psep > radius) return;
+  const float k_rel = 0.98f, k_abs = 0.001f;
+  int primary_edge; /* 1: edgeA axis, 0: polygon axis */
+  if (ptype == 0) primary_edge = 1;
+  else if (psep > k_rel * edge_sep + k_abs) primary_edge = 0;
+  else primary_edge = 1;
+  clipv_t ie[2];
+  int rf_i1, rf_i2;
+  v2 rf_v1, rf_v2, rf_normal;
+  if (primary_edge) {
+    mf->type = 1;
+    int best = 0;
+    float bestv = vdot(normal, pn[0]);
+    for (int i = 1; i < count; ++i) { float v = vdot(normal, pn[i]); if (v < bestv) { bestv = v; best = i; } }
+    int i1 = best, i2 = i1 + 1 < count ? i1 + 1 : 0;
+    ie[0].v = pv[i1]; ie[0].id.indexA = 0; ie[0].id.indexB = (uint8_t)i1; ie[0].id.typeA = 1; ie[0].id.typeB = 0;
+    ie[1].v = pv[i2]; ie[1].id.indexA = 0; ie[1].id.indexB = (uint8_t)i2; ie[1].id.typeA = 1; ie[1].id.typeB = 0;
+    if (front) { rf_i1 = 0; rf_i2 = 1; rf_v1 = ev1; rf_v2 = ev2; rf_normal = normal1; }
+    else { rf_i1 = 1; rf_i2 = 0; rf_v1 = ev2; rf_v2 = ev1; rf_normal = vneg(normal1); }
+  } else {
+    mf->type = 2;
+    ie[0].v = ev1; ie[0].id.indexA = 0; ie[0].id.indexB = (uint8_t)pindex; ie[0].id.typeA = 0; ie[0].id.typeB = 1;
+    ie[1].v = ev2; ie[1].id.indexA = 0; ie[1].id.indexB = (uint8_t)pindex; ie[1].id.typeA = 0; ie[1].id.typeB = 1;
+    rf_i1 = pindex; rf_i2 = rf_i1 + 1 < count ? rf_i1 + 1 : 0;
+    rf_v1 = pv[rf_i1]; rf_v2 = pv[rf_i2]; rf_normal = pn[rf_i1];
+  }
+  const v2 side1 = V(rf_normal.y, -rf_normal.x), side2 = vneg(side1);
+  const float off1 = vdot(side1, rf_v1), off2 = vdot(side2, rf_v2);
+  clipv_t c1[2], c2[2];
+  if (clip_segment(c1, ie, side1, off1, rf_i1) < 2) return;
+  if (clip_segment(c2, c1, side2, off2, rf_i2) < 2) return;
+  if (primary_edge) { mf->local_normal = rf_normal; mf->local_point = rf_v1; }
+  else { mf->local_normal = pb->n[rf_i1]; mf->local_point = pb->v[rf_i1]; }
+  int pc = 0;
+  for (int i = 0; i < 2; ++i) {
+    float sep = vdot(rf_normal, vsub(c2[i].v, rf_v1));
+    if (sep <= radius) {
+      mpoint_t* cp = &mf->points[pc];
+      if (primary_edge) { cp->local_point = xmulT(xf, c2[i].v); cp->id = c2[i].id; }
+      else {
+        cp->local_point = c2[i].v;
+        cp->id.typeA = c2[i].id.typeB; cp->id.typeB = c2[i].id.typeA;
+        cp->id.indexA = c2[i].id.indexB; cp->id.indexB = c2[i].id.indexA;
+      }
+      ++pc;
+    }
+  }
+  mf->count = pc;
+}
+
+/* --- contact listener (lunar_lander.py:58-76) --------------------------------------------------------------------- */
+static void begin_contact(lander_t* L, int dyn) {
+  if (dyn == 0) L->game_over = 1;
+  else L->leg_contact[dyn - 1] = 1;
+}
+static void end_contact(lander_t* L, int dyn) {
+  if (dyn >= 1) L->leg_contact[dyn - 1] = 0;
+}
+
+/* order contact indices most-recent-first */
+static int contacts_sorted(const lander_t* L, int* idx, int dyn_filter /* -1 = all */) {
+  int n = 0;
+  for (int k = 0; k < NPAIR; ++k)
+    if (L->contact[k].exists && (dyn_filter < 0 || k / NEDGE == dyn_filter)) idx[n++] = k;
+  for (int i = 1; i < n; ++i) { /* insertion sort, descending seq */
+    int k = idx[i], j = i - 1;
+    while (j >= 0 && L->contact[idx[j]].seq < L->contact[k].seq) { idx[j + 1] = idx[j]; --j; }
+    idx[j + 1] = k;
+  }
+  return n;
+}
+
+/* b2ContactManager::Collide + b2Contact::Update */
+static void collide(lander_t* L) {
+  int idx[NPAIR];
+  int n = contacts_sorted(L, idx, -1);
+  for (int t = 0; t < n; ++t) {
+    contact_t* c = &L->contact[idx[t]];
+    int dyn = idx[t] / NEDGE, e = idx[t] % NEDGE;
+    body_t* bB = &L->b[1 + dyn];
+    if (!bB->awake) continue; /* activeA (static) false, activeB = awake */
+    if (!aabb_overlap(L->edge_fat[e], L->poly_fat[dyn])) {
+      if (c->touching) end_contact(L, dyn);
+      c->exists = 0;
+      continue;
+    }
+    manifold_t old = c->m;
+    int was = c->touching;
+    collide_edge_polygon(&c->m, L->edge_v1[e], L->edge_v2[e], &L->poly[dyn], bB->xf);
+    int touching = c->m.count > 0;
+    for (int i = 0; i < c->m.count; ++i) {
+      mpoint_t* mp2 = &c->m.points[i];
+      mp2->normal_impulse = 0.0f; mp2->tangent_impulse = 0.0f;
+      for (int j = 0; j < old.count; ++j)
+        if (cid_key(old.points[j].id) == cid_key(mp2->id)) {
+          mp2->normal_impulse = old.points[j].normal_impulse;
+          mp2->tangent_impulse = old.points[j].tangent_impulse;
+          break;
+        }
+    }
+    if (touching != was) set_awake(bB, 1);
+    c->touching = touching;
+    if (!was && touching) begin_contact(L, dyn);
+    if (was && !touching) end_contact(L, dyn);
+  }
+}
+
+/* b2BroadPhase::UpdatePairs for the moved dynamic proxies -> b2ContactManager::AddPair (sorted by proxy ids) */
+static void find_new_contacts(lander_t* L, const int moved[NDYN]) {
+  for (int e = 0; e < NEDGE; ++e)       /* pairs sort by (edge proxy id, polygon proxy id) */
+    for (int d = 0; d < NDYN; ++d) {
+      if (!moved[d]) continue;
+      contact_t* c = &L->contact[d * NEDGE + e];
+      if (c->exists) continue;
+      if (!aabb_overlap(L->edge_fat[e], L->poly_fat[d])) continue;
+      memset(c, 0, sizeof(*c));
+      c->exists = 1;
+      c->seq = ++L->seq;
+      c->friction = sqrtf(L->edge_friction[e] * L->poly_friction[d]); /* b2MixFriction */
+      set_awake(&L->b[1 + d], 1);
+    }
+}
+
+/* --- b2RevoluteJoint -------------------------------------------------------------------------------------------- */
+typedef struct { v2 c; float a; } pos_t;
+typedef struct { v2 v; float w; } velo_t;
+
+static void solve33(float m[3][3], float bx, float by, float bz, float* x, float* y, float* z) {
+  /* b2Mat33::Solve33: columns ex=m[0], ey=m[1], ez=m[2] */
+  float exx = m[0][0], exy = m[0][1], exz = m[0][2], eyx = m[1][0], eyy = m[1][1], eyz = m[1][2];
+  float ezx = m[2][0], ezy = m[2][1], ezz = m[2][2];
+  float cx = eyy * ezz - eyz * ezy, cy = eyz * ezx - eyx * ezz, cz = eyx * ezy - eyy * ezx; /* cross(ey, ez) */
+  float det = exx * cx + exy * cy + exz * cz;
+  if (det != 0.0f) det = 1.0f / det;
+  *x = det * (bx * cx + by * cy + bz * cz);
+  float dx = by * ezz - bz * ezy, dy = bz * ezx - bx * ezz, dz = bx * ezy - by * ezx; /* cross(b, ez) */
+  *y = det * (exx * dx + exy * dy + exz * dz);
+  float fx = eyy * bz - eyz * by, fy = eyz * bx - eyx * bz, fz = eyx * by - eyy * bx; /* cross(ey, b) */
+  *z = det * (exx * fx + exy * fy + exz * fz);
+}
+static v2 solve22(float m[3][3], v2 b) {
+  float a11 = m[0][0], a12 = m[1][0], a21 = m[0][1], a22 = m[1][1];
+  float det = a11 * a22 - a12 * a21;
+  if (det != 0.0f) det = 1.0f / det;
+  return V(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
+}
+
+static void joint_init_velocity(joint_t* j, const lander_t* L, pos_t* P, velo_t* Vv, int ia, int ib, float dt_ratio) {
+  const body_t *A = &L->b[1], *B = &L->b[j->bodyB];
+  j->lcA = A->local_center; j->lcB = B->local_center;
+  j->mA = A->inv_mass; j->mB = B->inv_mass; j->iA = A->inv_I; j->iB = B->inv_I;
+  float aA = P[ia].a, aB = P[ib].a;
+  v2 vA = Vv[ia].v, vB = Vv[ib].v;
+  float wA = Vv[ia].w, wB = Vv[ib].w;
+  rot_t qA = rot_set(aA), qB = rot_set(aB);
+  j->rA = rmul(qA, vsub(j->local_anchor_a, j->lcA));
+  j->rB = rmul(qB, vsub(j->local_anchor_b, j->lcB));
+  float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
+  j->m[0][0] = mA + mB + j->rA.y * j->rA.y * iA + j->rB.y * j->rB.y * iB;
+  j->m[1][0] = -j->rA.y * j->rA.x * iA - j->rB.y * j->rB.x * iB;
+  j->m[2][0] = -j->rA.y * iA - j->rB.y * iB;
+  j->m[0][1] = j->m[1][0];
+  j->m[1][1] = mA + mB + j->rA.x * j->rA.x * iA + j->rB.x * j->rB.x * iB;
+  j->m[2][1] = j->rA.x * iA + j->rB.x * iB;
+  j->m[0][2] = j->m[2][0];
+  j->m[1][2] = j->m[2][1];
+  j->m[2][2] = iA + iB;
+  j->motor_mass = iA + iB;
+  if (j->motor_mass > 0.0f) j->motor_mass = 1.0f / j->motor_mass;
+  /* enableMotor = enableLimit = true, fixedRotation = false */
+  float angle = aB - aA - j->reference_angle;
+  if (fabsf(j->upper - j->lower) < 2.0f * ANGULAR_SLOP) j->limit_state = 3;
+  else if (angle <= j->lower) { if (j->limit_state != 1) j->imp_z = 0.0f; j->limit_state = 1; }
+  else if (angle >= j->upper) { if (j->limit_state != 2) j->imp_z = 0.0f; j->limit_state = 2; }
+  else { j->limit_state = 0; j->imp_z = 0.0f; }
+  /* warm starting */
+  j->imp_x *= dt_ratio; j->imp_y *= dt_ratio; j->imp_z *= dt_ratio; j->motor_impulse *= dt_ratio;
+  v2 Pi = V(j->imp_x, j->imp_y);
+  vA = vsub(vA, vscale(mA, Pi));
+  wA -= iA * (vcross(j->rA, Pi) + j->motor_impulse + j->imp_z);
+  vB = vadd(vB, vscale(mB, Pi));
+  wB += iB * (vcross(j->rB, Pi) + j->motor_impulse + j->imp_z);
+  Vv[ia].v = vA; Vv[ia].w = wA; Vv[ib].v = vB; Vv[ib].w = wB;
+}
+
+static void joint_solve_velocity(joint_t* j, velo_t* Vv, int ia, int ib, float dt) {
+  v2 vA = Vv[ia].v, vB = Vv[ib].v;
+  float wA = Vv[ia].w, wB = Vv[ib].w;
+  float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
+  if (j->limit_state != 3) { /* motor */
+    float Cdot = wB - wA - j->motor_speed;
+    float impulse = -j->motor_mass * Cdot;
+    float old = j->motor_impulse, maxi = dt * j->max_motor_torque;
+    j->motor_impulse = fclamp(old + impulse, -maxi, maxi);
+    impulse = j->motor_impulse - old;
+    wA -= iA * impulse;
+    wB += iB * impulse;
+  }
+  if (j->limit_state != 0) {
+    v2 Cdot1 = vsub(vsub(vadd(vB, vcross_sv(wB, j->rB)), vA), vcross_sv(wA, j->rA));
+    float Cdot2 = wB - wA;
+    float ix, iy, iz;
+    solve33(j->m, Cdot1.x, Cdot1.y, Cdot2, &ix, &iy, &iz);
+    ix = -ix; iy = -iy; iz = -iz;
+    if (j->limit_state == 3) { j->imp_x += ix; j->imp_y += iy; j->imp_z += iz; }
+    else if (j->limit_state == 1) {
+      float newi = j->imp_z + iz;
+      if (newi < 0.0f) {
+        v2 rhs = vadd(vneg(Cdot1), vscale(j->imp_z, V(j->m[2][0], j->m[2][1])));
+        v2 red = solve22(j->m, rhs);
+        ix = red.x; iy = red.y; iz = -j->imp_z;
+        j->imp_x += red.x; j->imp_y += red.y; j->imp_z = 0.0f;
+      } else { j->imp_x += ix; j->imp_y += iy; j->imp_z += iz; }
+    } else {
+      float newi = j->imp_z + iz;
+      if (newi > 0.0f) {
+        v2 rhs = vadd(vneg(Cdot1), vscale(j->imp_z, V(j->m[2][0], j->m[2][1])));
+        v2 red = solve22(j->m, rhs);
+        ix = red.x; iy = red.y; iz = -j->imp_z;
+        j->imp_x += red.x; j->imp_y += red.y; j->imp_z = 0.0f;
+      } else { j->imp_x += ix; j->imp_y += iy; j->imp_z += iz; }
+    }
+    v2 Pi = V(ix, iy);
+    vA = vsub(vA, vscale(mA, Pi));
+    wA -= iA * (vcross(j->rA, Pi) + iz);
+    vB = vadd(vB, vscale(mB, Pi));
+    wB += iB * (vcross(j->rB, Pi) + iz);
+  } else {
+    v2 Cdot = vsub(vsub(vadd(vB, vcross_sv(wB, j->rB)), vA), vcross_sv(wA, j->rA));
+    v2 imp = solve22(j->m, vneg(Cdot));
+    j->imp_x += imp.x; j->imp_y += imp.y;
+    vA = vsub(vA, vscale(mA, imp));
+    wA -= iA * vcross(j->rA, imp);
+    vB = vadd(vB, vscale(mB, imp));
+    wB += iB * vcross(j->rB, imp);
+  }
+  Vv[ia].v = vA; Vv[ia].w = wA; Vv[ib].v = vB; Vv[ib].w = wB;
+}
+
+static int joint_solve_position(joint_t* j, pos_t* P, int ia, int ib) {
+  v2 cA = P[ia].c, cB = P[ib].c;
+  float aA = P[ia].a, aB = P[ib].a;
+  float angular_error = 0.0f, position_error;
+  if (j->limit_state != 0) {
+    float angle = aB - aA - j->reference_angle, limit_impulse = 0.0f;
+    if (j->limit_state == 3) {
+      float C = fclamp(angle - j->lower, -MAX_ANGULAR_CORRECTION, MAX_ANGULAR_CORRECTION);
+      limit_impulse = -j->motor_mass * C; angular_error = fabsf(C);
+    } else if (j->limit_state == 1) {
+      float C = angle - j->lower;
+      angular_error = -C;
+      C = fclamp(C + ANGULAR_SLOP, -MAX_ANGULAR_CORRECTION, 0.0f);
+      limit_impulse = -j->motor_mass * C;
+    } else {
+      float C = angle - j->upper;
+      angular_error = C;
+      C = fclamp(C - ANGULAR_SLOP, 0.0f, MAX_ANGULAR_CORRECTION);
+      limit_impulse = -j->motor_mass * C;
+    }
+    aA -= j->iA * limit_impulse;
+    aB += j->iB * limit_impulse;
+  }
+  {
+    rot_t qA = rot_set(aA), qB = rot_set(aB);
+    v2 rA = rmul(qA, vsub(j->local_anchor_a, j->lcA)), rB = rmul(qB, vsub(j->local_anchor_b, j->lcB));
+    v2 C = vsub(vsub(vadd(cB, rB), cA), rA);
+    position_error = vlen(C);
+    float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
+    float k11 = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+    float k12 = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+    float k22 = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+    float det = k11 * k22 - k12 * k12; /* b2Mat22::Solve: a11*a22 - a12*a21 */
+    if (det != 0.0f) det = 1.0f / det;
+    v2 imp = V(-(det * (k22 * C.x - k12 * C.y)), -(det * (k11 * C.y - k12 * C.x)));
+    cA = vsub(cA, vscale(mA, imp));
+    aA -= iA * vcross(rA, imp);
+    cB = vadd(cB, vscale(mB, imp));
+    aB += iB * vcross(rB, imp);
+  }
+  P[ia].c = cA; P[ia].a = aA; P[ib].c = cB; P[ib].a = aB;
+  return position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
+}
+
+/* --- b2ContactSolver ------------------------------------------------------------------------------------------- */
+typedef struct {
+  v2 rA, rB;
+  float normal_impulse, tangent_impulse, normal_mass, tangent_mass, velocity_bias;
+} vcp_t;
+typedef struct {
+  contact_t* c;
+  int indexB, count, pos_count, type;
+  vcp_t p[2];
+  v2 normal, local_normal, local_point, local_points[2], lcB;
+  float K[2][2], NM[2][2]; /* columns: K[col][row] */
+  float friction, mB, iB;
+} vc_t;
+
+static void world_manifold(const manifold_t* m, xf_t xfB, v2* normal, v2 pts[2]) {
+  /* xfA = identity; radiusA = radiusB = b2_polygonRadius */
+  if (m->type == 1) {
+    *normal = m->local_normal; /* b2Mul(identity.q, n) */
+    v2 plane = m->local_point;
+    for (int i = 0; i < m->count; ++i) {
+      v2 clip = xmul(xfB, m->points[i].local_point);
+      v2 cA = vadd(clip, vscale(POLYGON_RADIUS - vdot(vsub(clip, plane), *normal), *normal));
+      v2 cB = vsub(clip, vscale(POLYGON_RADIUS, *normal));
+      pts[i] = vscale(0.5f, vadd(cA, cB));
+    }
+  } else {
+    *normal = rmul(xfB.q, m->local_normal);
+    v2 plane = xmul(xfB, m->local_point);
+    for (int i = 0; i < m->count; ++i) {
+      v2 clip = m->points[i].local_point; /* b2Mul(identity, p) */
+      v2 cB = vadd(clip, vscale(POLYGON_RADIUS - vdot(vsub(clip, plane), *normal), *normal));
+      v2 cA = vsub(clip, vscale(POLYGON_RADIUS, *normal));
+      pts[i] = vscale(0.5f, vadd(cA, cB));
+    }
+    *normal = vneg(*normal);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * b2World::Solve for the single island {lander, legs} (+ moon as a static participant) */
+static void solve_island(lander_t* L, float h, float dt_ratio, int vel_iters, int pos_iters) {
+  /* island body order follows the DFS from the most recently created body: legs[1] (body 3), lander, legs[0];
+   * the moon (static) is appended when a touching contact reaches it -- it has zero inverse mass so only the index
+   * differs.  Local indices here: 0 = moon, 1..3 = bodies 1..3. */
+  pos_t P[NBODY];
+  velo_t Vv[NBODY];
+  if (!L->b[1].awake && !L->b[2].awake && !L->b[3].awake) return;
+  for (int i = 1; i < NBODY; ++i) set_awake(&L->b[i], 1); /* "Make sure the body is awake" during island build */
+  P[0].c = V(0, 0); P[0].a = 0; Vv[0].v = V(0, 0); Vv[0].w = 0;
+  const v2 gravity = V(0.0f, L->gravity);
+  for (int i = 1; i < NBODY; ++i) {
+    body_t* b = &L->b[i];
+    v2 v = b->vel;
+    float w = b->w;
+    b->c0 = b->c; b->a0 = b->a;
+    v = vadd(v, vscale(h, vadd(vscale(1.0f, gravity), vscale(b->inv_mass, b->force))));
+    w += h * b->inv_I * b->torque;
+    v = vscale(1.0f / (1.0f + h * 0.0f), v);
+    w *= 1.0f / (1.0f + h * 0.0f);
+    P[i].c = b->c; P[i].a = b->a; Vv[i].v = v; Vv[i].w = w;
+  }
+  /* island contact order: contacts of legs[1], then lander, then legs[0] (each list most-recent-first); only touching */
+  vc_t vcs[NPAIR];
+  int nvc = 0;
+  const int dyn_order[3] = {2, 0, 1};
+  for (int t = 0; t < 3; ++t) {
+    int idx[NPAIR], n = contacts_sorted(L, idx, dyn_order[t]);
+    for (int k = 0; k < n; ++k) {
+      contact_t* c = &L->contact[idx[k]];
+      if (!c->touching) continue;
+      vc_t* vc = &vcs[nvc++];
+      memset(vc, 0, sizeof(*vc));
+      vc->c = c;
+      vc->indexB = 1 + dyn_order[t];
+      vc->friction = c->friction;
+      vc->count = vc->pos_count = c->m.count;
+      vc->type = c->m.type;
+      const body_t* B = &L->b[vc->indexB];
+      vc->mB = B->inv_mass; vc->iB = B->inv_I; vc->lcB = B->local_center;
+      vc->local_normal = c->m.local_normal; vc->local_point = c->m.local_point;
+      for (int j = 0; j < vc->count; ++j) {
+        vc->p[j].normal_impulse = dt_ratio * c->m.points[j].normal_impulse;
+        vc->p[j].tangent_impulse = dt_ratio * c->m.points[j].tangent_impulse;
+        vc->local_points[j] = c->m.points[j].local_point;
+      }
+    }
+  }
+  /* InitializeVelocityConstraints */
+  for (int k = 0; k < nvc; ++k) {
+    vc_t* vc = &vcs[k];
+    int ib = vc->indexB;
+    float mB = vc->mB, iB = vc->iB;
+    v2 cB = P[ib].c, vB = Vv[ib].v;
+    float aB = P[ib].a, wB = Vv[ib].w;
+    xf_t xfB;
+    xfB.q = rot_set(aB);
+    xfB.p = vsub(cB, rmul(xfB.q, vc->lcB));
+    v2 pts[2];
+    world_manifold(&vc->c->m, xfB, &vc->normal, pts);
+    for (int j = 0; j < vc->count; ++j) {
+      vcp_t* p = &vc->p[j];
+      p->rA = pts[j];               /* cA = 0 */
+      p->rB = vsub(pts[j], cB);
+      float rnB = vcross(p->rB, vc->normal);
+      float kN = mB + iB * rnB * rnB;   /* mA = iA = 0: 0 + mB + 0*rnA*rnA + iB*rnB*rnB */
+      p->normal_mass = kN > 0.0f ? 1.0f / kN : 0.0f;
+      v2 tangent = vcross_vs(vc->normal, 1.0f);
+      float rtB = vcross(p->rB, tangent);
+      float kT = mB + iB * rtB * rtB;
+      p->tangent_mass = kT > 0.0f ? 1.0f / kT : 0.0f;
+      p->velocity_bias = 0.0f; /* restitution 0: -0 * vRel */
+      (void)vB; (void)wB;
+    }
+    if (vc->count == 2) {
+      float rn1B = vcross(vc->p[0].rB, vc->normal), rn2B = vcross(vc->p[1].rB, vc->normal);
+      float k11 = mB + iB * rn1B * rn1B, k22 = mB + iB * rn2B * rn2B, k12 = mB + iB * rn1B * rn2B;
+      if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+        vc->K[0][0] = k11; vc->K[0][1] = k12; vc->K[1][0] = k12; vc->K[1][1] = k22;
+        float a = k11, b = k12, c = k12, d = k22, det = a * d - b * c;
+        if (det != 0.0f) det = 1.0f / det;
+        vc->NM[0][0] = det * d; vc->NM[1][0] = -det * b; vc->NM[0][1] = -det * c; vc->NM[1][1] = det * a;
+      } else vc->count = 1;
+    }
+  }
+  /* WarmStart */
+  for (int k = 0; k < nvc; ++k) {
+    vc_t* vc = &vcs[k];
+    int ib = vc->indexB;
+    v2 vB = Vv[ib].v;
+    float wB = Vv[ib].w;
+    v2 tangent = vcross_vs(vc->normal, 1.0f);
+    for (int j = 0; j < vc->count; ++j) {
+      v2 Pi = vadd(vscale(vc->p[j].normal_impulse, vc->normal), vscale(vc->p[j].tangent_impulse, tangent));
+      wB += vc->iB * vcross(vc->p[j].rB, Pi);
+      vB = vadd(vB, vscale(vc->mB, Pi));
+    }
+    Vv[ib].v = vB; Vv[ib].w = wB;
+  }
+  /* joints: island order = joint of legs[1] first, then legs[0] */
+  joint_init_velocity(&L->joint[1], L, P, Vv, 1, 3, dt_ratio);
+  joint_init_velocity(&L->joint[0], L, P, Vv, 1, 2, dt_ratio);
+  for (int it = 0; it < vel_iters; ++it) {
+    joint_solve_velocity(&L->joint[1], Vv, 1, 3, h);
+    joint_solve_velocity(&L->joint[0], Vv, 1, 2, h);
+    for (int k = 0; k < nvc; ++k) {
+      vc_t* vc = &vcs[k];
+      int ib = vc->indexB;
+      float mB = vc->mB, iB = vc->iB;
+      v2 vB = Vv[ib].v;
+      float wB = Vv[ib].w;
+      v2 normal = vc->normal, tangent = vcross_vs(normal, 1.0f);
+      for (int j = 0; j < vc->count; ++j) { /* friction first */
+        vcp_t* p = &vc->p[j];
+        v2 dv = vadd(vB, vcross_sv(wB, p->rB)); /* - vA - cross(wA, rA) with vA = wA = 0 */
+        float vt = vdot(dv, tangent) - 0.0f;
+        float lambda = p->tangent_mass * (-vt);
+        float maxf = vc->friction * p->normal_impulse;
+        float newi = fclamp(p->tangent_impulse + lambda, -maxf, maxf);
+        lambda = newi - p->tangent_impulse;
+        p->tangent_impulse = newi;
+        v2 Pi = vscale(lambda, tangent);
+        vB = vadd(vB, vscale(mB, Pi));
+        wB += iB * vcross(p->rB, Pi);
+      }
+      if (vc->count == 1) {
+        vcp_t* p = &vc->p[0];
+        v2 dv = vadd(vB, vcross_sv(wB, p->rB));
+        float vn = vdot(dv, normal);
+        float lambda = -p->normal_mass * (vn - p->velocity_bias);
+        float newi = fmaxf(p->normal_impulse + lambda, 0.0f);
+        lambda = newi - p->normal_impulse;
+        p->normal_impulse = newi;
+        v2 Pi = vscale(lambda, normal);
+        vB = vadd(vB, vscale(mB, Pi));
+        wB += iB * vcross(p->rB, Pi);
+      } else {
+        vcp_t *c1 = &vc->p[0], *c2 = &vc->p[1];
+        float ax = c1->normal_impulse, ay = c2->normal_impulse;
+        v2 dv1 = vadd(vB, vcross_sv(wB, c1->rB)), dv2 = vadd(vB, vcross_sv(wB, c2->rB));
+        float vn1 = vdot(dv1, normal), vn2 = vdot(dv2, normal);
+        float bx = vn1 - c1->velocity_bias, by = vn2 - c2->velocity_bias;
+        /* b -= K * a */
+        bx -= vc->K[0][0] * ax + vc->K[1][0] * ay;
+        by -= vc->K[0][1] * ax + vc->K[1][1] * ay;
+        float xx, xy;
+        int solved = 0;
+        /* case 1 */
+        xx = -(vc->NM[0][0] * bx + vc->NM[1][0] * by);
+        xy = -(vc->NM[0][1] * bx + vc->NM[1][1] * by);
+        if (xx >= 0.0f && xy >= 0.0f) solved = 1;
+        if (!solved) { /* case 2 */
+          xx = -c1->normal_mass * bx; xy = 0.0f;
+          vn2 = vc->K[0][1] * xx + by;
+          if (xx >= 0.0f && vn2 >= 0.0f) solved = 1;
+        }
+        if (!solved) { /* case 3 */
+          xx = 0.0f; xy = -c2->normal_mass * by;
+          vn1 = vc->K[1][0] * xy + bx;
+          if (xy >= 0.0f && vn1 >= 0.0f) solved = 1;
+        }
+        if (!solved) { /* case 4 */
+          xx = 0.0f; xy = 0.0f;
+          if (bx >= 0.0f && by >= 0.0f) solved = 1;
+        }
+        if (solved) {
+          float dx = xx - ax, dy = xy - ay;
+          v2 P1 = vscale(dx, normal), P2 = vscale(dy, normal);
+          vB = vadd(vB, vscale(mB, vadd(P1, P2)));
+          wB += iB * (vcross(c1->rB, P1) + vcross(c2->rB, P2));
+          c1->normal_impulse = xx; c2->normal_impulse = xy;
+        }
+      }
+      Vv[ib].v = vB; Vv[ib].w = wB;
+    }
+  }
+  /* StoreImpulses */
+  for (int k = 0; k < nvc; ++k)
+    for (int j = 0; j < vcs[k].count; ++j) {
+      vcs[k].c->m.points[j].normal_impulse = vcs[k].p[j].normal_impulse;
+      vcs[k].c->m.points[j].tangent_impulse = vcs[k].p[j].tangent_impulse;
+    }
+  /* integrate positions */
+  for (int i = 1; i < NBODY; ++i) {
+    v2 c = P[i].c, v = Vv[i].v;
+    float a = P[i].a, w = Vv[i].w;
+    v2 tr = vscale(h, v);
+    if (vdot(tr, tr) > MAX_TRANSLATION * MAX_TRANSLATION) { float ratio = MAX_TRANSLATION / vlen(tr); v = vscale(ratio, v); }
+    float rotn = h * w;
+    if (rotn * rotn > MAX_ROTATION * MAX_ROTATION) { float ratio = MAX_ROTATION / fabsf(rotn); w *= ratio; }
+    c = vadd(c, vscale(h, v));
+    a += h * w;
+    P[i].c = c; P[i].a = a; Vv[i].v = v; Vv[i].w = w;
+  }
+  /* position iterations */
+  int position_solved = 0;
+  for (int it = 0; it < pos_iters; ++it) {
+    float min_sep = 0.0f;
+    for (int k = 0; k < nvc; ++k) {
+      vc_t* vc = &vcs[k];
+      int ib = vc->indexB;
+      float mB = vc->mB, iB = vc->iB;
+      v2 cB = P[ib].c;
+      float aB = P[ib].a;
+      for (int j = 0; j < vc->pos_count; ++j) {
+        xf_t xfB;
+        xfB.q = rot_set(aB);
+        xfB.p = vsub(cB, rmul(xfB.q, vc->lcB));
+        v2 normal, point;
+        float sep;
+        if (vc->type == 1) {
+          normal = vc->local_normal;
+          v2 plane = vc->local_point, clip = xmul(xfB, vc->local_points[j]);
+          sep = vdot(vsub(clip, plane), normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+          point = clip;
+        } else {
+          normal = rmul(xfB.q, vc->local_normal);
+          v2 plane = xmul(xfB, vc->local_point), clip = vc->local_points[j];
+          sep = vdot(vsub(clip, plane), normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+          point = clip;
+          normal = vneg(normal);
+        }
+        v2 rB = vsub(point, cB);
+        min_sep = fminf(min_sep, sep);
+        float C = fclamp(BAUMGARTE * (sep + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
+        float rnB = vcross(rB, normal);
+        float K = mB + iB * rnB * rnB;
+        float impulse = K > 0.0f ? -C / K : 0.0f;
+        v2 Pi = vscale(impulse, normal);
+        cB = vadd(cB, vscale(mB, Pi));
+        aB += iB * vcross(rB, Pi);
+      }
+      P[ib].c = cB; P[ib].a = aB;
+    }
+    int contacts_ok = min_sep >= -3.0f * LINEAR_SLOP;
+    int j1 = joint_solve_position(&L->joint[1], P, 1, 3);
+    int j0 = joint_solve_position(&L->joint[0], P, 1, 2);
+    if (contacts_ok && j1 && j0) { position_solved = 1; break; }
+  }
+  for (int i = 1; i < NBODY; ++i) {
+    body_t* b = &L->b[i];
+    b->c = P[i].c; b->a = P[i].a; b->vel = Vv[i].v; b->w = Vv[i].w;
+    sync_transform(b);
+  }
+  /* sleep */
+  float min_sleep = 3.402823466e+38f;
+  const float lin2 = LINEAR_SLEEP_TOL * LINEAR_SLEEP_TOL, ang2 = ANGULAR_SLEEP_TOL * ANGULAR_SLEEP_TOL;
+  for (int i = 1; i < NBODY; ++i) {
+    body_t* b = &L->b[i];
+    if (b->w * b->w > ang2 || vdot(b->vel, b->vel) > lin2) { b->sleep_time = 0.0f; min_sleep = 0.0f; }
+    else { b->sleep_time += h; min_sleep = fminf(min_sleep, b->sleep_time); }
+  }
+  if (min_sleep >= TIME_TO_SLEEP && position_solved)
+    for (int i = 1; i < NBODY; ++i) set_awake(&L->b[i], 0);
+}
+
+/* b2World::Step(dt, 180, 60) without SolveTOI */
+static void world_step(lander_t* L, float dt, int vel_iters, int pos_iters) {
+  int moved[NDYN] = {1, 1, 1};
+  if (L->new_fixture) { find_new_contacts(L, moved); L->new_fixture = 0; }
+  float inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+  float dt_ratio = L->inv_dt0 * dt;
+  collide(L);
+  int was_awake = L->b[1].awake || L->b[2].awake || L->b[3].awake;
+  solve_island(L, dt, dt_ratio, vel_iters, pos_iters);
+  if (was_awake) {
+    /* SynchronizeFixtures for island bodies (most recently created first) + FindNewContacts */
+    for (int d = NDYN - 1; d >= 0; --d) {
+      body_t* b = &L->b[1 + d];
+      xf_t xf1;
+      xf1.q = rot_set(b->a0);
+      xf1.p = vsub(b->c0, rmul(xf1.q, b->local_center));
+      aabb_t a1 = poly_aabb(&L->poly[d], xf1), a2 = poly_aabb(&L->poly[d], b->xf);
+      aabb_t comb = {vmin(a1.lo, a2.lo), vmax(a1.hi, a2.hi)};
+      v2 disp = vsub(b->xf.p, xf1.p);
+      moved[d] = 0;
+      if (!aabb_contains(L->poly_fat[d], comb)) { /* b2DynamicTree::MoveProxy */
+        aabb_t fb = fatten(comb);
+        v2 dd = vscale(AABB_MULTIPLIER, disp);
+        if (dd.x < 0.0f) fb.lo.x += dd.x; else fb.hi.x += dd.x;
+        if (dd.y < 0.0f) fb.lo.y += dd.y; else fb.hi.y += dd.y;
+        L->poly_fat[d] = fb;
+        moved[d] = 1;
+      }
+    }
+    find_new_contacts(L, moved);
+  }
+  if (dt > 0.0f) L->inv_dt0 = inv_dt;
+  for (int i = 1; i < NBODY; ++i) { L->b[i].force = V(0, 0); L->b[i].torque = 0.0f; } /* ClearForces */
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * environment (lunar_lander.py) */
+#define FPS 50
+#define SCALE 30.0
+#define MAIN_ENGINE_POWER 13.0
+#define SIDE_ENGINE_POWER 0.6
+#define INITIAL_RANDOM 1000.0
+#define LEG_AWAY 20
+#define LEG_DOWN 18
+#define LEG_W 2
+#define LEG_H 8
+#define LEG_SPRING_TORQUE 40
+#define SIDE_ENGINE_HEIGHT 14
+#define SIDE_ENGINE_AWAY 12
+#define MAIN_ENGINE_Y_LOCATION 4
+#define VIEWPORT_W 600
+#define VIEWPORT_H 400
+
+static void apply_linear_impulse(body_t* b, v2 impulse, v2 point) {
+  if (!b->awake) set_awake(b, 1);
+  b->vel = vadd(b->vel, vscale(b->inv_mass, impulse));
+  b->w += b->inv_I * vcross(vsub(point, b->c), impulse);
+}
+
+typedef struct { double obs[8]; double reward; int terminated; } step_out_t;
+
+static void env_step(lander_t* L, int action, step_out_t* out);
+
+/* LunarLander.reset (lunar_lander.py:321-447); the RNG stream continues unless the caller re-seeded it */
+static void env_reset(lander_t* L, float gravity, step_out_t* out) {
+  pcg64_t rng = L->rng;
+  memset(L, 0, sizeof(*L));
+  L->rng = rng;
+  L->gravity = gravity;
+  const double W = VIEWPORT_W / SCALE, H = VIEWPORT_H / SCALE;
+  enum { CHUNKS = 11 };
+  double height[CHUNKS + 1], chunk_x[CHUNKS], smooth_y[CHUNKS];
+  for (int i = 0; i < CHUNKS + 1; ++i) height[i] = pcg64_uniform(&L->rng, 0, H / 2);
+  for (int i = 0; i < CHUNKS; ++i) chunk_x[i] = W / (CHUNKS - 1) * i;
+  L->helipad_y = H / 4;
+  for (int k = -2; k <= 2; ++k) height[CHUNKS / 2 + k] = L->helipad_y;
+  for (int i = 0; i < CHUNKS; ++i) {
+    int im = i - 1 < 0 ? CHUNKS : i - 1; /* height[-1] wraps to the last element (index CHUNKS) */
+    smooth_y[i] = 0.33 * (height[im] + height[i + 0] + height[i + 1]);
+  }
+  L->edge_v1[0] = V(0.0f, 0.0f); L->edge_v2[0] = V((float)W, 0.0f); L->edge_friction[0] = 0.2f;
+  for (int i = 0; i < CHUNKS - 1; ++i) {
+    L->edge_v1[i + 1] = V((float)chunk_x[i], (float)smooth_y[i]);
+    L->edge_v2[i + 1] = V((float)chunk_x[i + 1], (float)smooth_y[i + 1]);
+    L->edge_friction[i + 1] = 0.1f;
+  }
+  for (int e = 0; e < NEDGE; ++e) {
+    v2 lo = vmin(L->edge_v1[e], L->edge_v2[e]), hi = vmax(L->edge_v1[e], L->edge_v2[e]);
+    aabb_t t = {V(lo.x - POLYGON_RADIUS, lo.y - POLYGON_RADIUS), V(hi.x + POLYGON_RADIUS, hi.y + POLYGON_RADIUS)};
+    L->edge_fat[e] = fatten(t);
+  }
+  const double initial_y = VIEWPORT_H / SCALE, initial_x = VIEWPORT_W / SCALE / 2;
+  static const int LANDER_POLY[6][2] = {{-14, 17}, {-17, 0}, {-17, -10}, {17, -10}, {17, 0}, {14, 17}};
+  v2 lv[6];
+  for (int i = 0; i < 6; ++i) lv[i] = V((float)(LANDER_POLY[i][0] / SCALE), (float)(LANDER_POLY[i][1] / SCALE));
+  poly_set(&L->poly[0], lv, 6);
+  L->poly_friction[0] = 0.1f;
+  body_init_dynamic(&L->b[1], &L->poly[0], 5.0f, V((float)initial_x, (float)initial_y), 0.0f);
+  /* ApplyForceToCenter(uniform(+-1000), uniform(+-1000)) */
+  double fx = pcg64_uniform(&L->rng, -INITIAL_RANDOM, INITIAL_RANDOM);
+  double fy = pcg64_uniform(&L->rng, -INITIAL_RANDOM, INITIAL_RANDOM);
+  L->b[1].force = vadd(L->b[1].force, V((float)fx, (float)fy));
+  for (int k = 0; k < 2; ++k) {
+    int i = k == 0 ? -1 : +1;
+    poly_set_box(&L->poly[1 + k], (float)(LEG_W / SCALE), (float)(LEG_H / SCALE));
+    L->poly_friction[1 + k] = 0.2f;
+    body_init_dynamic(&L->b[2 + k], &L->poly[1 + k], 1.0f, V((float)(initial_x - i * LEG_AWAY / SCALE), (float)initial_y),
+                      (float)(i * 0.05));
+    joint_t* j = &L->joint[k];
+    memset(j, 0, sizeof(*j));
+    j->bodyB = 2 + k;
+    j->local_anchor_a = V(0.0f, 0.0f);
+    j->local_anchor_b = V((float)(i * LEG_AWAY / SCALE), (float)(LEG_DOWN / SCALE));
+    j->reference_angle = L->b[2 + k].a - L->b[1].a; /* pybox2d: bodyB.angle - bodyA.angle when not given */
+    j->max_motor_torque = (float)LEG_SPRING_TORQUE;
+    j->motor_speed = (float)(+0.3 * i);
+    if (i == -1) { j->lower = (float)(+0.9 - 0.5); j->upper = (float)+0.9; }
+    else { j->lower = (float)-0.9; j->upper = (float)(-0.9 + 0.5); }
+  }
+  L->b[0].dynamic = 0;
+  L->b[0].xf.q.c = 1.0f;
+  for (int d = 0; d < NDYN; ++d) L->poly_fat[d] = fatten(poly_aabb(&L->poly[d], L->b[1 + d].xf));
+  L->new_fixture = 1;
+  env_step(L, 0, out); /* return self.step(0)[0] */
+}
+
+/* LunarLander.step, discrete actions (lunar_lander.py:471-665), wind disabled */
+static void env_step(lander_t* L, int action, step_out_t* out) {
+  body_t* lander = &L->b[1];
+  const double angle = (double)lander->a;
+  const double tip0 = sin(angle), tip1 = cos(angle);
+  const double side0 = -tip1, side1 = tip0;
+  double dispersion[2];
+  dispersion[0] = pcg64_uniform(&L->rng, -1.0, +1.0) / SCALE;
+  dispersion[1] = pcg64_uniform(&L->rng, -1.0, +1.0) / SCALE;
+  double m_power = 0.0, s_power = 0.0;
+  if (action == 2) {
+    m_power = 1.0;
+    double ox = tip0 * (MAIN_ENGINE_Y_LOCATION / SCALE + 2 * dispersion[0]) + side0 * dispersion[1];
+    double oy = -tip1 * (MAIN_ENGINE_Y_LOCATION / SCALE + 2 * dispersion[0]) - side1 * dispersion[1];
+    double px = (double)lander->xf.p.x + ox, py = (double)lander->xf.p.y + oy;
+    apply_linear_impulse(lander, V((float)(-ox * MAIN_ENGINE_POWER * m_power), (float)(-oy * MAIN_ENGINE_POWER * m_power)),
+                         V((float)px, (float)py));
+  }
+  if (action == 1 || action == 3) {
+    double direction = action - 2;
+    s_power = 1.0;
+    double ox = tip0 * dispersion[0] + side0 * (3 * dispersion[1] + direction * SIDE_ENGINE_AWAY / SCALE);
+    double oy = -tip1 * dispersion[0] - side1 * (3 * dispersion[1] + direction * SIDE_ENGINE_AWAY / SCALE);
+    double px = (double)lander->xf.p.x + ox - tip0 * 17 / SCALE;
+    double py = (double)lander->xf.p.y + oy + tip1 * SIDE_ENGINE_HEIGHT / SCALE;
+    apply_linear_impulse(lander, V((float)(-ox * SIDE_ENGINE_POWER * s_power), (float)(-oy * SIDE_ENGINE_POWER * s_power)),
+                         V((float)px, (float)py));
+  }
+  world_step(L, (float)(1.0 / FPS), 6 * 30, 2 * 30);
+  const double posx = lander->xf.p.x, posy = lander->xf.p.y, velx = lander->vel.x, vely = lander->vel.y;
+  double* s = out->obs;
+  s[0] = (posx - VIEWPORT_W / SCALE / 2) / (VIEWPORT_W / SCALE / 2);
+  s[1] = (posy - (L->helipad_y + LEG_DOWN / SCALE)) / (VIEWPORT_H / SCALE / 2);
+  s[2] = velx * (VIEWPORT_W / SCALE / 2) / FPS;
+  s[3] = vely * (VIEWPORT_H / SCALE / 2) / FPS;
+  s[4] = (double)lander->a;
+  s[5] = 20.0 * (double)lander->w / FPS;
+  s[6] = L->leg_contact[0] ? 1.0 : 0.0;
+  s[7] = L->leg_contact[1] ? 1.0 : 0.0;
+  double reward = 0;
+  double shaping = -100 * sqrt(s[0] * s[0] + s[1] * s[1]) - 100 * sqrt(s[2] * s[2] + s[3] * s[3]) - 100 * fabs(s[4]) +
+                   10 * s[6] + 10 * s[7];
+  if (L->has_prev_shaping) reward = shaping - L->prev_shaping;
+  L->prev_shaping = shaping;
+  L->has_prev_shaping = 1;
+  reward -= m_power * 0.30;
+  reward -= s_power * 0.03;
+  int terminated = 0;
+  if (L->game_over || fabs(s[0]) >= 1.0) { terminated = 1; reward = -100; }
+  if (!lander->awake) { terminated = 1; reward = +100; }
+  out->reward = reward;
+  out->terminated = terminated;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * vector API used by oracle/lunar_lander.py (ctypes): SyncVectorEnv NEXT_STEP semantics + TimeLimit */
+typedef struct {
+  int n, max_episode_steps;
+  float gravity;
+  lander_t* env;
+  int *elapsed, *autoreset;
+} ll_vec_t;
+
+ll_vec_t* ll_create(int n, int max_episode_steps, double gravity) {
+  ll_vec_t* v = (ll_vec_t*)calloc(1, sizeof(ll_vec_t));
+  v->n = n; v->max_episode_steps = max_episode_steps; v->gravity = (float)gravity;
+  v->env = (lander_t*)calloc((size_t)n, sizeof(lander_t));
+  v->elapsed = (int*)calloc((size_t)n, sizeof(int));
+  v->autoreset = (int*)calloc((size_t)n, sizeof(int));
+  return v;
+}
+void ll_destroy(ll_vec_t* v) {
+  if (!v) return;
+  free(v->env); free(v->elapsed); free(v->autoreset); free(v);
+}
+static void write_obs(float* obs, const step_out_t* o) { for (int k = 0; k < 8; ++k) obs[k] = (float)o->obs[k]; }
+
+/* seeds may be NULL (streams continue); mask may be NULL (all) */
+void ll_reset(ll_vec_t* v, const uint64_t* seeds, const uint8_t* mask, float* obs) {
+  for (int i = 0; i < v->n; ++i) {
+    if (mask && !mask[i]) continue;
+    if (seeds) pcg64_seed(&v->env[i].rng, seeds[i]);
+    step_out_t o;
+    env_reset(&v->env[i], v->gravity, &o);
+    write_obs(obs + 8 * i, &o);
+    v->elapsed[i] = 0; v->autoreset[i] = 0;
+  }
+}
+void ll_step(ll_vec_t* v, const int64_t* actions, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated) {
+  for (int i = 0; i < v->n; ++i) {
+    step_out_t o;
+    if (v->autoreset[i]) {
+      env_reset(&v->env[i], v->gravity, &o);
+      write_obs(obs + 8 * i, &o);
+      reward[i] = 0.0; terminated[i] = 0; truncated[i] = 0;
+      v->elapsed[i] = 0; v->autoreset[i] = 0;
+      continue;
+    }
+    env_step(&v->env[i], (int)actions[i], &o);
+    write_obs(obs + 8 * i, &o);
+    reward[i] = o.reward;
+    terminated[i] = (uint8_t)o.terminated;
+    v->elapsed[i] += 1;
+    truncated[i] = v->max_episode_steps > 0 && v->elapsed[i] >= v->max_episode_steps;
+    v->autoreset[i] = terminated[i] || truncated[i];
+  }
+}
+/* introspection for tests: body state [3][7] = x, y, angle, vx, vy, w, awake; misc[8] */
+void ll_debug_state(const ll_vec_t* v, int i, float* bodies, float* misc) {
+  const lander_t* L = &v->env[i];
+  for (int b = 0; b < 3; ++b) {
+    const body_t* B = &L->b[1 + b];
+    float* o = bodies + 7 * b;
+    o[0] = B->xf.p.x; o[1] = B->xf.p.y; o[2] = B->a; o[3] = B->vel.x; o[4] = B->vel.y; o[5] = B->w; o[6] = (float)B->awake;
+  }
+  misc[0] = L->b[1].mass; misc[1] = L->b[1].I; misc[2] = L->b[2].mass; misc[3] = L->b[2].I;
+  misc[4] = L->b[1].local_center.x; misc[5] = L->b[1].local_center.y;
+  int nc = 0, nt = 0;
+  for (int k = 0; k < NPAIR; ++k) { nc += L->contact[k].exists; nt += L->contact[k].touching; }
+  misc[6] = (float)nc; misc[7] = (float)nt;
+}
+void ll_terrain(const ll_vec_t* v, int i, float* xy /* [11][4] */) {
+  const lander_t* L = &v->env[i];
+  for (int e = 0; e < NEDGE; ++e) {
+    xy[4 * e] = L->edge_v1[e].x; xy[4 * e + 1] = L->edge_v1[e].y; xy[4 * e + 2] = L->edge_v2[e].x; xy[4 * e + 3] = L->edge_v2[e].y;
+  }
+}

@@ -1,0 +1,100 @@
+"""ctypes front end of oracle/lunar_lander.c (the Box2D-subset LunarLander-v3 oracle).  Oracle only; PARITY UNPINNED
+(Box2D is absent from this image) -- see the header of lunar_lander.c."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liblunar_oracle.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "lunar_lander.c")
+        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+        l = C.CDLL(_LIB)
+        l.ll_create.restype = C.c_void_p
+        l.ll_create.argtypes = [C.c_int, C.c_int, C.c_double]
+        l.ll_destroy.argtypes = [C.c_void_p]
+        l.ll_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ll_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        l.ll_debug_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        l.ll_terrain.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib = l
+    return _lib
+
+
+class OracleLunarLander:
+    """SyncVectorEnv(LunarLander-v3 x N) semantics: seed+i PCG64 streams, NEXT_STEP autoreset, TimeLimit 1000."""
+
+    def __init__(self, num_envs, max_episode_steps=1000, gravity=-10.0):
+        self.num_envs = int(num_envs)
+        self._h = lib().ll_create(self.num_envs, int(max_episode_steps or 0), float(gravity))
+        self._obs = np.zeros((self.num_envs, 8), dtype=np.float32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ll_destroy(self._h)
+            self._h = None
+
+    def reset(self, *, seed=None, options=None):
+        n = self.num_envs
+        seeds = None
+        if seed is not None:
+            seeds = np.array([seed + i for i in range(n)] if isinstance(seed, (int, np.integer)) else list(seed),
+                             dtype=np.uint64)
+        mask = None
+        if options is not None and "reset_mask" in options:
+            mask = np.ascontiguousarray(options["reset_mask"]).astype(np.uint8)
+        lib().ll_reset(self._h, None if seeds is None else seeds.ctypes.data, None if mask is None else mask.ctypes.data,
+                       self._obs.ctypes.data)
+        return self._obs.copy(), {}
+
+    def step(self, actions):
+        n = self.num_envs
+        a = np.ascontiguousarray(actions, dtype=np.int64)
+        assert a.shape == (n,)
+        assert ((a >= 0) & (a < 4)).all(), f"invalid action in {a!r}"
+        reward = np.zeros(n, dtype=np.float64)
+        term = np.zeros(n, dtype=np.uint8)
+        trunc = np.zeros(n, dtype=np.uint8)
+        lib().ll_step(self._h, a.ctypes.data, self._obs.ctypes.data, reward.ctypes.data, term.ctypes.data, trunc.ctypes.data)
+        return self._obs.copy(), reward, term.astype(bool), trunc.astype(bool), {}
+
+    def debug_state(self, i=0):
+        bodies = np.zeros((3, 7), dtype=np.float32)
+        misc = np.zeros(8, dtype=np.float32)
+        lib().ll_debug_state(self._h, i, bodies.ctypes.data, misc.ctypes.data)
+        return bodies, misc
+
+    def terrain(self, i=0):
+        xy = np.zeros((11, 4), dtype=np.float32)
+        lib().ll_terrain(self._h, i, xy.ctypes.data)
+        return xy
+
+
+def heuristic(s):
+    """The reference's own demo/test policy, gymnasium/envs/box2d/lunar_lander.py:791-842 (discrete branch)."""
+    angle_targ = s[0] * 0.5 + s[2] * 1.0
+    angle_targ = min(max(angle_targ, -0.4), 0.4)
+    hover_targ = 0.55 * np.abs(s[0])
+    angle_todo = (angle_targ - s[4]) * 0.5 - (s[5]) * 1.0
+    hover_todo = (hover_targ - s[1]) * 0.5 - (s[3]) * 0.5
+    if s[6] or s[7]:
+        angle_todo = 0
+        hover_todo = -(s[3]) * 0.5
+    a = 0
+    if hover_todo > np.abs(angle_todo) and hover_todo > 0.05:
+        a = 2
+    elif angle_todo < -0.05:
+        a = 3
+    elif angle_todo > +0.05:
+        a = 1
+    return a
