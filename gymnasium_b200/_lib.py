@@ -54,6 +54,19 @@ class FrozenLakeCfg(C.Structure):
     ]
 
 
+class LunarLanderCfg(C.Structure):
+    """``b2e_lunarlander_cfg``."""
+
+    _fields_ = [("gravity", c_double), ("enable_wind", c_i32), ("continuous", c_i32)]
+
+
+class LunarLanderState(C.Structure):
+    """``b2e_lunarlander_state`` (device pointers)."""
+
+    _fields_ = [(k, c_void_p) for k in ("bodies", "joints", "terrain", "fat", "contacts", "flags", "prev_shaping",
+                                        "ctrl", "rng")]
+
+
 P = c_void_p
 _BP = C.POINTER(Batch)
 
@@ -69,6 +82,10 @@ SIGNATURES = {
     "b2e_cartpole_step": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P, P, P, P, P]),
     "b2e_cartpole_rollout": (C.c_int, [_BP, C.POINTER(CartPoleCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),
     "b2e_selftest_math": (C.c_int, [c_i64, c_u64, P, P]),
+    "b2e_lunarlander_state_words": (C.c_int, []),
+    "b2e_lunarlander_reset": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P]),
+    "b2e_lunarlander_step": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P, P, P, P,
+                                       P]),
     "b2e_frozenlake_reset": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P]),
     "b2e_frozenlake_step": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P, P, P, P, P, P]),
     "b2e_frozenlake_rollout": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),

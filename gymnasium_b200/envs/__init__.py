@@ -1,4 +1,5 @@
 from .cartpole import CartPoleVectorEnv
 from .frozen_lake import FrozenLakeVectorEnv
+from .lunar_lander import LunarLanderVectorEnv
 
-__all__ = ["CartPoleVectorEnv", "FrozenLakeVectorEnv"]
+__all__ = ["CartPoleVectorEnv", "FrozenLakeVectorEnv", "LunarLanderVectorEnv"]

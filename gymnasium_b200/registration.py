@@ -24,6 +24,8 @@ ENVS = {
                       "gymnasium.envs.toy_text.frozen_lake:FrozenLakeEnv", 100, 0.70, {"map_name": "4x4"}),
     "FrozenLake8x8-v1": ("gymnasium_b200.envs.frozen_lake:FrozenLakeVectorEnv",
                          "gymnasium.envs.toy_text.frozen_lake:FrozenLakeEnv", 200, 0.85, {"map_name": "8x8"}),
+    "LunarLander-v3": ("gymnasium_b200.envs.lunar_lander:LunarLanderVectorEnv",
+                       "gymnasium.envs.box2d.lunar_lander:LunarLander", 1000, 200, {}),
 }
 NAMESPACE = "B200"
 

@@ -139,6 +139,43 @@ int b2e_frozenlake_rollout(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, in
                            uint8_t* actions_out, int32_t* pstate, int32_t* ctrl, uint64_t* rng, int64_t* obs,
                            float* reward, uint8_t* terminated, uint8_t* truncated, void* stream);
 
+/* ---- LunarLander-v3: gymnasium/envs/box2d/lunar_lander.py:321-665 (+ the Box2D 2.3.x subset world.Step needs) -------
+ * Discrete actions (0 nop, 1 left, 2 main, 3 right), no wind.  Per-env state, struct-of-arrays over n envs (device):
+ *   bodies  : float32 [21][n]  for b in (lander, legs[0], legs[1]): c.x, c.y, angle, v.x, v.y, w, sleepTime
+ *   joints  : float32 [8][n]   for each revolute joint: impulse.x, .y, .z, motorImpulse
+ *   terrain : float32 [11][n]  smooth_y of the 11 terrain chunks
+ *   fat     : float32 [12][n]  broad-phase fat AABBs of the 3 polygons (lo.x, lo.y, hi.x, hi.y)
+ *   contacts: uint32  [b2e_lunarlander_state_words()][n]  most-recent-first list of contact manifolds
+ *   flags   : int32   [n]      awake, game_over, leg contacts, joint limit states, contact count (see lunarlander.cu)
+ *   prev_shaping: float64 [n]; ctrl / rng as for CartPole
+ * obs float32 [n][8]; reward float64 [n]; terminated/truncated uint8 [n]; final_obs float32 [n][8] (SAME_STEP only).
+ */
+typedef struct b2e_lunarlander_cfg {
+  double gravity;        /* LunarLander(gravity=-10.0) */
+  int32_t enable_wind;   /* must be 0 */
+  int32_t continuous;    /* must be 0 */
+} b2e_lunarlander_cfg;
+
+typedef struct b2e_lunarlander_state {
+  float* bodies;
+  float* joints;
+  float* terrain;
+  float* fat;
+  uint32_t* contacts;
+  int32_t* flags;
+  double* prev_shaping;
+  int32_t* ctrl;
+  uint64_t* rng;
+} b2e_lunarlander_state;
+
+int b2e_lunarlander_state_words(void);
+/* LunarLander.reset (incl. its embedded step(0), lunar_lander.py:447) for lanes with mask != 0 (NULL = all). */
+int b2e_lunarlander_reset(const b2e_batch* b, const b2e_lunarlander_cfg* cfg, const b2e_lunarlander_state* st,
+                          const uint8_t* mask, float* obs, void* stream);
+int b2e_lunarlander_step(const b2e_batch* b, const b2e_lunarlander_cfg* cfg, const b2e_lunarlander_state* st,
+                         const void* actions, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
+                         float* final_obs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,9 +87,40 @@ static inline float vlen(v2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
 static inline v2 vmin(v2 a, v2 b) { return V(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y); }
 static inline v2 vmax(v2 a, v2 b) { return V(a.x > b.x ? a.x : b.x, a.y > b.y ? a.y : b.y); }
 static inline float fclamp(float a, float lo, float hi) { return fmaxf(lo, fminf(a, hi)); }
-/* b2Rot::Set: sinf/cosf.  Evaluated as the correctly rounded float of the double result so that the CUDA engine,
- * which does the same, agrees bit for bit (glibc's sinf/cosf are correctly rounded too). */
-static inline rot_t rot_set(float a) { rot_t r = {(float)sin((double)a), (float)cos((double)a)}; return r; }
+/* sin/cos in double from a fixed sequence of IEEE operations (Cody-Waite reduction by pi/2 in two pieces + the classic
+ * fdlibm kernel polynomials, no FMA): the CUDA engine executes the very same sequence, so both sides agree bit for bit
+ * without depending on any libm.  Accurate to ~1e-16, i.e. its float rounding equals a correctly rounded sinf/cosf
+ * (what Box2D gets from glibc) except on ~1e-9 of inputs. */
+static inline void det_sincos(double x, double* sn, double* cs) {
+  const double fn = rint(x * 6.36619772367581382433e-01);
+  const double r = x - fn * 1.57079632673412561417e+00;
+  const double w = fn * 6.07710050650619224932e-11;
+  const double y = r - w;
+  const double z = y * y;
+  const double ps = 8.33333333332248946124e-03 +
+                    z * (-1.98412698298579493134e-04 +
+                         z * (2.75573137070700676789e-06 + z * (-2.50507602534068634195e-08 + z * 1.58969099521155010221e-10)));
+  const double sk = y + (z * y) * (-1.66666666666666324348e-01 + z * ps);
+  const double pc = z * (4.16666666666666019037e-02 +
+                         z * (-1.38888888888741095749e-03 +
+                              z * (2.48015872894767294178e-05 +
+                                   z * (-2.75573143513906633035e-07 +
+                                        z * (2.08757232129817482790e-09 + z * -1.13596475577881948265e-11)))));
+  const double ck = 1.0 - (0.5 * z - z * pc);
+  switch ((int)fn & 3) {
+    case 0: *sn = sk; *cs = ck; break;
+    case 1: *sn = ck; *cs = -sk; break;
+    case 2: *sn = -sk; *cs = -ck; break;
+    default: *sn = -ck; *cs = sk; break;
+  }
+}
+/* b2Rot::Set(angle): sinf/cosf */
+static inline rot_t rot_set(float a) {
+  double s, c;
+  det_sincos((double)a, &s, &c);
+  rot_t r = {(float)s, (float)c};
+  return r;
+}
 static inline v2 rmul(rot_t q, v2 v) { return V(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
 static inline v2 rmulT(rot_t q, v2 v) { return V(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
 static inline v2 xmul(xf_t T, v2 v) { return V((T.q.c * v.x - T.q.s * v.y) + T.p.x, (T.q.s * v.x + T.q.c * v.y) + T.p.y); }
@@ -1088,8 +1119,8 @@ static void env_reset(lander_t* L, float gravity, step_out_t* out) {
 /* LunarLander.step, discrete actions (lunar_lander.py:471-665), wind disabled */
 static void env_step(lander_t* L, int action, step_out_t* out) {
   body_t* lander = &L->b[1];
-  const double angle = (double)lander->a;
-  const double tip0 = sin(angle), tip1 = cos(angle);
+  double tip0, tip1; /* tip = (math.sin(angle), math.cos(angle)) */
+  det_sincos((double)lander->a, &tip0, &tip1);
   const double side0 = -tip1, side1 = tip0;
   double dispersion[2];
   dispersion[0] = pcg64_uniform(&L->rng, -1.0, +1.0) / SCALE;
