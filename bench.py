@@ -506,6 +506,29 @@ def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0)
                                     "frac_of_hbm_peak": bw / hbm_peak,
                                     "algorithmic_bytes_per_env_step": FROZENLAKE_STEP_BYTES,
                                     "l2_policy": f"ring of {ringf} batches of 1,048,576 envs (inputs larger than L2)"}
+        # (6) BASELINE config 4: LunarLander-v3, 16384 envs (latency-bound rigid-body solve; reported against its own
+        #     state traffic, not as an HBM-roofline claim)
+        nl = 16384
+        ll = gymnasium_b200.make_vec("LunarLander-v3", num_envs=nl, device=dev, copy=False)
+        ll.reset(seed=0)
+        la = torch.randint(0, 4, (8, nl), device=dev, dtype=torch.int64)
+        k = [0]
+
+        def lstep():
+            ll.step(la[k[0] % 8])
+            k[0] += 1
+
+        t = timed(lstep, 200, warm=20)
+        out["lunarlander_16384"] = {"steps_per_s": nl / t, "us_per_launch": t * 1e6,
+                                    "note": "one fused step+autoreset launch per call, random actions, 1 thread/env; "
+                                            "bit-exact vs oracle/lunar_lander.c (Box2D parity unpinned)"}
+        for big in (131072, 1048576):
+            ll = gymnasium_b200.make_vec("LunarLander-v3", num_envs=big, device=dev, copy=False)
+            ll.reset(seed=0)
+            la2 = torch.randint(0, 4, (big,), device=dev, dtype=torch.int64)
+            t = timed(lambda: ll.step(la2), 30, warm=60)
+            out[f"lunarlander_{big}"] = {"steps_per_s": big / t, "us_per_launch": t * 1e6}
+        del ll
     return out
 
 

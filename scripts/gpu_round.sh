@@ -8,15 +8,16 @@ python bench.py 2> $OUT/bench.err | tee $OUT/bench.json | cut -c1-1500
 tail -5 $OUT/bench.err
 python bench.py --impl reference --steps 20 --warmup 3 2>/dev/null | tee $OUT/bench_reference.json | cut -c1-600
 # launch list of the bench command (cold-cache, serialised: shares only)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 20 > $OUT/bench_under_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 330 -c 1500 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-extras --e2e-steps 20 > $OUT/bench_under_ncu.log 2>&1
 # full captures of the top kernels
-for T in step big rollout lake; do
+for T in step big rollout lake lander; do
   case $T in
     step) K=cartpole_step_kernel; S=80;;
     big) K=cartpole_step_kernel; S=3;;
     rollout) K=cartpole_rollout_kernel; S=1;;
     lake) K=frozenlake; S=8;;
+    lander) K=lunarlander_step; S=70;;
   esac
   ncu --set full --clock-control none --import-source on -k regex:$K -s $S -c 3 -f -o $OUT/ncu_$T \
       python scripts/ncu_targets.py $T > $OUT/ncu_$T.log 2>&1

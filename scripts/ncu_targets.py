@@ -52,3 +52,9 @@ if which in ("all", "lake"):
     f = fl[0]
     f.rollout(32)
     torch.cuda.synchronize()
+if which in ("all", "lander"):
+    ll = gymnasium_b200.make_vec("LunarLander-v3", num_envs=16384, copy=False)
+    ll.reset(seed=0)
+    for t in range(80):  # reach the mixed regime: some lanes flying, some on the ground, some resetting
+        ll.step(torch.randint(0, 4, (16384,), device=dev))
+    torch.cuda.synchronize()
