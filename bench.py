@@ -343,7 +343,7 @@ def run_b200(args):
     import torch as _t
     reset_frac = float(_t.stack([(e._ctrl < 0).float().mean() for e in envs]).mean().item())
     extras = {}
-    if not args.no_extras and rank == 0:
+    if not args.no_extras and rank == 0 and world == 1:  # supporting numbers belong to the 1-GPU line
         extras = run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, envs[0], acts[0])
 
     # ---- end to end through the public API ----------------------------------------------------------------------------
