@@ -352,20 +352,22 @@ def run_b200(args):
                                       output="numpy" if world == 1 else "torch", **kw)
     e2e_env.reset(seed=0)
     host_actions = np.random.default_rng(rank).integers(0, nact, size=(16, n)).astype(np.int64)
-    gather = BatchGather(world * n, world, rank, dst=0) if world > 1 else None
     pinned = {}
+    gathered = {}
 
     def e2e_step(k):
         out = e2e_env.step(host_actions[k % 16])
-        if gather is None:
-            return out  # numpy arrays on the host (pinned H2D of actions + D2H of obs/reward/flags inside step())
-        o, r, te, tr, _ = out
-        full = gather(obs=o, reward=r, terminated=te, truncated=tr)  # NCCL gather of the shard outputs to rank 0
+        if world == 1:
+            return out  # numpy arrays on the host (pinned H2D of actions + one D2H of the packed result inside step())
+        # N > 1: ONE NCCL gather of every shard's packed step outputs (obs | reward | flags) to rank 0, then one D2H of
+        # the gathered batch into pinned host memory ("a single host-side batch")
+        wire, _layout = e2e_env.packed_outputs()
+        if "buf" not in gathered:
+            gathered["buf"] = torch.empty((world, wire.numel()), dtype=torch.uint8, device=dev) if rank == 0 else None
+            pinned["buf"] = torch.empty((world, wire.numel()), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        dist.gather(wire, list(gathered["buf"].unbind(0)) if rank == 0 else None, dst=0)
         if rank == 0:
-            for key, t in full.items():
-                if key not in pinned:
-                    pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                pinned[key].copy_(t, non_blocking=True)
+            pinned["buf"].copy_(gathered["buf"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return pinned
 

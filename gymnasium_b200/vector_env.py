@@ -172,6 +172,11 @@ class B200VectorEnv(VectorEnv):
         self._wire_layout = [(k, shape, dt, offsets[k], nbytes) for k, shape, dt, nbytes in sizes]
         return out
 
+    def packed_outputs(self) -> tuple[torch.Tensor, list]:
+        """The last call's outputs as ONE contiguous uint8 device buffer + its layout
+        ``[(key, shape, dtype, byte_offset, nbytes), ...]`` -- what a multi-GPU gather should move (one collective)."""
+        return self._out["_wire"], list(self._wire_layout)
+
     def _to_host(self, out: dict[str, torch.Tensor]) -> dict[str, np.ndarray]:
         """One async D2H copy of the packed outputs into a cached pinned buffer + one stream sync -> numpy views."""
         wire = out["_wire"]
