@@ -67,6 +67,20 @@ class LunarLanderState(C.Structure):
                                         "ctrl", "rng")]
 
 
+class HumanoidCfg(C.Structure):
+    """``b2e_humanoid_cfg``."""
+
+    _fields_ = [(k, c_double) for k in ("reset_noise_scale", "forward_reward_weight", "ctrl_cost_weight",
+                                        "contact_cost_weight", "contact_cost_max", "healthy_reward", "healthy_z_min",
+                                        "healthy_z_max")] + [("terminate_when_unhealthy", c_i32), ("frame_skip", c_i32)]
+
+
+class HumanoidState(C.Structure):
+    """``b2e_humanoid_state`` (device pointers)."""
+
+    _fields_ = [(k, c_void_p) for k in ("qpos", "qvel", "qacc_warmstart", "com_xy", "ctrl", "rng", "overflow")]
+
+
 P = c_void_p
 _BP = C.POINTER(Batch)
 
@@ -86,6 +100,9 @@ SIGNATURES = {
     "b2e_lunarlander_reset": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P]),
     "b2e_lunarlander_step": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P, P, P, P,
                                        P]),
+    "b2e_humanoid_model_info": (C.c_int, [P, P, P]),
+    "b2e_humanoid_reset": (C.c_int, [_BP, C.POINTER(HumanoidCfg), C.POINTER(HumanoidState), P, P, P, P]),
+    "b2e_humanoid_step": (C.c_int, [_BP, C.POINTER(HumanoidCfg), C.POINTER(HumanoidState), P, P, P, P, P, P, P, P]),
     "b2e_frozenlake_reset": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P]),
     "b2e_frozenlake_step": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P, P, P, P, P, P]),
     "b2e_frozenlake_rollout": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),

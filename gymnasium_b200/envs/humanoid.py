@@ -1,0 +1,154 @@
+"""Humanoid-v5 on the B200 engine.
+
+Mirrors ``HumanoidEnv`` v5 (gymnasium/envs/mujoco/humanoid_v5.py:24-541) and the ``MujocoEnv`` plumbing it uses
+(gymnasium/envs/mujoco/mujoco_env.py:35-229) behind the vector API with SyncVectorEnv's conventions; the multibody
+dynamics the reference delegates to the MuJoCo wheel run in ``gymnasium_b200/csrc/humanoid.cu``.
+Numeric parity with the real MuJoCo wheel is unpinned (it cannot be installed here); see DESIGN.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._api import AutoresetMode, Box
+from ..vector_env import B200VectorEnv, ptr
+
+INFO_KEYS = ("x_position", "y_position", "tendon_length", "tendon_velocity", "distance_from_origin", "x_velocity",
+             "y_velocity", "reward_survive", "reward_forward", "reward_ctrl", "reward_contact")
+OBS_SIZE = 22 + 23 + 130 + 78 + 17 + 78  # humanoid_v5.py:376-393
+
+
+class HumanoidVectorEnv(B200VectorEnv):
+    """N Humanoid-v5 envs.  Observation ``(N, 348) float64``, action ``(N, 17) float32`` in [-0.4, 0.4], reward float64,
+    info = the 11 keys of ``HumanoidEnv.step`` as ``(N,)`` / ``(N, 2)`` arrays with their ``_key`` masks."""
+
+    metadata = {"render_modes": [], "render_fps": 67, "autoreset_mode": AutoresetMode.NEXT_STEP}
+    discrete_actions = False
+
+    def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 1000, xml_file: str = "humanoid.xml",
+                 frame_skip: int = 5, forward_reward_weight: float = 1.25, ctrl_cost_weight: float = 0.1,
+                 contact_cost_weight: float = 5e-7, contact_cost_range=(-np.inf, 10.0), healthy_reward: float = 5.0,
+                 terminate_when_unhealthy: bool = True, healthy_z_range=(1.0, 2.0), reset_noise_scale: float = 1e-2,
+                 exclude_current_positions_from_observation: bool = True, include_cinert_in_observation: bool = True,
+                 include_cvel_in_observation: bool = True, include_qfrc_actuator_in_observation: bool = True,
+                 include_cfrc_ext_in_observation: bool = True, render_mode: str | None = None, **engine_kwargs):
+        if xml_file != "humanoid.xml":
+            raise NotImplementedError("gymnasium_b200 compiles the stock humanoid.xml only")
+        if not (exclude_current_positions_from_observation and include_cinert_in_observation and include_cvel_in_observation
+                and include_qfrc_actuator_in_observation and include_cfrc_ext_in_observation):
+            raise NotImplementedError("only the default 348-dimensional observation layout is implemented")
+        if contact_cost_range[0] > 0 or not np.isneginf(contact_cost_range[0]) and contact_cost_range[0] != 0:
+            raise NotImplementedError("contact_cost_range lower bounds other than -inf/0 are not implemented")
+        obs_space = Box(low=-np.inf, high=np.inf, shape=(OBS_SIZE,), dtype=np.float64)  # humanoid_v5.py:395-397
+        act_space = Box(low=-0.4, high=0.4, shape=(17,), dtype=np.float32)             # ctrlrange, mujoco_env.py:105-110
+        super().__init__(num_envs, obs_space, act_space, max_episode_steps=max_episode_steps, render_mode=render_mode,
+                         **engine_kwargs)
+        n, dev = self.num_envs, self.device
+        self.frame_skip = int(frame_skip)
+        self.dt = 0.003 * self.frame_skip  # mujoco_env.py:189-191
+        self._cfg = _lib.HumanoidCfg(
+            reset_noise_scale=float(reset_noise_scale), forward_reward_weight=float(forward_reward_weight),
+            ctrl_cost_weight=float(ctrl_cost_weight), contact_cost_weight=float(contact_cost_weight),
+            contact_cost_max=float(contact_cost_range[1]), healthy_reward=float(healthy_reward),
+            healthy_z_min=float(healthy_z_range[0]), healthy_z_max=float(healthy_z_range[1]),
+            terminate_when_unhealthy=int(bool(terminate_when_unhealthy)), frame_skip=self.frame_skip)
+        self._s = {
+            "qpos": torch.zeros((24, n), dtype=torch.float64, device=dev),
+            "qvel": torch.zeros((23, n), dtype=torch.float64, device=dev),
+            "qacc_warmstart": torch.zeros((23, n), dtype=torch.float64, device=dev),
+            "com_xy": torch.zeros((2, n), dtype=torch.float64, device=dev),
+            "overflow": torch.zeros(1, dtype=torch.int32, device=dev),
+        }
+        self._state = _lib.HumanoidState(ctrl=self._ctrl.data_ptr(), rng=ptr(self._rng),
+                                         **{k: v.data_ptr() for k, v in self._s.items()})
+
+    def _alloc_outputs(self):
+        n = self.num_envs
+        layout = {"obs": ((n, OBS_SIZE), torch.float64), "reward": ((n,), torch.float64), "info": ((13, n), torch.float64),
+                  "terminated": ((n,), torch.bool), "truncated": ((n,), torch.bool)}
+        if self.autoreset_mode == AutoresetMode.SAME_STEP:
+            layout["final_obs"] = ((n, OBS_SIZE), torch.float64)
+        out = self._alloc_packed(layout)
+        if "final_obs" in out:
+            out["final_obs"].zero_()
+        return out
+
+    def _prepare_actions(self, actions):
+        n = self.num_envs
+        if isinstance(actions, torch.Tensor):
+            t = actions
+            if t.dim() != 2 or tuple(t.shape) != (n, 17):
+                raise ValueError(f"Action dimension mismatch. Expected {(n, 17)}, found {tuple(t.shape)}")  # mujoco_env.py:198-201
+            if t.dtype not in (torch.float32, torch.float64):
+                t = t.to(torch.float32)
+            return t.to(self.device).contiguous()
+        a = np.asarray(actions)
+        if a.ndim == 0:
+            raise TypeError(f"actions must have a leading dimension of num_envs={n}, got a scalar")
+        if a.shape != (n, 17):
+            raise ValueError(f"Action dimension mismatch. Expected {(n, 17)}, found {a.shape}")
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float32)
+        return super()._prepare_actions(np.ascontiguousarray(a))
+
+    def _reset_kernel(self, mask, options, out):
+        if mask is not None:
+            if self.copy and self._has_reset:
+                out["obs"].copy_(self._last_obs)
+            out["info"].zero_()
+        _lib.check(
+            self._lib.b2e_humanoid_reset(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state),
+                                         ptr(None if mask is None else mask.view(torch.uint8)), ptr(out["obs"]),
+                                         ptr(out["info"]), self._stream),
+            "b2e_humanoid_reset",
+        )
+        self._last_obs = out["obs"]
+
+    def _step_kernel(self, actions, out):
+        _lib.check(
+            self._lib.b2e_humanoid_step(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state), ptr(actions),
+                                        ptr(out["obs"]), ptr(out["reward"]), ptr(out["terminated"]),
+                                        ptr(out["truncated"]), ptr(out["info"]), ptr(out.get("final_obs")), self._stream),
+            "b2e_humanoid_step",
+        )
+        self._last_obs = out["obs"]
+
+    def _info_dict(self, out, mask, keys):
+        raw = out["info"]
+        host = isinstance(raw, np.ndarray)
+        n = self.num_envs
+        if mask is None:
+            mask = np.ones(n, dtype=np.bool_) if host else torch.ones(n, dtype=torch.bool, device=self.device)
+        rows = {"x_position": raw[0], "y_position": raw[1], "tendon_length": raw[2:4].T, "tendon_velocity": raw[4:6].T,
+                "distance_from_origin": raw[6], "x_velocity": raw[7], "y_velocity": raw[8], "reward_survive": raw[9],
+                "reward_forward": raw[10], "reward_ctrl": raw[11], "reward_contact": raw[12]}
+        info = {}
+        for k in keys:
+            info[k] = rows[k]
+            info["_" + k] = mask
+        return info
+
+    def _reset_info(self, out, mask):
+        # HumanoidEnv._get_reset_info (humanoid_v5.py:534-541): the five state keys
+        return self._info_dict(out, mask, INFO_KEYS[:5])
+
+    def _step_info(self, out):
+        info = self._info_dict(out, None, INFO_KEYS)
+        if self.autoreset_mode == AutoresetMode.SAME_STEP:
+            done = out["terminated"] | out["truncated"]
+            info.update({"final_obs": out["final_obs"], "_final_obs": done})
+        return info
+
+    # introspection -------------------------------------------------------------------------------------------------
+    def qpos(self) -> torch.Tensor:
+        return self._s["qpos"].t().contiguous()
+
+    def qvel(self) -> torch.Tensor:
+        return self._s["qvel"].t().contiguous()
+
+    def buffer_overflow(self) -> bool:
+        """True if any env ever exhausted the per-env contact (16) or constraint-row (64) buffers."""
+        return bool(self._s["overflow"].item())

@@ -26,6 +26,8 @@ ENVS = {
                          "gymnasium.envs.toy_text.frozen_lake:FrozenLakeEnv", 200, 0.85, {"map_name": "8x8"}),
     "LunarLander-v3": ("gymnasium_b200.envs.lunar_lander:LunarLanderVectorEnv",
                        "gymnasium.envs.box2d.lunar_lander:LunarLander", 1000, 200, {}),
+    "Humanoid-v5": ("gymnasium_b200.envs.humanoid:HumanoidVectorEnv",
+                    "gymnasium.envs.mujoco.humanoid_v5:HumanoidEnv", 1000, None, {}),
 }
 NAMESPACE = "B200"
 

@@ -176,6 +176,48 @@ int b2e_lunarlander_step(const b2e_batch* b, const b2e_lunarlander_cfg* cfg, con
                          const void* actions, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
                          float* final_obs, void* stream);
 
+/* ---- Humanoid-v5: gymnasium/envs/mujoco/humanoid_v5.py:436-532, mujoco_env.py:132-155, assets/humanoid.xml ---------
+ * (+ the MuJoCo subset mj_step/mj_forward/mj_rnePostConstraint need for this model; see csrc/humanoid.cu)
+ * Per-env state, struct-of-arrays over n envs (device, float64):
+ *   qpos [24][n], qvel [23][n], qacc_warmstart [23][n], com_xy [2][n] (mass centre of the last forward evaluation);
+ *   ctrl / rng as for CartPole; overflow int32 [1] (sticky: a contact/constraint buffer was exhausted)
+ * actions float32 or float64 [n][17] (b->action_dtype = B2E_ACT_F32 / B2E_ACT_F64)
+ * obs float64 [n][348]; reward float64 [n]; terminated/truncated uint8 [n];
+ * info float64 [13][n]: x_position, y_position, tendon_length[2], tendon_velocity[2], distance_from_origin,
+ *                       x_velocity, y_velocity, reward_survive, reward_forward, reward_ctrl, reward_contact
+ * final_obs float64 [n][348] (SAME_STEP only).
+ */
+typedef struct b2e_humanoid_cfg {
+  double reset_noise_scale;      /* 1e-2 */
+  double forward_reward_weight;  /* 1.25 */
+  double ctrl_cost_weight;       /* 0.1 */
+  double contact_cost_weight;    /* 5e-7 */
+  double contact_cost_max;       /* contact_cost_range[1] = 10 */
+  double healthy_reward;         /* 5.0 */
+  double healthy_z_min, healthy_z_max; /* (1.0, 2.0) */
+  int32_t terminate_when_unhealthy;    /* 1 */
+  int32_t frame_skip;                  /* 5 */
+} b2e_humanoid_cfg;
+
+typedef struct b2e_humanoid_state {
+  double* qpos;
+  double* qvel;
+  double* qacc_warmstart;
+  double* com_xy;
+  int32_t* ctrl;
+  uint64_t* rng;
+  int32_t* overflow;
+} b2e_humanoid_state;
+
+/* Host-side view of the compiled model constants (no GPU needed): body_mass[14], misc[8] = {meaninertia, n collision
+ * pairs, total mass, ...}, invweight[14*2 + 23] = body_invweight0 then dof_invweight0. */
+int b2e_humanoid_model_info(double* body_mass, double* misc, double* invweight);
+int b2e_humanoid_reset(const b2e_batch* b, const b2e_humanoid_cfg* cfg, const b2e_humanoid_state* st,
+                       const uint8_t* mask, double* obs, double* info, void* stream);
+int b2e_humanoid_step(const b2e_batch* b, const b2e_humanoid_cfg* cfg, const b2e_humanoid_state* st,
+                      const void* actions, double* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
+                      double* info, double* final_obs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

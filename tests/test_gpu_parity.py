@@ -405,3 +405,64 @@ def test_lunarlander_api():
         xb = [b[0].step(act[:32]), b[1].step(act[32:])]
         for k in range(4):
             np.testing.assert_array_equal(xa[k], np.concatenate([xb[0][k], xb[1][k]]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Humanoid-v5: the checker is oracle/humanoid.c (MuJoCo-subset restatement, parity with the real wheel unpinned)
+def test_humanoid_matches_oracle_bit_exact():
+    from oracle.humanoid import OracleHumanoid
+
+    n, T, seed = 48, 90, 31
+    env = make("Humanoid-v5", n)
+    ora = OracleHumanoid(n)
+    o1, i1 = env.reset(seed=seed)
+    o2, i2 = ora.reset(seed=seed)
+    assert o1.shape == (n, 348) and o1.dtype == np.float64
+    np.testing.assert_array_equal(o1, o2)
+    np.testing.assert_array_equal(i1["x_position"], i2["x_position"])
+    rs = np.random.default_rng(9)
+    n_term = 0
+    for t in range(T):
+        a = rs.uniform(-0.4, 0.4, size=(n, 17)).astype(np.float32)
+        x, y = env.step(a), ora.step(a)
+        np.testing.assert_array_equal(x[0], y[0], err_msg=f"obs differ at step {t}")
+        np.testing.assert_array_equal(x[1], y[1], err_msg=f"reward differs at step {t}")
+        np.testing.assert_array_equal(x[2], y[2])
+        np.testing.assert_array_equal(x[3], y[3])
+        for k in ("x_velocity", "y_velocity", "reward_survive", "reward_forward", "reward_ctrl", "reward_contact",
+                  "distance_from_origin"):
+            np.testing.assert_array_equal(x[4][k], y[4][k], err_msg=k)
+        np.testing.assert_array_equal(x[4]["tendon_length"][:, 0], y[4]["tendon_length0"])
+        np.testing.assert_array_equal(x[4]["tendon_velocity"][:, 1], y[4]["tendon_velocity1"])
+        n_term += int(y[2].sum())
+    assert n_term >= n // 2  # random actions make the humanoid fall within ~40-80 steps
+    assert not env.buffer_overflow()
+
+
+def test_humanoid_reference_structural_pins_on_gpu():
+    """The reference's own checks for this boundary (tests/envs/mujoco/test_mujoco_v5.py), through the engine."""
+    import torch
+
+    env = make("Humanoid-v5", 4, reset_noise_scale=0.0)
+    obs, info = env.reset(seed=0)
+    np.testing.assert_array_equal(obs[:, 0], 1.4)              # z of the noise-free init state (:693-710)
+    assert set(info) >= {"x_position", "y_position", "tendon_length", "tendon_velocity", "distance_from_origin"}  # :454-476
+    assert env.single_observation_space.shape == (348,) and env.single_action_space.shape == (17,)
+    rs = np.random.default_rng(2)
+    terminated_at = None
+    for step in range(80):                                        # test_verify_reward_survive (:159-191)
+        a = rs.uniform(-0.4, 0.4, size=(4, 17)).astype(np.float32)
+        obs, r, te, tr, info = env.step(a)
+        total = info["reward_survive"] + info["reward_forward"] + info["reward_ctrl"] + info["reward_contact"]
+        np.testing.assert_allclose(r, total, atol=1e-12)          # :221-231
+        if te[0]:
+            assert info["reward_survive"][0] == 0 and not (1.0 < obs[0, 0] < 2.0)
+            terminated_at = step
+            break
+        assert info["reward_survive"][0] == 5.0
+    assert terminated_at is not None
+    with pytest.raises(ValueError, match="Action dimension mismatch"):
+        env.step(np.zeros((4, 16), dtype=np.float32))
+    t = make("Humanoid-v5", 2, output="torch")
+    o, _ = t.reset(seed=1)
+    assert o.dtype == torch.float64 and o.shape == (2, 348)

@@ -39,6 +39,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.FrozenLakeCfg) == 8 + 16 + 72
     assert C.sizeof(_lib.LunarLanderCfg) == 16 and C.sizeof(_lib.LunarLanderState) == 72
     assert _lib.load().b2e_lunarlander_state_words() == 12 * 16
+    assert C.sizeof(_lib.HumanoidCfg) == 72 and C.sizeof(_lib.HumanoidState) == 56
 
 
 def test_argument_errors_do_not_need_a_gpu():
@@ -95,3 +96,20 @@ def test_registry_ids():
     assert set(gymnasium_b200.registration.ENVS) >= {"CartPole-v1", "FrozenLake-v1", "FrozenLake8x8-v1"}
     with pytest.raises(KeyError):
         gymnasium_b200.make_vec("NoSuchEnv-v0", 2)
+
+
+def test_humanoid_compiled_model_matches_oracle_compile():
+    """The product's own compile of humanoid.xml (host side of csrc/humanoid.cu) against the oracle's independent one:
+    inertia-from-geoms, meaninertia and the invweight0 constants, bit for bit."""
+    from oracle.humanoid import OracleHumanoid
+
+    lib = _lib.load()
+    mass = np.zeros(14); misc = np.zeros(8); inv = np.zeros(14 * 2 + 23)
+    assert lib.b2e_humanoid_model_info(mass.ctypes.data, misc.ctypes.data, inv.ctypes.data) == 0
+    om, omisc, oinv = OracleHumanoid(1).model_info()
+    np.testing.assert_array_equal(mass, om)
+    np.testing.assert_array_equal(misc[:3], omisc[:3])
+    np.testing.assert_array_equal(inv, oinv)
+    known = [0, 8.90746237, 2.26194671, 6.61619413, 4.75175093, 2.75569617, 1.76714587, 4.75175093, 2.75569617,
+             1.76714587, 1.66108048, 1.22954019, 1.66108048, 1.22954019]  # mjModel.body_mass of the stock humanoid.xml
+    np.testing.assert_allclose(mass, known, rtol=2e-8)
