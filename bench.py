@@ -159,6 +159,8 @@ def run_reference(args):
         have_ref, why = False, repr(e)
 
     alternatives = {}
+    if have_ref and args.env in ("LunarLander-v3", "Humanoid-v5"):
+        have_ref, why = False, "Box2D / mujoco wheels are not installable here (no runnable reference for this env)"
     if have_ref:
         import warnings
 
@@ -204,22 +206,34 @@ def run_reference(args):
         from oracle.cartpole import OracleCartPole
         from oracle.frozenlake import OracleFrozenLake
 
-        n = args.num_envs if args.env.startswith("CartPole") else 4096
-        env = OracleCartPole(n) if args.env.startswith("CartPole") else OracleFrozenLake(n, map_name="8x8")
-        nact = 2 if args.env.startswith("CartPole") else 4
+        if args.env == "LunarLander-v3":
+            from oracle.lunar_lander import OracleLunarLander
+
+            n, env = 1024, OracleLunarLander(1024)
+        elif args.env == "Humanoid-v5":
+            from oracle.humanoid import OracleHumanoid
+
+            n, env = 64, OracleHumanoid(64)
+        elif args.env.startswith("CartPole"):
+            n = args.num_envs or 65536
+            env = OracleCartPole(n)
+        else:
+            n, env = 4096, OracleFrozenLake(4096, map_name="8x8")
         rs = np.random.default_rng(0)
+        pool = host_action_pool(np, args.env, 8, n, 0)
         env.reset(seed=0)
         t0 = time.perf_counter()
-        for _ in range(max(args.warmup, 3)):
-            env.step(rs.integers(0, nact, n))
+        for k in range(max(args.warmup, 3)):
+            env.step(pool[k % 8])
         t_call = (time.perf_counter() - t0) / max(args.warmup, 3)
         steps = max(1, min(args.steps, int(budget / t_call)))
         t0 = time.perf_counter()
-        for _ in range(steps):
-            env.step(rs.integers(0, nact, n))
+        for k in range(steps):
+            env.step(pool[k % 8])
         dt = time.perf_counter() - t0
         total, value = steps * n, steps * n / dt
-        sample = f"oracle numpy port, N={n}, {steps} vector steps (gymnasium not importable: {why})"
+        sample = f"oracle port (1 core), N={n}, {steps} vector steps ({why})"
+        args.steps = steps
         kind, cores = "port", 1
     line.update({
         "value": value, "ms_per_step": dt / args.steps * 1e3,
@@ -234,6 +248,36 @@ def run_reference(args):
 
 def env_kwargs(env_id):
     return {"map_name": "8x8"} if env_id.startswith("FrozenLake") else {}
+
+
+# per-family bench facts: algorithmic HBM bytes per env-step, dominant kernel, arithmetic type, default batch per GPU
+ENV_FACTS = {
+    "CartPole-v1": dict(step_bytes=CARTPOLE_STEP_BYTES, kernel="cartpole_step_kernel<int64>", dtype="f64", nact=2,
+                        out_bytes=16 + 8 + 1 + 1, act_bytes=8, default_n=65536),
+    "FrozenLake-v1": dict(step_bytes=FROZENLAKE_STEP_BYTES, kernel="frozenlake_step_kernel<int64>", dtype="int32+f64",
+                          nact=4, out_bytes=8 + 8 + 8 + 1 + 1, act_bytes=8, default_n=1 << 20),
+    # state r/w (21+8+12 floats, flags, prev_shaping, ctrl, rng words) + action + outputs; contact slots excluded
+    "LunarLander-v3": dict(step_bytes=2 * (41 * 4 + 4 + 8 + 4) + 32 + 8 + 32 + 8 + 2, kernel="lunarlander_step_kernel<int64>",
+                           dtype="f32+f64", nact=4, out_bytes=32 + 8 + 1 + 1, act_bytes=8, default_n=16384),
+    # qpos/qvel/warmstart/com r+w (72 doubles x 2) + action 17 f32 + obs 348 f64 + reward + info 13 f64 + flags
+    "Humanoid-v5": dict(step_bytes=2 * 72 * 8 + 68 + 348 * 8 + 8 + 13 * 8 + 2 + 8, kernel="humanoid_step_kernel<float>",
+                        dtype="f64", nact=0, out_bytes=348 * 8 + 8 + 13 * 8 + 2, act_bytes=68, default_n=8192),
+}
+
+
+def device_actions(torch, env_id, shape_prefix, n, dev, gen=None):
+    f = ENV_FACTS[env_id]
+    if f["nact"]:
+        return torch.randint(0, f["nact"], (*shape_prefix, n), device=dev, dtype=torch.int64, generator=gen)
+    return (torch.rand((*shape_prefix, n, 17), device=dev, generator=gen) * 0.8 - 0.4).float()
+
+
+def host_action_pool(np, env_id, count, n, seed):
+    f = ENV_FACTS[env_id]
+    rs = np.random.default_rng(seed)
+    if f["nact"]:
+        return rs.integers(0, f["nact"], size=(count, n)).astype(np.int64)
+    return rs.uniform(-0.4, 0.4, size=(count, n, 17)).astype(np.float32)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -255,10 +299,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     info = _lib.device_info(local_rank)
     hbm_peak, peak_src = load_peaks()
-    n = args.num_envs
+    facts = ENV_FACTS[args.env]
+    n = args.num_envs or facts["default_n"]
+    args.num_envs = n
     is_cartpole = args.env.startswith("CartPole")
-    nact = 2 if is_cartpole else 4
-    step_bytes = CARTPOLE_STEP_BYTES if is_cartpole else FROZENLAKE_STEP_BYTES
+    step_bytes = facts["step_bytes"]
     kw = env_kwargs(args.env)
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
 
@@ -278,6 +323,8 @@ def run_b200(args):
     # ---- ring of independent batches, total footprint > 2 x L2 ------------------------------------------------------
     foot = n * (step_bytes + 32)  # + the PCG64 words each batch also owns
     ring = args.ring or max(2, math.ceil(2.0 * info["l2_bytes"] / foot))
+    if args.env in ("LunarLander-v3", "Humanoid-v5") and not args.ring:
+        ring = min(ring, 4)  # latency/FLOP-bound families: L2 residency is irrelevant, keep set-up short
     T = 8  # distinct action vectors per batch
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     envs, acts = [], []
@@ -285,7 +332,7 @@ def run_b200(args):
         e = gymnasium_b200.make_vec(args.env, num_envs=n, device=dev, copy=False, env_offset=(rank * ring + j) * n, **kw)
         e.reset(seed=0)
         envs.append(e)
-        acts.append(torch.randint(0, nact, (T, n), device=dev, dtype=torch.int64, generator=gen))
+        acts.append(device_actions(torch, args.env, (T,), n, dev, gen))
     torch.cuda.synchronize()
 
     def launch(k):  # one bench step = one fused step launch on the next batch of the ring
@@ -351,7 +398,7 @@ def run_b200(args):
     e2e_env = gymnasium_b200.make_vec(args.env, num_envs=n, device=dev, copy=False, env_offset=rank * n,
                                       output="numpy" if world == 1 else "torch", **kw)
     e2e_env.reset(seed=0)
-    host_actions = np.random.default_rng(rank).integers(0, nact, size=(16, n)).astype(np.int64)
+    host_actions = host_action_pool(np, args.env, 16, n, rank)
     pinned = {}
     gathered = {}
 
@@ -386,8 +433,8 @@ def run_b200(args):
     if ctx:
         ctx.__exit__()
     e2e_value = world * Ke * n / e2e_elapsed
-    out_bytes = n * ((16 + 8 + 1 + 1) if is_cartpole else (8 + 8 + 1 + 1 + 8 + 1))
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": out_bytes,
+    out_bytes = n * facts["out_bytes"]
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * facts["act_bytes"], "d2h_bytes_per_step": out_bytes,
            "steps": Ke, "ms_per_step": e2e_elapsed / Ke * 1e3,
            "path": "gymnasium_b200.make_vec(...).step(numpy int64 actions) -> numpy arrays"
                    + ("" if world == 1 else " + NCCL gather of every shard's outputs to rank 0 + D2H of the gathered batch")}
@@ -398,11 +445,11 @@ def run_b200(args):
         cpu_baseline = cpu_baseline_subprocess(args)
 
     if rank == 0:
-        kname = "cartpole_step_kernel<int64>" if is_cartpole else "frozenlake_step_kernel<int64>"
+        kname = facts["kernel"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if is_cartpole else "int32+f64", "data": "synthetic",
+            "dtype": facts["dtype"], "data": "synthetic",
             "config": {
                 "workload": f"{args.env} {n} envs per GPU, fused step+auto-reset kernel, random actions, NEXT_STEP "
                             f"autoreset, TimeLimit, numpy-parity PCG64 streams",
@@ -435,8 +482,11 @@ def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0)
     L2-resident single-batch rate, FrozenLake at its BASELINE size, and the reset-call fraction."""
     out = {}
     is_cartpole = args.env.startswith("CartPole")
-    nact = 2 if is_cartpole else 4
+    facts = ENV_FACTS[args.env]
+    nact = facts["nact"]
     kw = env_kwargs(args.env)
+    if not nact or args.env == "LunarLander-v3":
+        return out  # the supporting numbers below are for the HBM-bound discrete families
 
     def timed(fn, iters, warm=3):
         for _ in range(warm):
@@ -557,8 +607,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--env", default="CartPole-v1", choices=["CartPole-v1", "FrozenLake-v1"])
-    ap.add_argument("--num-envs", type=int, default=65536)
+    ap.add_argument("--env", default="CartPole-v1", choices=sorted(ENV_FACTS))
+    ap.add_argument("--num-envs", type=int, default=0, help="envs per GPU (0 = the BASELINE size of --env)")
     ap.add_argument("--ring", type=int, default=0, help="batches in the L2-defeating ring (0 = auto: > 2 x L2)")
     ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--ref-budget", type=float, default=20.0, help="seconds of CPU work for the reference arm")

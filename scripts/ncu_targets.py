@@ -58,3 +58,9 @@ if which in ("all", "lander"):
     for t in range(80):  # reach the mixed regime: some lanes flying, some on the ground, some resetting
         ll.step(torch.randint(0, 4, (16384,), device=dev))
     torch.cuda.synchronize()
+if which in ("all", "humanoid"):
+    hm = gymnasium_b200.make_vec("Humanoid-v5", num_envs=8192, copy=False)
+    hm.reset(seed=0)
+    for t in range(14):  # feet reach the floor around step 10: contacts + PGS active
+        hm.step((torch.rand((8192, 17), device=dev) * 0.8 - 0.4).float())
+    torch.cuda.synchronize()
