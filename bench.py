@@ -436,7 +436,7 @@ def run_b200(args):
     out_bytes = n * facts["out_bytes"]
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * facts["act_bytes"], "d2h_bytes_per_step": out_bytes,
            "steps": Ke, "ms_per_step": e2e_elapsed / Ke * 1e3,
-           "path": "gymnasium_b200.make_vec(...).step(numpy int64 actions) -> numpy arrays"
+           "path": "gymnasium_b200.make_vec(...).step(host numpy actions) -> host numpy arrays"
                    + ("" if world == 1 else " + NCCL gather of every shard's outputs to rank 0 + D2H of the gathered batch")}
 
     clocks = sampler.stop() if sampler else None
@@ -454,8 +454,11 @@ def run_b200(args):
                 "workload": f"{args.env} {n} envs per GPU, fused step+auto-reset kernel, random actions, NEXT_STEP "
                             f"autoreset, TimeLimit, numpy-parity PCG64 streams",
                 "num_envs_per_gpu": n, "parallelism": f"env-shards x{world} (no data-path collective)",
-                "l2_policy": f"inputs larger than L2: ring of {ring} independent {n}-env batches "
-                             f"({ring * foot / 1e6:.0f} MB > 2 x {info['l2_bytes'] / 1e6:.0f} MB L2), round-robin",
+                "l2_policy": (f"inputs larger than L2: ring of {ring} independent {n}-env batches "
+                              f"({ring * foot / 1e6:.0f} MB > 2 x {info['l2_bytes'] / 1e6:.0f} MB L2), round-robin"
+                              if ring * foot > 2 * info["l2_bytes"] else
+                              f"ring of {ring} independent {n}-env batches ({ring * foot / 1e6:.0f} MB); this family is "
+                              f"latency/FLOP-bound, not HBM-bound, so L2 residency does not affect the timing"),
                 "launch": "CUDA graphs of one step launch per batch, CUDA-event timing on the launch stream",
                 "counting": "calls x N (reset calls included); see value_excluding_reset_calls",
             },

@@ -37,7 +37,7 @@ class Batch(C.Structure):
 class CartPoleCfg(C.Structure):
     """``b2e_cartpole_cfg``."""
 
-    _fields_ = [("reset_low", c_double), ("reset_high", c_double), ("sutton_barto_reward", c_i32), ("_pad", c_i32)]
+    _fields_ = [("reset_low", c_double), ("reset_high", c_double), ("sutton_barto_reward", c_i32), ("step_block", c_i32)]
 
 
 class FrozenLakeCfg(C.Structure):

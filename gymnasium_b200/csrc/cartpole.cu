@@ -186,14 +186,15 @@ __device__ __forceinline__ void step_env(const CartPoleArgs& a, int64_t i, int32
   __stcs(reinterpret_cast<float4*>(a.obs) + i, to_obs(s));
 }
 
-// One thread per env, 128-thread CTAs.  All loads are issued before the first use (one memory round trip).  Launch
-// geometry was swept on a B200 at N=65536 / 262144 (graph-chained launches, us per launch): block 64/128/256 x 1/2/4
-// envs per thread -> 128 x 1 is fastest (3.30 / 6.50 us; 2 envs/thread 4.10 / 7.00; 4 envs/thread 6.3 / 8.1), and
-// programmatic dependent launch made N >= 65536 slower (4.07 vs 3.27 us), so it is opt-in (B2E_PDL=1).
-constexpr int kStepBlock = 128;
+// One thread per env.  All loads are issued before the first use (one memory round trip).  Launch geometry was swept
+// on a B200 at N=65536 (graph-chained launches, us per launch, L2-resident / HBM-cold ring): CTA 64: 3.01 / 3.91,
+// 128: 3.21 / 4.05, 256: 3.33 / 4.08, 448 (one CTA per SM): 3.28 / 4.01, 1024: 4.65 / 5.29; 2 or 4 envs per thread
+// were slower (4.10 / 6.3 us L2-resident); programmatic dependent launch made N >= 65536 slower (4.07 vs 3.27 us) and
+// is opt-in (B2E_PDL=1).  b2e_cartpole_cfg.step_block overrides the CTA size.
+constexpr int kStepBlock = 64;
 
 template <typename ActT>
-__global__ void __launch_bounds__(kStepBlock) cartpole_step_kernel(const CartPoleArgs a) {
+__global__ void __launch_bounds__(1024) cartpole_step_kernel(const CartPoleArgs a) {
   pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
@@ -204,8 +205,9 @@ __global__ void __launch_bounds__(kStepBlock) cartpole_step_kernel(const CartPol
 }
 
 template <typename ActT>
-cudaError_t launch_step(const CartPoleArgs& a, cudaStream_t st) {
-  return launch_pdl(cartpole_step_kernel<ActT>, grid_for(a.n, kStepBlock), kStepBlock, 0, st, a);
+cudaError_t launch_step(const CartPoleArgs& a, cudaStream_t st, int block) {
+  if (block < 32 || block > 1024 || (block & 31)) block = kStepBlock;
+  return launch_pdl(cartpole_step_kernel<ActT>, grid_for(a.n, block), block, 0, st, a);
 }
 
 struct RolloutArgs {
@@ -358,9 +360,9 @@ extern "C" int b2e_cartpole_step(const b2e_batch* b, const b2e_cartpole_cfg* cfg
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   switch (b->action_dtype) {
-    case B2E_ACT_I64: e = launch_step<int64_t>(a, st); break;
-    case B2E_ACT_I32: e = launch_step<int32_t>(a, st); break;
-    case B2E_ACT_U8: e = launch_step<uint8_t>(a, st); break;
+    case B2E_ACT_I64: e = launch_step<int64_t>(a, st, cfg->step_block); break;
+    case B2E_ACT_I32: e = launch_step<int32_t>(a, st, cfg->step_block); break;
+    case B2E_ACT_U8: e = launch_step<uint8_t>(a, st, cfg->step_block); break;
     default: set_error("b2e_cartpole_step: action_dtype %d is not a discrete dtype", b->action_dtype); return B2E_EINVAL;
   }
   return cuda_status(e, "b2e_cartpole_step");

@@ -85,7 +85,7 @@ int b2e_rng_random(const b2e_batch* b, uint64_t* rng, int32_t k, double* out, vo
 typedef struct b2e_cartpole_cfg {
   double reset_low, reset_high; /* cartpole.py:236-241 (+ options low/high, classic_control/utils.py:17-46) */
   int32_t sutton_barto_reward;  /* cartpole.py:205-220 */
-  int32_t _pad;
+  int32_t step_block;           /* threads per CTA of the step kernel; 0 = library default (tuning knob) */
 } b2e_cartpole_cfg;
 
 /* CartPoleEnv.reset for lanes with mask!=0 (NULL = all); clears elapsed/autoreset; writes obs for those lanes. */
