@@ -22,6 +22,8 @@
 // chain per env), not HBM-bound: ~1.3 KB moved per env-step.
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b2e {
@@ -617,11 +619,24 @@ struct VC {
   float k00, k01, k11, n00, n10, n01, n11, friction;
 };
 
+// Static dispatch on a body index: the solver keeps the three bodies' positions/velocities in registers, so every
+// access must use a compile-time index; the (divergent) runtime index of a contact's body selects one of three inlined
+// instantiations instead of forcing the arrays into local memory.
+template <class F>
+DI void with_body(int ib, F&& f) {
+  switch (ib) {
+    case 0: f(std::integral_constant<int, 0>{}); break;
+    case 1: f(std::integral_constant<int, 1>{}); break;
+    default: f(std::integral_constant<int, 2>{}); break;
+  }
+}
+
 // b2World::Solve for the one island {legs[1], lander, legs[0]} (+ the static moon); local body indices 0..2 = lander, legs
 __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, float gravity) {
   const Model& M = g_model;
   Pos P[kND];
   Vel Vv[kND];
+  Joint j0 = L.j[0], j1 = L.j[1];  // register copies for the 180-iteration loop
   const V2 g = mk(0.0f, gravity);
 #pragma unroll
   for (int i = 0; i < kND; ++i) {
@@ -661,146 +676,152 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
     }
   for (int k = 0; k < nvc; ++k) {  // InitializeVelocityConstraints (bodyA = static moon at the origin)
     VC& vc = vcs[k];
-    const int ib = vc.ib;
-    const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
-    const V2 cB = P[ib].c;
-    Xf xfB;
-    xfB.q = rot_set(P[ib].a);
-    xfB.p = cB - rmul(xfB.q, M.local_center[ib]);
-    V2 pts[2];
-    if (vc.type == 1) {  // b2WorldManifold::Initialize, e_faceA
-      vc.normal = vc.local_normal;
-      const V2 plane = vc.local_point;
+    with_body(vc.ib, [&](auto IB) {
+      constexpr int ib = decltype(IB)::value;
+      const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
+      const V2 cB = P[ib].c;
+      Xf xfB;
+      xfB.q = rot_set(P[ib].a);
+      xfB.p = cB - rmul(xfB.q, M.local_center[ib]);
+      V2 pts[2];
+      if (vc.type == 1) {  // b2WorldManifold::Initialize, e_faceA
+        vc.normal = vc.local_normal;
+        const V2 plane = vc.local_point;
+        for (int j = 0; j < vc.count; ++j) {
+          const V2 clip = xmul(xfB, vc.lpts[j]);
+          const V2 cA = clip + (kPolyRadius - dot(clip - plane, vc.normal)) * vc.normal;
+          const V2 cBp = clip - kPolyRadius * vc.normal;
+          pts[j] = 0.5f * (cA + cBp);
+        }
+      } else {  // e_faceB
+        V2 nrm = rmul(xfB.q, vc.local_normal);
+        const V2 plane = xmul(xfB, vc.local_point);
+        for (int j = 0; j < vc.count; ++j) {
+          const V2 clip = vc.lpts[j];
+          const V2 cBp = clip + (kPolyRadius - dot(clip - plane, nrm)) * nrm;
+          const V2 cA = clip - kPolyRadius * nrm;
+          pts[j] = 0.5f * (cA + cBp);
+        }
+        vc.normal = -nrm;
+      }
       for (int j = 0; j < vc.count; ++j) {
-        const V2 clip = xmul(xfB, vc.lpts[j]);
-        const V2 cA = clip + (kPolyRadius - dot(clip - plane, vc.normal)) * vc.normal;
-        const V2 cBp = clip - kPolyRadius * vc.normal;
-        pts[j] = 0.5f * (cA + cBp);
+        VCP& p = vc.p[j];
+        p.rB = pts[j] - cB;
+        const float rnB = cross(p.rB, vc.normal);
+        const float kN = mB + iB * rnB * rnB;
+        p.normal_mass = kN > 0.0f ? 1.0f / kN : 0.0f;
+        const V2 tangent = cross_vs(vc.normal, 1.0f);
+        const float rtB = cross(p.rB, tangent);
+        const float kT = mB + iB * rtB * rtB;
+        p.tangent_mass = kT > 0.0f ? 1.0f / kT : 0.0f;
       }
-    } else {  // e_faceB
-      V2 nrm = rmul(xfB.q, vc.local_normal);
-      const V2 plane = xmul(xfB, vc.local_point);
-      for (int j = 0; j < vc.count; ++j) {
-        const V2 clip = vc.lpts[j];
-        const V2 cBp = clip + (kPolyRadius - dot(clip - plane, nrm)) * nrm;
-        const V2 cA = clip - kPolyRadius * nrm;
-        pts[j] = 0.5f * (cA + cBp);
+      if (vc.count == 2) {
+        const float rn1B = cross(vc.p[0].rB, vc.normal), rn2B = cross(vc.p[1].rB, vc.normal);
+        const float k11 = mB + iB * rn1B * rn1B, k22 = mB + iB * rn2B * rn2B, k12 = mB + iB * rn1B * rn2B;
+        if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+          vc.k00 = k11; vc.k01 = k12; vc.k11 = k22;
+          float det = k11 * k22 - k12 * k12;
+          if (det != 0.0f) det = 1.0f / det;
+          vc.n00 = det * k22; vc.n10 = -det * k12; vc.n01 = -det * k12; vc.n11 = det * k11;
+        } else {
+          vc.count = 1;
+        }
       }
-      vc.normal = -nrm;
-    }
-    for (int j = 0; j < vc.count; ++j) {
-      VCP& p = vc.p[j];
-      p.rB = pts[j] - cB;
-      const float rnB = cross(p.rB, vc.normal);
-      const float kN = mB + iB * rnB * rnB;
-      p.normal_mass = kN > 0.0f ? 1.0f / kN : 0.0f;
-      const V2 tangent = cross_vs(vc.normal, 1.0f);
-      const float rtB = cross(p.rB, tangent);
-      const float kT = mB + iB * rtB * rtB;
-      p.tangent_mass = kT > 0.0f ? 1.0f / kT : 0.0f;
-    }
-    if (vc.count == 2) {
-      const float rn1B = cross(vc.p[0].rB, vc.normal), rn2B = cross(vc.p[1].rB, vc.normal);
-      const float k11 = mB + iB * rn1B * rn1B, k22 = mB + iB * rn2B * rn2B, k12 = mB + iB * rn1B * rn2B;
-      if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
-        vc.k00 = k11; vc.k01 = k12; vc.k11 = k22;
-        float det = k11 * k22 - k12 * k12;
-        if (det != 0.0f) det = 1.0f / det;
-        vc.n00 = det * k22; vc.n10 = -det * k12; vc.n01 = -det * k12; vc.n11 = det * k11;
-      } else {
-        vc.count = 1;
-      }
-    }
+    });
   }
   for (int k = 0; k < nvc; ++k) {  // WarmStart
     VC& vc = vcs[k];
-    const int ib = vc.ib;
-    V2 vB = Vv[ib].v;
-    float wB = Vv[ib].w;
-    const V2 tangent = cross_vs(vc.normal, 1.0f);
-    for (int j = 0; j < vc.count; ++j) {
-      const V2 Pi = (vc.p[j].ni * vc.normal) + (vc.p[j].ti * tangent);
-      wB += M.inv_I[ib] * cross(vc.p[j].rB, Pi);
-      vB = vB + M.inv_mass[ib] * Pi;
-    }
-    Vv[ib].v = vB; Vv[ib].w = wB;
-  }
-  joint_init_velocity(L.j[1], 1, P[0], P[2], Vv[0], Vv[2], dt_ratio);
-  joint_init_velocity(L.j[0], 0, P[0], P[1], Vv[0], Vv[1], dt_ratio);
-  for (int it = 0; it < 180; ++it) {
-    joint_solve_velocity(L.j[1], 1, Vv[0], Vv[2], h);
-    joint_solve_velocity(L.j[0], 0, Vv[0], Vv[1], h);
-    for (int k = 0; k < nvc; ++k) {
-      VC& vc = vcs[k];
-      const int ib = vc.ib;
-      const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
+    with_body(vc.ib, [&](auto IB) {
+      constexpr int ib = decltype(IB)::value;
       V2 vB = Vv[ib].v;
       float wB = Vv[ib].w;
-      const V2 normal = vc.normal, tangent = cross_vs(normal, 1.0f);
+      const V2 tangent = cross_vs(vc.normal, 1.0f);
       for (int j = 0; j < vc.count; ++j) {
-        VCP& p = vc.p[j];
-        const V2 dv = vB + cross_sv(wB, p.rB);
-        const float vt = dot(dv, tangent) - 0.0f;
-        float lambda = p.tangent_mass * (-vt);
-        const float maxf = vc.friction * p.ni;
-        const float newi = clampf(p.ti + lambda, -maxf, maxf);
-        lambda = newi - p.ti;
-        p.ti = newi;
-        const V2 Pi = lambda * tangent;
-        vB = vB + mB * Pi;
-        wB += iB * cross(p.rB, Pi);
-      }
-      if (vc.count == 1) {
-        VCP& p = vc.p[0];
-        const V2 dv = vB + cross_sv(wB, p.rB);
-        const float vn = dot(dv, normal);
-        float lambda = -p.normal_mass * (vn - 0.0f);
-        const float newi = fmaxf(p.ni + lambda, 0.0f);
-        lambda = newi - p.ni;
-        p.ni = newi;
-        const V2 Pi = lambda * normal;
-        vB = vB + mB * Pi;
-        wB += iB * cross(p.rB, Pi);
-      } else {
-        VCP &c1 = vc.p[0], &c2 = vc.p[1];
-        const float ax = c1.ni, ay = c2.ni;
-        const V2 dv1 = vB + cross_sv(wB, c1.rB), dv2 = vB + cross_sv(wB, c2.rB);
-        float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-        float bx = vn1 - 0.0f, by = vn2 - 0.0f;
-        bx -= vc.k00 * ax + vc.k01 * ay;
-        by -= vc.k01 * ax + vc.k11 * ay;
-        float xx, xy;
-        bool solved = false;
-        xx = -(vc.n00 * bx + vc.n10 * by);
-        xy = -(vc.n01 * bx + vc.n11 * by);
-        if (xx >= 0.0f && xy >= 0.0f) solved = true;
-        if (!solved) {
-          xx = -c1.normal_mass * bx;
-          xy = 0.0f;
-          vn2 = vc.k01 * xx + by;
-          if (xx >= 0.0f && vn2 >= 0.0f) solved = true;
-        }
-        if (!solved) {
-          xx = 0.0f;
-          xy = -c2.normal_mass * by;
-          vn1 = vc.k01 * xy + bx;
-          if (xy >= 0.0f && vn1 >= 0.0f) solved = true;
-        }
-        if (!solved) {
-          xx = 0.0f;
-          xy = 0.0f;
-          if (bx >= 0.0f && by >= 0.0f) solved = true;
-        }
-        if (solved) {
-          const float dx = xx - ax, dy = xy - ay;
-          const V2 P1 = dx * normal, P2 = dy * normal;
-          vB = vB + mB * (P1 + P2);
-          wB += iB * (cross(c1.rB, P1) + cross(c2.rB, P2));
-          c1.ni = xx;
-          c2.ni = xy;
-        }
+        const V2 Pi = (vc.p[j].ni * vc.normal) + (vc.p[j].ti * tangent);
+        wB += M.inv_I[ib] * cross(vc.p[j].rB, Pi);
+        vB = vB + M.inv_mass[ib] * Pi;
       }
       Vv[ib].v = vB; Vv[ib].w = wB;
+    });
+  }
+  joint_init_velocity(j1, 1, P[0], P[2], Vv[0], Vv[2], dt_ratio);
+  joint_init_velocity(j0, 0, P[0], P[1], Vv[0], Vv[1], dt_ratio);
+  for (int it = 0; it < 180; ++it) {
+    joint_solve_velocity(j1, 1, Vv[0], Vv[2], h);
+    joint_solve_velocity(j0, 0, Vv[0], Vv[1], h);
+    for (int k = 0; k < nvc; ++k) {
+      VC& vc = vcs[k];
+      with_body(vc.ib, [&](auto IB) {
+        constexpr int ib = decltype(IB)::value;
+        const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
+        V2 vB = Vv[ib].v;
+        float wB = Vv[ib].w;
+        const V2 normal = vc.normal, tangent = cross_vs(normal, 1.0f);
+        for (int j = 0; j < vc.count; ++j) {
+          VCP& p = vc.p[j];
+          const V2 dv = vB + cross_sv(wB, p.rB);
+          const float vt = dot(dv, tangent) - 0.0f;
+          float lambda = p.tangent_mass * (-vt);
+          const float maxf = vc.friction * p.ni;
+          const float newi = clampf(p.ti + lambda, -maxf, maxf);
+          lambda = newi - p.ti;
+          p.ti = newi;
+          const V2 Pi = lambda * tangent;
+          vB = vB + mB * Pi;
+          wB += iB * cross(p.rB, Pi);
+        }
+        if (vc.count == 1) {
+          VCP& p = vc.p[0];
+          const V2 dv = vB + cross_sv(wB, p.rB);
+          const float vn = dot(dv, normal);
+          float lambda = -p.normal_mass * (vn - 0.0f);
+          const float newi = fmaxf(p.ni + lambda, 0.0f);
+          lambda = newi - p.ni;
+          p.ni = newi;
+          const V2 Pi = lambda * normal;
+          vB = vB + mB * Pi;
+          wB += iB * cross(p.rB, Pi);
+        } else {
+          VCP &c1 = vc.p[0], &c2 = vc.p[1];
+          const float ax = c1.ni, ay = c2.ni;
+          const V2 dv1 = vB + cross_sv(wB, c1.rB), dv2 = vB + cross_sv(wB, c2.rB);
+          float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+          float bx = vn1 - 0.0f, by = vn2 - 0.0f;
+          bx -= vc.k00 * ax + vc.k01 * ay;
+          by -= vc.k01 * ax + vc.k11 * ay;
+          float xx, xy;
+          bool solved = false;
+          xx = -(vc.n00 * bx + vc.n10 * by);
+          xy = -(vc.n01 * bx + vc.n11 * by);
+          if (xx >= 0.0f && xy >= 0.0f) solved = true;
+          if (!solved) {
+            xx = -c1.normal_mass * bx;
+            xy = 0.0f;
+            vn2 = vc.k01 * xx + by;
+            if (xx >= 0.0f && vn2 >= 0.0f) solved = true;
+          }
+          if (!solved) {
+            xx = 0.0f;
+            xy = -c2.normal_mass * by;
+            vn1 = vc.k01 * xy + bx;
+            if (xy >= 0.0f && vn1 >= 0.0f) solved = true;
+          }
+          if (!solved) {
+            xx = 0.0f;
+            xy = 0.0f;
+            if (bx >= 0.0f && by >= 0.0f) solved = true;
+          }
+          if (solved) {
+            const float dx = xx - ax, dy = xy - ay;
+            const V2 P1 = dx * normal, P2 = dy * normal;
+            vB = vB + mB * (P1 + P2);
+            wB += iB * (cross(c1.rB, P1) + cross(c2.rB, P2));
+            c1.ni = xx;
+            c2.ni = xy;
+          }
+        }
+        Vv[ib].v = vB; Vv[ib].w = wB;
+      });
     }
   }
   for (int k = 0; k < nvc; ++k)  // StoreImpulses
@@ -831,48 +852,52 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
     float min_sep = 0.0f;
     for (int k = 0; k < nvc; ++k) {
       const VC& vc = vcs[k];
-      const int ib = vc.ib;
-      const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
-      V2 cB = P[ib].c;
-      float aB = P[ib].a;
-      for (int j = 0; j < vc.pos_count; ++j) {
-        Xf xfB;
-        xfB.q = rot_set(aB);
-        xfB.p = cB - rmul(xfB.q, M.local_center[ib]);
-        V2 normal, point;
-        float sep;
-        if (vc.type == 1) {
-          normal = vc.local_normal;
-          const V2 clip = xmul(xfB, vc.lpts[j]);
-          sep = dot(clip - vc.local_point, normal) - kPolyRadius - kPolyRadius;
-          point = clip;
-        } else {
-          normal = rmul(xfB.q, vc.local_normal);
-          const V2 plane = xmul(xfB, vc.local_point), clip = vc.lpts[j];
-          sep = dot(clip - plane, normal) - kPolyRadius - kPolyRadius;
-          point = clip;
-          normal = -normal;
+      with_body(vc.ib, [&](auto IB) {
+        constexpr int ib = decltype(IB)::value;
+        const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
+        V2 cB = P[ib].c;
+        float aB = P[ib].a;
+        for (int j = 0; j < vc.pos_count; ++j) {
+          Xf xfB;
+          xfB.q = rot_set(aB);
+          xfB.p = cB - rmul(xfB.q, M.local_center[ib]);
+          V2 normal, point;
+          float sep;
+          if (vc.type == 1) {
+            normal = vc.local_normal;
+            const V2 clip = xmul(xfB, vc.lpts[j]);
+            sep = dot(clip - vc.local_point, normal) - kPolyRadius - kPolyRadius;
+            point = clip;
+          } else {
+            normal = rmul(xfB.q, vc.local_normal);
+            const V2 plane = xmul(xfB, vc.local_point), clip = vc.lpts[j];
+            sep = dot(clip - plane, normal) - kPolyRadius - kPolyRadius;
+            point = clip;
+            normal = -normal;
+          }
+          const V2 rB = point - cB;
+          min_sep = fminf(min_sep, sep);
+          const float C = clampf(kBaumgarte * (sep + kLinearSlop), -kMaxLinCorr, 0.0f);
+          const float rnB = cross(rB, normal);
+          const float K = mB + iB * rnB * rnB;
+          const float impulse = K > 0.0f ? -C / K : 0.0f;
+          const V2 Pi = impulse * normal;
+          cB = cB + mB * Pi;
+          aB += iB * cross(rB, Pi);
         }
-        const V2 rB = point - cB;
-        min_sep = fminf(min_sep, sep);
-        const float C = clampf(kBaumgarte * (sep + kLinearSlop), -kMaxLinCorr, 0.0f);
-        const float rnB = cross(rB, normal);
-        const float K = mB + iB * rnB * rnB;
-        const float impulse = K > 0.0f ? -C / K : 0.0f;
-        const V2 Pi = impulse * normal;
-        cB = cB + mB * Pi;
-        aB += iB * cross(rB, Pi);
-      }
-      P[ib].c = cB; P[ib].a = aB;
+        P[ib].c = cB; P[ib].a = aB;
+      });
     }
     const bool contacts_ok = min_sep >= -3.0f * kLinearSlop;
-    const bool j1 = joint_solve_position(L.j[1], 1, P[0], P[2]);
-    const bool j0 = joint_solve_position(L.j[0], 0, P[0], P[1]);
-    if (contacts_ok && j1 && j0) {
+    const bool ok1 = joint_solve_position(j1, 1, P[0], P[2]);
+    const bool ok0 = joint_solve_position(j0, 0, P[0], P[1]);
+    if (contacts_ok && ok1 && ok0) {
       position_solved = true;
       break;
     }
   }
+  L.j[0] = j0;
+  L.j[1] = j1;
   float min_sleep = kFltMax;
 #pragma unroll
   for (int i = 0; i < kND; ++i) {
