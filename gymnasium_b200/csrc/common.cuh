@@ -57,6 +57,19 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Sparse lane mapping for the divergent, latency-bound physics kernels: only the first `lanes` lanes of every warp own
+// an env (env = warp * lanes + lane).  Fewer envs per warp = fewer distinct control paths serialised inside a warp and
+// more warps to hide latency when the batch alone cannot fill the machine.
+__device__ __forceinline__ int64_t sparse_env_index(int lanes) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = (int)(gtid & 31);
+  return lane < lanes ? (gtid >> 5) * lanes + lane : -1;
+}
+inline unsigned sparse_grid(int64_t n, int lanes, int block) {
+  const int64_t warps = (n + lanes - 1) / lanes;
+  return (unsigned)((warps * 32 + block - 1) / block);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // control word: bits 0..30 = TimeLimit elapsed steps, bit 31 = autoreset pending (NEXT_STEP)
 constexpr int32_t kPending = (int32_t)0x80000000u;

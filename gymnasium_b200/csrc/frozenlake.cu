@@ -223,8 +223,12 @@ size_t table_smem_bytes(const LakeArgs& a) {
   return total <= kMaxSharedEntries ? (size_t)total * sizeof(uint32_t) : 0;
 }
 
-// grid-stride launch: at most 8 CTAs of 256 threads per SM (full occupancy), so big batches re-use the staged table
+// Launch geometry: one env per thread (grid = ceil(n / 256)) by default.  A capped grid-stride launch (8 CTAs per SM,
+// table staged once per CTA) was measured slower at N = 1,048,576 because 1M / 303k threads = 3.46 passes leaves the
+// last pass half empty; staging 3 KB per CTA from L2 is cheap.  B2E_LAKE_PERSISTENT=1 restores the capped grid.
 unsigned persistent_grid(int64_t n) {
+  static const bool capped = getenv("B2E_LAKE_PERSISTENT") != nullptr;
+  if (!capped) return grid_for(n);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;

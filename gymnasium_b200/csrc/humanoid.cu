@@ -919,7 +919,7 @@ int upload_model() {
 // ---- kernels -------------------------------------------------------------------------------------------------------------------
 struct HumanoidArgs {
   int64_t n, env_offset;
-  int32_t max_steps, mode, rng_mode, act_f64, frame_skip, terminate_when_unhealthy;
+  int32_t max_steps, mode, rng_mode, lanes, frame_skip, terminate_when_unhealthy;
   uint64_t philox_seed, call_counter;
   double noise, w_forward, w_ctrl, w_contact, contact_max, healthy_reward, z_min, z_max;
   double* __restrict__ qpos;   // [24][n]
@@ -1011,10 +1011,11 @@ __device__ void store_state(const HumanoidArgs& a, int64_t i, const HData& d) {
 }
 
 constexpr int kHumanoidBlock = 32;
+constexpr int kHumanoidLanes = 32;  // default envs per warp (b2e_humanoid_cfg.lanes_per_warp overrides)
 
 __global__ void __launch_bounds__(kHumanoidBlock) humanoid_reset_kernel(const HumanoidArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+  const int64_t i = sparse_env_index(a.lanes);
+  if (i < 0 || i >= a.n) return;
   if (a.mask != nullptr && a.mask[i] == 0) return;
   HData d;
   d.overflow = 0;
@@ -1030,8 +1031,8 @@ __global__ void __launch_bounds__(kHumanoidBlock) humanoid_reset_kernel(const Hu
 
 template <typename ActT>
 __global__ void __launch_bounds__(kHumanoidBlock) humanoid_step_kernel(const HumanoidArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+  const int64_t i = sparse_env_index(a.lanes);
+  if (i < 0 || i >= a.n) return;
   const HModel& m = g_hmodel;
   const int32_t c = a.ctrl[i];
   HData d;
@@ -1118,6 +1119,7 @@ int fill(const b2e_batch* b, const b2e_humanoid_cfg* cfg, const b2e_humanoid_sta
   a.n = b->n; a.env_offset = b->env_offset; a.max_steps = b->max_episode_steps; a.mode = b->autoreset_mode;
   a.rng_mode = b->rng_mode; a.philox_seed = b->philox_seed; a.call_counter = b->call_counter;
   a.frame_skip = cfg->frame_skip; a.terminate_when_unhealthy = cfg->terminate_when_unhealthy;
+  a.lanes = (cfg->lanes_per_warp >= 1 && cfg->lanes_per_warp <= 32) ? cfg->lanes_per_warp : kHumanoidLanes;
   a.noise = cfg->reset_noise_scale; a.w_forward = cfg->forward_reward_weight; a.w_ctrl = cfg->ctrl_cost_weight;
   a.w_contact = cfg->contact_cost_weight; a.contact_max = cfg->contact_cost_max; a.healthy_reward = cfg->healthy_reward;
   a.z_min = cfg->healthy_z_min; a.z_max = cfg->healthy_z_max;
@@ -1155,7 +1157,7 @@ extern "C" int b2e_humanoid_reset(const b2e_batch* b, const b2e_humanoid_cfg* cf
   }
   if (b->n == 0) return 0;
   a.mask = mask; a.obs = obs; a.info = info;
-  humanoid_reset_kernel<<<grid_for(b->n, kHumanoidBlock), kHumanoidBlock, 0, (cudaStream_t)stream>>>(a);
+  humanoid_reset_kernel<<<sparse_grid(b->n, a.lanes, kHumanoidBlock), kHumanoidBlock, 0, (cudaStream_t)stream>>>(a);
   return cuda_status(cudaGetLastError(), "b2e_humanoid_reset");
 }
 
@@ -1172,7 +1174,7 @@ extern "C" int b2e_humanoid_step(const b2e_batch* b, const b2e_humanoid_cfg* cfg
   if (b->n == 0) return 0;
   a.actions = actions; a.obs = obs; a.reward = reward; a.term = terminated; a.trunc = truncated; a.info = info;
   a.final_obs = final_obs;
-  const unsigned grid = grid_for(b->n, kHumanoidBlock);
+  const unsigned grid = sparse_grid(b->n, a.lanes, kHumanoidBlock);
   cudaStream_t s = (cudaStream_t)stream;
   switch (b->action_dtype) {
     case B2E_ACT_F32: humanoid_step_kernel<float><<<grid, kHumanoidBlock, 0, s>>>(a); break;

@@ -956,7 +956,7 @@ DI void world_step(Lander& L, float dt, float dt_ratio, float gravity, bool firs
 // ---- kernel arguments / global layout -------------------------------------------------------------------------------------
 struct LanderArgs {
   int64_t n, env_offset;
-  int32_t max_steps, mode, rng_mode;
+  int32_t max_steps, mode, rng_mode, lanes;
   uint64_t philox_seed, call_counter;
   float gravity;
   float* __restrict__ bodies;        // [21][n]
@@ -1237,11 +1237,12 @@ DI void write_obs(float* __restrict__ obs, int64_t i, const StepOut& o) {
   p[1] = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
 }
 
-constexpr int kLanderBlock = 64;  // N=16384 -> 256 CTAs: every SM gets work; the kernel is latency- not occupancy-bound
+constexpr int kLanderBlock = 64;  // small CTAs: every SM gets work; the kernel is latency- not occupancy-bound
+constexpr int kLanderLanes = 32;  // default envs per warp (b2e_lunarlander_cfg.lanes_per_warp overrides)
 
 __global__ void __launch_bounds__(kLanderBlock) lunarlander_reset_kernel(const LanderArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+  const int64_t i = sparse_env_index(a.lanes);
+  if (i < 0 || i >= a.n) return;
   if (a.mask != nullptr && a.mask[i] == 0) return;
   Lander L;
   L.overflow = 0;
@@ -1258,8 +1259,8 @@ __global__ void __launch_bounds__(kLanderBlock) lunarlander_reset_kernel(const L
 
 template <typename ActT>
 __global__ void __launch_bounds__(kLanderBlock) lunarlander_step_kernel(const LanderArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+  const int64_t i = sparse_env_index(a.lanes);
+  if (i < 0 || i >= a.n) return;
   const int32_t c = a.ctrl[i];
   int action = load_action<ActT>(a.actions, i);
   action = min(max(action, 0), 3);
@@ -1469,6 +1470,7 @@ int fill(const b2e_batch* b, const b2e_lunarlander_cfg* cfg, const b2e_lunarland
   a.philox_seed = b->philox_seed;
   a.call_counter = b->call_counter;
   a.gravity = (float)cfg->gravity;
+  a.lanes = (cfg->lanes_per_warp >= 1 && cfg->lanes_per_warp <= 32) ? cfg->lanes_per_warp : kLanderLanes;
   a.bodies = st->bodies;
   a.joints = st->joints;
   a.terrain = st->terrain;
@@ -1499,7 +1501,7 @@ extern "C" int b2e_lunarlander_reset(const b2e_batch* b, const b2e_lunarlander_c
   if (b->n == 0) return 0;
   a.mask = mask;
   a.obs = obs;
-  lunarlander_reset_kernel<<<grid_for(b->n, kLanderBlock), kLanderBlock, 0, (cudaStream_t)stream>>>(a);
+  lunarlander_reset_kernel<<<sparse_grid(b->n, a.lanes, kLanderBlock), kLanderBlock, 0, (cudaStream_t)stream>>>(a);
   return cuda_status(cudaGetLastError(), "b2e_lunarlander_reset");
 }
 
@@ -1520,7 +1522,7 @@ extern "C" int b2e_lunarlander_step(const b2e_batch* b, const b2e_lunarlander_cf
   a.term = terminated;
   a.trunc = truncated;
   a.final_obs = final_obs;
-  const unsigned grid = grid_for(b->n, kLanderBlock);
+  const unsigned grid = sparse_grid(b->n, a.lanes, kLanderBlock);
   cudaStream_t s = (cudaStream_t)stream;
   switch (b->action_dtype) {
     case B2E_ACT_I64: lunarlander_step_kernel<int64_t><<<grid, kLanderBlock, 0, s>>>(a); break;

@@ -154,6 +154,8 @@ typedef struct b2e_lunarlander_cfg {
   double gravity;        /* LunarLander(gravity=-10.0) */
   int32_t enable_wind;   /* must be 0 */
   int32_t continuous;    /* must be 0 */
+  int32_t lanes_per_warp; /* envs mapped to each warp (1..32); 0 = library default. Fewer lanes = less divergence */
+  int32_t _pad;
 } b2e_lunarlander_cfg;
 
 typedef struct b2e_lunarlander_state {
@@ -197,6 +199,8 @@ typedef struct b2e_humanoid_cfg {
   double healthy_z_min, healthy_z_max; /* (1.0, 2.0) */
   int32_t terminate_when_unhealthy;    /* 1 */
   int32_t frame_skip;                  /* 5 */
+  int32_t lanes_per_warp;              /* envs mapped to each warp (1..32); 0 = library default */
+  int32_t _pad;
 } b2e_humanoid_cfg;
 
 typedef struct b2e_humanoid_state {
