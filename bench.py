@@ -350,6 +350,11 @@ def run_b200(args):
     with torch.cuda.stream(side):  # warm every code path once before capture
         for k in range(ring):
             launch(k)
+        # physics families: bring every batch to its steady-state mix of flying / contact / resetting lanes first
+        # (a fresh Humanoid batch is in free fall for ~10 steps and would time 2.4x too fast); part of set-up, untimed
+        burn_in = {"LunarLander-v3": 120, "Humanoid-v5": 60}.get(args.env, 0)
+        for k in range(ring, ring * (1 + burn_in)):
+            launch(k)
     torch.cuda.synchronize()
     G = ring * T
     K, W = args.steps, args.warmup
@@ -461,6 +466,8 @@ def run_b200(args):
                               f"latency/FLOP-bound, not HBM-bound, so L2 residency does not affect the timing"),
                 "launch": "CUDA graphs of one step launch per batch, CUDA-event timing on the launch stream",
                 "counting": "calls x N (reset calls included); see value_excluding_reset_calls",
+                "steady_state": {"LunarLander-v3": "120 untimed burn-in steps per batch before warm-up",
+                                 "Humanoid-v5": "60 untimed burn-in steps per batch before warm-up"}.get(args.env),
             },
             "value_excluding_reset_calls": value * (1 - reset_frac), "reset_call_fraction": reset_frac,
             "gpu_launches": K,
