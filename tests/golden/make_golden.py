@@ -32,9 +32,14 @@ def rollout(envs, seed, actions, options=None, state_attr=None):
     states = []
     if state_attr:
         states.append(np.stack([np.asarray(s, dtype=np.float64) for s in envs.get_attr(state_attr)]))
+    disabled = envs.metadata.get("autoreset_mode") == AutoresetMode.DISABLED
     for t in range(T):
         o, r, te, tr, info = envs.step(actions[t])
         obs[t + 1], rew[t], term[t], trunc[t] = o, r, te, tr
+        if disabled and (te | tr).any():  # the caller resets finished sub-envs itself (test_autoreset_mode.py:105-260)
+            o2, _ = envs.reset(options={"reset_mask": te | tr})
+            extras.setdefault("reset_obs", np.zeros((T,) + o2.shape, dtype=np.float64))
+            extras["reset_obs"][t] = o2
         for k, v in info.items():
             if k in ("final_obs", "_final_obs", "final_info", "_final_info"):
                 continue
@@ -42,7 +47,7 @@ def rollout(envs, seed, actions, options=None, state_attr=None):
             extras[k][t] = v
         if state_attr:
             states.append(np.stack([np.asarray(s, dtype=np.float64) for s in envs.get_attr(state_attr)]))
-    out = dict(obs=obs, reward=rew, terminated=term, truncated=trunc, actions=actions, seed=np.int64(seed))
+    out = dict(obs=obs, reward=rew, terminated=term, truncated=trunc, actions=actions, seed=np.uint64(seed))
     for k, v in extras.items():
         out["info_" + k] = v
     if state_attr:
@@ -65,7 +70,9 @@ def cartpole(name, n, T, seed, max_episode_steps=None, policy="random", options=
         for t in range(T):
             a = actions[t]
             a[n // 2:] = (o[n // 2:, 2] + 0.5 * o[n // 2:, 3] > 0).astype(np.int64)
-            o, *_ = e2.step(a)
+            o, _, te_, tr_, _ = e2.step(a)
+            if mode == AutoresetMode.DISABLED and (te_ | tr_).any():
+                o, _ = e2.reset(options={"reset_mask": te_ | tr_})
         e2.close()
     out = rollout(envs, seed, actions, options=options, state_attr="state")
     out["max_episode_steps"] = np.int64(max_episode_steps or 500)
@@ -102,3 +109,12 @@ if __name__ == "__main__":
     frozenlake("frozenlake8x8_n8_s9_noslip.npz", 8, 150, 9, map_name="8x8", is_slippery=False)
     frozenlake("frozenlake8x8_n8_s21_limit25.npz", 8, 200, 21, map_name="8x8", max_episode_steps=25)
     frozenlake("frozenlake8x8_n6_s4_samestep.npz", 6, 300, 4, map_name="8x8", mode=AutoresetMode.SAME_STEP)
+    # round-1 additions: DISABLED mode with caller-driven partial resets, odd batch sizes, custom map / probabilities /
+    # reward schedule, a two-start-tile map (non-trivial initial-state distribution), near-2^64 seeds
+    cartpole("cartpole_n5_s9_disabled.npz", 5, 160, 9, max_episode_steps=30, policy="balance", mode=AutoresetMode.DISABLED)
+    cartpole("cartpole_n1_s77.npz", 1, 120, 77)
+    cartpole("cartpole_n33_s3_limit20.npz", 33, 90, 3, max_episode_steps=20)
+    cartpole("cartpole_n2_s2p64m9.npz", 2, 40, 2**64 - 9)
+    frozenlake("frozenlake8x8_n7_s6_disabled.npz", 7, 260, 6, map_name="8x8", mode=AutoresetMode.DISABLED)
+    frozenlake("frozenlakecustom_n9_s8_p80.npz", 9, 220, 8, desc=["SFFHF", "FHFFF", "FFSFH", "HFFFG"], map_name=None,
+               success_rate=0.8, reward_schedule=(10, -5, -1), max_episode_steps=40)

@@ -7,7 +7,8 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import fixture_kwargs, fixture_options, golden, golden_files, have_cuda
+from conftest import (check_reset_obs, fixture_kwargs, fixture_options, golden, golden_files, have_cuda,
+                      replay_fixture)
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="needs a CUDA device")]
 
@@ -93,7 +94,8 @@ def test_cartpole_matches_reference_golden(name):
     g = golden(name)
     n = g["actions"].shape[1]
     env = make("CartPole-v1", n, max_episode_steps=int(g["max_episode_steps"]), **fixture_kwargs(name))
-    out = replay(env, int(g["seed"]), g["actions"], fixture_options(name))
+    out = replay_fixture(env, g, fixture_options(name), disabled="disabled" in name)
+    check_reset_obs(out, g)  # reset draws are exact fp64 RNG math
     np.testing.assert_array_equal(out["obs"][0], g["obs"][0])  # reset draws: exact fp64 RNG math
     np.testing.assert_array_equal(out["terminated"], g["terminated"])
     np.testing.assert_array_equal(out["truncated"], g["truncated"])
@@ -200,7 +202,8 @@ def test_frozenlake_matches_reference_golden_bit_exact(name):
     g = golden(name)
     n = g["actions"].shape[1]
     env = make("FrozenLake-v1", n, max_episode_steps=int(g["max_episode_steps"]), **fixture_kwargs(name))
-    out = replay(env, int(g["seed"]), g["actions"])
+    out = replay_fixture(env, g, disabled="disabled" in name)
+    check_reset_obs(out, g)
     assert out["obs"].dtype == np.int64
     np.testing.assert_array_equal(out["obs"], g["obs"])
     np.testing.assert_array_equal(out["reward"], g["reward"])

@@ -4,7 +4,7 @@
 import numpy as np
 import pytest
 
-from conftest import fixture_kwargs, fixture_options, golden, golden_files
+from conftest import check_reset_obs, fixture_kwargs, fixture_options, golden, golden_files, replay_fixture
 from oracle.cartpole import OracleCartPole
 from oracle.frozenlake import OracleFrozenLake, build_table
 
@@ -24,7 +24,8 @@ def test_cartpole_oracle_matches_reference(name):
     g = golden(name)
     n = g["actions"].shape[1]
     env = OracleCartPole(n, max_episode_steps=int(g["max_episode_steps"]), **fixture_kwargs(name))
-    out = replay(env, g, fixture_options(name))
+    out = replay_fixture(env, g, fixture_options(name), disabled="disabled" in name)
+    check_reset_obs(out, g)
     # bit-exact: same numpy ufuncs, same op order
     np.testing.assert_array_equal(out["obs"], g["obs"])
     np.testing.assert_array_equal(out["reward"], g["reward"])
@@ -37,7 +38,8 @@ def test_frozenlake_oracle_matches_reference(name):
     g = golden(name)
     n = g["actions"].shape[1]
     env = OracleFrozenLake(n, max_episode_steps=int(g["max_episode_steps"]), **fixture_kwargs(name))
-    out = replay(env, g)
+    out = replay_fixture(env, g, disabled="disabled" in name)
+    check_reset_obs(out, g)
     np.testing.assert_array_equal(out["obs"], g["obs"])
     assert out["obs"].dtype == np.int64
     np.testing.assert_array_equal(out["reward"], g["reward"])
