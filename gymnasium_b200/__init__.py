@@ -9,13 +9,15 @@ from .vector_env import B200VectorEnv
 
 __version__ = "0.1.0"
 __all__ = ["AutoresetMode", "B200VectorEnv", "HAVE_GYMNASIUM", "install", "make_vec", "register_envs", "uninstall",
-           "CartPoleVectorEnv", "FrozenLakeVectorEnv", "HumanoidVectorEnv", "LunarLanderVectorEnv"]
+           "CartPoleVectorEnv", "CliffWalkingVectorEnv", "FrozenLakeVectorEnv", "HumanoidVectorEnv", "LunarLanderVectorEnv",
+           "TaxiVectorEnv"]
 
 register_envs()
 
 
 def __getattr__(name):
-    if name in ("CartPoleVectorEnv", "FrozenLakeVectorEnv", "HumanoidVectorEnv", "LunarLanderVectorEnv"):
+    if name in ("CartPoleVectorEnv", "CliffWalkingVectorEnv", "FrozenLakeVectorEnv", "HumanoidVectorEnv",
+                "LunarLanderVectorEnv", "TaxiVectorEnv"):
         from . import envs
 
         return getattr(envs, name)

@@ -86,33 +86,25 @@ def pack_transition_table(desc, is_slippery: bool, success_rate: float, reward_s
     return table.reshape(-1), cum3, p3, np.cumsum(isd), nS, (nrow, ncol)
 
 
-class FrozenLakeVectorEnv(B200VectorEnv):
-    """N FrozenLake-v1 envs.  Observation ``(N,) int64``, action ``(N,) int64`` in {0..3}, reward float64, and
-    ``info = {"prob": float64 (N,), "_prob": bool (N,)}`` as ``SyncVectorEnv`` batches it."""
+class TabularVectorEnv(B200VectorEnv):
+    """N copies of a tabular MDP ``P[s][a] = [(p, s', r, done), ...]`` with 1 or 3 outcomes per (s, a) -- the structure
+    every ``gymnasium/envs/toy_text`` grid world has -- stepped by ``csrc/frozenlake.cu``.  Observation ``(N,) int64``,
+    reward float64, ``info = {"prob": float64 (N,), "_prob": bool (N,)}`` as ``SyncVectorEnv`` batches it."""
 
     metadata = {"render_modes": [], "render_fps": 4, "autoreset_mode": AutoresetMode.NEXT_STEP}
 
-    def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 100, desc=None, map_name: str | None = "4x4",
-                 is_slippery: bool = True, success_rate: float = 1.0 / 3.0, reward_schedule=(1, 0, 0),
-                 render_mode: str | None = None, **engine_kwargs):
-        if desc is None and map_name is None:
-            raise NotImplementedError("random maps (desc=None, map_name=None) are not supported; pass desc=")
-        if desc is None:
-            desc = MAPS[map_name]
-        table, cum3, p3, isd_cum, nS, shape = pack_transition_table(desc, is_slippery, success_rate, reward_schedule)
-        super().__init__(num_envs, Discrete(nS), Discrete(4), max_episode_steps=max_episode_steps,
-                         render_mode=render_mode, **engine_kwargs)
-        self.desc = np.asarray([list(r) for r in desc], dtype="c")
-        self.nrow, self.ncol = shape
+    def __init__(self, num_envs, n_states, n_actions, table, cum3, p3, isd_cum, rewards, *, max_episode_steps,
+                 render_mode=None, **engine_kwargs):
+        super().__init__(num_envs, Discrete(int(n_states)), Discrete(int(n_actions)),
+                         max_episode_steps=max_episode_steps, render_mode=render_mode, **engine_kwargs)
         dev = self.device
-        self._table = torch.from_numpy(table.view(np.int32)).to(dev)
-        self._isd_cum = torch.from_numpy(isd_cum).to(dev)
-        # reward classes G, H, F from the schedule, class 3 = the literal 0 of terminal self-loops
-        self._cfg = _lib.FrozenLakeCfg(n_states=nS, n_actions=4, table=self._table.data_ptr(),
+        self._table = torch.from_numpy(np.ascontiguousarray(table, dtype=np.uint32).view(np.int32)).to(dev)
+        self._isd_cum = torch.from_numpy(np.ascontiguousarray(isd_cum, dtype=np.float64)).to(dev)
+        self._cfg = _lib.FrozenLakeCfg(n_states=int(n_states), n_actions=int(n_actions), table=self._table.data_ptr(),
                                        isd_cum=self._isd_cum.data_ptr())
         for k in range(3):
             self._cfg.cum3[k], self._cfg.p3[k] = float(cum3[k]), float(p3[k])
-            self._cfg.rewards[k] = float(reward_schedule[k])
+            self._cfg.rewards[k] = float(rewards[k])
         self._pstate = torch.zeros(self.num_envs, dtype=torch.int32, device=dev)
 
     def _alloc_outputs(self):
@@ -211,3 +203,21 @@ class FrozenLakeVectorEnv(B200VectorEnv):
             )
             self._batch.call_counter += K
         return out
+
+
+class FrozenLakeVectorEnv(TabularVectorEnv):
+    """N FrozenLake-v1 envs.  Observation ``(N,) int64``, action ``(N,) int64`` in {0..3}, reward float64, and
+    ``info = {"prob": float64 (N,), "_prob": bool (N,)}`` as ``SyncVectorEnv`` batches it."""
+
+    def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 100, desc=None, map_name: str | None = "4x4",
+                 is_slippery: bool = True, success_rate: float = 1.0 / 3.0, reward_schedule=(1, 0, 0),
+                 render_mode: str | None = None, **engine_kwargs):
+        if desc is None and map_name is None:
+            raise NotImplementedError("random maps (desc=None, map_name=None) are not supported; pass desc=")
+        if desc is None:
+            desc = MAPS[map_name]
+        table, cum3, p3, isd_cum, nS, shape = pack_transition_table(desc, is_slippery, success_rate, reward_schedule)
+        super().__init__(num_envs, nS, 4, table, cum3, p3, isd_cum, reward_schedule,
+                         max_episode_steps=max_episode_steps, render_mode=render_mode, **engine_kwargs)
+        self.desc = np.asarray([list(r) for r in desc], dtype="c")
+        self.nrow, self.ncol = shape

@@ -24,6 +24,11 @@ ENVS = {
                       "gymnasium.envs.toy_text.frozen_lake:FrozenLakeEnv", 100, 0.70, {"map_name": "4x4"}),
     "FrozenLake8x8-v1": ("gymnasium_b200.envs.frozen_lake:FrozenLakeVectorEnv",
                          "gymnasium.envs.toy_text.frozen_lake:FrozenLakeEnv", 200, 0.85, {"map_name": "8x8"}),
+    "CliffWalking-v1": ("gymnasium_b200.envs.toy_text:CliffWalkingVectorEnv",
+                        "gymnasium.envs.toy_text.cliffwalking:CliffWalkingEnv", None, None, {}),
+    "CliffWalkingSlippery-v1": ("gymnasium_b200.envs.toy_text:CliffWalkingVectorEnv",
+                                "gymnasium.envs.toy_text.cliffwalking:CliffWalkingEnv", None, None, {"is_slippery": True}),
+    "Taxi-v4": ("gymnasium_b200.envs.toy_text:TaxiVectorEnv", "gymnasium.envs.toy_text.taxi:TaxiEnv", 200, 8, {}),
     "LunarLander-v3": ("gymnasium_b200.envs.lunar_lander:LunarLanderVectorEnv",
                        "gymnasium.envs.box2d.lunar_lander:LunarLander", 1000, 200, {}),
     "Humanoid-v5": ("gymnasium_b200.envs.humanoid:HumanoidVectorEnv",

@@ -95,6 +95,19 @@ def frozenlake(name, n, T, seed, mode=AutoresetMode.NEXT_STEP, **kw):
           out["truncated"].sum(), "reward", out["reward"].sum())
 
 
+def tabular(name, env_id, n, T, seed, nA, **kw):
+    envs = gym.make_vec(env_id, num_envs=n, vectorization_mode="sync", **kw)
+    rng = np.random.default_rng(3000 + seed)
+    actions = rng.integers(0, nA, size=(T, n)).astype(np.int64)
+    out = rollout(envs, seed, actions)
+    mes = envs.envs[0].spec.max_episode_steps
+    out["max_episode_steps"] = np.int64(kw.get("max_episode_steps", mes if mes is not None else 0))
+    envs.close()
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")}, "term", out["terminated"].sum(), "trunc",
+          out["truncated"].sum(), "reward", out["reward"].sum())
+
+
 if __name__ == "__main__":
     assert "reference" in gym.__file__ or "_ref" in gym.__file__, gym.__file__
     print("reference:", gym.__version__, gym.__file__, "numpy", np.__version__)
@@ -116,5 +129,10 @@ if __name__ == "__main__":
     cartpole("cartpole_n33_s3_limit20.npz", 33, 90, 3, max_episode_steps=20)
     cartpole("cartpole_n2_s2p64m9.npz", 2, 40, 2**64 - 9)
     frozenlake("frozenlake8x8_n7_s6_disabled.npz", 7, 260, 6, map_name="8x8", mode=AutoresetMode.DISABLED)
+    tabular("cliffwalking_n8_s1_T400.npz", "CliffWalking-v1", 8, 400, 1, 4)
+    tabular("cliffwalking_n8_s2_limit50.npz", "CliffWalking-v1", 8, 300, 2, 4, max_episode_steps=50)
+    tabular("cliffwalkingslippery_n8_s3_T400.npz", "CliffWalkingSlippery-v1", 8, 400, 3, 4)
+    tabular("taxi_n12_s4_T500.npz", "Taxi-v4", 12, 500, 4, 6)
+    tabular("taxi_n6_s5_limit30.npz", "Taxi-v4", 6, 200, 5, 6, max_episode_steps=30)
     frozenlake("frozenlakecustom_n9_s8_p80.npz", 9, 220, 8, desc=["SFFHF", "FHFFF", "FFSFH", "HFFFG"], map_name=None,
                success_rate=0.8, reward_schedule=(10, -5, -1), max_episode_steps=40)

@@ -469,3 +469,27 @@ def test_humanoid_reference_structural_pins_on_gpu():
     t = make("Humanoid-v5", 2, output="torch")
     o, _ = t.reset(seed=1)
     assert o.dtype == torch.float64 and o.shape == (2, 348)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CliffWalking-v1 / Taxi-v4 through the generic tabular kernel (pinned to the live reference)
+@pytest.mark.parametrize("name", golden_files("cliffwalking") + golden_files("taxi"))
+def test_toy_text_matches_reference_golden_bit_exact(name):
+    g = golden(name)
+    n = g["actions"].shape[1]
+    mes = int(g["max_episode_steps"]) or None
+    if name.startswith("taxi"):
+        env = make("Taxi-v4", n, max_episode_steps=mes)
+    else:
+        env = make("CliffWalkingSlippery-v1" if "slippery" in name else "CliffWalking-v1", n, max_episode_steps=mes)
+    out = replay_fixture(env, g)
+    np.testing.assert_array_equal(out["obs"], g["obs"])
+    np.testing.assert_array_equal(out["reward"], g["reward"])
+    np.testing.assert_array_equal(out["terminated"], g["terminated"])
+    np.testing.assert_array_equal(out["truncated"], g["truncated"])
+    for t, info in enumerate(out["info"][1:]):
+        ref = g["info_prob"][t]
+        assert ((ref == info["prob"]) | (ref == np.floor(info["prob"]))).all()
+        if name.startswith("taxi"):
+            np.testing.assert_array_equal(info["action_mask"], g["info_action_mask"][t])
+            assert info["action_mask"].dtype == np.int8

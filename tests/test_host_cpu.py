@@ -113,3 +113,32 @@ def test_humanoid_compiled_model_matches_oracle_compile():
     known = [0, 8.90746237, 2.26194671, 6.61619413, 4.75175093, 2.75569617, 1.76714587, 4.75175093, 2.75569617,
              1.76714587, 1.66108048, 1.22954019, 1.66108048, 1.22954019]  # mjModel.body_mass of the stock humanoid.xml
     np.testing.assert_allclose(mass, known, rtol=2e-8)
+
+
+def test_packed_cliffwalking_and_taxi_tables_equal_reference_P():
+    from gymnasium_b200.envs.toy_text import pack_cliffwalking, pack_taxi
+    from oracle.toy_text import build_cliff, build_taxi, taxi_action_mask
+
+    def check(table, cum3, p3, isd_cum, nS, nA, rewards, P, isd):
+        table = table.reshape(nS, nA, 3)
+        np.testing.assert_array_equal(np.cumsum(isd), isd_cum)
+        for s in range(nS):
+            for a in range(nA):
+                tr = P[s][a]
+                assert int(table[s, a, 0] >> 20) == len(tr)
+                for k, (p, s2, r, d) in enumerate(tr):
+                    e = int(table[s, a, k])
+                    assert (e & 0xFFFF) == s2 and bool((e >> 16) & 1) == d and rewards[(e >> 17) & 3] == r
+                    assert (p3[k] if len(tr) == 3 else 1.0) == p
+                if len(tr) == 3:
+                    assert list(cum3) == list(np.cumsum([t[0] for t in tr]))
+
+    for slip in (False, True):
+        t, c3, p3, ic, nS, nA, rw = pack_cliffwalking(slip)
+        P, isd = build_cliff(slip)
+        check(t, c3, p3, ic, nS, nA, rw, P, isd)
+    t, c3, p3, ic, nS, nA, rw, mask = pack_taxi()
+    P, isd = build_taxi()
+    check(t, c3, p3, ic, nS, nA, rw, P, isd)
+    for s in range(500):
+        np.testing.assert_array_equal(mask[s], taxi_action_mask(s))

@@ -96,3 +96,19 @@ def test_reset_mask_errors():
         env.reset(options={"reset_mask": np.zeros(3, dtype=bool)})
     with pytest.raises(ValueError):
         env.reset(seed=[1, 2])
+
+
+@pytest.mark.parametrize("name", golden_files("cliffwalking") + golden_files("taxi"))
+def test_toy_text_oracles_match_reference(name):
+    from oracle.toy_text import OracleCliffWalking, OracleTaxi
+
+    g = golden(name)
+    n = g["actions"].shape[1]
+    mes = int(g["max_episode_steps"]) or None
+    env = OracleTaxi(n, max_episode_steps=mes) if name.startswith("taxi") else OracleCliffWalking(
+        n, is_slippery="slippery" in name, max_episode_steps=mes)
+    out = replay_fixture(env, g)
+    np.testing.assert_array_equal(out["obs"], g["obs"])
+    np.testing.assert_array_equal(out["reward"], g["reward"])
+    np.testing.assert_array_equal(out["terminated"], g["terminated"])
+    np.testing.assert_array_equal(out["truncated"], g["truncated"])
