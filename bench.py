@@ -404,6 +404,14 @@ def run_b200(args):
                                       output="numpy" if world == 1 else "torch", **kw)
     e2e_env.reset(seed=0)
     host_actions = host_action_pool(np, args.env, 16, n, rank)
+    if burn_in:  # same steady-state mix as the device-resident batches (untimed set-up)
+        dev_pool = device_actions(torch, args.env, (4,), n, dev, gen)
+        keep = e2e_env.output
+        e2e_env.output = "torch"
+        for k in range(burn_in):
+            e2e_env.step(dev_pool[k % 4])
+        e2e_env.output = keep
+        torch.cuda.synchronize()
     pinned = {}
     gathered = {}
 

@@ -10,14 +10,16 @@ from .vector_env import B200VectorEnv
 __version__ = "0.1.0"
 __all__ = ["AutoresetMode", "B200VectorEnv", "HAVE_GYMNASIUM", "install", "make_vec", "register_envs", "uninstall",
            "CartPoleVectorEnv", "CliffWalkingVectorEnv", "FrozenLakeVectorEnv", "HumanoidVectorEnv", "LunarLanderVectorEnv",
-           "TaxiVectorEnv"]
+           "TaxiVectorEnv", "AcrobotVectorEnv", "MountainCarVectorEnv", "MountainCarContinuousVectorEnv",
+           "PendulumVectorEnv"]
 
 register_envs()
 
 
 def __getattr__(name):
     if name in ("CartPoleVectorEnv", "CliffWalkingVectorEnv", "FrozenLakeVectorEnv", "HumanoidVectorEnv",
-                "LunarLanderVectorEnv", "TaxiVectorEnv"):
+                "LunarLanderVectorEnv", "TaxiVectorEnv", "AcrobotVectorEnv", "MountainCarVectorEnv",
+                "MountainCarContinuousVectorEnv", "PendulumVectorEnv"):
         from . import envs
 
         return getattr(envs, name)

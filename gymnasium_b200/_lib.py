@@ -54,6 +54,13 @@ class FrozenLakeCfg(C.Structure):
     ]
 
 
+class ClassicCfg(C.Structure):
+    """``b2e_classic_cfg``."""
+
+    _fields_ = [("family", c_i32), ("_pad", c_i32), ("p", c_double * 4), ("state", c_void_p), ("sflag", c_void_p),
+                ("ctrl", c_void_p), ("rng", c_void_p)]
+
+
 class LunarLanderCfg(C.Structure):
     """``b2e_lunarlander_cfg``."""
 
@@ -98,6 +105,8 @@ SIGNATURES = {
     "b2e_cartpole_step": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P, P, P, P, P]),
     "b2e_cartpole_rollout": (C.c_int, [_BP, C.POINTER(CartPoleCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),
     "b2e_selftest_math": (C.c_int, [c_i64, c_u64, P, P]),
+    "b2e_classic_reset": (C.c_int, [_BP, C.POINTER(ClassicCfg), P, P, P]),
+    "b2e_classic_step": (C.c_int, [_BP, C.POINTER(ClassicCfg), P, P, P, P, P, P, P]),
     "b2e_lunarlander_state_words": (C.c_int, []),
     "b2e_lunarlander_reset": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P]),
     "b2e_lunarlander_step": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P, P, P, P,

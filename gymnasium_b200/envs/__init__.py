@@ -1,8 +1,11 @@
 from .cartpole import CartPoleVectorEnv
+from .classic_control import (AcrobotVectorEnv, MountainCarContinuousVectorEnv, MountainCarVectorEnv,
+                              PendulumVectorEnv)
 from .frozen_lake import FrozenLakeVectorEnv, TabularVectorEnv
 from .humanoid import HumanoidVectorEnv
 from .lunar_lander import LunarLanderVectorEnv
 from .toy_text import CliffWalkingVectorEnv, TaxiVectorEnv
 
-__all__ = ["CartPoleVectorEnv", "CliffWalkingVectorEnv", "FrozenLakeVectorEnv", "HumanoidVectorEnv",
-           "LunarLanderVectorEnv", "TabularVectorEnv", "TaxiVectorEnv"]
+__all__ = ["AcrobotVectorEnv", "CartPoleVectorEnv", "CliffWalkingVectorEnv", "FrozenLakeVectorEnv", "HumanoidVectorEnv",
+           "LunarLanderVectorEnv", "MountainCarContinuousVectorEnv", "MountainCarVectorEnv", "PendulumVectorEnv",
+           "TabularVectorEnv", "TaxiVectorEnv"]

@@ -24,6 +24,15 @@ ENVS = {
                       "gymnasium.envs.toy_text.frozen_lake:FrozenLakeEnv", 100, 0.70, {"map_name": "4x4"}),
     "FrozenLake8x8-v1": ("gymnasium_b200.envs.frozen_lake:FrozenLakeVectorEnv",
                          "gymnasium.envs.toy_text.frozen_lake:FrozenLakeEnv", 200, 0.85, {"map_name": "8x8"}),
+    "MountainCar-v0": ("gymnasium_b200.envs.classic_control:MountainCarVectorEnv",
+                       "gymnasium.envs.classic_control.mountain_car:MountainCarEnv", 200, -110.0, {}),
+    "MountainCarContinuous-v0": ("gymnasium_b200.envs.classic_control:MountainCarContinuousVectorEnv",
+                                 "gymnasium.envs.classic_control.continuous_mountain_car:Continuous_MountainCarEnv",
+                                 999, 90.0, {}),
+    "Pendulum-v1": ("gymnasium_b200.envs.classic_control:PendulumVectorEnv",
+                    "gymnasium.envs.classic_control.pendulum:PendulumEnv", 200, None, {}),
+    "Acrobot-v1": ("gymnasium_b200.envs.classic_control:AcrobotVectorEnv",
+                   "gymnasium.envs.classic_control.acrobot:AcrobotEnv", 500, -100.0, {}),
     "CliffWalking-v1": ("gymnasium_b200.envs.toy_text:CliffWalkingVectorEnv",
                         "gymnasium.envs.toy_text.cliffwalking:CliffWalkingEnv", None, None, {}),
     "CliffWalkingSlippery-v1": ("gymnasium_b200.envs.toy_text:CliffWalkingVectorEnv",

@@ -139,6 +139,32 @@ int b2e_frozenlake_rollout(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, in
                            uint8_t* actions_out, int32_t* pstate, int32_t* ctrl, uint64_t* rng, int64_t* obs,
                            float* reward, uint8_t* terminated, uint8_t* truncated, void* stream);
 
+/* ---- remaining classic-control families (gymnasium/envs/classic_control/{mountain_car,continuous_mountain_car,
+ * pendulum,acrobot}.py): one generic entry point pair, `family` selects the dynamics.
+ *   state float64 [k][n] (k = 2, 2, 2, 4); sflag uint8 [n] (MountainCarContinuous only); ctrl / rng as for CartPole
+ *   p[4]: MountainCar(-Continuous): reset low, reset high, goal_velocity; Pendulum: x_init, y_init, g;
+ *         Acrobot: reset low, reset high
+ *   actions: int64/int32/uint8 [n] (MountainCar, Acrobot) or float32 [n][1] (MountainCarContinuous, Pendulum)
+ *   obs float32 [n][2|2|3|6]; reward float64 [n]; flags uint8 [n]
+ */
+#define B2E_CLASSIC_MOUNTAINCAR 0
+#define B2E_CLASSIC_MOUNTAINCAR_CONTINUOUS 1
+#define B2E_CLASSIC_PENDULUM 2
+#define B2E_CLASSIC_ACROBOT 3
+typedef struct b2e_classic_cfg {
+  int32_t family;
+  int32_t _pad;
+  double p[4];
+  double* state;
+  uint8_t* sflag;
+  int32_t* ctrl;
+  uint64_t* rng;
+} b2e_classic_cfg;
+
+int b2e_classic_reset(const b2e_batch* b, const b2e_classic_cfg* cfg, const uint8_t* mask, float* obs, void* stream);
+int b2e_classic_step(const b2e_batch* b, const b2e_classic_cfg* cfg, const void* actions, float* obs, double* reward,
+                     uint8_t* terminated, uint8_t* truncated, float* final_obs, void* stream);
+
 /* ---- LunarLander-v3: gymnasium/envs/box2d/lunar_lander.py:321-665 (+ the Box2D 2.3.x subset world.Step needs) -------
  * Discrete actions (0 nop, 1 left, 2 main, 3 right), no wind.  Per-env state, struct-of-arrays over n envs (device):
  *   bodies  : float32 [21][n]  for b in (lander, legs[0], legs[1]): c.x, c.y, angle, v.x, v.y, w, sleepTime

@@ -95,6 +95,29 @@ def frozenlake(name, n, T, seed, mode=AutoresetMode.NEXT_STEP, **kw):
           out["truncated"].sum(), "reward", out["reward"].sum())
 
 
+def classic(name, env_id, n, T, seed, options=None, act_scale=None, nA=None, state_attr="state", policy=None, **kw):
+    envs = gym.make_vec(env_id, num_envs=n, vectorization_mode="sync", **kw)
+    rng = np.random.default_rng(4000 + seed)
+    if nA:
+        actions = rng.integers(0, nA, size=(T, n)).astype(np.int64)
+    else:  # a few out-of-bound torques/forces exercise the clip paths
+        actions = (rng.uniform(-1.15, 1.15, size=(T, n, 1)) * act_scale).astype(np.float32)
+    if policy is not None:  # closed-loop tape on the second half of the lanes so that episodes actually terminate
+        e2 = gym.make_vec(env_id, num_envs=n, vectorization_mode="sync", **kw)
+        o, _ = e2.reset(seed=seed, options=options)
+        for t in range(T):
+            a = actions[t]
+            a[n // 2:] = policy(o[n // 2:]).astype(a.dtype).reshape(a[n // 2:].shape)
+            o, *_ = e2.step(a)
+        e2.close()
+    out = rollout(envs, seed, actions, options=options, state_attr=state_attr)
+    out["max_episode_steps"] = np.int64(kw.get("max_episode_steps", envs.envs[0].spec.max_episode_steps))
+    envs.close()
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")}, "term", out["terminated"].sum(), "trunc",
+          out["truncated"].sum(), "reward %.3f" % out["reward"].sum())
+
+
 def tabular(name, env_id, n, T, seed, nA, **kw):
     envs = gym.make_vec(env_id, num_envs=n, vectorization_mode="sync", **kw)
     rng = np.random.default_rng(3000 + seed)
@@ -134,5 +157,15 @@ if __name__ == "__main__":
     tabular("cliffwalkingslippery_n8_s3_T400.npz", "CliffWalkingSlippery-v1", 8, 400, 3, 4)
     tabular("taxi_n12_s4_T500.npz", "Taxi-v4", 12, 500, 4, 6)
     tabular("taxi_n6_s5_limit30.npz", "Taxi-v4", 6, 200, 5, 6, max_episode_steps=30)
+    classic("mountaincar_n8_s1_T500.npz", "MountainCar-v0", 8, 500, 1, nA=3, policy=lambda o: np.where(o[:, 1] > 0, 2, 0))
+    classic("mountaincar_n4_s2_bounds.npz", "MountainCar-v0", 4, 120, 2, nA=3, options={"low": -0.7, "high": -0.3},
+            max_episode_steps=40)
+    classic("mountaincarcontinuous_n8_s3_T400.npz", "MountainCarContinuous-v0", 8, 400, 3, act_scale=1.0,
+            max_episode_steps=150, policy=lambda o: np.where(o[:, 1] > 0, 1.0, -1.0))
+    classic("pendulum_n8_s4_T450.npz", "Pendulum-v1", 8, 450, 4, act_scale=2.0)
+    classic("pendulum_n4_s5_init.npz", "Pendulum-v1", 4, 90, 5, act_scale=2.0, options={"x_init": 1.0, "y_init": 0.5},
+            max_episode_steps=30)
+    classic("acrobot_n8_s6_T600.npz", "Acrobot-v1", 8, 600, 6, nA=3, policy=lambda o: np.where(o[:, 5] > 0, 2, 0))
+    classic("acrobot_n4_s7_limit50.npz", "Acrobot-v1", 4, 200, 7, nA=3, max_episode_steps=50)
     frozenlake("frozenlakecustom_n9_s8_p80.npz", 9, 220, 8, desc=["SFFHF", "FHFFF", "FFSFH", "HFFFG"], map_name=None,
                success_rate=0.8, reward_schedule=(10, -5, -1), max_episode_steps=40)

@@ -493,3 +493,28 @@ def test_toy_text_matches_reference_golden_bit_exact(name):
         if name.startswith("taxi"):
             np.testing.assert_array_equal(info["action_mask"], g["info_action_mask"][t])
             assert info["action_mask"].dtype == np.int8
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MountainCar-v0 / MountainCarContinuous-v0 / Pendulum-v1 / Acrobot-v1 (csrc/classic.cu), pinned to the live reference
+CLASSIC = {"mountaincar_": "MountainCar-v0", "mountaincarcontinuous_": "MountainCarContinuous-v0",
+           "pendulum_": "Pendulum-v1", "acrobot_": "Acrobot-v1"}
+
+
+@pytest.mark.parametrize("name", sum((golden_files(p) for p in CLASSIC), []))
+def test_classic_control_matches_reference_golden(name):
+    g = golden(name)
+    env_id = next(v for k, v in CLASSIC.items() if name.startswith(k))
+    n = g["actions"].shape[1]
+    options = {"low": -0.7, "high": -0.3} if "bounds" in name else {"x_init": 1.0, "y_init": 0.5} if "init" in name else None
+    env = make(env_id, n, max_episode_steps=int(g["max_episode_steps"]))
+    out = replay_fixture(env, g, options)
+    np.testing.assert_array_equal(out["terminated"], g["terminated"])
+    np.testing.assert_array_equal(out["truncated"], g["truncated"])
+    assert out["obs"].dtype == np.float32 and out["reward"].dtype == np.float64
+    np.testing.assert_allclose(out["obs"], g["obs"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out["reward"], g["reward"], rtol=RTOL, atol=ATOL)
+    # the reset observation comes from exact fp64 RNG math (cos/sin of it for Pendulum/Acrobot: within float32 rounding)
+    np.testing.assert_allclose(out["obs"][0], g["obs"][0], rtol=0, atol=1e-7)
+    worst = float(np.max(np.abs(out["obs"].astype(np.float64) - g["obs"])))
+    assert worst < 2e-6, worst
