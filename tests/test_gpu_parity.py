@@ -532,5 +532,6 @@ def test_classic_control_matches_reference_golden(name):
         np.testing.assert_array_equal(tr, g["truncated"][t])
         worst_obs = max(worst_obs, float(np.max(np.abs(o.astype(np.float64) - g["obs"][t + 1]))))
         worst_state = max(worst_state, float(np.max(np.abs(env.state.cpu().numpy() - g["state"][t + 1]))))
-        np.testing.assert_allclose(r, g["reward"][t], rtol=1e-12, atol=1e-12)
+        # 1e-9: the reference squares float32 torques with powf (pendulum.py:137), which is not always u*u to the last ulp
+        np.testing.assert_allclose(r, g["reward"][t], rtol=1e-9, atol=1e-9)
     assert worst_obs < 5e-7 and worst_state < 1e-12, (worst_obs, worst_state)
