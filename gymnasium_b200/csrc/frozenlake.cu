@@ -43,9 +43,13 @@ struct LakeArgs {
 
 // categorical_sample over the initial-state distribution: first index with cumsum > u, argmax-of-all-False = 0
 __device__ __forceinline__ int sample_initial_state(const LakeArgs& a, double u) {
-  for (int s = 0; s < a.n_states; ++s)
-    if (__ldg(a.isd_cum + s) > u) return s;
-  return 0;
+  // the cumulative sums are non-decreasing, so the first index with cum > u is an upper bound search
+  int lo = 0, hi = a.n_states;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a.isd_cum + mid) > u) hi = mid; else lo = mid + 1;
+  }
+  return lo < a.n_states ? lo : 0;
 }
 
 // stage the packed table into (dynamic) shared memory; returns the pointer the CTA should read entries from
@@ -226,9 +230,11 @@ size_t table_smem_bytes(const LakeArgs& a) {
 // Launch geometry: one env per thread (grid = ceil(n / 256)) by default.  A capped grid-stride launch (8 CTAs per SM,
 // table staged once per CTA) was measured slower at N = 1,048,576 because 1M / 303k threads = 3.46 passes leaves the
 // last pass half empty; staging 3 KB per CTA from L2 is cheap.  B2E_LAKE_PERSISTENT=1 restores the capped grid.
-unsigned persistent_grid(int64_t n) {
+unsigned persistent_grid(int64_t n, size_t table_bytes) {
+  // small tables (FrozenLake 8x8: 3 KB): one env per thread; big tables (Taxi: 36 KB) amortise the staging over a
+  // grid-stride loop -- measured at N = 8M: Taxi 581 us plain grid (staging 140 B/env of extra L2 traffic)
   static const bool capped = getenv("B2E_LAKE_PERSISTENT") != nullptr;
-  if (!capped) return grid_for(n);
+  if (!capped && table_bytes <= 8192) return grid_for(n);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -327,7 +333,7 @@ extern "C" int b2e_frozenlake_step(const b2e_batch* b, const b2e_frozenlake_cfg*
   a.final_obs = final_obs;
   a.final_prob = final_prob;
   const size_t smem = table_smem_bytes(a);
-  const unsigned grid = persistent_grid(b->n);
+  const unsigned grid = persistent_grid(b->n, smem);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t ce = cudaSuccess;
   if (int e = launch_by_dtype(b->action_dtype, "b2e_frozenlake_step", [&](auto tag) {
@@ -364,7 +370,7 @@ extern "C" int b2e_frozenlake_rollout(const b2e_batch* b, const b2e_frozenlake_c
   a.term = terminated;
   a.trunc = truncated;
   const size_t smem = table_smem_bytes(a);
-  const unsigned grid = persistent_grid(b->n);
+  const unsigned grid = persistent_grid(b->n, smem);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t ce = cudaSuccess;
   if (!actions) {

