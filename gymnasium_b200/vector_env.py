@@ -63,6 +63,7 @@ class B200VectorEnv(VectorEnv):
         env_offset: int = 0,
         output: str = "torch",
         copy: bool = True,
+        validate_actions: bool = False,
         render_mode: str | None = None,
     ):
         if render_mode is not None:
@@ -86,6 +87,9 @@ class B200VectorEnv(VectorEnv):
         self.env_offset = int(env_offset)
         self.output = output
         self.copy = bool(copy)
+        # opt-in: the reference asserts `action_space.contains(action)` per sub-env (e.g. cartpole.py:165-167); checking
+        # on the device costs a reduction + a host sync per step, so by default the kernels clamp instead
+        self.validate_actions = bool(validate_actions)
 
         # ---- device + library: no fallback -------------------------------------------------------------------
         self._lib = _lib.load()
@@ -337,6 +341,18 @@ class B200VectorEnv(VectorEnv):
             t = t.to(self.device)
         return t.contiguous()
 
+    def _check_actions(self, t: torch.Tensor) -> None:
+        space = self.single_action_space
+        if self.discrete_actions:
+            bad = (t < int(getattr(space, "start", 0))) | (t >= int(getattr(space, "start", 0)) + int(space.n))
+        else:
+            lo = torch.as_tensor(space.low, device=t.device, dtype=t.dtype)
+            hi = torch.as_tensor(space.high, device=t.device, dtype=t.dtype)
+            bad = ((t < lo) | (t > hi) | torch.isnan(t)).reshape(t.shape[0], -1).any(dim=1)
+        if bool(bad.any()):
+            i = int(torch.nonzero(bad)[0])
+            raise AssertionError(f"{t[i].tolist()!r} ({t.dtype}) invalid (sub-environment {i})")
+
     def step(self, actions):
         """SyncVectorEnv.step (gymnasium/vector/sync_vector_env.py:266-337) as one fused launch."""
         if not self._has_reset:
@@ -346,6 +362,8 @@ class B200VectorEnv(VectorEnv):
             raise errors.ResetNeeded("Cannot call env.step() before calling env.reset()")
         with torch.cuda.device(self.device):
             t = self._prepare_actions(actions)
+            if self.validate_actions:
+                self._check_actions(t)
             out = self._outputs()
             self._batch.action_dtype = _ACT_DTYPES[t.dtype]
             self._step_kernel(t, out)

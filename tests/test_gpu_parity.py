@@ -315,6 +315,17 @@ def test_api_errors_and_reset_mask():
     assert env.closed
 
 
+def test_validate_actions_mode_raises_like_the_reference():
+    env = make("CartPole-v1", 4, validate_actions=True)
+    env.reset(seed=0)
+    env.step(np.array([0, 1, 1, 0]))
+    with pytest.raises(AssertionError, match="invalid"):  # cartpole.py:165-167, tests/envs/test_action_dim_check.py:59-86
+        env.step(np.array([0, 1, 2, 0]))
+    lenient = make("CartPole-v1", 4)
+    lenient.reset(seed=0)
+    lenient.step(np.array([0, 1, 7, -3]))  # default: clamped in-kernel, no host sync
+
+
 def test_torch_outputs_and_devices():
     import torch
 
