@@ -147,6 +147,7 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     budget = float(args.ref_budget)
+    args.num_envs = args.num_envs or ENV_FACTS[args.env]["default_n"]
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "gpu_launches": 0}
