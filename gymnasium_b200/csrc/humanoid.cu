@@ -20,6 +20,7 @@
 // Jacobian, A = J M^-1 J^T + R) lives in thread-local memory (~55 KB/env) in this first version; persistent state is
 // 74 doubles per env in struct-of-arrays layout.  FLOP-bound in principle (~0.7 MFLOP fp64 per env-step); this mapping
 // is latency-bound.
+#include <assert.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -29,7 +30,7 @@ namespace {
 
 #define HD __host__ __device__ inline
 
-constexpr int NB = 14, NQ = 24, NV = 23, NU = 17, NJ = 18, NG = 18, MAXCON = 16, MAXEFC = 64, MAXPAIR = 160;
+constexpr int NB = 14, NQ = 24, NV = 23, NU = 17, NJ = 18, NG = 18, MAXCON = 12, MAXEFC = 32, MAXPAIR = 160;
 constexpr double MINVAL = 1e-15, PI = 3.14159265358979323846;
 constexpr int G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3;
 
@@ -49,6 +50,13 @@ struct HModel {
   double timestep, gravity[3], meaninertia, margin, solref[2], solimp[5], tolerance;
   int iterations, npair, pair_g1[MAXPAIR], pair_g2[MAXPAIR];
   double qpos0[NQ];
+  // tables for the warp-per-env kernel
+  int body_depth[NB];           // world 0, torso 1, ...
+  int dof_chain_len[NV];        // number of ancestors of dof i
+  int dof_chain[NV][13];        // ancestors of dof i, nearest first
+  unsigned body_dofmask[NB];    // bit i set: dof i moves body b (ancestor-or-self of its last dof)
+  int lvl_parents[7][3];        // bodies of depth lvl that have children (-1 padded)
+  int children[NB][3];          // children of body b in descending index order (-1 padded)
 };
 
 struct Contact {
@@ -598,24 +606,29 @@ HD void forward_constraint(const HModel& m, HData& d) {
     jar -= d.efc_aref[i];
     d.efc_force[i] = jar < 0 ? -d.efc_D[i] * jar : 0.0;
   }
+  double res[MAXEFC], ainv[MAXEFC];  /* running residual AR f + b of every row, 1 / AR[i][i] */
   for (int i = 0; i < n; ++i) {
     double s = 0;
     for (int j = 0; j < n; ++j) s += d.efc_AR[i][j] * d.efc_force[j];
     cost += d.efc_force[i] * (0.5 * s + d.efc_b[i]);
+    res[i] = d.efc_b[i] + s;
+    ainv[i] = 1.0 / d.efc_AR[i][i];
   }
-  if (cost > 0) for (int i = 0; i < n; ++i) d.efc_force[i] = 0;
+  if (cost > 0)
+    for (int i = 0; i < n; ++i) { d.efc_force[i] = 0; res[i] = d.efc_b[i]; }
   const double scale = 1.0 / (m.meaninertia * (NV > 1 ? NV : 1));
+  /* Gauss-Seidel sweeps in residual-update form: after row j moves by delta, every residual moves by AR[:, j] * delta
+     (same sweep as recomputing AR[j, :] f + b per row; the update form is what maps onto one lane per row) */
   for (int it = 0; it < m.iterations; ++it) {
     double improvement = 0;
-    for (int i = 0; i < n; ++i) {
-      double res = d.efc_b[i];
-      for (int j = 0; j < n; ++j) res += d.efc_AR[i][j] * d.efc_force[j];
-      const double old = d.efc_force[i];
-      double f = old - res / d.efc_AR[i][i];
+    for (int j = 0; j < n; ++j) {
+      const double old = d.efc_force[j], r = res[j];
+      double f = old - r * ainv[j];
       if (f < 0) f = 0;
-      d.efc_force[i] = f;
+      d.efc_force[j] = f;
       const double delta = f - old;
-      improvement -= 0.5 * delta * delta * d.efc_AR[i][i] + delta * res;
+      improvement -= 0.5 * delta * delta * d.efc_AR[j][j] + delta * r;
+      for (int i = 0; i < n; ++i) res[i] += d.efc_AR[i][j] * delta;
     }
     if (improvement * scale < m.tolerance) break;
   }
@@ -855,6 +868,27 @@ void build_model(HModel& m) {
         }
     }
   m.qpos0[2] = 1.4; m.qpos0[3] = 1.0;
+  for (int b = 1; b < NB; ++b) m.body_depth[b] = m.body_depth[m.parent[b]] + 1;
+  for (int i = 0; i < NV; ++i) {
+    int len = 0;
+    for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) m.dof_chain[i][len++] = j;
+    m.dof_chain_len[i] = len;
+  }
+  for (int b = 1; b < NB; ++b)
+    for (int i = m.body_lastdof[b]; i >= 0; i = m.dof_parent[i]) m.body_dofmask[b] |= 1u << i;
+  for (int l = 0; l < 7; ++l) for (int k = 0; k < 3; ++k) m.lvl_parents[l][k] = -1;
+  for (int b = 0; b < NB; ++b) {
+    int nc = 0;
+    for (int k = 0; k < 3; ++k) m.children[b][k] = -1;
+    for (int c = NB - 1; c >= 1; --c)
+      if (m.parent[c] == b) { assert(nc < 3); m.children[b][nc++] = c; }
+    if (nc) {
+      int* row = m.lvl_parents[m.body_depth[b]];
+      int k = 0;
+      while (row[k] >= 0) { ++k; assert(k < 3); }
+      row[k] = b;
+    }
+  }
   // constants MuJoCo derives at qpos0 (mj_setConst): meaninertia, dof/body invweight0 -- with the same physics core
   HData* d = new HData();
   memset(d, 0, sizeof(HData));
@@ -1011,6 +1045,8 @@ __device__ void store_state(const HumanoidArgs& a, int64_t i, const HData& d) {
 }
 
 constexpr int kHumanoidBlock = 32;
+constexpr int kWarpImplDefault = 4 | 16;           // warp mapping: envs per CTA (1, 2, 4, 8), | 16 = CTA barrier per mj_forward
+constexpr bool kHumanoidDefaultWarp = true;   // warp per env is the default mapping (thread per env: impl = 1)
 constexpr int kHumanoidLanes = 32;  // default envs per warp (b2e_humanoid_cfg.lanes_per_warp overrides)
 
 __global__ void __launch_bounds__(kHumanoidBlock) humanoid_reset_kernel(const HumanoidArgs a) {
@@ -1104,6 +1140,25 @@ __global__ void __launch_bounds__(kHumanoidBlock) humanoid_step_kernel(const Hum
   a.ctrl[i] = cn;
 }
 
+
+#include "humanoid_warp.cuh"  // warp-per-env mapping of the same physics (shares every HD helper above)
+
+template <typename ActT, int W>
+int launch_warp_step(const HumanoidArgs& a, cudaStream_t s) {
+  static bool configured = false;  // opt in to > 48 KB of dynamic shared memory once per instantiation
+  const int smem = W * (int)sizeof(WS);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(humanoid_step_warp_kernel<ActT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e, "b2e_humanoid_step (shared memory opt-in)");
+    configured = true;
+  }
+  humanoid_step_warp_kernel<ActT, W><<<(unsigned)((a.n + W - 1) / W), 32 * W, smem, s>>>(a);
+  return cuda_status(cudaGetLastError(), "b2e_humanoid_step");
+}
+
+// implementation choice: b2e_humanoid_cfg.impl 1 = thread per env, 2 = warp per env, 0 = library default
+inline bool use_warp_impl(const b2e_humanoid_cfg* cfg) { return cfg->impl == 2 || (cfg->impl == 0 && kHumanoidDefaultWarp); }
+
 int fill(const b2e_batch* b, const b2e_humanoid_cfg* cfg, const b2e_humanoid_state* st, HumanoidArgs& a, const char* fn) {
   if (int e = check_batch(b, fn)) return e;
   if (!cfg || !st || !st->qpos || !st->qvel || !st->qacc_warmstart || !st->com_xy || !st->ctrl || !st->overflow ||
@@ -1119,7 +1174,7 @@ int fill(const b2e_batch* b, const b2e_humanoid_cfg* cfg, const b2e_humanoid_sta
   a.n = b->n; a.env_offset = b->env_offset; a.max_steps = b->max_episode_steps; a.mode = b->autoreset_mode;
   a.rng_mode = b->rng_mode; a.philox_seed = b->philox_seed; a.call_counter = b->call_counter;
   a.frame_skip = cfg->frame_skip; a.terminate_when_unhealthy = cfg->terminate_when_unhealthy;
-  a.lanes = (cfg->lanes_per_warp >= 1 && cfg->lanes_per_warp <= 32) ? cfg->lanes_per_warp : kHumanoidLanes;
+  a.lanes = (cfg->lanes_per_warp >= 1 && cfg->lanes_per_warp <= 32 && cfg->impl == 1) ? cfg->lanes_per_warp : kHumanoidLanes;
   a.noise = cfg->reset_noise_scale; a.w_forward = cfg->forward_reward_weight; a.w_ctrl = cfg->ctrl_cost_weight;
   a.w_contact = cfg->contact_cost_weight; a.contact_max = cfg->contact_cost_max; a.healthy_reward = cfg->healthy_reward;
   a.z_min = cfg->healthy_z_min; a.z_max = cfg->healthy_z_max;
@@ -1157,7 +1212,10 @@ extern "C" int b2e_humanoid_reset(const b2e_batch* b, const b2e_humanoid_cfg* cf
   }
   if (b->n == 0) return 0;
   a.mask = mask; a.obs = obs; a.info = info;
-  humanoid_reset_kernel<<<sparse_grid(b->n, a.lanes, kHumanoidBlock), kHumanoidBlock, 0, (cudaStream_t)stream>>>(a);
+  if (use_warp_impl(cfg))
+    humanoid_reset_warp_kernel<<<(unsigned)b->n, 32, 0, (cudaStream_t)stream>>>(a);
+  else
+    humanoid_reset_kernel<<<sparse_grid(b->n, a.lanes, kHumanoidBlock), kHumanoidBlock, 0, (cudaStream_t)stream>>>(a);
   return cuda_status(cudaGetLastError(), "b2e_humanoid_reset");
 }
 
@@ -1176,6 +1234,24 @@ extern "C" int b2e_humanoid_step(const b2e_batch* b, const b2e_humanoid_cfg* cfg
   a.final_obs = final_obs;
   const unsigned grid = sparse_grid(b->n, a.lanes, kHumanoidBlock);
   cudaStream_t s = (cudaStream_t)stream;
+  if (use_warp_impl(cfg)) {
+    const int knob = cfg->lanes_per_warp > 0 ? cfg->lanes_per_warp : kWarpImplDefault;  // envs per CTA | 16 = CTA barriers
+    const int W = knob & 15;
+    a.lanes = knob;
+    const bool f64 = b->action_dtype == B2E_ACT_F64;
+    if (b->action_dtype != B2E_ACT_F32 && !f64) {
+      set_error("b2e_humanoid_step: action_dtype %d is not a float dtype", b->action_dtype);
+      return B2E_EINVAL;
+    }
+    switch (W) {
+      case 1: return f64 ? launch_warp_step<double, 1>(a, s) : launch_warp_step<float, 1>(a, s);
+      case 2: return f64 ? launch_warp_step<double, 2>(a, s) : launch_warp_step<float, 2>(a, s);
+      case 4: return f64 ? launch_warp_step<double, 4>(a, s) : launch_warp_step<float, 4>(a, s);
+      case 8: return f64 ? launch_warp_step<double, 8>(a, s) : launch_warp_step<float, 8>(a, s);
+      default: set_error("b2e_humanoid_step: warp mapping supports 1, 2, 4 or 8 envs per CTA, got %d", W); return B2E_EINVAL;
+    }
+    return cuda_status(cudaGetLastError(), "b2e_humanoid_step");
+  }
   switch (b->action_dtype) {
     case B2E_ACT_F32: humanoid_step_kernel<float><<<grid, kHumanoidBlock, 0, s>>>(a); break;
     case B2E_ACT_F64: humanoid_step_kernel<double><<<grid, kHumanoidBlock, 0, s>>>(a); break;

@@ -8,6 +8,7 @@ Numeric parity with the real MuJoCo wheel is unpinned (it cannot be installed he
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -18,6 +19,7 @@ from ..vector_env import B200VectorEnv, ptr
 
 INFO_KEYS = ("x_position", "y_position", "tendon_length", "tendon_velocity", "distance_from_origin", "x_velocity",
              "y_velocity", "reward_survive", "reward_forward", "reward_ctrl", "reward_contact")
+_IMPLS = {"default": 0, "thread": 1, "warp": 2}  # b2e_humanoid_cfg.impl: kernel mapping (same results bit for bit)
 OBS_SIZE = 22 + 23 + 130 + 78 + 17 + 78  # humanoid_v5.py:376-393
 
 
@@ -34,7 +36,11 @@ class HumanoidVectorEnv(B200VectorEnv):
                  terminate_when_unhealthy: bool = True, healthy_z_range=(1.0, 2.0), reset_noise_scale: float = 1e-2,
                  exclude_current_positions_from_observation: bool = True, include_cinert_in_observation: bool = True,
                  include_cvel_in_observation: bool = True, include_qfrc_actuator_in_observation: bool = True,
-                 include_cfrc_ext_in_observation: bool = True, render_mode: str | None = None, **engine_kwargs):
+                 include_cfrc_ext_in_observation: bool = True, render_mode: str | None = None,
+                 impl: str | None = None, **engine_kwargs):
+        impl = impl or os.environ.get("B2E_HUMANOID_IMPL") or "default"
+        if impl not in _IMPLS:
+            raise ValueError(f"impl must be one of {sorted(_IMPLS)}, got {impl!r}")
         if xml_file != "humanoid.xml":
             raise NotImplementedError("gymnasium_b200 compiles the stock humanoid.xml only")
         if not (exclude_current_positions_from_observation and include_cinert_in_observation and include_cvel_in_observation
@@ -54,7 +60,7 @@ class HumanoidVectorEnv(B200VectorEnv):
             ctrl_cost_weight=float(ctrl_cost_weight), contact_cost_weight=float(contact_cost_weight),
             contact_cost_max=float(contact_cost_range[1]), healthy_reward=float(healthy_reward),
             healthy_z_min=float(healthy_z_range[0]), healthy_z_max=float(healthy_z_range[1]),
-            terminate_when_unhealthy=int(bool(terminate_when_unhealthy)), frame_skip=self.frame_skip)
+            terminate_when_unhealthy=int(bool(terminate_when_unhealthy)), frame_skip=self.frame_skip, impl=_IMPLS[impl])
         self._s = {
             "qpos": torch.zeros((24, n), dtype=torch.float64, device=dev),
             "qvel": torch.zeros((23, n), dtype=torch.float64, device=dev),
@@ -150,5 +156,5 @@ class HumanoidVectorEnv(B200VectorEnv):
         return self._s["qvel"].t().contiguous()
 
     def buffer_overflow(self) -> bool:
-        """True if any env ever exhausted the per-env contact (16) or constraint-row (64) buffers."""
+        """True if any env ever exhausted the per-env contact (12) or constraint-row (32) buffers."""
         return bool(self._s["overflow"].item())

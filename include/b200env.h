@@ -225,8 +225,8 @@ typedef struct b2e_humanoid_cfg {
   double healthy_z_min, healthy_z_max; /* (1.0, 2.0) */
   int32_t terminate_when_unhealthy;    /* 1 */
   int32_t frame_skip;                  /* 5 */
-  int32_t lanes_per_warp;              /* envs mapped to each warp (1..32); 0 = library default */
-  int32_t _pad;
+  int32_t lanes_per_warp;              /* thread-per-env mapping: envs per warp (1..32); 0 = library default */
+  int32_t impl;                        /* 0 = library default, 1 = thread per env, 2 = warp per env (shared memory) */
 } b2e_humanoid_cfg;
 
 typedef struct b2e_humanoid_state {

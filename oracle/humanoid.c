@@ -35,8 +35,8 @@
 #define NU 17
 #define NJ 18
 #define NG 18
-#define MAXCON 16
-#define MAXEFC 64
+#define MAXCON 12
+#define MAXEFC 32
 #define MINVAL 1e-15
 #define PI 3.14159265358979323846
 
@@ -909,24 +909,29 @@ static void forward_constraint(const model_t* m, data_t* d) {
     jar -= d->efc_aref[i];
     d->efc_force[i] = jar < 0 ? -d->efc_D[i] * jar : 0.0;
   }
+  double res[MAXEFC], ainv[MAXEFC];  /* running residual AR f + b of every row, 1 / AR[i][i] */
   for (int i = 0; i < n; ++i) {
     double s = 0;
     for (int j = 0; j < n; ++j) s += d->efc_AR[i][j] * d->efc_force[j];
     cost += d->efc_force[i] * (0.5 * s + d->efc_b[i]);
+    res[i] = d->efc_b[i] + s;
+    ainv[i] = 1.0 / d->efc_AR[i][i];
   }
-  if (cost > 0) for (int i = 0; i < n; ++i) d->efc_force[i] = 0;
+  if (cost > 0)
+    for (int i = 0; i < n; ++i) { d->efc_force[i] = 0; res[i] = d->efc_b[i]; }
   const double scale = 1.0 / (m->meaninertia * (NV > 1 ? NV : 1));
+  /* Gauss-Seidel sweeps in residual-update form: after row j moves by delta, every residual moves by AR[:, j] * delta
+     (same sweep as recomputing AR[j, :] f + b per row; the update form is what maps onto one lane per row) */
   for (int it = 0; it < m->iterations; ++it) {
     double improvement = 0;
-    for (int i = 0; i < n; ++i) {
-      double res = d->efc_b[i];
-      for (int j = 0; j < n; ++j) res += d->efc_AR[i][j] * d->efc_force[j];
-      double old = d->efc_force[i];
-      double f = old - res / d->efc_AR[i][i];
+    for (int j = 0; j < n; ++j) {
+      const double old = d->efc_force[j], r = res[j];
+      double f = old - r * ainv[j];
       if (f < 0) f = 0;
-      d->efc_force[i] = f;
-      double delta = f - old;
-      improvement -= 0.5 * delta * delta * d->efc_AR[i][i] + delta * res;
+      d->efc_force[j] = f;
+      const double delta = f - old;
+      improvement -= 0.5 * delta * delta * d->efc_AR[j][j] + delta * r;
+      for (int i = 0; i < n; ++i) res[i] += d->efc_AR[i][j] * delta;
     }
     d->solver_iter = it + 1;
     if (improvement * scale < m->tolerance) break;

@@ -26,7 +26,7 @@ for lanes in [32, 16, 8, 4, 2]:
     print(f"LunarLander n={n} lanes/warp {lanes:2d}: {t*1e6:8.1f} us/step  {n/t:.3e} steps/s")
 n = 8192
 for lanes in [32, 16, 8, 4, 2]:
-    e = gymnasium_b200.make_vec("Humanoid-v5", num_envs=n, copy=False)
+    e = gymnasium_b200.make_vec("Humanoid-v5", num_envs=n, copy=False, impl="thread")
     e._cfg.lanes_per_warp = lanes
     e.reset(seed=0)
     a = (torch.rand((4, n, 17), device="cuda") * 0.8 - 0.4).float()

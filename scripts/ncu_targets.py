@@ -64,3 +64,12 @@ if which in ("all", "humanoid"):
     for t in range(14):  # feet reach the floor around step 10: contacts + PGS active
         hm.step((torch.rand((8192, 17), device=dev) * 0.8 - 0.4).float())
     torch.cuda.synchronize()
+if which in ("humanoid", "humanoid_warp", "humanoid_thread"):
+    impl = {"humanoid": "default", "humanoid_warp": "warp", "humanoid_thread": "thread"}[which]
+    hn = int(os.environ.get("B2E_NCU_N", "8192"))
+    h = gymnasium_b200.make_vec("Humanoid-v5", num_envs=hn, copy=False, impl=impl)
+    h.reset(seed=0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    for t in range(64):  # steady state: standing / falling / on the ground / resetting envs all present
+        h.step(torch.rand((hn, 17), device=dev, generator=g) * 0.8 - 0.4)
+    torch.cuda.synchronize()

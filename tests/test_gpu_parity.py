@@ -423,11 +423,12 @@ def test_lunarlander_api():
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Humanoid-v5: the checker is oracle/humanoid.c (MuJoCo-subset restatement, parity with the real wheel unpinned)
-def test_humanoid_matches_oracle_bit_exact():
+@pytest.mark.parametrize("impl", ["thread", "warp"])
+def test_humanoid_matches_oracle_bit_exact(impl):
     from oracle.humanoid import OracleHumanoid
 
     n, T, seed = 48, 90, 31
-    env = make("Humanoid-v5", n)
+    env = make("Humanoid-v5", n, impl=impl)
     ora = OracleHumanoid(n)
     o1, i1 = env.reset(seed=seed)
     o2, i2 = ora.reset(seed=seed)
@@ -451,6 +452,27 @@ def test_humanoid_matches_oracle_bit_exact():
         n_term += int(y[2].sum())
     assert n_term >= n // 2  # random actions make the humanoid fall within ~40-80 steps
     assert not env.buffer_overflow()
+
+
+@pytest.mark.parametrize("mode", ["NextStep", "SameStep"])
+def test_humanoid_warp_and_thread_mappings_agree(mode):
+    """The two kernel mappings of the same physics must agree bit for bit, including through autoresets."""
+    n, T = 1000, 70
+    kw = dict(autoreset_mode=mode, max_episode_steps=40)
+    a_env, b_env = make("Humanoid-v5", n, impl="thread", **kw), make("Humanoid-v5", n, impl="warp", **kw)
+    o1, _ = a_env.reset(seed=5)
+    o2, _ = b_env.reset(seed=5)
+    np.testing.assert_array_equal(o1, o2)
+    rs = np.random.default_rng(3)
+    for t in range(T):
+        a = rs.uniform(-0.4, 0.4, size=(n, 17)).astype(np.float32)
+        x, y = a_env.step(a), b_env.step(a)
+        for k in range(4):
+            np.testing.assert_array_equal(x[k], y[k], err_msg=f"output {k} differs at step {t}")
+        for k in x[4]:
+            if isinstance(x[4][k], np.ndarray) and x[4][k].dtype != object:
+                np.testing.assert_array_equal(x[4][k], y[4][k], err_msg=k)
+    assert not a_env.buffer_overflow() and not b_env.buffer_overflow()
 
 
 def test_humanoid_reference_structural_pins_on_gpu():
