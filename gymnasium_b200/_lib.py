@@ -87,7 +87,8 @@ class HumanoidCfg(C.Structure):
 class HumanoidState(C.Structure):
     """``b2e_humanoid_state`` (device pointers)."""
 
-    _fields_ = [(k, c_void_p) for k in ("qpos", "qvel", "qacc_warmstart", "com_xy", "ctrl", "rng", "overflow")]
+    _fields_ = [(k, c_void_p) for k in ("qpos", "qvel", "qacc_warmstart", "com_xy", "ctrl", "rng", "overflow", "work",
+                                           "order")]
 
 
 P = c_void_p

@@ -932,6 +932,17 @@ void build_model(HModel& m) {
 
 __device__ HModel g_hmodel;  // global (not __constant__): the pair list / tables are indexed divergently
 
+#include "humanoid_tree.inc"
+// what the warp-per-env kernels read: the model plus the index tables of the packed L / M storage (humanoid_tree.inc);
+// the step kernel stages one copy per CTA in shared memory
+struct alignas(16) WModel {
+  HModel m;
+  unsigned short fac_start[NV + 1], fac_pair[B2E_FAC_NPAIR];
+  unsigned char rowoff[NV + 1];
+};
+static_assert(sizeof(WModel) % 16 == 0, "WModel is copied as 16-byte words");
+__device__ WModel g_wmodel;
+
 const HModel& host_model() {
   static HModel M;
   static bool built = false;
@@ -945,6 +956,13 @@ int upload_model() {
   if (done[dev]) return 0;
   const HModel& M = host_model();
   cudaError_t e = cudaMemcpyToSymbol(g_hmodel, &M, sizeof(HModel));
+  if (e != cudaSuccess) return cuda_status(e, "humanoid model upload");
+  static WModel W;  // zero-initialised padding
+  W.m = M;
+  memcpy(W.fac_start, B2E_FAC_START_H, sizeof(B2E_FAC_START_H));
+  memcpy(W.fac_pair, B2E_FAC_PAIR_H, sizeof(B2E_FAC_PAIR_H));
+  memcpy(W.rowoff, B2E_LD_ROWOFF_H, sizeof(B2E_LD_ROWOFF_H));
+  e = cudaMemcpyToSymbol(g_wmodel, &W, sizeof(WModel));
   if (e != cudaSuccess) return cuda_status(e, "humanoid model upload");
   done[dev] = true;
   return 0;
@@ -963,6 +981,8 @@ struct HumanoidArgs {
   int32_t* __restrict__ ctrl;
   uint64_t* __restrict__ rng;
   int32_t* __restrict__ overflow;  // [1] sticky
+  int32_t* __restrict__ work;      // [n] or null: solver work of the last step
+  int32_t* __restrict__ order;     // [n] or null: envs grouped by work (warp mapping only)
   double* __restrict__ obs;        // [n][348]
   double* __restrict__ reward;
   uint8_t* __restrict__ term;
@@ -1045,7 +1065,7 @@ __device__ void store_state(const HumanoidArgs& a, int64_t i, const HData& d) {
 }
 
 constexpr int kHumanoidBlock = 32;
-constexpr int kWarpImplDefault = 4 | 16;           // warp mapping: envs per CTA (1, 2, 4, 8), | 16 = CTA barrier per mj_forward
+constexpr int kWarpImplDefault = 8 | 16;           // warp mapping: envs per CTA (1, 2, 4, 8), | 16 = CTA barrier per mj_forward
 constexpr bool kHumanoidDefaultWarp = true;   // warp per env is the default mapping (thread per env: impl = 1)
 constexpr int kHumanoidLanes = 32;  // default envs per warp (b2e_humanoid_cfg.lanes_per_warp overrides)
 
@@ -1146,12 +1166,13 @@ __global__ void __launch_bounds__(kHumanoidBlock) humanoid_step_kernel(const Hum
 template <typename ActT, int W>
 int launch_warp_step(const HumanoidArgs& a, cudaStream_t s) {
   static bool configured = false;  // opt in to > 48 KB of dynamic shared memory once per instantiation
-  const int smem = W * (int)sizeof(WS);
+  const int smem = (int)sizeof(WModel) + W * (int)sizeof(WS);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(humanoid_step_warp_kernel<ActT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "b2e_humanoid_step (shared memory opt-in)");
     configured = true;
   }
+  if (a.order) humanoid_group_kernel<<<1, 1024, 0, s>>>(a.work, a.order, a.n);
   humanoid_step_warp_kernel<ActT, W><<<(unsigned)((a.n + W - 1) / W), 32 * W, smem, s>>>(a);
   return cuda_status(cudaGetLastError(), "b2e_humanoid_step");
 }
@@ -1180,6 +1201,7 @@ int fill(const b2e_batch* b, const b2e_humanoid_cfg* cfg, const b2e_humanoid_sta
   a.z_min = cfg->healthy_z_min; a.z_max = cfg->healthy_z_max;
   a.qpos = st->qpos; a.qvel = st->qvel; a.warm = st->qacc_warmstart; a.com_xy = st->com_xy; a.ctrl = st->ctrl;
   a.rng = st->rng; a.overflow = st->overflow;
+  a.work = st->work; a.order = (st->work && st->order) ? st->order : nullptr;
   return upload_model();
 }
 
@@ -1238,6 +1260,7 @@ extern "C" int b2e_humanoid_step(const b2e_batch* b, const b2e_humanoid_cfg* cfg
     const int knob = cfg->lanes_per_warp > 0 ? cfg->lanes_per_warp : kWarpImplDefault;  // envs per CTA | 16 = CTA barriers
     const int W = knob & 15;
     a.lanes = knob;
+    if (W == 1 || !(knob & 16) || (knob & 64)) a.order = nullptr;  // grouping only matters to CTA-synchronised warps; | 64 disables it
     const bool f64 = b->action_dtype == B2E_ACT_F64;
     if (b->action_dtype != B2E_ACT_F32 && !f64) {
       set_error("b2e_humanoid_step: action_dtype %d is not a float dtype", b->action_dtype);

@@ -6,7 +6,6 @@
 // the smooth acceleration) run at once, one right-hand side per lane, with the operand vector in registers and
 // statically indexed (humanoid_tree.inc).  Every output element is still produced by ONE lane executing the same
 // operation order as the thread-per-env code above, so results are bit-identical to it and to oracle/humanoid.c.
-#include "humanoid_tree.inc"
 
 // Shared-memory working set of one env (~24 KB: 8 envs resident per SM, which is also what the register file allows).
 // Arrays whose lifetimes do not overlap share storage: position-stage temporaries, velocity-stage temporaries and the
@@ -21,10 +20,10 @@ struct WS {
   double LDp[B2E_LD_NPACK], dinv[NV], tmp[16], rowk[16];
   double passive[NV], actuator[NV], smooth[NV], qacc_smooth[NV], qacc[NV];
   double ten_length[2], ten_velocity[2];
-  int ncon, nefc, overflow, pad;
+  int ncon, nefc, overflow, work;  // work: constraint-solver effort of this step (scheduling hint for the next one)
   Contact con[MAXCON];
   union {
-    struct { double xpos[NB][3], xquat[NB][4], xmat[NB][9], xanchor[NJ][3], xaxis[NJ][3], crb[NB][10]; } p;  // position stage
+    struct { double xpos[NB][3], xquat[NB][4], xmat[NB][9], xanchor[NJ][3], xaxis[NJ][3], crb[NB][10], ql[NJ][4]; } p;  // position stage
     struct { double cdof_dot[NV][6], cacc[NB][6], cfrc[NB][6]; } v;                                          // velocity stage
     double J[MAXEFC][NV];                                                                                    // constraint stage
   } u;
@@ -57,9 +56,7 @@ __device__ void w_kin_body(const HModel& m, WS& w, int b) {
       quat_rot(v, xquat, m.jnt_pos[j]);
       for (int k = 0; k < 3; ++k) w.u.p.xanchor[j][k] = xpos[k] + v[k];
       quat_rot(w.u.p.xaxis[j], xquat, m.jnt_axis[j]);
-      double ql[4];
-      quat_axisangle(ql, m.jnt_axis[j], q[m.jnt_qposadr[j]] - m.qpos0[m.jnt_qposadr[j]]);
-      quat_mul(xquat, xquat, ql);
+      quat_mul(xquat, xquat, w.u.p.ql[j]);  // joint rotation, precomputed for all joints at once
       quat_rot(v, xquat, m.jnt_pos[j]);
       for (int k = 0; k < 3; ++k) xpos[k] = w.u.p.xanchor[j][k] - v[k];
     }
@@ -68,9 +65,6 @@ __device__ void w_kin_body(const HModel& m, WS& w, int b) {
   cp3(w.u.p.xpos[b], xpos);
   for (int k = 0; k < 4; ++k) w.u.p.xquat[b][k] = xquat[k];
   quat2mat(w.u.p.xmat[b], xquat);
-  double t[3];
-  mulmatvec3(t, w.u.p.xmat[b], m.body_ipos[b]);
-  for (int k = 0; k < 3; ++k) w.xipos[b][k] = xpos[k] + t[k];
 }
 
 // narrow phase of one geom pair; returns the number of contacts (0..2) written to out[]
@@ -186,13 +180,15 @@ __device__ __forceinline__ void w_tree_sum(const HModel& m, double* arr /*[NB][K
 }
 
 #define LDP(o) w.LDp[o]
+#define B2E_SOLVE_FENCE() __syncwarp(solve_mask)  // ptxas keeps shared loads behind it: bounds the loads in flight
 #define DINV(i) w.dinv[i]
 
 // mj_forward for the env of this warp; inputs w.qpos, w.qvel, w.warm, w.ctrl; output w.qacc (+ all derived arrays)
 // stage_sync: the warps of the CTA also meet at 6 CTA barriers between the stages (callers guarantee that every live warp of
 // the CTA executes the same number of barriers)
 #define STAGE_SYNC() do { if (stage_sync) __syncthreads(); } while (0)
-__device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool stage_sync) {
+__device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane, bool stage_sync) {
+  const HModel& m = wm.m;
   // ---- position stage ----------------------------------------------------------------------------------------------------
   if (lane == 0) {
     quat_normalize(w.qpos + 3);
@@ -200,10 +196,17 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
     w.u.p.xquat[0][0] = 1; w.u.p.xquat[0][1] = w.u.p.xquat[0][2] = w.u.p.xquat[0][3] = 0;
     for (int k = 0; k < 9; ++k) w.u.p.xmat[0][k] = (k % 4 == 0) ? 1.0 : 0.0;
   }
+  if (lane >= 1 && lane < NJ)  // everything of mj_kinematics that does not depend on the parent body: the joint rotations
+    quat_axisangle(w.u.p.ql[lane], m.jnt_axis[lane], w.qpos[m.jnt_qposadr[lane]] - m.qpos0[m.jnt_qposadr[lane]]);
   WSYNC();
   for (int lvl = 1; lvl <= 6; ++lvl) {
     if (lane > 0 && lane < NB && m.body_depth[lane] == lvl) w_kin_body(m, w, lane);
     WSYNC();
+  }
+  if (lane > 0 && lane < NB) {
+    double t[3];
+    mulmatvec3(t, w.u.p.xmat[lane], m.body_ipos[lane]);
+    for (int k = 0; k < 3; ++k) w.xipos[lane][k] = w.u.p.xpos[lane][k] + t[k];
   }
   if (lane < NG) {
     const int g = lane, b = m.geom_body[g];
@@ -273,7 +276,7 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
   WSYNC();
   w_tree_sum<10>(m, &w.u.p.crb[0][0], lane, 1);
   if (lane < NV) {  // row i of M in the packed tree storage: diagonal, then the ancestors of dof i (nearest first)
-    const int i = lane, ro = B2E_LD_ROWOFF[i];
+    const int i = lane, ro = wm.rowoff[i];
     double buf[6];
     mul_inert_vec(buf, w.u.p.crb[m.dof_body[i]], w.cdof[i]);
     w.LDp[ro] = m.dof_armature[i] + dot6(w.cdof[i], buf);
@@ -283,19 +286,22 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
   WSYNC();
   // mj_factorM: pivots in sequence; the row scaling of a pivot, then all of its (i, j) updates, each in parallel
   for (int k = NV - 1; k >= 0; --k) {
-    const int len = m.dof_chain_len[k], ro = B2E_LD_ROWOFF[k];
+    const int len = m.dof_chain_len[k], ro = wm.rowoff[k];
     const double dkk = w.LDp[ro];
-    if (lane < len) {
-      const double old = w.LDp[ro + 1 + lane], t = old / dkk;
-      w.rowk[lane] = old;
-      w.tmp[lane] = t;
-      w.LDp[ro + 1 + lane] = t;
+    {  // one division sequence serves the row scaling (lanes < len) and 1 / D[k] (lane 31)
+      const double num = lane < len ? w.LDp[ro + 1 + lane] : 1.0;
+      const double q = num / dkk;
+      if (lane < len) {
+        w.rowk[lane] = num;
+        w.tmp[lane] = q;
+        w.LDp[ro + 1 + lane] = q;
+      }
+      if (lane == 31) w.dinv[k] = q;
     }
-    if (lane == 31) w.dinv[k] = 1.0 / dkk;
     if (len == 0) continue;
     WSYNC();
-    for (int p = B2E_FAC_START[k] + lane, pe = B2E_FAC_START[k + 1]; p < pe; p += 32) {
-      const unsigned e = B2E_FAC_PAIR[p];
+    for (int p = wm.fac_start[k] + lane, pe = wm.fac_start[k + 1]; p < pe; p += 32) {
+      const unsigned e = wm.fac_pair[p];
       w.LDp[e & 255u] -= w.rowk[(e >> 8) & 15u] * w.tmp[e >> 12];
     }
     WSYNC();
@@ -358,7 +364,7 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
   }
   if (lane == 0) for (int k = 0; k < 3; ++k) { w.u.v.cacc[0][k] = 0; w.u.v.cacc[0][3 + k] = -m.gravity[k]; }
   WSYNC();
-  for (int lvl = 1; lvl <= 6; ++lvl) {  // mj_rne forward sweep
+  for (int lvl = 1; lvl <= 6; ++lvl) {  // mj_rne forward sweep: only the accelerations depend on the parent body
     if (lane > 0 && lane < NB && m.body_depth[lane] == lvl) {
       const int b = lane;
       double cacc[6];
@@ -368,14 +374,18 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
         for (int k = 0; k < 6; ++k) cacc[k] += w.u.v.cdof_dot[da][k] * w.qvel[da];
       }
       for (int k = 0; k < 6; ++k) w.u.v.cacc[b][k] = cacc[k];
-      double t1[6], t2[6], t3[6];
-      mul_inert_vec(t1, w.cinert[b], cacc);
-      mul_inert_vec(t2, w.cinert[b], w.cvel[b]);
-      cross_force(t3, w.cvel[b], t2);
-      for (int k = 0; k < 6; ++k) w.u.v.cfrc[b][k] = t1[k] + t3[k];
     }
     WSYNC();
   }
+  if (lane > 0 && lane < NB) {  // cfrc_body = I * cacc + cvel x* (I * cvel), all bodies at once
+    const int b = lane;
+    double t1[6], t2[6], t3[6];
+    mul_inert_vec(t1, w.cinert[b], w.u.v.cacc[b]);
+    mul_inert_vec(t2, w.cinert[b], w.cvel[b]);
+    cross_force(t3, w.cvel[b], t2);
+    for (int k = 0; k < 6; ++k) w.u.v.cfrc[b][k] = t1[k] + t3[k];
+  }
+  WSYNC();
   w_tree_sum<6>(m, &w.u.v.cfrc[0][0], lane, 1);  // backward sweep (the world body's total is never used)
   if (lane < NV) w.actuator[lane] = 0;
   WSYNC();
@@ -514,6 +524,7 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
 #pragma unroll
         for (int k = 0; k < NV; ++k) x[k] = w.smooth[k];
       }
+      const unsigned solve_mask = __ballot_sync(0xffffffffu, row || smooth);
       if (row || smooth) { B2E_SOLVE_M_UNROLLED(x); }
       if (row) {  // mj_projectConstraint row: AR[r][j] = J_j . (M^-1 J_r), j <= r
         for (int j = 0; j <= lane; ++j) {
@@ -573,20 +584,26 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
     const double scale = 1.0 / (m.meaninertia * (NV > 1 ? NV : 1));
     const int iters = m.iterations;
     const double tol = m.tolerance;
+    const int tri0 = lane * (lane + 1) / 2;
     for (int it = 0; it < iters; ++it) {
-      double improvement = 0;
+      double d_own = 0, r_own = 0;  // this lane's move and the residual it was computed from (for the cost change)
+      int idx = tri0;               // index of AR[lane][j] in the packed lower triangle
       for (int j = 0; j < n; ++j) {
         double f = f_i - r_i * ainv;
         if (f < 0) f = 0;
         const double delta = f - f_i;
-        const double gain = 0.5 * delta * delta * aii + delta * r_i;
         const double dj = __shfl_sync(0xffffffffu, delta, j);
-        improvement -= __shfl_sync(0xffffffffu, gain, j);
-        if (lane == j) f_i = f;
-        if (lane < n) r_i += w.AR[tri(lane, j)] * dj;
+        if (lane == j) { f_i = f; d_own = delta; r_own = r_i; }
+        if (lane < n) r_i += w.AR[idx] * dj;
+        idx += j < lane ? 1 : j + 1;
       }
+      const double gain = 0.5 * d_own * d_own * aii + d_own * r_own;
+      double improvement = 0;
+      for (int j = 0; j < n; ++j) improvement -= __shfl_sync(0xffffffffu, gain, j);
+      if (lane == 0) w.work += n + 1;  // one sweep over n rows
       if (improvement * scale < tol) break;
     }
+    if (lane == 0) w.work += 8 * n;    // the per-row set-up (solves, AR) that envs without constraints skip
   }
   if (lane < n) w.force[lane] = f_i;
   WSYNC();
@@ -600,6 +617,7 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
     double x[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) x[k] = w.passive[k];
+    const unsigned solve_mask = 1u;
     B2E_SOLVE_M_UNROLLED(x);
 #pragma unroll
     for (int k = 0; k < NV; ++k) w.qacc[k] = w.qacc_smooth[k] + x[k];
@@ -607,6 +625,7 @@ __device__ __noinline__ void w_forward(const HModel& m, WS& w, int lane, bool st
   WSYNC();
 }
 #undef LDP
+#undef B2E_SOLVE_FENCE
 #undef DINV
 
 
@@ -628,7 +647,8 @@ __device__ __forceinline__ void w_integrate_pos(WS& w, const double* vel, double
 }
 
 // mj_RungeKutta(4): four mj_forward evaluations (one call site), Butcher combination per dof lane
-__device__ void w_step_rk4(const HModel& m, WS& w, int lane, bool cta_sync, bool stage_sync) {
+__device__ void w_step_rk4(const WModel& wm, WS& w, int lane, bool cta_sync, bool stage_sync) {
+  const HModel& m = wm.m;
   const double h = m.timestep;
   const double A[3][3] = {{0.5, 0, 0}, {0, 0.5, 0}, {0, 0, 1.0}}, Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
 #pragma unroll 1
@@ -650,7 +670,7 @@ __device__ void w_step_rk4(const HModel& m, WS& w, int lane, bool cta_sync, bool
       WSYNC();
     }
     if (cta_sync) __syncthreads();  // keeps the warps of a CTA inside the same code region (shared instruction cache)
-    w_forward(m, w, lane, stage_sync);
+    w_forward(wm, w, lane, stage_sync);
     if (i == 0) {  // X0 is the state after the first evaluation: mj_kinematics normalises the quaternion inside qpos
       for (int k = lane; k < NQ; k += 32) w.X0q[k] = w.qpos[k];
       if (lane < NV) w.Xv[0][lane] = w.qvel[lane];
@@ -699,21 +719,21 @@ __device__ void w_mass_center(const HModel& m, const WS& w, double* xy) {
   for (int b = 0; b < NB; ++b) { nx += m.body_mass[b] * w.xipos[b][0]; ny += m.body_mass[b] * w.xipos[b][1]; den += m.body_mass[b]; }
   xy[0] = nx / den; xy[1] = ny / den;
 }
-__device__ void w_store_state(const HumanoidArgs& a, int64_t i, const WS& w, int lane) {
+__device__ void w_store_state(const HModel& m, const HumanoidArgs& a, int64_t i, const WS& w, int lane) {
   const int64_t n = a.n;
   for (int k = lane; k < NQ; k += 32) a.qpos[k * n + i] = w.qpos[k];
   if (lane < NV) { a.qvel[lane * n + i] = w.qvel[lane]; a.warm[lane * n + i] = w.warm[lane]; }
   if (lane == 0) {
     double xy[2];
-    w_mass_center(g_hmodel, w, xy);
+    w_mass_center(m, w, xy);
     a.com_xy[i] = xy[0];
     a.com_xy[n + i] = xy[1];
     if (w.overflow) *a.overflow = 1;
   }
 }
 // MujocoEnv.reset + reset_model for this warp's env; the RNG stream is advanced by lane 0 only
-__device__ void w_env_reset(const HumanoidArgs& a, int64_t i, WS& w, int lane, double* __restrict__ obs) {
-  const HModel& m = g_hmodel;
+__device__ void w_env_reset(const WModel& wm, const HumanoidArgs& a, int64_t i, WS& w, int lane, double* __restrict__ obs) {
+  const HModel& m = wm.m;
   if (lane == 0) {
     HDraws D;
     D.numpy = a.rng_mode == B2E_RNG_NUMPY;
@@ -728,7 +748,7 @@ __device__ void w_env_reset(const HumanoidArgs& a, int64_t i, WS& w, int lane, d
   if (lane < NU) w.ctrl[lane] = 0;
   for (int e = lane; e < NB * 6; e += 32) (&w.cfrc_ext[0][0])[e] = 0;
   WSYNC();
-  w_forward(m, w, lane, false);
+  w_forward(wm, w, lane, false);
   w_write_obs(w, obs, lane);
   if (lane == 0) {
     for (int k = 7; k < 13; ++k) a.info[k * a.n + i] = 0.0;
@@ -741,12 +761,15 @@ __global__ void __launch_bounds__(32) humanoid_reset_warp_kernel(const HumanoidA
   const int64_t i = blockIdx.x;
   const int lane = threadIdx.x;
   if (a.mask != nullptr && a.mask[i] == 0) return;
-  if (lane == 0) w.overflow = 0;
+  if (lane == 0) { w.overflow = 0; w.work = 0; }
   WSYNC();
-  w_env_reset(a, i, w, lane, a.obs + 348 * i);
+  w_env_reset(g_wmodel, a, i, w, lane, a.obs + 348 * i);
   WSYNC();
-  w_store_state(a, i, w, lane);
-  if (lane == 0) a.ctrl[i] = 0;
+  w_store_state(g_wmodel.m, a, i, w, lane);
+  if (lane == 0) {
+    a.ctrl[i] = 0;
+    if (a.work) a.work[i] = 0;
+  }
 }
 
 // W envs per CTA, one warp each (the warps never exchange data; sharing a CTA only co-schedules them).  With
@@ -756,19 +779,24 @@ __global__ void __launch_bounds__(32) humanoid_reset_warp_kernel(const HumanoidA
 template <typename ActT, int W>
 __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const HumanoidArgs a) {
   extern __shared__ __align__(16) unsigned char w_smem[];
-  const HModel& m = g_hmodel;
+  const WModel& wm = *reinterpret_cast<const WModel*>(w_smem);  // per-CTA copy of the model and index tables
+  const HModel& m = wm.m;
+  for (int e = threadIdx.x; e < (int)(sizeof(WModel) / 16); e += 32 * W)
+    reinterpret_cast<uint4*>(w_smem)[e] = reinterpret_cast<const uint4*>(&g_wmodel)[e];
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * W + warp, n = a.n;
+  const int64_t slot = (int64_t)blockIdx.x * W + warp, n = a.n;
   const bool cta_sync = W > 1 && (a.lanes & 16), stage_sync = cta_sync && (a.lanes & 32);
   const int n_sync = cta_sync ? 4 * a.frame_skip * (stage_sync ? 7 : 1) : 0;
-  if (i >= n) {
+  if (slot >= n) {
     for (int k = 0; k < n_sync; ++k) __syncthreads();
     return;
   }
-  WS& w = reinterpret_cast<WS*>(w_smem)[warp];
+  const int64_t i = a.order ? a.order[slot] : slot;  // envs of similar cost share a CTA (they wait for each other)
+  WS& w = reinterpret_cast<WS*>(w_smem + sizeof(WModel))[warp];
   const int32_t c = a.ctrl[i];
   double* __restrict__ obs = a.obs + 348 * i;
-  if (lane == 0) w.overflow = 0;
+  if (lane == 0) { w.overflow = 0; w.work = 0; }
   WSYNC();
   bool reset = a.mode == B2E_AUTORESET_NEXT_STEP && ctrl_pending(c);  // this call is the env's reset step
   int32_t cn = 0;
@@ -785,7 +813,7 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
     if (lane < NU) w.ctrl[lane] = (double)reinterpret_cast<const ActT*>(a.actions)[i * NU + lane];
     WSYNC();
 #pragma unroll 1
-    for (int k = 0; k < a.frame_skip; ++k) w_step_rk4(m, w, lane, cta_sync, stage_sync);
+    for (int k = 0; k < a.frame_skip; ++k) w_step_rk4(wm, w, lane, cta_sync, stage_sync);
     if (lane == 0) {  // mj_rnePostConstraint (cfrc_ext only): a short sequential tail
       for (int b = 0; b < NB; ++b) for (int k = 0; k < 6; ++k) w.cfrc_ext[b][k] = 0;
       for (int cc = 0; cc < w.ncon; ++cc) {
@@ -852,10 +880,33 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
     WSYNC();
   }
   if (reset) {  // one call site for both autoreset flavours
-    w_env_reset(a, i, w, lane, obs);
+    w_env_reset(wm, a, i, w, lane, obs);
     WSYNC();
   }
-  w_store_state(a, i, w, lane);
-  if (lane == 0) a.ctrl[i] = cn;
+  w_store_state(m, a, i, w, lane);
+  if (lane == 0) {
+    a.ctrl[i] = cn;
+    if (a.work) a.work[i] = ctrl_pending(cn) ? -1 : w.work;  // -1: the next call only resets this env
+  }
+}
+
+// Scheduling helper for the CTA-synchronised step kernel: order[] = env indices bucketed by the solver work of their last
+// step, heaviest first (envs that only reset go last).  One CTA; the order inside a bucket is arbitrary, which is fine:
+// which envs share a CTA changes how long warps wait for each other, never what they compute.
+__global__ void __launch_bounds__(1024) humanoid_group_kernel(const int32_t* __restrict__ work, int32_t* __restrict__ order,
+                                                              int64_t n) {
+  __shared__ int hist[256], cursor[256];
+  const int tid = threadIdx.x;
+  if (tid < 256) hist[tid] = 0;
+  __syncthreads();
+  auto bucket = [](int32_t wk) { return wk < 0 ? 255 : 254 - min(wk >> 6, 254); };
+  for (int64_t i = tid; i < n; i += 1024) atomicAdd(&hist[bucket(work[i])], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int k = 0; k < 256; ++k) { cursor[k] = acc; acc += hist[k]; }
+  }
+  __syncthreads();
+  for (int64_t i = tid; i < n; i += 1024) order[atomicAdd(&cursor[bucket(work[i])], 1)] = (int32_t)i;
 }
 

@@ -67,6 +67,8 @@ class HumanoidVectorEnv(B200VectorEnv):
             "qacc_warmstart": torch.zeros((23, n), dtype=torch.float64, device=dev),
             "com_xy": torch.zeros((2, n), dtype=torch.float64, device=dev),
             "overflow": torch.zeros(1, dtype=torch.int32, device=dev),
+            "work": torch.zeros(n, dtype=torch.int32, device=dev),    # solver work of the last step (scheduling hint)
+            "order": torch.zeros(n, dtype=torch.int32, device=dev),   # scratch: envs grouped by that work
         }
         self._state = _lib.HumanoidState(ctrl=self._ctrl.data_ptr(), rng=ptr(self._rng),
                                          **{k: v.data_ptr() for k, v in self._s.items()})

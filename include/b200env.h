@@ -237,6 +237,9 @@ typedef struct b2e_humanoid_state {
   int32_t* ctrl;
   uint64_t* rng;
   int32_t* overflow;
+  int32_t* work;   /* [n] optional (may be NULL with order): constraint-solver work of every env in its last step */
+  int32_t* order;  /* [n] optional scratch: env indices sorted by `work`; the warp-per-env step kernel then puts envs of
+                      similar cost into the same CTA (scheduling only: results do not depend on it) */
 } b2e_humanoid_state;
 
 /* Host-side view of the compiled model constants (no GPU needed): body_mass[14], misc[8] = {meaninertia, n collision

@@ -33,6 +33,6 @@ for impl, knob in configs:
     sig = (out[0].double().sum().item(), out[1].sum().item(), int(out[2].sum().item()))
     same = "" if ref is None else ("same" if sig == ref else f"DIFFERENT {sig} vs {ref}")
     ref = ref or sig
-    label = f"{impl} envs/CTA={knob & 15} barrier={'stage' if knob & 32 else 'fwd' if knob & 16 else 'no'}" if impl == "warp" else "thread"
-    print(f"Humanoid n={n} {label:34s}: {dt*1e3:8.2f} ms/step  {n/dt:.3e} steps/s  {same}", flush=True)
+    label = f"{impl} envs/CTA={knob & 15} barrier={'stage' if knob & 32 else 'fwd' if knob & 16 else 'no'} grouped={'n' if knob & 64 or not knob & 16 else 'y'}" if impl == "warp" else "thread"
+    print(f"Humanoid n={n} {label:46s}: {dt*1e3:8.2f} ms/step  {n/dt:.3e} steps/s  {same}", flush=True)
     del e
