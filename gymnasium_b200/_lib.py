@@ -106,6 +106,7 @@ SIGNATURES = {
     "b2e_cartpole_step": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P, P, P, P, P]),
     "b2e_cartpole_rollout": (C.c_int, [_BP, C.POINTER(CartPoleCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),
     "b2e_selftest_math": (C.c_int, [c_i64, c_u64, P, P]),
+    "b2e_fma_probe": (C.c_int, [C.c_int, c_i64, C.POINTER(c_i64), P, P]),
     "b2e_classic_reset": (C.c_int, [_BP, C.POINTER(ClassicCfg), P, P, P]),
     "b2e_classic_step": (C.c_int, [_BP, C.POINTER(ClassicCfg), P, P, P, P, P, P, P]),
     "b2e_lunarlander_state_words": (C.c_int, []),

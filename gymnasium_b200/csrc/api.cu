@@ -85,6 +85,36 @@ extern "C" int b2e_device_info(int device, int* sm_count, int* cc_major, int* cc
   return 0;
 }
 
+// SIMT FMA throughput probe (the denominator of the FLOP roofline of the physics families): 8 independent chains per thread
+template <typename T>
+__global__ void __launch_bounds__(256) fma_probe_kernel(int64_t iters, T* sink) {
+  T a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = (T)(threadIdx.x + k) * (T)1e-3;
+  const T b = (T)0.999, c = (T)1e-6;
+  for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+  }
+  T acc = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc += a[k];
+  if (acc == (T)-1) sink[0] = acc;  // never true: keeps the chains alive
+}
+extern "C" int b2e_fma_probe(int fp64, int64_t iters, int64_t* flops, void* sink, void* stream) {
+  int dev = 0, sms = 0;
+  if (!sink || iters <= 0 || cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    set_error("b2e_fma_probe: bad arguments or no device");
+    return B2E_EINVAL;
+  }
+  const int grid = sms * 8;
+  if (fp64) fma_probe_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, (double*)sink);
+  else fma_probe_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, (float*)sink);
+  if (flops) *flops = (int64_t)grid * 256 * iters * 8 * 2;
+  return cuda_status(cudaGetLastError(), "b2e_fma_probe");
+}
+
 extern "C" int b2e_rng_seed(const b2e_batch* b, uint64_t base_seed, const uint64_t* seeds, const uint8_t* mask,
                             uint64_t* rng, void* stream) {
   if (int e = check_batch(b, "b2e_rng_seed")) return e;

@@ -108,6 +108,9 @@ int b2e_cartpole_rollout(const b2e_batch* b, const b2e_cartpole_cfg* cfg, int32_
 /* Device self-test of the CartPole fast math paths on n pseudo-random inputs: counts uint64 [3] (device, caller-zeroed)
  * receives {const-division results != IEEE division, sin/cos more than 1 ulp from libdevice, exactly 1 ulp}. */
 int b2e_selftest_math(int64_t n, uint64_t seed, uint64_t* counts, void* stream);
+/* Measurement aid (bench.py): enqueues a SIMT FMA loop that fills the device (8 independent chains per thread, fp64 != 0:
+ * double, else float) and reports the flops it performs in *flops; the caller times it with events.  sink: >= 8 bytes. */
+int b2e_fma_probe(int fp64, int64_t iters, int64_t* flops, void* sink, void* stream);
 
 /* ---- FrozenLake-v1: gymnasium/envs/toy_text/frozen_lake.py:232-348, toy_text/utils.py:4-8 -----------------------
  * Transition table (device, immutable, built by the host from the map exactly as frozen_lake.py:256-300):

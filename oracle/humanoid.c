@@ -787,7 +787,7 @@ static void make_constraint(const model_t* m, data_t* d) {
   }
   for (int i = 0; i < n; ++i) d->efc_D[i] = 1.0 / d->efc_R[i];
   /* mj_projectConstraint: AR = J M^-1 J^T + diag(R) */
-  static double X[MAXEFC][NV];
+  double X[MAXEFC][NV];  /* on the stack: the library is called from several host threads */
   for (int i = 0; i < n; ++i) {
     memcpy(X[i], d->efc_J[i], sizeof(X[i]));
     solve_M(m, d, X[i]);

@@ -12,7 +12,7 @@ src = os.path.join("gpurun_out", tag)
 os.makedirs("profiles", exist_ok=True)
 KEYS = {"step": "cartpole_step_kernel<int64>", "big": "cartpole_step_kernel<int64> N=16M",
         "rollout": "cartpole_rollout_kernel<philox>", "lake": "frozenlake_step_kernel<int64>",
-        "lander": "lunarlander_step_kernel<int64>"}
+        "lander": "lunarlander_step_kernel<int64>", "humanoid": "humanoid_step_warp_kernel<float, 8>"}
 summary, lines = {}, []
 for name, key in KEYS.items():
     p = os.path.join(src, f"ncu_{name}.ncu-rep")
@@ -47,6 +47,10 @@ for name, key in KEYS.items():
         "issue_active_pct": r0.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "warp_instructions": r0.get("smsp__inst_executed.sum"),
         "kernel_name": r0.get("Kernel Name"),
+        "threads_active_per_instruction": r0.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "stall_cycles_per_issue": {k: r0.get(f"smsp__average_warps_issue_stalled_{k}_per_issue_active.ratio")
+                                   for k in ("long_scoreboard", "barrier", "wait", "no_instruction", "short_scoreboard",
+                                             "branch_resolving", "math_pipe_throttle")},
     }
 # bench.py reads profiles/ncu_summary.json for roofline.traffic
 flat = {k.replace(" N=16M", "_16M"): v for k, v in summary.items()}
