@@ -71,6 +71,26 @@ inline unsigned sparse_grid(int64_t n, int lanes, int block) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Scheduling helper shared by the physics families: order[] = env indices bucket-sorted by a small integer key
+// (bucket 0 first).  Called by all threads of ONE CTA.  The order inside a bucket is arbitrary, which is fine: which envs
+// share a warp / CTA changes how much they wait for each other, never what an env computes.
+template <int NBUCKET, typename KeyFn>
+__device__ __forceinline__ void group_envs_by_key(KeyFn key, int32_t* __restrict__ order, int64_t n) {
+  __shared__ int hist[NBUCKET], cursor[NBUCKET];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = tid; k < NBUCKET; k += nt) hist[k] = 0;
+  __syncthreads();
+  for (int64_t i = tid; i < n; i += nt) atomicAdd(&hist[key(i)], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int k = 0; k < NBUCKET; ++k) { cursor[k] = acc; acc += hist[k]; }
+  }
+  __syncthreads();
+  for (int64_t i = tid; i < n; i += nt) order[atomicAdd(&cursor[key(i)], 1)] = (int32_t)i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // control word: bits 0..30 = TimeLimit elapsed steps, bit 31 = autoreset pending (NEXT_STEP)
 constexpr int32_t kPending = (int32_t)0x80000000u;
 __device__ __forceinline__ bool ctrl_pending(int32_t c) { return c < 0; }

@@ -891,22 +891,9 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
 }
 
 // Scheduling helper for the CTA-synchronised step kernel: order[] = env indices bucketed by the solver work of their last
-// step, heaviest first (envs that only reset go last).  One CTA; the order inside a bucket is arbitrary, which is fine:
-// which envs share a CTA changes how long warps wait for each other, never what they compute.
+// step, heaviest first (envs that only reset go last); see group_envs_by_key.
 __global__ void __launch_bounds__(1024) humanoid_group_kernel(const int32_t* __restrict__ work, int32_t* __restrict__ order,
                                                               int64_t n) {
-  __shared__ int hist[256], cursor[256];
-  const int tid = threadIdx.x;
-  if (tid < 256) hist[tid] = 0;
-  __syncthreads();
-  auto bucket = [](int32_t wk) { return wk < 0 ? 255 : 254 - min(wk >> 6, 254); };
-  for (int64_t i = tid; i < n; i += 1024) atomicAdd(&hist[bucket(work[i])], 1);
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int k = 0; k < 256; ++k) { cursor[k] = acc; acc += hist[k]; }
-  }
-  __syncthreads();
-  for (int64_t i = tid; i < n; i += 1024) order[atomicAdd(&cursor[bucket(work[i])], 1)] = (int32_t)i;
+  group_envs_by_key<256>([work](int64_t i) { const int32_t wk = work[i]; return wk < 0 ? 255 : 254 - min(wk >> 6, 254); },
+                         order, n);
 }
-
