@@ -475,6 +475,32 @@ def test_humanoid_warp_and_thread_mappings_agree(mode):
     assert not a_env.buffer_overflow() and not b_env.buffer_overflow()
 
 
+def test_humanoid_cta_grouping_is_scheduling_only():
+    """Envs are regrouped into CTAs by last step's solver work; that must never change results, and `order` must be a
+    permutation of the env indices."""
+    import torch
+
+    n, T = 777, 45  # not a multiple of the 8 envs per CTA: the last CTA has idle warps
+    envs = []
+    for knob in (8 | 16, 8 | 16 | 64, 4 | 16, 1):  # grouped, grouping off, 4 envs per CTA, one env per CTA / no barriers
+        e = make("Humanoid-v5", n, impl="warp", max_episode_steps=30)
+        e._cfg.lanes_per_warp = knob
+        e.reset(seed=11)
+        envs.append(e)
+    rs = np.random.default_rng(4)
+    for t in range(T):
+        a = rs.uniform(-0.4, 0.4, size=(n, 17)).astype(np.float32)
+        outs = [e.step(a) for e in envs]
+        for o in outs[1:]:
+            for k in range(4):
+                np.testing.assert_array_equal(outs[0][k], o[k], err_msg=f"output {k} differs at step {t}")
+    order = envs[0]._s["order"].cpu().numpy()
+    assert sorted(order.tolist()) == list(range(n))
+    work = envs[0]._s["work"].cpu().numpy()
+    assert (work >= -1).all() and work.max() > 0
+    torch.cuda.synchronize()
+
+
 def test_humanoid_reference_structural_pins_on_gpu():
     """The reference's own checks for this boundary (tests/envs/mujoco/test_mujoco_v5.py), through the engine."""
     import torch
