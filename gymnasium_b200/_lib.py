@@ -81,7 +81,8 @@ class HumanoidCfg(C.Structure):
     _fields_ = [(k, c_double) for k in ("reset_noise_scale", "forward_reward_weight", "ctrl_cost_weight",
                                         "contact_cost_weight", "contact_cost_max", "healthy_reward", "healthy_z_min",
                                         "healthy_z_max")] + [("terminate_when_unhealthy", c_i32), ("frame_skip", c_i32),
-                                                             ("lanes_per_warp", c_i32), ("impl", c_i32)]
+                                                             ("lanes_per_warp", c_i32), ("impl", c_i32),
+                                                             ("envs_per_cta", c_i32), ("schedule", c_i32)]
 
 
 class HumanoidState(C.Structure):

@@ -971,7 +971,7 @@ int upload_model() {
 // ---- kernels -------------------------------------------------------------------------------------------------------------------
 struct HumanoidArgs {
   int64_t n, env_offset;
-  int32_t max_steps, mode, rng_mode, lanes, frame_skip, terminate_when_unhealthy;
+  int32_t max_steps, mode, rng_mode, lanes, frame_skip, terminate_when_unhealthy, cta_sync;
   uint64_t philox_seed, call_counter;
   double noise, w_forward, w_ctrl, w_contact, contact_max, healthy_reward, z_min, z_max;
   double* __restrict__ qpos;   // [24][n]
@@ -1065,7 +1065,7 @@ __device__ void store_state(const HumanoidArgs& a, int64_t i, const HData& d) {
 }
 
 constexpr int kHumanoidBlock = 32;
-constexpr int kWarpImplDefault = 8 | 16;           // warp mapping: envs per CTA (1, 2, 4, 8), | 16 = CTA barrier per mj_forward
+constexpr int kWarpEnvsPerCta = 8;  // warp mapping: envs (warps) per CTA unless b2e_humanoid_cfg.envs_per_cta says otherwise
 constexpr bool kHumanoidDefaultWarp = true;   // warp per env is the default mapping (thread per env: impl = 1)
 constexpr int kHumanoidLanes = 32;  // default envs per warp (b2e_humanoid_cfg.lanes_per_warp overrides)
 
@@ -1195,7 +1195,8 @@ int fill(const b2e_batch* b, const b2e_humanoid_cfg* cfg, const b2e_humanoid_sta
   a.n = b->n; a.env_offset = b->env_offset; a.max_steps = b->max_episode_steps; a.mode = b->autoreset_mode;
   a.rng_mode = b->rng_mode; a.philox_seed = b->philox_seed; a.call_counter = b->call_counter;
   a.frame_skip = cfg->frame_skip; a.terminate_when_unhealthy = cfg->terminate_when_unhealthy;
-  a.lanes = (cfg->lanes_per_warp >= 1 && cfg->lanes_per_warp <= 32 && cfg->impl == 1) ? cfg->lanes_per_warp : kHumanoidLanes;
+  a.cta_sync = 0;
+  a.lanes = (cfg->lanes_per_warp >= 1 && cfg->lanes_per_warp <= 32) ? cfg->lanes_per_warp : kHumanoidLanes;
   a.noise = cfg->reset_noise_scale; a.w_forward = cfg->forward_reward_weight; a.w_ctrl = cfg->ctrl_cost_weight;
   a.w_contact = cfg->contact_cost_weight; a.contact_max = cfg->contact_cost_max; a.healthy_reward = cfg->healthy_reward;
   a.z_min = cfg->healthy_z_min; a.z_max = cfg->healthy_z_max;
@@ -1257,10 +1258,9 @@ extern "C" int b2e_humanoid_step(const b2e_batch* b, const b2e_humanoid_cfg* cfg
   const unsigned grid = sparse_grid(b->n, a.lanes, kHumanoidBlock);
   cudaStream_t s = (cudaStream_t)stream;
   if (use_warp_impl(cfg)) {
-    const int knob = cfg->lanes_per_warp > 0 ? cfg->lanes_per_warp : kWarpImplDefault;  // envs per CTA | 16 = CTA barriers
-    const int W = knob & 15;
-    a.lanes = knob;
-    if (W == 1 || !(knob & 16) || (knob & 64)) a.order = nullptr;  // grouping only matters to CTA-synchronised warps; | 64 disables it
+    const int W = cfg->envs_per_cta > 0 ? cfg->envs_per_cta : kWarpEnvsPerCta;
+    a.cta_sync = W > 1 && !(cfg->schedule & 1);
+    if (!a.cta_sync || (cfg->schedule & 2)) a.order = nullptr;  // grouping only matters to warps that wait for each other
     const bool f64 = b->action_dtype == B2E_ACT_F64;
     if (b->action_dtype != B2E_ACT_F32 && !f64) {
       set_error("b2e_humanoid_step: action_dtype %d is not a float dtype", b->action_dtype);

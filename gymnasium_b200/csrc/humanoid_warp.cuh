@@ -184,10 +184,7 @@ __device__ __forceinline__ void w_tree_sum(const HModel& m, double* arr /*[NB][K
 #define DINV(i) w.dinv[i]
 
 // mj_forward for the env of this warp; inputs w.qpos, w.qvel, w.warm, w.ctrl; output w.qacc (+ all derived arrays)
-// stage_sync: the warps of the CTA also meet at 6 CTA barriers between the stages (callers guarantee that every live warp of
-// the CTA executes the same number of barriers)
-#define STAGE_SYNC() do { if (stage_sync) __syncthreads(); } while (0)
-__device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane, bool stage_sync) {
+__device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane) {
   const HModel& m = wm.m;
   // ---- position stage ----------------------------------------------------------------------------------------------------
   if (lane == 0) {
@@ -270,7 +267,6 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane, bool s
   }
   if (lane < 2) w.ten_length[lane] = -w.qpos[m.ten_q[lane][0]] + w.qpos[m.ten_q[lane][1]];
   WSYNC();
-  STAGE_SYNC();
   // mj_crb
   for (int e = lane; e < NB * 10; e += 32) (&w.u.p.crb[0][0])[e] = (&w.cinert[0][0])[e];
   WSYNC();
@@ -306,7 +302,6 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane, bool s
     }
     WSYNC();
   }
-  STAGE_SYNC();
   // mj_collision: pair p = 32 * round + lane, contacts appended in pair order
   {
     int base = 0;
@@ -327,7 +322,6 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane, bool s
     if (lane == 0) w.ncon = base < MAXCON ? base : MAXCON;
   }
   WSYNC();  // the position-stage temporaries (w.u.p) are dead from here on
-  STAGE_SYNC();
   // ---- velocity stage (independent of the constraint rows; runs first so that its temporaries can share w.u) -----------
   if (lane == 0) for (int k = 0; k < 6; ++k) w.cvel[0][k] = 0;
   WSYNC();
@@ -400,7 +394,6 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane, bool s
     w.smooth[lane] = w.passive[lane] - bias + w.actuator[lane];
   }
   WSYNC();  // the velocity-stage temporaries (w.u.v) are dead from here on; w.u.J takes their place
-  STAGE_SYNC();
   // ---- mj_makeConstraint: joint-limit rows (joint order, lower side then upper side), then contact rows -----------------
   double* const c_pos = w.b;        // row scratch that is only needed until R / aref are known shares b / force / term
   double* const c_margin = w.force;
@@ -508,7 +501,6 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane, bool s
   }
   WSYNC();
   if (lane < n) w.D[lane] = 1.0 / w.R[lane];
-  STAGE_SYNC();
   // ---- all M^-1 solves at once: lane r < n takes constraint row r, the next lane takes qfrc_smooth ------------------------
   {
     double x[NV];
@@ -542,7 +534,6 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane, bool s
     }
   }
   WSYNC();
-  STAGE_SYNC();
   // ---- mj_fwdConstraint (PGS) --------------------------------------------------------------------------------------------------
   if (n == 0) {
     if (lane < NV) w.qacc[lane] = w.qacc_smooth[lane];
@@ -647,7 +638,7 @@ __device__ __forceinline__ void w_integrate_pos(WS& w, const double* vel, double
 }
 
 // mj_RungeKutta(4): four mj_forward evaluations (one call site), Butcher combination per dof lane
-__device__ void w_step_rk4(const WModel& wm, WS& w, int lane, bool cta_sync, bool stage_sync) {
+__device__ void w_step_rk4(const WModel& wm, WS& w, int lane, bool cta_sync) {
   const HModel& m = wm.m;
   const double h = m.timestep;
   const double A[3][3] = {{0.5, 0, 0}, {0, 0.5, 0}, {0, 0, 1.0}}, Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
@@ -670,7 +661,7 @@ __device__ void w_step_rk4(const WModel& wm, WS& w, int lane, bool cta_sync, boo
       WSYNC();
     }
     if (cta_sync) __syncthreads();  // keeps the warps of a CTA inside the same code region (shared instruction cache)
-    w_forward(wm, w, lane, stage_sync);
+    w_forward(wm, w, lane);
     if (i == 0) {  // X0 is the state after the first evaluation: mj_kinematics normalises the quaternion inside qpos
       for (int k = lane; k < NQ; k += 32) w.X0q[k] = w.qpos[k];
       if (lane < NV) w.Xv[0][lane] = w.qvel[lane];
@@ -748,7 +739,7 @@ __device__ void w_env_reset(const WModel& wm, const HumanoidArgs& a, int64_t i, 
   if (lane < NU) w.ctrl[lane] = 0;
   for (int e = lane; e < NB * 6; e += 32) (&w.cfrc_ext[0][0])[e] = 0;
   WSYNC();
-  w_forward(wm, w, lane, false);
+  w_forward(wm, w, lane);
   w_write_obs(w, obs, lane);
   if (lane == 0) {
     for (int k = 7; k < 13; ++k) a.info[k * a.n + i] = 0.0;
@@ -773,9 +764,9 @@ __global__ void __launch_bounds__(32) humanoid_reset_warp_kernel(const HumanoidA
 }
 
 // W envs per CTA, one warp each (the warps never exchange data; sharing a CTA only co-schedules them).  With
-// a.lanes & 16 the warps also meet at a CTA barrier before every mj_forward evaluation, so they walk the ~200 KB of code
-// together and share instruction-cache lines (a.lanes & 32: six more barriers between the stages of mj_forward); every
-// live warp executes the same number of barriers.
+// a.cta_sync the warps also meet at a CTA barrier before every mj_forward evaluation, so they walk the ~165 KB of code
+// together and share instruction-cache lines (barriers between the stages of mj_forward as well were measured: no further
+// gain); every live warp executes the same number of barriers.
 template <typename ActT, int W>
 __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const HumanoidArgs a) {
   extern __shared__ __align__(16) unsigned char w_smem[];
@@ -786,8 +777,8 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t slot = (int64_t)blockIdx.x * W + warp, n = a.n;
-  const bool cta_sync = W > 1 && (a.lanes & 16), stage_sync = cta_sync && (a.lanes & 32);
-  const int n_sync = cta_sync ? 4 * a.frame_skip * (stage_sync ? 7 : 1) : 0;
+  const bool cta_sync = W > 1 && a.cta_sync;
+  const int n_sync = cta_sync ? 4 * a.frame_skip : 0;
   if (slot >= n) {
     for (int k = 0; k < n_sync; ++k) __syncthreads();
     return;
@@ -813,7 +804,7 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
     if (lane < NU) w.ctrl[lane] = (double)reinterpret_cast<const ActT*>(a.actions)[i * NU + lane];
     WSYNC();
 #pragma unroll 1
-    for (int k = 0; k < a.frame_skip; ++k) w_step_rk4(wm, w, lane, cta_sync, stage_sync);
+    for (int k = 0; k < a.frame_skip; ++k) w_step_rk4(wm, w, lane, cta_sync);
     if (lane == 0) {  // mj_rnePostConstraint (cfrc_ext only): a short sequential tail
       for (int b = 0; b < NB; ++b) for (int k = 0; k < 6; ++k) w.cfrc_ext[b][k] = 0;
       for (int cc = 0; cc < w.ncon; ++cc) {

@@ -245,3 +245,77 @@ class NormalizeReward(_Base):
             self.accumulated_reward = torch.where(self._prev_dones, torch.zeros_like(self.accumulated_reward),
                                                   self.accumulated_reward)
         return obs, r64 / torch.sqrt(self.return_rms.var + self.epsilon), term, trunc, info
+
+
+class DictInfoToList(_Base):
+    """``info`` dict of batched arrays + ``_key`` masks -> list of per-env dicts
+    (gymnasium/wrappers/vector/dict_info_to_list.py:16-163).  The list is host data by definition, so tensors are
+    brought to the host ONCE per call (one ``.cpu()`` per info array) instead of once per element; nested dicts and
+    masks behave as in the reference.  Must be the outermost wrapper, like the reference's."""
+
+    def reset(self, *, seed=None, options=None):
+        obs, infos = self.env.reset(seed=seed, options=options)
+        return obs, self._convert(infos)
+
+    def step(self, actions):
+        obs, reward, terminated, truncated, infos = self.env.step(actions)
+        return obs, reward, terminated, truncated, self._convert(infos)
+
+    def _convert(self, vector_infos):
+        assert isinstance(vector_infos, dict)
+        n = self.num_envs
+        out = [{} for _ in range(n)]
+        for key, value in vector_infos.items():
+            if key.startswith("_"):
+                continue
+            mask = vector_infos.get(f"_{key}")
+            if isinstance(mask, torch.Tensor):
+                mask = mask.cpu().numpy()
+            if isinstance(value, dict):
+                value = self._convert(value)
+            elif isinstance(value, torch.Tensor):
+                value = value.cpu().numpy()
+            assert len(value) == n, f"Expects {key!r} to have length equal to the num-envs ({n}), actual length is {len(value)}"
+            if mask is not None:
+                assert len(mask) == n, f"Expects {'_' + key!r} to have length equal to the num-envs ({n}), actual length is {len(mask)}"
+            for i in range(n):
+                if mask is None or mask[i]:
+                    out[i][key] = value[i]
+        return out
+
+
+class NumpyToTorch(_Base):
+    """Drop-in for ``gymnasium.wrappers.vector.NumpyToTorch`` (numpy_to_torch.py:15-80) around an engine env.
+
+    The reference wrapper converts a NumPy env's outputs to torch tensors (and torch actions back to NumPy) on every call.
+    An engine env already computes on the device: with ``output="torch"`` this wrapper is a no-op pass-through (actions
+    may be torch tensors on any device or numpy arrays; nothing is copied to the host), and with ``output="numpy"`` it
+    switches the env to torch outputs instead of converting back and forth.  ``device`` moves the outputs if it differs
+    from the env's device."""
+
+    def __init__(self, env, device=None):
+        super().__init__(env)
+        base = getattr(env, "unwrapped", env)
+        if getattr(base, "output", "torch") == "numpy":
+            base.output = "torch"  # stop producing host arrays that would only be converted back
+        self.device = None if device is None else torch.device(device)
+
+    def _out(self, x):
+        if isinstance(x, dict):
+            return {k: self._out(v) for k, v in x.items()}
+        if isinstance(x, tuple):
+            return tuple(self._out(v) for v in x)
+        if not isinstance(x, torch.Tensor):
+            try:
+                x = torch.as_tensor(x)
+            except (TypeError, ValueError, RuntimeError):
+                return x
+        return x if self.device is None or x.device == self.device else x.to(self.device)
+
+    def reset(self, *, seed=None, options=None):
+        obs, info = self.env.reset(seed=seed, options=options)
+        return self._out(obs), self._out(info)
+
+    def step(self, actions):
+        obs, reward, terminated, truncated, info = self.env.step(actions)
+        return self._out(obs), self._out(reward), self._out(terminated), self._out(truncated), self._out(info)

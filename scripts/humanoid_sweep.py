@@ -14,13 +14,14 @@ n = int(os.environ.get("B2E_N", "8192"))
 steps = int(os.environ.get("B2E_STEPS", "6"))
 g = torch.Generator(device=dev).manual_seed(1)
 acts = [torch.rand((n, 17), device=dev, generator=g) * 0.8 - 0.4 for _ in range(60 + steps)]
-configs = [("thread", 0)] + [("warp", k) for k in (1, 4, 2 | 16, 4 | 16, 8 | 16, 2 | 48, 4 | 48, 8 | 48)]
+# (impl, envs per CTA, schedule bits: 1 = no CTA barrier, 2 = no work grouping)
+configs = [("thread", 0, 0)] + [("warp", w, sch) for w, sch in ((1, 0), (4, 1), (2, 0), (4, 2), (4, 0), (8, 2), (8, 0))]
 if len(sys.argv) > 1:
-    configs = [(c.split(":")[0], int(c.split(":")[1])) for c in sys.argv[1:]]
+    configs = [(c.split(":")[0], int(c.split(":")[1]), int(c.split(":")[2])) for c in sys.argv[1:]]
 ref = None
-for impl, knob in configs:
+for impl, per_cta, schedule in configs:
     e = gymnasium_b200.make_vec("Humanoid-v5", num_envs=n, copy=False, impl=impl)
-    e._cfg.lanes_per_warp = knob
+    e._cfg.envs_per_cta, e._cfg.schedule = per_cta, schedule
     e.reset(seed=0)
     for t in range(60):
         e.step(acts[t])
@@ -33,6 +34,7 @@ for impl, knob in configs:
     sig = (out[0].double().sum().item(), out[1].sum().item(), int(out[2].sum().item()))
     same = "" if ref is None else ("same" if sig == ref else f"DIFFERENT {sig} vs {ref}")
     ref = ref or sig
-    label = f"{impl} envs/CTA={knob & 15} barrier={'stage' if knob & 32 else 'fwd' if knob & 16 else 'no'} grouped={'n' if knob & 64 or not knob & 16 else 'y'}" if impl == "warp" else "thread"
+    label = (f"warp envs/CTA={per_cta} barrier={'n' if schedule & 1 or per_cta == 1 else 'y'} "
+             f"grouped={'n' if schedule & 3 or per_cta == 1 else 'y'}") if impl == "warp" else "thread"
     print(f"Humanoid n={n} {label:46s}: {dt*1e3:8.2f} ms/step  {n/dt:.3e} steps/s  {same}", flush=True)
     del e

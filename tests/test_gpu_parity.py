@@ -482,9 +482,9 @@ def test_humanoid_cta_grouping_is_scheduling_only():
 
     n, T = 777, 45  # not a multiple of the 8 envs per CTA: the last CTA has idle warps
     envs = []
-    for knob in (8 | 16, 8 | 16 | 64, 4 | 16, 1):  # grouped, grouping off, 4 envs per CTA, one env per CTA / no barriers
+    for per_cta, schedule in ((8, 0), (8, 2), (4, 0), (2, 1), (1, 0)):  # default; grouping off; smaller CTAs; no barriers
         e = make("Humanoid-v5", n, impl="warp", max_episode_steps=30)
-        e._cfg.lanes_per_warp = knob
+        e._cfg.envs_per_cta, e._cfg.schedule = per_cta, schedule
         e.reset(seed=11)
         envs.append(e)
     rs = np.random.default_rng(4)
@@ -625,3 +625,34 @@ def test_wrappers_run_on_device_without_host_sync():
         total_done += int(done.sum())
     assert abs(float(o.mean())) < 0.2 and 0.5 < float(o.std()) < 1.5
     assert env.env.env.episode_count == total_done and total_done > n
+
+
+def test_dict_info_to_list_and_numpy_to_torch_on_the_engine():
+    """§8f rank 1: DictInfoToList over FrozenLake's masked `prob` info and Humanoid's 11 info keys; NumpyToTorch turns an
+    output="numpy" engine env into a torch one without a host round trip."""
+    import torch
+    from gymnasium_b200 import wrappers as W
+
+    n = 64
+    raw = make("FrozenLake-v1", n, map_name="8x8")
+    env = W.DictInfoToList(make("FrozenLake-v1", n, map_name="8x8", output="torch"))
+    (_, i0), (_, l0) = raw.reset(seed=1), env.reset(seed=1)
+    assert isinstance(l0, list) and len(l0) == n and all(d["prob"] == 1 for d in l0)
+    rs = np.random.default_rng(0)
+    for t in range(40):
+        a = rs.integers(0, 4, n)
+        info, lst = raw.step(a)[4], env.step(a)[4]
+        for i in range(n):
+            assert ("prob" in lst[i]) == bool(info["_prob"][i])
+            if info["_prob"][i]:
+                assert lst[i]["prob"] == info["prob"][i]
+    h = W.DictInfoToList(make("Humanoid-v5", 3))
+    _, li = h.reset(seed=0)
+    assert set(li[0]) >= {"x_position", "tendon_length"} and li[2]["tendon_length"].shape == (2,)
+    t = W.NumpyToTorch(make("CartPole-v1", 16, output="numpy"))
+    o, _ = t.reset(seed=0)
+    o2, r, te, tr, _ = t.step(torch.zeros(16, dtype=torch.int64))
+    assert o.is_cuda and o2.is_cuda and r.dtype == torch.float64 and te.dtype == torch.bool
+    ref = make("CartPole-v1", 16)
+    ref.reset(seed=0)
+    np.testing.assert_array_equal(ref.step(np.zeros(16, dtype=np.int64))[0], o2.cpu().numpy())

@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.FrozenLakeCfg) == 8 + 16 + 72
     assert C.sizeof(_lib.LunarLanderCfg) == 24 and C.sizeof(_lib.LunarLanderState) == 72
     assert _lib.load().b2e_lunarlander_state_words() == 12 * 16
-    assert C.sizeof(_lib.HumanoidCfg) == 80 and C.sizeof(_lib.HumanoidState) == 72
+    assert C.sizeof(_lib.HumanoidCfg) == 88 and C.sizeof(_lib.HumanoidState) == 72
 
 
 def test_argument_errors_do_not_need_a_gpu():

@@ -98,3 +98,76 @@ def test_normalize_observation_and_reward_match_reference():
         W.NormalizeObservation(ScriptedEnv(2, 3, 0, True), epsilon=0)
     with pytest.raises(ValueError):
         W.NormalizeReward(ScriptedEnv(2, 3, 0, True), gamma=1.5)
+
+
+class InfoEnv(ScriptedEnv):
+    """ScriptedEnv whose infos carry masked arrays and a nested dict, as SyncVectorEnv builds them (vector_env.py:277-338)."""
+
+    def _info(self, t):
+        n = self.num_envs
+        rs = np.random.default_rng(1000 + t)
+        m1, m2 = rs.random(n) < 0.5, rs.random(n) < 0.3
+        info = {"k": rs.normal(size=n), "_k": m1, "always": np.arange(n, dtype=np.int64) + t,
+                "nest": {"z": rs.normal(size=n).astype(np.float32), "_z": m2}, "_nest": m2}
+        if self.as_torch:
+            info = {"k": torch.from_numpy(info["k"]), "_k": torch.from_numpy(m1), "always": torch.from_numpy(info["always"]),
+                    "nest": {"z": torch.from_numpy(info["nest"]["z"]), "_z": torch.from_numpy(m2)}, "_nest": torch.from_numpy(m2)}
+        return info
+
+    def reset(self, *, seed=None, options=None):
+        o, _ = super().reset(seed=seed, options=options)
+        return o, self._info(0)
+
+    def step(self, actions):
+        out = super().step(actions)
+        return out[:4] + (self._info(self.t),)
+
+
+def test_dict_info_to_list_matches_reference():
+    from gymnasium.wrappers.vector import DictInfoToList as Ref
+
+    n, T = 6, 12
+    ref, ours = Ref(InfoEnv(n, T, 3, False)), W.DictInfoToList(InfoEnv(n, T, 3, True))
+    (_, ia), (_, ib) = ref.reset(seed=0), ours.reset(seed=0)
+    for t in range(T + 1):
+        assert isinstance(ib, list) and len(ib) == n
+        for a, b in zip(ia, ib):
+            assert set(a) == set(b)
+            for k in a:
+                if isinstance(a[k], dict):
+                    assert set(a[k]) == set(b[k])
+                    for kk in a[k]:
+                        assert a[k][kk] == b[k][kk] and np.asarray(b[k][kk]).dtype == np.asarray(a[k][kk]).dtype
+                else:
+                    assert a[k] == b[k] and np.asarray(b[k]).dtype == np.asarray(a[k]).dtype
+        if t < T:
+            ia, ib = ref.step(np.zeros(n, dtype=np.int64))[4], ours.step(np.zeros(n, dtype=np.int64))[4]
+
+
+def test_numpy_to_torch_outputs_are_the_numpy_env_outputs_as_tensors():
+    """The reference wrapper (numpy_to_torch.py:15-80) needs `array_api_compat`, which is not installed here; its
+    contract is "same values, torch types" (tests/wrappers/vector/test_numpy_to_torch.py), checked against the raw env."""
+    n, T = 5, 8
+    raw, ours = InfoEnv(n, T, 4, False), W.NumpyToTorch(InfoEnv(n, T, 4, True))
+    (oa, ia), (ob, ib) = raw.reset(seed=0), ours.reset(seed=0)
+    assert isinstance(ob, torch.Tensor) and np.array_equal(oa, ob.numpy()) and np.array_equal(ia["k"], ib["k"].numpy())
+    for t in range(T):
+        a = raw.step(np.zeros(n, dtype=np.int64))
+        b = ours.step(torch.zeros(n, dtype=torch.int64))
+        for x, y in zip(a[:4], b[:4]):
+            assert isinstance(y, torch.Tensor) and np.array_equal(x, y.numpy()) and y.numpy().dtype == x.dtype
+        assert np.array_equal(a[4]["nest"]["z"], b[4]["nest"]["z"].numpy()) and np.array_equal(a[4]["_k"], b[4]["_k"].numpy())
+
+
+def test_numpy_to_torch_switches_a_numpy_engine_env_to_torch_outputs():
+    class Fake(ScriptedEnv):
+        output = "numpy"
+
+        @property
+        def unwrapped(self):
+            return self
+
+    e = Fake(3, 4, 0, False)
+    w = W.NumpyToTorch(e)
+    assert e.output == "torch"
+    assert isinstance(w.reset()[0], torch.Tensor)  # host arrays a non-engine env still returns are converted
