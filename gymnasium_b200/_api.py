@@ -12,17 +12,17 @@ try:
     if _os.environ.get("B200ENV_FORCE_COMPAT"):
         raise ImportError("B200ENV_FORCE_COMPAT is set")
     import gymnasium as _gym
-    from gymnasium.spaces import Box, Discrete, MultiDiscrete
+    from gymnasium.spaces import Box, Discrete, MultiDiscrete, Tuple
     from gymnasium.vector import AutoresetMode, VectorEnv
     from gymnasium.vector.utils import batch_space
 
     HAVE_GYMNASIUM = True
     gymnasium = _gym
 except ImportError:  # pragma: no cover - exercised on boxes without the host framework
-    from ._compat import AutoresetMode, Box, Discrete, MultiDiscrete, VectorEnv, batch_space
+    from ._compat import AutoresetMode, Box, Discrete, MultiDiscrete, Tuple, VectorEnv, batch_space
 
     HAVE_GYMNASIUM = False
     gymnasium = None
 
-__all__ = ["AutoresetMode", "Box", "Discrete", "MultiDiscrete", "VectorEnv", "batch_space", "HAVE_GYMNASIUM",
+__all__ = ["AutoresetMode", "Box", "Discrete", "MultiDiscrete", "Tuple", "VectorEnv", "batch_space", "HAVE_GYMNASIUM",
            "gymnasium"]

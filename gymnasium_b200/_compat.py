@@ -20,8 +20,8 @@ class AutoresetMode(Enum):
 
 class Space:
     def __init__(self, shape, dtype, seed=None):
-        self.shape = tuple(shape)
-        self.dtype = np.dtype(dtype)
+        self.shape = None if shape is None else tuple(shape)
+        self.dtype = None if dtype is None else np.dtype(dtype)
         self._rng = None
         if seed is not None:
             self.seed(seed)
@@ -91,7 +91,30 @@ class MultiDiscrete(Space):
         return f"MultiDiscrete({self.nvec})"
 
 
+class Tuple(Space):
+    def __init__(self, spaces, seed=None):
+        self.spaces = tuple(spaces)
+        super().__init__(None, None, seed)
+
+    def sample(self):
+        return tuple(s.sample() for s in self.spaces)
+
+    def contains(self, x):
+        return isinstance(x, (tuple, list)) and len(x) == len(self.spaces) and all(s.contains(v) for s, v in zip(self.spaces, x))
+
+    def __len__(self):
+        return len(self.spaces)
+
+    def __getitem__(self, i):
+        return self.spaces[i]
+
+    def __repr__(self):
+        return "Tuple(" + ", ".join(map(repr, self.spaces)) + ")"
+
+
 def batch_space(space, n=1):
+    if isinstance(space, Tuple):
+        return Tuple(tuple(batch_space(s, n) for s in space.spaces))
     if isinstance(space, Box):
         reps = (n,) + (1,) * space.low.ndim
         return Box(np.tile(space.low, reps), np.tile(space.high, reps), dtype=space.dtype)

@@ -61,6 +61,13 @@ class ClassicCfg(C.Structure):
                 ("ctrl", c_void_p), ("rng", c_void_p)]
 
 
+class BlackjackCfg(C.Structure):
+    """``b2e_blackjack_cfg``."""
+
+    _fields_ = [("natural", c_i32), ("sab", c_i32), ("hand", c_void_p), ("u32buf", c_void_p), ("ctrl", c_void_p),
+                ("rng", c_void_p)]
+
+
 class LunarLanderCfg(C.Structure):
     """``b2e_lunarlander_cfg``."""
 
@@ -111,6 +118,8 @@ SIGNATURES = {
     "b2e_classic_reset": (C.c_int, [_BP, C.POINTER(ClassicCfg), P, P, P]),
     "b2e_classic_step": (C.c_int, [_BP, C.POINTER(ClassicCfg), P, P, P, P, P, P, P]),
     "b2e_lunarlander_state_words": (C.c_int, []),
+    "b2e_blackjack_reset": (C.c_int, [_BP, C.POINTER(BlackjackCfg), P, P, P]),
+    "b2e_blackjack_step": (C.c_int, [_BP, C.POINTER(BlackjackCfg), P, P, P, P, P, P, P]),
     "b2e_lunarlander_reset": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P]),
     "b2e_lunarlander_step": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P, P, P, P,
                                        P]),

@@ -37,6 +37,8 @@ ENVS = {
                         "gymnasium.envs.toy_text.cliffwalking:CliffWalkingEnv", None, None, {}),
     "CliffWalkingSlippery-v1": ("gymnasium_b200.envs.toy_text:CliffWalkingVectorEnv",
                                 "gymnasium.envs.toy_text.cliffwalking:CliffWalkingEnv", None, None, {"is_slippery": True}),
+    "Blackjack-v1": ("gymnasium_b200.envs.blackjack:BlackjackVectorEnv", "gymnasium.envs.toy_text.blackjack:BlackjackEnv",
+                     None, None, {"sab": True, "natural": False}),
     "Taxi-v4": ("gymnasium_b200.envs.toy_text:TaxiVectorEnv", "gymnasium.envs.toy_text.taxi:TaxiEnv", 200, 8, {}),
     "LunarLander-v3": ("gymnasium_b200.envs.lunar_lander:LunarLanderVectorEnv",
                        "gymnasium.envs.box2d.lunar_lander:LunarLander", 1000, 200, {}),

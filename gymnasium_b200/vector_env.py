@@ -242,9 +242,14 @@ class B200VectorEnv(VectorEnv):
                                        ptr(self._rng), self._stream),
                 "b2e_rng_seed",
             )
+            self._on_streams_seeded(mask)
         else:
             self._batch.philox_seed = (base if seeds_dev is None else int(seed[0])) & _U64
         self._seeded = True
+
+    def _on_streams_seeded(self, lanes: torch.Tensor | None) -> None:
+        """Hook: the numpy-parity streams of `lanes` (bool mask, None = all) were just (re)seeded; families that keep extra
+        generator state next to the PCG64 words (Blackjack: numpy's 32-bit word buffer) reset it here."""
 
     def _parse_reset_mask(self, options: dict | None):
         """Validation and messages of sync_vector_env.py:214-231 (torch bool tensors are accepted too)."""

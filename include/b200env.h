@@ -142,6 +142,26 @@ int b2e_frozenlake_rollout(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, in
                            uint8_t* actions_out, int32_t* pstate, int32_t* ctrl, uint64_t* rng, int64_t* obs,
                            float* reward, uint8_t* terminated, uint8_t* truncated, void* stream);
 
+/* ---- Blackjack-v1: gymnasium/envs/toy_text/blackjack.py:10-238 ------------------------------------------------------------
+ *   hand   : int32 [n]  packed (player sum/ace/count, dealer sum/ace/count, dealer's first card), see blackjack.cu
+ *   u32buf : int64 [n]  PCG64's one-word 32-bit buffer (bit 32 = valid); zero it for an env whenever its stream is
+ *                       (re)seeded, as numpy does for a fresh Generator; unused in Philox mode (may be NULL)
+ *   ctrl / rng as for CartPole
+ * obs int64 [3][n] (player sum, dealer's first card, usable ace: the three Discrete components of the reference's Tuple
+ * observation, one array each); reward float64 [n] in {-1, 0, 1, 1.5}; final_obs int64 [3][n] (SAME_STEP only).
+ * actions: 0 = stick, anything else = hit (the reference asserts {0, 1}). */
+typedef struct b2e_blackjack_cfg {
+  int32_t natural;   /* BlackjackEnv(natural=False) */
+  int32_t sab;       /* BlackjackEnv(sab=False); the registered Blackjack-v1 passes sab=True */
+  int32_t* hand;
+  int64_t* u32buf;
+  int32_t* ctrl;
+  uint64_t* rng;
+} b2e_blackjack_cfg;
+int b2e_blackjack_reset(const b2e_batch* b, const b2e_blackjack_cfg* cfg, const uint8_t* mask, int64_t* obs, void* stream);
+int b2e_blackjack_step(const b2e_batch* b, const b2e_blackjack_cfg* cfg, const void* actions, int64_t* obs, double* reward,
+                       uint8_t* terminated, uint8_t* truncated, int64_t* final_obs, void* stream);
+
 /* ---- remaining classic-control families (gymnasium/envs/classic_control/{mountain_car,continuous_mountain_car,
  * pendulum,acrobot}.py): one generic entry point pair, `family` selects the dynamics.
  *   state float64 [k][n] (k = 2, 2, 2, 4); sflag uint8 [n] (MountainCarContinuous only); ctrl / rng as for CartPole

@@ -80,6 +80,7 @@ class PCG64:
         initseq = (u[2] << 64) | u[3]
         self.inc = ((initseq << 1) | 1) & M128
         self.state = 0
+        self.has_uint32, self.uinteger = False, 0  # pcg64_next32's one-word buffer (numpy/random/src/pcg64/pcg64.h)
         self._step()
         self.state = (self.state + initstate) & M128
         self._step()
@@ -102,3 +103,28 @@ class PCG64:
     def uniform(self, low: float, high: float) -> float:
         """``Generator.uniform(low, high)`` = ``low + (high-low)*next_double`` (two roundings)."""
         return low + (high - low) * self.next_double()
+
+    def next_uint32(self) -> int:
+        """``pcg64_next32``: the low half of a fresh 64-bit draw now, the high half on the next call."""
+        if self.has_uint32:
+            self.has_uint32 = False
+            return self.uinteger
+        x = self.next_uint64()
+        self.has_uint32, self.uinteger = True, x >> 32
+        return x & M32
+
+    def bounded_uint32(self, n_excl: int) -> int:
+        """Uniform integer in ``[0, n_excl)`` for ``1 <= n_excl <= 2**32``: Lemire's multiply-and-reject on buffered
+        32-bit words (``buffered_bounded_lemire_uint32``, numpy/random/src/distributions/distributions.c).  This is
+        what ``Generator.choice(seq)`` (no ``p``, scalar) and ``Generator.integers(0, n)`` reduce to for small ranges."""
+        rng = n_excl - 1
+        if rng == 0:
+            return 0
+        m = self.next_uint32() * n_excl
+        leftover = m & M32
+        if leftover < n_excl:
+            threshold = (M32 - rng) % n_excl
+            while leftover < threshold:
+                m = self.next_uint32() * n_excl
+                leftover = m & M32
+        return m >> 32

@@ -16,6 +16,7 @@ FAM = [
     ("FrozenLake-v1", {"map_name": "8x8"}, 4, None, 98),
     ("CliffWalking-v1", {}, 4, None, 98),
     ("Taxi-v4", {}, 6, None, 98),
+    ("Blackjack-v1", {}, 2, None, 118),
 ]
 n = 1 << 23
 for fam, kw, nact, scale, nbytes in FAM:

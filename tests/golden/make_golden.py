@@ -131,9 +131,42 @@ def tabular(name, env_id, n, T, seed, nA, **kw):
           out["truncated"].sum(), "reward", out["reward"].sum())
 
 
+def blackjack(name, n, T, seed, mode=AutoresetMode.NEXT_STEP, **kw):
+    """Blackjack-v1: the observation is a Tuple of three Discrete spaces, batched by SyncVectorEnv into a tuple of three
+    (n,) int64 arrays (vector/utils/space_utils.py:120-131); stored here stacked as (T+1, n, 3)."""
+    envs = gym.make_vec("Blackjack-v1", num_envs=n, vectorization_mode="sync", vector_kwargs={"autoreset_mode": mode}, **kw)
+    rng = np.random.default_rng(5000 + seed)
+    actions = rng.integers(0, 2, size=(T, n)).astype(np.int64)
+    o, _ = envs.reset(seed=seed)
+    assert isinstance(o, tuple) and len(o) == 3 and o[0].dtype == np.int64
+    obs = np.zeros((T + 1, n, 3), np.int64)
+    obs[0] = np.stack(o, axis=1)
+    rew, term, trunc = np.zeros((T, n)), np.zeros((T, n), bool), np.zeros((T, n), bool)
+    final = np.full((T, n, 3), -1, np.int64)
+    for t in range(T):
+        o, r, te, tr, info = envs.step(actions[t])
+        obs[t + 1], rew[t], term[t], trunc[t] = np.stack(o, axis=1), r, te, tr
+        if "final_obs" in info:
+            for i in np.flatnonzero(info["_final_obs"]):
+                final[t, i] = np.asarray(info["final_obs"][i])
+    out = dict(seed=np.uint64(seed), actions=actions, obs=obs, reward=rew, terminated=term, truncated=trunc, final_obs=final,
+               natural=np.int64(kw.get("natural", False)), sab=np.int64(kw.get("sab", True)), mode=np.str_(mode.value),
+               max_episode_steps=np.int64(0))
+    envs.close()
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.shape}, "term", term.sum(), "reward",
+          rew.sum(), "rewards seen", sorted(set(rew.ravel().tolist())))
+
+
 if __name__ == "__main__":
     assert "reference" in gym.__file__ or "_ref" in gym.__file__, gym.__file__
     print("reference:", gym.__version__, gym.__file__, "numpy", np.__version__)
+    if len(sys.argv) > 1 and sys.argv[1] == "blackjack":  # regenerate only the Blackjack fixtures
+        blackjack("blackjack_sab_n32_s11.npz", 32, 400, 11)
+        blackjack("blackjack_natural_n32_s12.npz", 32, 400, 12, natural=True, sab=False)
+        blackjack("blackjack_plain_n17_s13.npz", 17, 300, 13, natural=False, sab=False)
+        blackjack("blackjack_samestep_n16_s14.npz", 16, 300, 14, mode=AutoresetMode.SAME_STEP)
+        sys.exit(0)
     cartpole("cartpole_n8_s42_T300.npz", 8, 300, 42)
     cartpole("cartpole_n16_s7_T400_limit60_balance.npz", 16, 400, 7, max_episode_steps=60, policy="balance")
     cartpole("cartpole_n4_s123_bounds.npz", 4, 60, 123, options={"low": -0.1, "high": 0.1})

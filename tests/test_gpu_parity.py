@@ -656,3 +656,47 @@ def test_dict_info_to_list_and_numpy_to_torch_on_the_engine():
     ref = make("CartPole-v1", 16)
     ref.reset(seed=0)
     np.testing.assert_array_equal(ref.step(np.zeros(16, dtype=np.int64))[0], o2.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Blackjack-v1: Tuple observation, Generator.choice draws on PCG64's buffered 32-bit words
+@pytest.mark.parametrize("name", golden_files("blackjack"))
+def test_blackjack_matches_reference_golden_bit_exact(name):
+    g = golden(name)
+    n = g["actions"].shape[1]
+    env = make("Blackjack-v1", n, natural=bool(g["natural"]), sab=bool(g["sab"]), autoreset_mode=str(g["mode"]))
+    obs, info = env.reset(seed=int(g["seed"]))
+    assert isinstance(obs, tuple) and len(obs) == 3 and obs[0].dtype == np.int64 and info == {}
+    np.testing.assert_array_equal(np.stack(obs, axis=1), g["obs"][0])
+    for t, a in enumerate(g["actions"]):
+        o, r, te, tr, info = env.step(a)
+        np.testing.assert_array_equal(np.stack(o, axis=1), g["obs"][t + 1], err_msg=f"obs at step {t}")
+        np.testing.assert_array_equal(r, g["reward"][t])
+        np.testing.assert_array_equal(te, g["terminated"][t])
+        assert not tr.any()
+        if str(g["mode"]) == "SameStep":
+            done = te | tr
+            np.testing.assert_array_equal(info["_final_obs"], done)
+            np.testing.assert_array_equal(np.stack(info["final_obs"], axis=1)[done], g["final_obs"][t][done])
+
+
+def test_blackjack_reseeding_and_reset_mask():
+    """Re-seeding an env empties its 32-bit word buffer (a fresh numpy Generator has none); unmasked tables keep theirs."""
+    n = 8
+    env, ref = make("Blackjack-v1", n, sab=True), make("Blackjack-v1", n, sab=True)
+    env.reset(seed=5)
+    for t in range(7):
+        env.step(np.ones(n, dtype=np.int64))          # leaves odd/even buffer states behind
+    o1, _ = env.reset(seed=5)
+    o2, _ = ref.reset(seed=5)
+    for a, b in zip(o1, o2):
+        np.testing.assert_array_equal(a, b)
+    mask = np.array([True, False] * 4)
+    seeds = [100 + i if m else None for i, m in enumerate(mask)]
+    before = [x.copy() for x in o1]
+    o3, _ = env.reset(seed=seeds, options={"reset_mask": mask})
+    fresh, _ = make("Blackjack-v1", n, sab=True).reset(seed=[100 + i for i in range(n)])
+    for k in range(3):
+        np.testing.assert_array_equal(o3[k][mask], fresh[k][mask])
+        np.testing.assert_array_equal(o3[k][~mask], before[k][~mask])
+    assert env.single_observation_space.contains((int(o3[0][0]), int(o3[1][0]), int(o3[2][0])))

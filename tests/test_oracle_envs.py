@@ -112,3 +112,41 @@ def test_toy_text_oracles_match_reference(name):
     np.testing.assert_array_equal(out["reward"], g["reward"])
     np.testing.assert_array_equal(out["terminated"], g["terminated"])
     np.testing.assert_array_equal(out["truncated"], g["truncated"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Blackjack-v1: oracle vs live-reference fixtures, and the Generator.choice restatement vs numpy
+@pytest.mark.parametrize("name", golden_files("blackjack"))
+def test_blackjack_oracle_matches_reference_golden(name):
+    from oracle.blackjack import OracleBlackjack
+
+    g = golden(name)
+    n = g["actions"].shape[1]
+    env = OracleBlackjack(n, natural=bool(g["natural"]), sab=bool(g["sab"]), autoreset_mode=str(g["mode"]))
+    obs, _ = env.reset(seed=int(g["seed"]))
+    np.testing.assert_array_equal(obs, g["obs"][0])
+    for t, a in enumerate(g["actions"]):
+        o, r, te, tr, info = env.step(a)
+        np.testing.assert_array_equal(o, g["obs"][t + 1], err_msg=f"obs at step {t}")
+        np.testing.assert_array_equal(r, g["reward"][t])
+        np.testing.assert_array_equal(te, g["terminated"][t])
+        assert not tr.any()
+
+
+def test_generator_choice_restatement_matches_numpy():
+    """np_random.choice(seq) == seq[bounded_uint32(len(seq))] with the one-word 32-bit buffer, also interleaved with
+    random() (which does not touch the buffer)."""
+    from oracle.np_rng import PCG64
+
+    deck = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 10, 10, 10]
+    for seed in (0, 1, 7, 2**40 + 5, 2**64 - 3):
+        ref = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        mine = PCG64(seed)
+        for k in range(300):
+            if k % 7 == 3:
+                assert ref.random() == mine.next_double()
+            elif k % 5 == 0:
+                n = (4, 3, 2, 1000, 2**31 + 11)[k % 25 // 5]
+                assert int(ref.integers(0, n)) == mine.bounded_uint32(n)
+            else:
+                assert int(ref.choice(deck)) == deck[mine.bounded_uint32(13)]
