@@ -637,38 +637,39 @@ __device__ __forceinline__ void w_integrate_pos(WS& w, const double* vel, double
   if (lane >= 6 && lane < NV) w.qpos[lane + 1] += h * vel[lane];
 }
 
-// mj_RungeKutta(4): four mj_forward evaluations (one call site), Butcher combination per dof lane
-__device__ void w_step_rk4(const WModel& wm, WS& w, int lane, bool cta_sync) {
+// mj_RungeKutta(4) in two pieces so that the caller owns the loop (and the CTA barrier in it): stage i = set the state of
+// evaluation i, run mj_forward, keep its acceleration; finish = Butcher combination, one dof per lane
+__device__ void w_rk4_stage(const WModel& wm, WS& w, int lane, int i) {
   const HModel& m = wm.m;
   const double h = m.timestep;
-  const double A[3][3] = {{0.5, 0, 0}, {0, 0.5, 0}, {0, 0, 1.0}}, Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
-#pragma unroll 1
-  for (int i = 0; i < 4; ++i) {
-    if (i > 0) {
-      if (lane < NV) {
-        double dv = 0, da = 0;
-        for (int j = 0; j < i; ++j) { dv += A[i - 1][j] * w.Xv[j][lane]; da += A[i - 1][j] * w.F[j][lane]; }
-        w.sv[lane] = dv;
-        w.sa[lane] = da;
-      }
-      for (int k = lane; k < NQ; k += 32) w.qpos[k] = w.X0q[k];
-      WSYNC();
-      w_integrate_pos(w, w.sv, h, lane);
-      if (lane < NV) {
-        w.qvel[lane] = w.Xv[0][lane] + h * w.sa[lane];
-        w.Xv[i][lane] = w.qvel[lane];
-      }
-      WSYNC();
+  const double A[3][3] = {{0.5, 0, 0}, {0, 0.5, 0}, {0, 0, 1.0}};
+  if (i > 0) {
+    if (lane < NV) {
+      double dv = 0, da = 0;
+      for (int j = 0; j < i; ++j) { dv += A[i - 1][j] * w.Xv[j][lane]; da += A[i - 1][j] * w.F[j][lane]; }
+      w.sv[lane] = dv;
+      w.sa[lane] = da;
     }
-    if (cta_sync) __syncthreads();  // keeps the warps of a CTA inside the same code region (shared instruction cache)
-    w_forward(wm, w, lane);
-    if (i == 0) {  // X0 is the state after the first evaluation: mj_kinematics normalises the quaternion inside qpos
-      for (int k = lane; k < NQ; k += 32) w.X0q[k] = w.qpos[k];
-      if (lane < NV) w.Xv[0][lane] = w.qvel[lane];
+    for (int k = lane; k < NQ; k += 32) w.qpos[k] = w.X0q[k];
+    WSYNC();
+    w_integrate_pos(w, w.sv, h, lane);
+    if (lane < NV) {
+      w.qvel[lane] = w.Xv[0][lane] + h * w.sa[lane];
+      w.Xv[i][lane] = w.qvel[lane];
     }
-    if (lane < NV) w.F[i][lane] = w.qacc[lane];
     WSYNC();
   }
+  w_forward(wm, w, lane);
+  if (i == 0) {  // X0 is the state after the first evaluation: mj_kinematics normalises the quaternion inside qpos
+    for (int k = lane; k < NQ; k += 32) w.X0q[k] = w.qpos[k];
+    if (lane < NV) w.Xv[0][lane] = w.qvel[lane];
+  }
+  if (lane < NV) w.F[i][lane] = w.qacc[lane];
+  WSYNC();
+}
+__device__ void w_rk4_finish(const WModel& wm, WS& w, int lane) {
+  const double h = wm.m.timestep;
+  const double Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
   if (lane < NV) {
     double dv = 0, da = 0;
     for (int j = 0; j < 4; ++j) { dv += Bw[j] * w.Xv[j][lane]; da += Bw[j] * w.F[j][lane]; }
@@ -763,10 +764,11 @@ __global__ void __launch_bounds__(32) humanoid_reset_warp_kernel(const HumanoidA
   }
 }
 
-// W envs per CTA, one warp each (the warps never exchange data; sharing a CTA only co-schedules them).  With
-// a.cta_sync the warps also meet at a CTA barrier before every mj_forward evaluation, so they walk the ~165 KB of code
-// together and share instruction-cache lines (barriers between the stages of mj_forward as well were measured: no further
-// gain); every live warp executes the same number of barriers.
+// W envs per CTA, one warp each (the warps never exchange data; sharing a CTA only co-schedules them).  With a.cta_sync the
+// warps also meet at a CTA barrier before every mj_forward evaluation, so they walk the ~165 KB of code together and share
+// instruction-cache lines (barriers between the stages of mj_forward as well were measured: no further gain).  The
+// barrier is ONE instruction inside a loop that every warp of the CTA runs to the end -- warps without an env and warps
+// whose env only resets in this call skip the work, never the barrier.
 template <typename ActT, int W>
 __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const HumanoidArgs a) {
   extern __shared__ __align__(16) unsigned char w_smem[];
@@ -777,34 +779,37 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t slot = (int64_t)blockIdx.x * W + warp, n = a.n;
-  const bool cta_sync = W > 1 && a.cta_sync;
-  const int n_sync = cta_sync ? 4 * a.frame_skip : 0;
-  if (slot >= n) {
-    for (int k = 0; k < n_sync; ++k) __syncthreads();
-    return;
-  }
-  const int64_t i = a.order ? a.order[slot] : slot;  // envs of similar cost share a CTA (they wait for each other)
+  const bool cta_sync = W > 1 && a.cta_sync, live = slot < n;
+  const int64_t i = !live ? 0 : a.order ? a.order[slot] : slot;  // envs of similar cost share a CTA (they wait for each other)
   WS& w = reinterpret_cast<WS*>(w_smem + sizeof(WModel))[warp];
-  const int32_t c = a.ctrl[i];
+  const int32_t c = live ? a.ctrl[i] : 0;
   double* __restrict__ obs = a.obs + 348 * i;
   if (lane == 0) { w.overflow = 0; w.work = 0; }
   WSYNC();
-  bool reset = a.mode == B2E_AUTORESET_NEXT_STEP && ctrl_pending(c);  // this call is the env's reset step
+  bool reset = live && a.mode == B2E_AUTORESET_NEXT_STEP && ctrl_pending(c);  // this call is the env's reset step
+  const bool stepping = live && !reset;
   int32_t cn = 0;
-  if (reset) {
-    if (lane == 0) {
-      a.reward[i] = 0.0;
-      a.term[i] = 0;
-      a.trunc[i] = 0;
-    }
-    for (int k = 0; k < n_sync; ++k) __syncthreads();
-  } else {
+  if (reset && lane == 0) {
+    a.reward[i] = 0.0;
+    a.term[i] = 0;
+    a.trunc[i] = 0;
+  }
+  if (stepping) {
     for (int k = lane; k < NQ; k += 32) w.qpos[k] = a.qpos[k * n + i];
     if (lane < NV) { w.qvel[lane] = a.qvel[lane * n + i]; w.warm[lane] = a.warm[lane * n + i]; }
     if (lane < NU) w.ctrl[lane] = (double)reinterpret_cast<const ActT*>(a.actions)[i * NU + lane];
     WSYNC();
+  }
 #pragma unroll 1
-    for (int k = 0; k < a.frame_skip; ++k) w_step_rk4(wm, w, lane, cta_sync);
+  for (int k = 0; k < a.frame_skip; ++k) {  // mj_step x frame_skip (mujoco_env.py:150)
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+      if (cta_sync) __syncthreads();
+      if (stepping) w_rk4_stage(wm, w, lane, st);
+    }
+    if (stepping) w_rk4_finish(wm, w, lane);
+  }
+  if (stepping) {
     if (lane == 0) {  // mj_rnePostConstraint (cfrc_ext only): a short sequential tail
       for (int b = 0; b < NB; ++b) for (int k = 0; k < 6; ++k) w.cfrc_ext[b][k] = 0;
       for (int cc = 0; cc < w.ncon; ++cc) {
@@ -870,6 +875,7 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
     }
     WSYNC();
   }
+  if (!live) return;
   if (reset) {  // one call site for both autoreset flavours
     w_env_reset(wm, a, i, w, lane, obs);
     WSYNC();
