@@ -578,19 +578,24 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane) {
     const int tri0 = lane * (lane + 1) / 2;
     for (int it = 0; it < iters; ++it) {
       double d_own = 0, r_own = 0;  // this lane's move and the residual it was computed from (for the cost change)
-      int idx = tri0;               // index of AR[lane][j] in the packed lower triangle
+      int idx = tri0;               // index of AR[lane][j] in the packed lower triangle (in bounds for every lane)
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         double f = f_i - r_i * ainv;
         if (f < 0) f = 0;
         const double delta = f - f_i;
         const double dj = __shfl_sync(0xffffffffu, delta, j);
         if (lane == j) { f_i = f; d_own = delta; r_own = r_i; }
-        if (lane < n) r_i += w.AR[idx] * dj;
+        r_i += w.AR[idx] * dj;      // lanes >= n accumulate junk nobody reads
         idx += j < lane ? 1 : j + 1;
       }
-      const double gain = 0.5 * d_own * d_own * aii + d_own * r_own;
+      // cost change of the sweep: the per-row gains added in row order by every lane (warp-uniform break, no broadcast)
+      double* const gains = (it & 1) ? w.term : w.b;  // b_i is in registers; two buffers: no barrier after the reads
+      gains[lane] = 0.5 * d_own * d_own * aii + d_own * r_own;
+      WSYNC();
       double improvement = 0;
-      for (int j = 0; j < n; ++j) improvement -= __shfl_sync(0xffffffffu, gain, j);
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) improvement -= gains[j];
       if (lane == 0) w.work += n + 1;  // one sweep over n rows
       if (improvement * scale < tol) break;
     }

@@ -13,7 +13,7 @@ for E in Humanoid-v5 LunarLander-v3; do
   python bench.py --env $E --impl reference --steps 5 --warmup 3 2>/dev/null | tee $OUT/bench_reference_$E.json | cut -c1-400
 done
 # launch list of the bench command (cold-cache, serialised: shares only)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 330 -c 1500 --csv --log-file $OUT/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 2500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-extras --e2e-steps 20 > $OUT/bench_under_ncu.log 2>&1
 # full captures of the top kernels
 for T in step big rollout lake lander humanoid; do

@@ -77,7 +77,7 @@ if os.path.exists(lp):
     tot = sum(a[1] for a in agg.values())
     with open(f"profiles/{rnd}_launches_bench.md", "w") as f:
         f.write(f"# ncu launch list of `python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-extras --e2e-steps 20` ({tag})\n\n"
-                "`ncu --metrics gpu__time_duration.sum --clock-control none -s 330 -c 1500` (the first 330 launches are set-up: ring allocation, seeding, resets); per-launch times are cold-cache and "
+                "`ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 2500` (the first 100 launches are skipped: ring allocation, seeding); per-launch times are cold-cache and "
                 "serialised, so only the SHARES are meaningful.\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
         for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{name}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |\n")
