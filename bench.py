@@ -189,7 +189,8 @@ def run_reference(args):
         total = args.steps * calls_per_step * C
         value = total / dt
         sample = (f"AsyncVectorEnv({args.env}) num_envs={C} (one process per env; 65536 processes is not runnable), "
-                  f"{calls_per_step} vector calls per bench step, host action sampling included")
+                  f"{calls_per_step} vector calls per bench step, host action sampling included "
+                  f"(host budget: {host_cpu_budget()})")
         kind = "reference"
         line["value_excluding_reset_calls"] = counted / dt
         if not args.no_extras:
@@ -255,7 +256,8 @@ def run_reference(args):
                 th.join()
             total, value = steps * n * T, steps * n * T / dt
             sample = (f"oracle port (C restatement), {T} host threads x {n} envs, {steps} vector steps each ({why}); "
-                      f"one thread alone: {n / t_call:.4g} env-steps/s")
+                      f"one thread alone: {n / t_call:.4g} env-steps/s, all threads: {value / (n / t_call):.1f}x that "
+                      f"(host budget: {host_cpu_budget()})")
             args.steps = steps
             kind, cores = "port", T
             if args.env == "Humanoid-v5":  # inputs of the FLOP model: constraint rows and PGS sweeps per mj_forward
@@ -365,6 +367,21 @@ def flop_roofline(env_id, steps_per_s_per_gpu, peak_tflops, cpu_baseline):
             "peak_source": "b2e_fma_probe measured in this run (8 FMA chains/thread, 8 CTAs x 256 threads per SM)",
             "note": "serial dependency chains per env (tree recursions, factorisation pivots, Gauss-Seidel sweeps): the "
                     "kernel is bound by dependent-issue latency at 8 warps/SM, see profiles/ for the stall breakdown"}
+
+
+def host_cpu_budget():
+    """What the container may actually use: os.cpu_count() counts the machine's CPUs, the cgroup quota can be smaller."""
+    out = {"os_cpu_count": os.cpu_count()}
+    try:
+        out["sched_affinity"] = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        out["cgroup_cpu_max"] = None if quota == "max" else round(int(quota) / int(period), 2)
+    except Exception:  # noqa: BLE001
+        pass
+    return out
 
 
 def host_action_pool(np, env_id, count, n, seed):
