@@ -1,5 +1,6 @@
 // humanoid.cu -- fused Humanoid-v5 step + TimeLimit + autoreset kernel (sm_100a): articulated-body forward dynamics with
-// a PGS contact/limit solve, RK4 x frame_skip, one thread per env (round-1 mapping; warp-per-env is the planned next step).
+// a PGS contact/limit solve, RK4 x frame_skip.  Two mappings of the same physics core: one thread per env (this file) and
+// one warp per env with the working set in shared memory (humanoid_warp.cuh, the default); they agree bit for bit.
 //
 // Replaces, for a batch of n envs in one launch:
 //   HumanoidEnv.step / _get_obs / _get_rew / reset_model   gymnasium/envs/mujoco/humanoid_v5.py:436-532
@@ -17,9 +18,9 @@
 // Arithmetic: float64 like MuJoCo, one IEEE rounding per operation (--fmad=false), sin/cos from the fixed sequence shared
 // with the oracle.  The physics core is __host__ __device__: the host runs it once at qpos0 to derive the compile-time
 // constants MuJoCo stores in mjModel (body/dof invweight0, meaninertia).  Per-env working set (mass matrix, constraint
-// Jacobian, A = J M^-1 J^T + R) lives in thread-local memory (~55 KB/env) in this first version; persistent state is
-// 74 doubles per env in struct-of-arrays layout.  FLOP-bound in principle (~0.7 MFLOP fp64 per env-step); this mapping
-// is latency-bound.
+// Jacobian, A = J M^-1 J^T + R): thread-local memory (~36 KB/env) in the thread mapping, 24 KB of shared memory in the warp
+// mapping; persistent state is 74 doubles per env in struct-of-arrays layout.  ~0.9 MFLOP fp64 per env-step; both
+// mappings are bound by dependent-issue latency, not by FLOP/s or HBM.
 #include <assert.h>
 #include <string.h>
 
