@@ -3,7 +3,7 @@
 Host-side table builders mirror ``CliffWalkingEnv.__init__/_calculate_transition_prob``
 (gymnasium/envs/toy_text/cliffwalking.py:102-177) and ``TaxiEnv.__init__/_build_dry_transitions/_pickup/_dropoff``
 (gymnasium/envs/toy_text/taxi.py:172-235, :299-371) and pack ``P[s][a]`` for ``csrc/frozenlake.cu`` (entry layout in
-include/b200env.h).  Taxi: the registered default only (``is_rainy=False, fickle_passenger=False``).
+include/b200env.h).  Taxi: dry (the registered default) and ``is_rainy=True``; ``fickle_passenger`` is not implemented.
 """
 from __future__ import annotations
 
@@ -53,8 +53,25 @@ def _taxi_encode(row, col, pass_loc, dest):  # taxi.py:373-382
     return ((row * 5 + col) * 5 + pass_loc) * 4 + dest
 
 
-def pack_taxi():
-    """Dry, non-fickle Taxi-v4: 500 states x 6 actions, one outcome each; reward classes (-1, -10, +20)."""
+# rainy Taxi (taxi.py:246-307): a move that is possible goes as intended with p = rainy_probability and drifts to the
+# heading's left / right cell with (1 - p) / 2 each; (forward, left, right) per action 0..3 = south, north, east, west
+_RAINY_MOVES = {0: ((1, 0), (0, 1), (0, -1)), 1: ((-1, 0), (0, -1), (0, 1)), 2: ((0, 1), (-1, 0), (1, 0)),
+                3: ((0, -1), (1, 0), (-1, 0))}
+
+
+def _taxi_shift(desc, row, col, move):  # taxi.py:227-244: clamp to the grid, east/west moves stop at walls
+    dr, dc = move
+    nr, nc = max(0, min(row + dr, 4)), max(0, min(col + dc, 4))
+    if dc == 1 and desc[1 + nr, 2 * nc] != b":":
+        return row, col
+    if dc == -1 and desc[1 + nr, 2 * nc + 2] != b":":
+        return row, col
+    return nr, nc
+
+
+def pack_taxi(is_rainy: bool = False, rainy_probability: float = 0.8):
+    """Non-fickle Taxi-v4: 500 states x 6 actions; reward classes (-1, -10, +20).  Dry: one outcome per (s, a).  Rainy:
+    three outcomes (intended, left drift, right drift) for the four moves, one for pickup / dropoff."""
     desc = np.asarray(_TAXI_MAP, dtype="c")
     nS, nA = 500, 6
     table = np.zeros((nS, nA, 3), dtype=np.uint32)
@@ -92,7 +109,14 @@ def pack_taxi():
                                 np_ = _TAXI_LOCS.index(here)
                             else:
                                 rc = 1
-                        table[s, a, :] = _entry(_taxi_encode(nr, nc, np_, dest), term, rc, 1)
+                        if is_rainy and a <= 3:
+                            can_move = (row < 4, row > 0, east_open, west_open)[a]
+                            cells = [(nr, nc)] + ([_taxi_shift(desc, row, col, mv) for mv in _RAINY_MOVES[a][1:]]
+                                                  if can_move else [here, here])
+                            for k, (r2, c2) in enumerate(cells):
+                                table[s, a, k] = _entry(_taxi_encode(r2, c2, p, dest), False, 0, 3)
+                        else:
+                            table[s, a, :] = _entry(_taxi_encode(nr, nc, np_, dest), term, rc, 1)
                     # action mask (taxi.py:398-419)
                     mask[s, 0] = row < 4
                     mask[s, 1] = row > 0
@@ -101,8 +125,9 @@ def pack_taxi():
                     mask[s, 4] = p < 4 and here == _TAXI_LOCS[p]
                     mask[s, 5] = p == 4 and (here == _TAXI_LOCS[dest] or here in _TAXI_LOCS)
     isd /= isd.sum()
-    one = np.array([1.0, 1.0, 1.0])
-    return table.reshape(-1), np.cumsum(one), one, np.cumsum(isd), nS, nA, (-1.0, -10.0, 20.0), mask
+    lateral = (1.0 - rainy_probability) / 2.0
+    p3 = np.array([rainy_probability, lateral, lateral]) if is_rainy else np.array([1.0, 1.0, 1.0])
+    return table.reshape(-1), np.cumsum(p3), p3, np.cumsum(isd), nS, nA, (-1.0, -10.0, 20.0), mask
 
 
 class CliffWalkingVectorEnv(TabularVectorEnv):
@@ -123,10 +148,12 @@ class TaxiVectorEnv(TabularVectorEnv):
     (taxi.py:457, :470)."""
 
     def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 200, is_rainy: bool = False,
-                 fickle_passenger: bool = False, render_mode: str | None = None, **engine_kwargs):
-        if is_rainy or fickle_passenger:
-            raise NotImplementedError("gymnasium_b200 implements the default dry, non-fickle Taxi-v4 only")
-        table, cum3, p3, isd_cum, nS, nA, rewards, mask = pack_taxi()
+                 fickle_passenger: bool = False, rainy_probability: float = 0.8, fickle_probability: float = 0.3,
+                 render_mode: str | None = None, **engine_kwargs):
+        if fickle_passenger:
+            raise NotImplementedError("gymnasium_b200 does not implement fickle_passenger=True (stateful destination changes)")
+        table, cum3, p3, isd_cum, nS, nA, rewards, mask = pack_taxi(bool(is_rainy), float(rainy_probability))
+        self.is_rainy = bool(is_rainy)
         super().__init__(num_envs, nS, nA, table, cum3, p3, isd_cum, rewards, max_episode_steps=max_episode_steps,
                          render_mode=render_mode, **engine_kwargs)
         self._mask_host = mask

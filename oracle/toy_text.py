@@ -62,7 +62,22 @@ def taxi_decode(i):
     return i, col, p, dest
 
 
-def build_taxi():
+_RAINY = {0: ((0, 1), (0, -1)), 1: ((0, -1), (0, 1)), 2: ((-1, 0), (1, 0)), 3: ((1, 0), (-1, 0))}  # (left, right) drift per heading
+
+
+def _shift(desc, row, col, dr, dc):
+    """``TaxiEnv._calc_new_position`` (taxi.py:227-244)."""
+    nr, nc = max(0, min(row + dr, 4)), max(0, min(col + dc, 4))
+    if dc == 1 and desc[1 + nr, 2 * nc] != b":":
+        return row, col
+    if dc == -1 and desc[1 + nr, 2 * nc + 2] != b":":
+        return row, col
+    return nr, nc
+
+
+def build_taxi(is_rainy=False, rainy_probability=0.8):
+    """``_build_dry_transitions`` (taxi.py:207-225) or ``_build_rainy_transitions`` (taxi.py:246-307)."""
+    lateral = (1.0 - rainy_probability) / 2.0
     desc = np.asarray(TAXI_MAP, dtype="c")
     locs = TAXI_LOCS
     P = {s: {a: [] for a in range(6)} for s in range(500)}
@@ -98,7 +113,14 @@ def build_taxi():
                                 npass = locs.index(taxi_loc)
                             else:
                                 reward = -10
-                        P[state][action].append((1.0, taxi_encode(nr, nc, npass, dest_idx), reward, term))
+                        if is_rainy and action <= 3:
+                            ok = (row < 4, row > 0, desc[1 + row, 2 * col + 2] == b":", desc[1 + row, 2 * col] == b":")[action]
+                            left, right = [(_shift(desc, row, col, *mv) if ok else taxi_loc) for mv in _RAINY[action]]
+                            P[state][action].append((rainy_probability, taxi_encode(nr, nc, pass_idx, dest_idx), -1, False))
+                            P[state][action].append((lateral, taxi_encode(left[0], left[1], pass_idx, dest_idx), -1, False))
+                            P[state][action].append((lateral, taxi_encode(right[0], right[1], pass_idx, dest_idx), -1, False))
+                        else:
+                            P[state][action].append((1.0, taxi_encode(nr, nc, npass, dest_idx), reward, term))
     isd /= isd.sum()
     return P, isd
 
@@ -149,8 +171,8 @@ class OracleCliffWalking(OracleTabular):
 
 
 class OracleTaxi(OracleTabular):
-    def __init__(self, num_envs, max_episode_steps=200, autoreset_mode="NextStep"):
-        P, isd = build_taxi()
+    def __init__(self, num_envs, max_episode_steps=200, autoreset_mode="NextStep", is_rainy=False):
+        P, isd = build_taxi(is_rainy)
         super().__init__(num_envs, P, isd, max_episode_steps, autoreset_mode)
 
     def action_mask(self):

@@ -167,6 +167,9 @@ if __name__ == "__main__":
         blackjack("blackjack_plain_n17_s13.npz", 17, 300, 13, natural=False, sab=False)
         blackjack("blackjack_samestep_n16_s14.npz", 16, 300, 14, mode=AutoresetMode.SAME_STEP)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "taxi_rainy":  # regenerate only the rainy-Taxi fixture
+        tabular("taxi_rainy_n16_s6_T400.npz", "Taxi-v4", 16, 400, 6, 6, is_rainy=True)
+        sys.exit(0)
     cartpole("cartpole_n8_s42_T300.npz", 8, 300, 42)
     cartpole("cartpole_n16_s7_T400_limit60_balance.npz", 16, 400, 7, max_episode_steps=60, policy="balance")
     cartpole("cartpole_n4_s123_bounds.npz", 4, 60, 123, options={"low": -0.1, "high": 0.1})
