@@ -85,6 +85,9 @@ class BlackjackVectorEnv(B200VectorEnv):
         done = out["terminated"] | out["truncated"]
         return {"final_obs": self._as_tuple(out["final_obs"]), "_final_obs": done, "final_info": {}, "_final_info": done}
 
+    def _host_obs(self, host):
+        return self._as_tuple(host["obs"])
+
     def reset(self, *, seed=None, options=None):
         obs, info = super().reset(seed=seed, options=options)
         return self._as_tuple(obs), info

@@ -123,6 +123,7 @@ class B200VectorEnv(VectorEnv):
         self._base_seed: int | None = None
         self._seed_list: list[int] | None = None
         self._has_reset = False
+        self._pending: tuple | None = None  # ("reset" | "step", result, reset mask) between *_async and *_wait
         self._pinned_actions: torch.Tensor | None = None
         self._out: dict[str, torch.Tensor] = {}
         self._pinned_wire: torch.Tensor | None = None
@@ -283,6 +284,7 @@ class B200VectorEnv(VectorEnv):
 
     def reset(self, *, seed: int | list[int | None] | None = None, options: dict[str, Any] | None = None):
         """SyncVectorEnv.reset (gymnasium/vector/sync_vector_env.py:187-264) on device."""
+        self._assert_open()
         options, mask = self._parse_reset_mask(options)
         with torch.cuda.device(self.device):
             self._seed_streams(seed, mask)
@@ -360,6 +362,7 @@ class B200VectorEnv(VectorEnv):
 
     def step(self, actions):
         """SyncVectorEnv.step (gymnasium/vector/sync_vector_env.py:266-337) as one fused launch."""
+        self._assert_open()
         if not self._has_reset:
             # OrderEnforcing.step (gymnasium/wrappers/common.py:393-397) raises ResetNeeded per sub-env
             from . import errors
@@ -416,3 +419,102 @@ class B200VectorEnv(VectorEnv):
             v = getattr(self, name)
             return tuple(v for _ in range(self.num_envs)) if not isinstance(v, (torch.Tensor, tuple)) else v
         raise AttributeError(f"{type(self).__name__} has no per-env attribute {name!r}")
+
+    def call(self, name: str, *args, **kwargs) -> tuple:
+        """``SyncVectorEnv.call`` (sync_vector_env.py:343-367): one result per sub-env.  A method of the batched env is called
+        once and its result repeated; per-env tensors / tuples are returned as they are."""
+        attr = getattr(self, name, None)
+        if attr is None:
+            raise AttributeError(f"{type(self).__name__} has no attribute {name!r}")
+        if callable(attr):
+            v = attr(*args, **kwargs)
+            return v if isinstance(v, (tuple, torch.Tensor)) and len(v) == self.num_envs else tuple(v for _ in range(self.num_envs))
+        return self.get_attr(name)
+
+    def set_attr(self, name: str, values) -> None:
+        """``SyncVectorEnv.set_attr`` (sync_vector_env.py:380-398) for the scalar parameters of a family: every sub-env shares
+        one kernel configuration here, so all values must agree (per-env parameters would need per-env kernel arguments)."""
+        if not isinstance(values, (list, tuple)):
+            values = [values for _ in range(self.num_envs)]
+        if len(values) != self.num_envs:
+            raise ValueError(
+                "Values must be a list or tuple with length equal to the number of environments. "
+                f"Got `{len(values)}` values for {self.num_envs} environments."
+            )
+        if any(v != values[0] for v in values[1:]):
+            raise ValueError(f"{type(self).__name__}.set_attr needs the same value for every sub-environment (one kernel "
+                             f"configuration per batch), got {values!r}")
+        if not hasattr(self, name):
+            raise AttributeError(f"{type(self).__name__} has no attribute {name!r}")
+        setattr(self, name, values[0])
+        cfg = getattr(self, "_cfg", None)
+        if cfg is not None and any(f[0] == name for f in type(cfg)._fields_):
+            setattr(cfg, name, values[0])
+
+    # ---- AsyncVectorEnv's split calls (async_vector_env.py:310-521).  A kernel launch IS asynchronous: *_async enqueues the
+    # work on the stream and returns, *_wait hands out the result (and, for output="numpy", is where the host copy is made)
+    def _assert_open(self):
+        if getattr(self, "closed", False):
+            from . import errors
+
+            raise errors.ClosedEnvironmentError(f"Trying to operate on `{type(self).__name__}`, after a call to `close()`.")
+
+    def reset_async(self, seed=None, options=None) -> None:
+        from . import errors
+
+        self._assert_open()
+        if self._pending is not None:
+            raise errors.AlreadyPendingCallError(
+                f"Calling `reset_async` while waiting for a pending call to `{self._pending[0]}` to complete", self._pending[0])
+        output, self.output = self.output, "torch"
+        try:
+            res = self.reset(seed=seed, options=options)
+        finally:
+            self.output = output
+        mask = None if options is None else options.get("reset_mask")
+        self._pending = ("reset", res, mask)
+
+    def reset_wait(self, timeout: float | None = None):
+        from . import errors
+
+        self._assert_open()
+        if self._pending is None or self._pending[0] != "reset":
+            raise errors.NoAsyncCallError("Calling `reset_wait` without any prior call to `reset_async`.", "reset")
+        _, (obs, info), mask = self._pending
+        self._pending = None
+        if self.output == "numpy":
+            host = self._to_host(self._out)  # the buffers the pending launch wrote
+            m = None if mask is None else np.asarray(mask.cpu() if isinstance(mask, torch.Tensor) else mask)
+            return self._host_obs(host), self._reset_info(host, m)
+        return obs, info
+
+    def step_async(self, actions) -> None:
+        from . import errors
+
+        self._assert_open()
+        if self._pending is not None:
+            raise errors.AlreadyPendingCallError(
+                f"Calling `step_async` while waiting for a pending call to `{self._pending[0]}` to complete.", self._pending[0])
+        output, self.output = self.output, "torch"
+        try:
+            res = self.step(actions)
+        finally:
+            self.output = output
+        self._pending = ("step", res, None)
+
+    def step_wait(self, timeout: float | None = None):
+        from . import errors
+
+        self._assert_open()
+        if self._pending is None or self._pending[0] != "step":
+            raise errors.NoAsyncCallError("Calling `step_wait` without any prior call to `step_async`.", "step")
+        _, res, _ = self._pending
+        self._pending = None
+        if self.output == "numpy":
+            host = self._to_host(self._out)
+            return self._host_obs(host), host["reward"], host["terminated"], host["truncated"], self._step_info(host)
+        return res
+
+    def _host_obs(self, host):
+        """Observation as the family's reset()/step() return it (overridden where that is not the raw array)."""
+        return host["obs"]

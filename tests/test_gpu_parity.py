@@ -700,3 +700,55 @@ def test_blackjack_reseeding_and_reset_mask():
         np.testing.assert_array_equal(o3[k][mask], fresh[k][mask])
         np.testing.assert_array_equal(o3[k][~mask], before[k][~mask])
     assert env.single_observation_space.contains((int(o3[0][0]), int(o3[1][0]), int(o3[2][0])))
+
+
+def test_async_call_api_and_attr_access():
+    """AsyncVectorEnv's split calls (async_vector_env.py:310-521) and SyncVectorEnv.call/get_attr/set_attr
+    (sync_vector_env.py:343-398) on the engine: same results as reset()/step(), same exception types and messages."""
+    from gymnasium_b200 import errors
+
+    for output in ("numpy", "torch"):
+        a, b = make("CartPole-v1", 9, output=output), make("CartPole-v1", 9, output=output)
+        with pytest.raises(errors.NoAsyncCallError, match="without any prior call to `reset_async`"):
+            a.reset_wait()
+        a.reset_async(seed=4)
+        with pytest.raises(errors.AlreadyPendingCallError, match="pending call to `reset`"):
+            a.step_async(np.zeros(9, dtype=np.int64))
+        o1, i1 = a.reset_wait()
+        o2, i2 = b.reset(seed=4)
+        as_np = (lambda x: x.cpu().numpy()) if output == "torch" else (lambda x: x)
+        np.testing.assert_array_equal(as_np(o1), as_np(o2))
+        rs = np.random.default_rng(1)
+        for t in range(40):
+            act = rs.integers(0, 2, 9)
+            a.step_async(act)
+            with pytest.raises(errors.AlreadyPendingCallError, match="pending call to `step`"):
+                a.reset_async()
+            x, y = a.step_wait(), b.step(act)
+            for k in range(4):
+                np.testing.assert_array_equal(as_np(x[k]), as_np(y[k]))
+        with pytest.raises(errors.NoAsyncCallError, match="without any prior call to `step_async`"):
+            a.step_wait()
+    bj = make("Blackjack-v1", 5)
+    bj.reset_async(seed=2)
+    o, _ = bj.reset_wait()
+    assert isinstance(o, tuple) and len(o) == 3 and isinstance(o[0], np.ndarray)
+    bj.step_async(np.ones(5, dtype=np.int64))
+    assert isinstance(bj.step_wait()[0], tuple)
+    fl = make("FrozenLake-v1", 4, map_name="8x8")
+    mask = np.array([True, False, True, False])
+    fl.reset(seed=0)
+    fl.reset_async(seed=[7, None, 8, None], options={"reset_mask": mask})
+    _, info = fl.reset_wait()
+    np.testing.assert_array_equal(info["_prob"], mask)
+    # attribute access
+    h = make("Humanoid-v5", 3)
+    assert h.get_attr("frame_skip") == (5, 5, 5) and h.call("elapsed_steps").shape == (3,)
+    cp = make("CartPole-v1", 3)
+    with pytest.raises(ValueError, match="same value for every sub-environment"):
+        cp.set_attr("max_episode_steps", [1, 2, 3])
+    with pytest.raises(ValueError, match="length equal to the number of environments"):
+        cp.set_attr("max_episode_steps", [1, 2])
+    cp.close()
+    with pytest.raises(errors.ClosedEnvironmentError):
+        cp.reset(seed=0)
