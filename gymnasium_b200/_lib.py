@@ -118,6 +118,8 @@ SIGNATURES = {
     "b2e_classic_reset": (C.c_int, [_BP, C.POINTER(ClassicCfg), P, P, P]),
     "b2e_classic_step": (C.c_int, [_BP, C.POINTER(ClassicCfg), P, P, P, P, P, P, P]),
     "b2e_lunarlander_state_words": (C.c_int, []),
+    "b2e_taxi_fickle_reset": (C.c_int, [_BP, c_double, P, P, P, P]),
+    "b2e_taxi_fickle_step": (C.c_int, [_BP, c_double, P, P, P, P, P, P, P, P]),
     "b2e_blackjack_reset": (C.c_int, [_BP, C.POINTER(BlackjackCfg), P, P, P]),
     "b2e_blackjack_step": (C.c_int, [_BP, C.POINTER(BlackjackCfg), P, P, P, P, P, P, P]),
     "b2e_lunarlander_reset": (C.c_int, [_BP, C.POINTER(LunarLanderCfg), C.POINTER(LunarLanderState), P, P, P]),

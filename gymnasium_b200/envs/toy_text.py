@@ -3,13 +3,18 @@
 Host-side table builders mirror ``CliffWalkingEnv.__init__/_calculate_transition_prob``
 (gymnasium/envs/toy_text/cliffwalking.py:102-177) and ``TaxiEnv.__init__/_build_dry_transitions/_pickup/_dropoff``
 (gymnasium/envs/toy_text/taxi.py:172-235, :299-371) and pack ``P[s][a]`` for ``csrc/frozenlake.cu`` (entry layout in
-include/b200env.h).  Taxi: dry (the registered default) and ``is_rainy=True``; ``fickle_passenger`` is not implemented.
+include/b200env.h).  Taxi: dry (the registered default), ``is_rainy=True`` and ``fickle_passenger=True`` (csrc/taxi.cu).
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
 
+from .. import _lib
+from .._api import AutoresetMode
+from ..vector_env import ptr
 from .frozen_lake import TabularVectorEnv
 
 # cliffwalking.py:11-20
@@ -150,14 +155,49 @@ class TaxiVectorEnv(TabularVectorEnv):
     def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 200, is_rainy: bool = False,
                  fickle_passenger: bool = False, rainy_probability: float = 0.8, fickle_probability: float = 0.3,
                  render_mode: str | None = None, **engine_kwargs):
-        if fickle_passenger:
-            raise NotImplementedError("gymnasium_b200 does not implement fickle_passenger=True (stateful destination changes)")
         table, cum3, p3, isd_cum, nS, nA, rewards, mask = pack_taxi(bool(is_rainy), float(rainy_probability))
-        self.is_rainy = bool(is_rainy)
+        self.is_rainy, self.fickle_passenger = bool(is_rainy), bool(fickle_passenger)
+        self.fickle_probability = float(fickle_probability)
         super().__init__(num_envs, nS, nA, table, cum3, p3, isd_cum, rewards, max_episode_steps=max_episode_steps,
                          render_mode=render_mode, **engine_kwargs)
         self._mask_host = mask
         self._mask_dev = torch.from_numpy(mask).to(self.device)
+        if self.fickle_passenger:  # taxi.py:436-452, :466-468 -> csrc/taxi.cu fix-up kernels around the tabular step
+            if self.rng_mode != "numpy" or self.autoreset_mode == AutoresetMode.SAME_STEP:
+                raise NotImplementedError("fickle_passenger=True needs rng='numpy' and NEXT_STEP or DISABLED autoreset")
+            n, dev = self.num_envs, self.device
+            self._fickle = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self._u32buf = torch.zeros(n, dtype=torch.int64, device=dev)
+            self._prev_state = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def _on_streams_seeded(self, lanes):
+        if self.fickle_passenger:  # a freshly seeded numpy Generator starts with an empty 32-bit word buffer
+            if lanes is None:
+                self._u32buf.zero_()
+            else:
+                self._u32buf.masked_fill_(lanes, 0)
+
+    def _reset_kernel(self, mask, options, out):
+        super()._reset_kernel(mask, options, out)
+        if self.fickle_passenger:
+            _lib.check(
+                self._lib.b2e_taxi_fickle_reset(C.byref(self._batch), self.fickle_probability,
+                                                ptr(None if mask is None else mask.view(torch.uint8)), ptr(self._rng),
+                                                ptr(self._fickle), self._stream),
+                "b2e_taxi_fickle_reset",
+            )
+
+    def _step_kernel(self, actions, out):
+        if self.fickle_passenger:
+            self._prev_state.copy_(self._pstate)
+        super()._step_kernel(actions, out)
+        if self.fickle_passenger:
+            _lib.check(
+                self._lib.b2e_taxi_fickle_step(C.byref(self._batch), self.fickle_probability, ptr(self._prev_state),
+                                               ptr(self._pstate), ptr(self._ctrl), ptr(self._rng), ptr(self._u32buf),
+                                               ptr(self._fickle), ptr(out["obs"]), self._stream),
+                "b2e_taxi_fickle_step",
+            )
 
     def _with_mask(self, info, obs, valid):
         if isinstance(obs, np.ndarray):

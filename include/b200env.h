@@ -142,6 +142,15 @@ int b2e_frozenlake_rollout(const b2e_batch* b, const b2e_frozenlake_cfg* cfg, in
                            uint8_t* actions_out, int32_t* pstate, int32_t* ctrl, uint64_t* rng, int64_t* obs,
                            float* reward, uint8_t* terminated, uint8_t* truncated, void* stream);
 
+/* ---- Taxi-v4 `fickle_passenger=True` (gymnasium/envs/toy_text/taxi.py:436-452, :466-468): fix-up kernels launched right
+ * after b2e_frozenlake_reset / b2e_frozenlake_step on the same stream (they continue the env's RNG stream).
+ *   fickle : uint8 [n] fickle_step flags;  u32buf : int64 [n] as for Blackjack;  prev_state : int32 [n] copy of pstate taken
+ *   before the step;  pstate / ctrl / rng / obs: the tabular kernel's buffers.  numpy-parity RNG, NEXT_STEP or DISABLED. */
+int b2e_taxi_fickle_reset(const b2e_batch* b, double fickle_probability, const uint8_t* mask, uint64_t* rng, uint8_t* fickle,
+                          void* stream);
+int b2e_taxi_fickle_step(const b2e_batch* b, double fickle_probability, const int32_t* prev_state, int32_t* pstate,
+                         const int32_t* ctrl, uint64_t* rng, int64_t* u32buf, uint8_t* fickle, int64_t* obs, void* stream);
+
 /* ---- Blackjack-v1: gymnasium/envs/toy_text/blackjack.py:10-238 ------------------------------------------------------------
  *   hand   : int32 [n]  packed (player sum/ace/count, dealer sum/ace/count, dealer's first card), see blackjack.cu
  *   u32buf : int64 [n]  PCG64's one-word 32-bit buffer (bit 32 = valid); zero it for an env whenever its stream is

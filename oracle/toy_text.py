@@ -171,9 +171,35 @@ class OracleCliffWalking(OracleTabular):
 
 
 class OracleTaxi(OracleTabular):
-    def __init__(self, num_envs, max_episode_steps=200, autoreset_mode="NextStep", is_rainy=False):
+    """``TaxiEnv`` (taxi.py:309-487).  ``fickle_passenger`` (taxi.py:436-452, :466-468): a passenger who rides changes
+    his mind once per episode with probability ``fickle_probability`` -- decided by one extra ``random()`` draw at reset
+    -- on the first step in which the taxi moves with him on board; the new destination is
+    ``np_random.choice`` of the three other locations."""
+
+    def __init__(self, num_envs, max_episode_steps=200, autoreset_mode="NextStep", is_rainy=False, fickle_passenger=False,
+                 fickle_probability=0.3):
         P, isd = build_taxi(is_rainy)
         super().__init__(num_envs, P, isd, max_episode_steps, autoreset_mode)
+        self.fickle_passenger, self.fickle_probability = bool(fickle_passenger), fickle_probability
+        self.fickle_step = np.zeros(num_envs, dtype=bool)
+
+    def _reset_env(self, i, options):
+        super()._reset_env(i, options)
+        self.fickle_step[i] = self.fickle_passenger and self._rng(i).random() < self.fickle_probability
+
+    def _step_lanes(self, lanes, actions):
+        before = self.s.copy()
+        out = super()._step_lanes(lanes, actions)
+        if self.fickle_passenger:
+            for i in lanes:
+                i = int(i)
+                r0, c0, p0, d0 = taxi_decode(int(before[i]))
+                r1, c1, p1, _ = taxi_decode(int(self.s[i]))
+                if self.fickle_step[i] and p0 == 4 and (r1 != r0 or c1 != c0):
+                    self.fickle_step[i] = False
+                    dest = int(self._rng(i).choice([k for k in range(4) if k != d0]))
+                    self.s[i] = taxi_encode(r1, c1, p1, dest)
+        return out
 
     def action_mask(self):
         return np.stack([taxi_action_mask(int(s)) for s in self.s])

@@ -118,10 +118,16 @@ def classic(name, env_id, n, T, seed, options=None, act_scale=None, nA=None, sta
           out["truncated"].sum(), "reward %.3f" % out["reward"].sum())
 
 
-def tabular(name, env_id, n, T, seed, nA, **kw):
+def tabular(name, env_id, n, T, seed, nA, policy="random", **kw):
     envs = gym.make_vec(env_id, num_envs=n, vectorization_mode="sync", **kw)
     rng = np.random.default_rng(3000 + seed)
     actions = rng.integers(0, nA, size=(T, n)).astype(np.int64)
+    if policy == "pickup":  # Taxi: pick the passenger up / drop him whenever the action mask allows it, so that rides happen
+        _, info = envs.reset(seed=seed)
+        for t in range(T):
+            m = info["action_mask"]
+            actions[t] = np.where(m[:, 4] == 1, 4, np.where((m[:, 5] == 1) & (rng.random(n) < 0.3), 5, actions[t]))
+            _, _, _, _, info = envs.step(actions[t])
     out = rollout(envs, seed, actions)
     mes = envs.envs[0].spec.max_episode_steps
     out["max_episode_steps"] = np.int64(kw.get("max_episode_steps", mes if mes is not None else 0))
@@ -169,6 +175,11 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "taxi_rainy":  # regenerate only the rainy-Taxi fixture
         tabular("taxi_rainy_n16_s6_T400.npz", "Taxi-v4", 16, 400, 6, 6, is_rainy=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "taxi_fickle":  # regenerate only the fickle-passenger fixtures
+        tabular("taxi_fickle_n24_s7_T600.npz", "Taxi-v4", 24, 600, 7, 6, policy="pickup", fickle_passenger=True)
+        tabular("taxi_fickle_rainy_n24_s8_T600.npz", "Taxi-v4", 24, 600, 8, 6, policy="pickup", fickle_passenger=True,
+                is_rainy=True)
         sys.exit(0)
     cartpole("cartpole_n8_s42_T300.npz", 8, 300, 42)
     cartpole("cartpole_n16_s7_T400_limit60_balance.npz", 16, 400, 7, max_episode_steps=60, policy="balance")

@@ -538,7 +538,7 @@ def test_toy_text_matches_reference_golden_bit_exact(name):
     n = g["actions"].shape[1]
     mes = int(g["max_episode_steps"]) or None
     if name.startswith("taxi"):
-        env = make("Taxi-v4", n, max_episode_steps=mes, is_rainy="rainy" in name)
+        env = make("Taxi-v4", n, max_episode_steps=mes, is_rainy="rainy" in name, fickle_passenger="fickle" in name)
     else:
         env = make("CliffWalkingSlippery-v1" if "slippery" in name else "CliffWalking-v1", n, max_episode_steps=mes)
     out = replay_fixture(env, g)

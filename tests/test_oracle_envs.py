@@ -105,7 +105,8 @@ def test_toy_text_oracles_match_reference(name):
     g = golden(name)
     n = g["actions"].shape[1]
     mes = int(g["max_episode_steps"]) or None
-    env = OracleTaxi(n, max_episode_steps=mes, is_rainy="rainy" in name) if name.startswith("taxi") else OracleCliffWalking(
+    env = OracleTaxi(n, max_episode_steps=mes, is_rainy="rainy" in name, fickle_passenger="fickle" in name) if name.startswith(
+        "taxi") else OracleCliffWalking(
         n, is_slippery="slippery" in name, max_episode_steps=mes)
     out = replay_fixture(env, g)
     np.testing.assert_array_equal(out["obs"], g["obs"])
