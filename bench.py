@@ -234,15 +234,17 @@ def run_reference(args):
                 e.reset(seed=1000 * t)
             t0 = time.perf_counter()
             for k in range(3):
-                envs[0].step(pool[k % 8])
+                envs[0].step_inplace(np.ascontiguousarray(pool[k % 8]))
             t_call = (time.perf_counter() - t0) / 3
             steps = max(2, min(args.steps * 50, int(budget / t_call)))  # every thread steps its own batch `steps` times
             gate = threading.Barrier(T + 1)
 
+            pool = [np.ascontiguousarray(a) for a in pool]
+
             def work(e):
                 gate.wait()
                 for k in range(steps):
-                    e.step(pool[k % 8])
+                    e.step_inplace(pool[k % 8])  # no allocations / copies under the GIL; the C call releases it
                 gate.wait()
 
             threads = [threading.Thread(target=work, args=(e,)) for e in envs]

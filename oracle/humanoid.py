@@ -77,6 +77,16 @@ class OracleHumanoid:
                       trunc.ctypes.data, self._info.ctypes.data)
         return self._obs.copy(), reward, term.astype(bool), trunc.astype(bool), self._info_dict()
 
+    def step_inplace(self, actions_f32):
+        """step() without per-call allocations or copies (results stay in internal buffers): the call the multi-threaded CPU
+        baseline of bench.py makes, so that almost no time is spent holding the GIL.  `actions_f32`: contiguous float32 [n, 17]."""
+        if not hasattr(self, "_scratch"):
+            n = self.num_envs
+            self._scratch = (np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8))
+            r, te, tr = self._scratch
+            self._ptrs = (self._obs.ctypes.data, r.ctypes.data, te.ctypes.data, tr.ctypes.data, self._info.ctypes.data)
+        lib().hm_step(self._h, actions_f32.ctypes.data, *self._ptrs)
+
     def model_info(self):
         mass = np.zeros(14); misc = np.zeros(8); inv = np.zeros(14 * 2 + 23)
         lib().hm_model_info(self._h, mass.ctypes.data, misc.ctypes.data, inv.ctypes.data)

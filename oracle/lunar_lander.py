@@ -68,6 +68,15 @@ class OracleLunarLander:
         lib().ll_step(self._h, a.ctypes.data, self._obs.ctypes.data, reward.ctypes.data, term.ctypes.data, trunc.ctypes.data)
         return self._obs.copy(), reward, term.astype(bool), trunc.astype(bool), {}
 
+    def step_inplace(self, actions_i64):
+        """step() without per-call allocations or copies (results stay in internal buffers): the call the multi-threaded CPU
+        baseline of bench.py makes, so that almost no time is spent holding the GIL.  `actions_i64`: contiguous int64 [n]."""
+        if not hasattr(self, "_scratch"):
+            n = self.num_envs
+            self._scratch = (np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8))
+            self._ptrs = tuple(x.ctypes.data for x in (self._obs,) + self._scratch)
+        lib().ll_step(self._h, actions_i64.ctypes.data, *self._ptrs)
+
     def debug_state(self, i=0):
         bodies = np.zeros((3, 7), dtype=np.float32)
         misc = np.zeros(8, dtype=np.float32)
