@@ -145,7 +145,7 @@ def run_reference(args):
         sys.path.insert(0, ref)
     import numpy as np
 
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     budget = float(args.ref_budget)
     args.num_envs = args.num_envs or ENV_FACTS[args.env]["default_n"]
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -166,33 +166,51 @@ def run_reference(args):
         import warnings
 
         warnings.filterwarnings("ignore")
-        C = max(2, min(cores, 256))
-        envs = gym.make_vec(args.env, num_envs=C, vectorization_mode="async", **env_kwargs(args.env))
-        envs.action_space.seed(0)
-        envs.reset(seed=0)
-        t0 = time.perf_counter()
-        for _ in range(max(args.warmup, 3)):
-            envs.step(envs.action_space.sample())
-        t_call = (time.perf_counter() - t0) / max(args.warmup, 3)
-        calls_per_step = max(1, int(budget / max(args.steps * t_call, 1e-9)))
-        calls_per_step = min(calls_per_step, 200)
-        done_prev = np.zeros(C, dtype=bool)
-        counted = 0
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            for _ in range(calls_per_step):
-                _, _, te, tr, _ = envs.step(envs.action_space.sample())
-                counted += C - int(done_prev.sum())  # gymnasium/utils/performance.py:88-90
-                done_prev = te | tr
-        dt = time.perf_counter() - t0
-        envs.close()
-        total = args.steps * calls_per_step * C
-        value = total / dt
-        sample = (f"AsyncVectorEnv({args.env}) num_envs={C} (one process per env; 65536 processes is not runnable), "
-                  f"{calls_per_step} vector calls per bench step, host action sampling included "
-                  f"(host budget: {host_cpu_budget()})")
+
+        def time_async(C, seconds):
+            """AsyncVectorEnv with C worker processes for ~`seconds`: (steps/s calls x C, steps/s without reset calls, calls)."""
+            envs = gym.make_vec(args.env, num_envs=C, vectorization_mode="async", **env_kwargs(args.env))
+            envs.action_space.seed(0)
+            envs.reset(seed=0)
+            for _ in range(max(args.warmup, 3)):
+                envs.step(envs.action_space.sample())
+            done_prev = np.zeros(C, dtype=bool)
+            counted = calls = 0
+            t0 = time.perf_counter()
+            while True:
+                for _ in range(20):
+                    _, _, te, tr, _ = envs.step(envs.action_space.sample())
+                    counted += C - int(done_prev.sum())  # gymnasium/utils/performance.py:88-90
+                    done_prev = te | tr
+                calls += 20
+                dt = time.perf_counter() - t0
+                if dt >= seconds:
+                    break
+            envs.close()
+            return calls * C / dt, counted / dt, calls, dt
+
+        # BASELINE.md section 4: C in {cores, 2 cores, 4 cores} worker processes, keep the best and say which
+        tried = {}
+        best = None
+        for mult in (1, 2, 4):
+            C = max(2, min(cores * mult, 512))
+            try:
+                r = time_async(C, budget / 3.0)
+            except Exception as ex:  # noqa: BLE001
+                tried[f"num_envs={C}"] = f"failed: {ex!r}"
+                continue
+            tried[f"num_envs={C}"] = r[0]
+            if best is None or r[0] > best[1][0]:
+                best = (C, r)
+        C, (value, value_excl, calls, dt) = best
+        args.steps = calls
+        total = calls * C
+        sample = (f"AsyncVectorEnv({args.env}), one worker process per sub-env (65536 processes is not runnable): best of "
+                  f"num_envs in {{C, 2C, 4C}} for C = {cores} effective host cores -> num_envs={C}, {calls} vector calls in "
+                  f"{dt:.1f} s, host action sampling included (host budget: {host_cpu_budget()})")
         kind = "reference"
-        line["value_excluding_reset_calls"] = counted / dt
+        alternatives["async_by_num_envs"] = tried
+        line["value_excluding_reset_calls"] = value_excl
         if not args.no_extras:
             for mode, n, kw in [("sync", 4, {}), ("vector_entry_point", args.num_envs, {})]:
                 if mode == "vector_entry_point" and not args.env.startswith("CartPole"):
@@ -203,6 +221,13 @@ def run_reference(args):
                     e.close()
                 except Exception as ex:  # noqa: BLE001
                     alternatives[f"{mode}_n{n}"] = f"failed: {ex!r}"
+        else:
+            try:
+                e = gym.make_vec(args.env, num_envs=4, vectorization_mode="sync", **env_kwargs(args.env))
+                alternatives["sync_n4"] = benchmark_vector_step(e, target_duration=2, seed=0)
+                e.close()
+            except Exception as ex:  # noqa: BLE001
+                alternatives["sync_n4"] = f"failed: {ex!r}"
     else:
         # oracle port (numpy restatement), one core
         from oracle.cartpole import OracleCartPole
@@ -354,12 +379,13 @@ def flop_roofline(env_id, steps_per_s_per_gpu, peak_tflops, cpu_baseline):
     """Algorithmic FLOPs per env-step (SURVEY.md 8d model) x measured steps/s against the measured SIMT FMA peak."""
     if env_id == "Humanoid-v5":
         st = (cpu_baseline or {}).get("solver_stats") or {}
-        nefc, sweeps = st.get("mean_nefc", 6.0), st.get("mean_pgs_sweeps", 12.0)
+        nefc = st.get("mean_nefc", HUMANOID_NOMINAL_STATS["mean_nefc"])
+        sweeps = st.get("mean_pgs_sweeps", HUMANOID_NOMINAL_STATS["mean_pgs_sweeps"])
         nv = 23
         f_fwd = 30e3 + 10e3 + nefc * (2 * nv * nv + 2 * nefc * nv) + sweeps * 2 * nefc * nefc
         flops = 20 * f_fwd + 2e3
         model = (f"20 x (30k smooth + 10k collision + nefc(2 nv^2 + 2 nefc nv) + sweeps 2 nefc^2) + 2k, nv=23, "
-                 f"nefc={nefc:.2f}, sweeps={sweeps:.2f} ({'measured on the oracle sample' if st else 'nominal'})")
+                 f"nefc={nefc:.2f}, sweeps={sweeps:.2f} ({'measured on the oracle sample of this run' if st else 'oracle sample of ' + HUMANOID_NOMINAL_STATS['source']})")
         dtype = "f64"
     else:
         flops, model, dtype = 47.5e3, "nominal 45-50 kflop per Box2D step (180 velocity + 60 position iterations)", "f32"
@@ -369,6 +395,16 @@ def flop_roofline(env_id, steps_per_s_per_gpu, peak_tflops, cpu_baseline):
             "peak_source": "b2e_fma_probe measured in this run (8 FMA chains/thread, 8 CTAs x 256 threads per SM)",
             "note": "serial dependency chains per env (tree recursions, factorisation pivots, Gauss-Seidel sweeps): the "
                     "kernel is bound by dependent-issue latency at 8 warps/SM, see profiles/ for the stall breakdown"}
+
+
+def effective_cores():
+    """CPUs this process may really use: min(scheduler affinity, cgroup CPU quota) -- os.cpu_count() counts the machine."""
+    b = host_cpu_budget()
+    c = b.get("sched_affinity") or b.get("os_cpu_count") or 1
+    q = b.get("cgroup_cpu_max")
+    if q:
+        c = min(c, max(1, int(math.ceil(q))))
+    return max(1, int(c))
 
 
 def host_cpu_budget():
@@ -395,226 +431,400 @@ def host_action_pool(np, env_id, count, n, seed):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def run_b200(args):
+BURN_IN = {"LunarLander-v3": 120, "Humanoid-v5": 60}  # untimed steps per batch that bring a physics family to its steady mix
+PIPE_DEPTH = 3
+# constraint rows / PGS sweeps per mj_forward of the random-action steady state (oracle sample, profiles/r1_bench_humanoid.json);
+# used for the FLOP model when the run has no fresh oracle sample (N > 1)
+HUMANOID_NOMINAL_STATS = {"mean_nefc": 2.71, "mean_pgs_sweeps": 12.29, "source": "profiles/r1_bench_humanoid.json"}
+
+
+class Ctx:
+    pass
+
+
+def make_ctx(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    import gymnasium_b200
     from gymnasium_b200 import _lib
-    from gymnasium_b200.distributed import BatchGather, env_rank_world
+    from gymnasium_b200.distributed import env_rank_world
 
-    rank, local_rank, world = env_rank_world()
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    info = _lib.device_info(local_rank)
-    hbm_peak, peak_src = load_peaks()
-    facts = ENV_FACTS[args.env]
-    n = args.num_envs or facts["default_n"]
-    args.num_envs = n
-    is_cartpole = args.env.startswith("CartPole")
-    step_bytes = facts["step_bytes"]
-    kw = env_kwargs(args.env)
-    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    cx = Ctx()
+    cx.np, cx.torch, cx.dist = np, torch, dist
+    cx.rank, cx.local_rank, cx.world = env_rank_world()
+    if cx.world != args.gpus and cx.world > 1:
+        args.gpus = cx.world
+    torch.cuda.set_device(cx.local_rank)
+    cx.dev = torch.device("cuda", cx.local_rank)
+    if cx.world > 1:
+        dist.init_process_group("nccl", device_id=cx.dev)
+    cx.info = _lib.device_info(cx.local_rank)
+    cx.hbm_peak, cx.peak_src = load_peaks()
+    cx.sampler = ClockSampler(cx.local_rank).start() if cx.rank == 0 else None
+    return cx
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+def sync_all(cx):
+    cx.torch.cuda.synchronize()
+    if cx.world > 1:
+        cx.dist.barrier()
+        cx.torch.cuda.synchronize()
 
-    # ---- ring of independent batches, total footprint > 2 x L2 ------------------------------------------------------
-    foot = n * (step_bytes + 32)  # + the PCG64 words each batch also owns
-    ring = args.ring or max(2, math.ceil(2.0 * info["l2_bytes"] / foot))
-    if args.env in ("LunarLander-v3", "Humanoid-v5") and not args.ring:
+
+def max_over_ranks(cx, x):
+    if cx.world == 1:
+        return x
+    t = cx.torch.tensor([x], dtype=cx.torch.float64, device=cx.dev)
+    cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+class _NullWindow:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def clock_window(cx):
+    return cx.sampler.window() if cx.sampler else _NullWindow()
+
+
+def percentile(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    k = (len(xs) - 1) * q
+    lo, hi = int(math.floor(k)), int(math.ceil(k))
+    return xs[lo] + (xs[hi] - xs[lo]) * (k - lo)
+
+
+def measure_device(cx, args, env_id, n, K, W, ring_arg=0, min_region_s=0.05):
+    """`value`: inputs resident in HBM.  A ring of independent n-env batches (footprint > 2 x L2 for the HBM-bound families)
+    is stepped round-robin, one fused launch per bench step.  W plain warm-up launches, then ONE CUDA graph that starts at
+    the ring position after the warm-up and holds q consecutive K-step segments (q*K a multiple of the ring, >= ~10 ms), so
+    replaying it continues the round-robin and every timed launch finds its batch evicted from L2.  The graph is replayed
+    until the timed region is >= 50 ms (CUDA events on the launch stream around every replay; max over ranks)."""
+    import gymnasium_b200
+
+    torch, dev, rank = cx.torch, cx.dev, cx.rank
+    facts = ENV_FACTS[env_id]
+    kw = env_kwargs(env_id)
+    foot = n * (facts["step_bytes"] + 32)  # + the PCG64 words each batch also owns
+    ring = ring_arg or max(2, math.ceil(2.0 * cx.info["l2_bytes"] / foot))
+    if env_id in FLOP_BOUND and not ring_arg:
         ring = min(ring, 4)  # latency/FLOP-bound families: L2 residency is irrelevant, keep set-up short
     T = 8  # distinct action vectors per batch
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     envs, acts = [], []
     for j in range(ring):
-        e = gymnasium_b200.make_vec(args.env, num_envs=n, device=dev, copy=False, env_offset=(rank * ring + j) * n, **kw)
+        e = gymnasium_b200.make_vec(env_id, num_envs=n, device=dev, copy=False, env_offset=(rank * ring + j) * n, **kw)
         e.reset(seed=0)
         envs.append(e)
-        acts.append(device_actions(torch, args.env, (T,), n, dev, gen))
+        acts.append(device_actions(torch, env_id, (T,), n, dev, gen))
     torch.cuda.synchronize()
 
-    def launch(k):  # one bench step = one fused step launch on the next batch of the ring
-        j = k % ring
-        envs[j].step(acts[j][(k // ring) % T])
+    def launch(i):  # one bench step = one fused step launch on the next batch of the ring
+        j = i % ring
+        envs[j].step(acts[j][(i // ring) % T])
 
-    def capture(count, start=0):
+    def capture(start, count):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for k in range(start, start + count):
-                launch(k)
+            for i in range(start, start + count):
+                launch(i)
         return g
 
-    side = torch.cuda.Stream(device=dev)
-    with torch.cuda.stream(side):  # warm every code path once before capture
-        for k in range(ring):
-            launch(k)
-        # physics families: bring every batch to its steady-state mix of flying / contact / resetting lanes first
-        # (a fresh Humanoid batch is in free fall for ~10 steps and would time 2.4x too fast); part of set-up, untimed
-        burn_in = {"LunarLander-v3": 120, "Humanoid-v5": 60}.get(args.env, 0)
-        for k in range(ring, ring * (1 + burn_in)):
-            launch(k)
+    burn = BURN_IN.get(env_id, 0)
+    for i in range(ring * (1 + burn)):  # every code path once + the steady-state mix of a physics family (set-up, untimed)
+        launch(i)
+    for i in range(W):  # the W warm-up launches; the timed graph starts at the ring position right after them
+        launch(i)
     torch.cuda.synchronize()
-    G = ring * T
+    s0 = W
+    Kc = K if K <= 4096 else ring * T
+    base = Kc * ring // math.gcd(Kc, ring)
+    g = capture(s0, base)
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    t_base = max_over_ranks(cx, a.elapsed_time(b) * 1e-3)
+    q = max(1, min(math.ceil(0.010 / t_base), max(1, 60000 // base)))
+    if q > 1:
+        del g
+        g = capture(s0, base * q)
+        g.replay()  # uploads the graph; also >= W further untimed launches
+    M = base * q
+    replays = int(min(2000, max(5, math.ceil(min_region_s / (t_base * q)), math.ceil(K / M))))
+    replays = int(max_over_ranks(cx, float(replays)))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(replays + 1)]
+    sync_all(cx)
+    with clock_window(cx):
+        sync_all(cx)
+        ev[0].record()
+        for r in range(replays):
+            g.replay()
+            ev[r + 1].record()
+        sync_all(cx)
+    elapsed = max_over_ranks(cx, ev[0].elapsed_time(ev[-1]) * 1e-3)
+    per_step_ms = [ev[r].elapsed_time(ev[r + 1]) / M for r in range(replays)]
+    timed = replays * M
+    del g
+    reset_frac = float(torch.stack([(e._ctrl < 0).float().mean() for e in envs]).mean().item())
+    cold = ring * foot > 2 * cx.info["l2_bytes"]
+    return {
+        "value": cx.world * timed * n / elapsed, "elapsed_s": elapsed, "timed_steps": timed, "graph_launches": M,
+        "replays": replays, "reps_of_K": timed / K, "ms_per_step": elapsed / timed * 1e3,
+        "ms_per_step_p50": percentile(per_step_ms, 0.5), "ms_per_step_p95": percentile(per_step_ms, 0.95),
+        "ms_per_step_min": min(per_step_ms), "ring": ring, "foot": foot, "reset_frac": reset_frac, "envs": envs,
+        "acts": acts,
+        "l2_policy": (f"inputs larger than L2: ring of {ring} independent {n}-env batches ({ring * foot / 1e6:.0f} MB > 2 x "
+                      f"{cx.info['l2_bytes'] / 1e6:.0f} MB L2) stepped round-robin; the timed graph starts at the ring position "
+                      f"after the warm-up launches and its length is a multiple of the ring, so no timed launch is L2-warm"
+                      if cold else
+                      f"ring of {ring} independent {n}-env batches ({ring * foot / 1e6:.0f} MB); this family is latency/FLOP-"
+                      f"bound, not HBM-bound, so L2 residency does not affect the timing"),
+    }
+
+
+def measure_e2e(cx, args, env_id, n, mode, tag):
+    """End to end through the public API with HOST buffers: every step copies that step's actions from pinned host memory to
+    the device, runs the fused launch and lands the step's outputs in the single host-side batch
+    (gymnasium_b200.distributed.HostBatchPipeline).  mode 'dma': every rank writes its rows over its own PCIe link;
+    'nccl': one NCCL gather to rank 0 + rank 0's D2H.  Both overlap step k's copies with step k+1's kernel.  Wall clock
+    around K_e steps + the drain of the last one, barrier on both sides, max over ranks."""
+    import gymnasium_b200
+    from gymnasium_b200.distributed import HostBatchPipeline
+
+    torch, np, dev, rank, world = cx.torch, cx.np, cx.dev, cx.rank, cx.world
+    facts = ENV_FACTS[env_id]
+    kw = env_kwargs(env_id)
+    env = gymnasium_b200.make_vec(env_id, num_envs=n, device=dev, copy=False, out_buffers=PIPE_DEPTH, env_offset=rank * n, **kw)
+    env.reset(seed=0)
+    burn = BURN_IN.get(env_id, 0)
+    if burn:  # same steady-state mix as the device-resident batches (untimed set-up)
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        dev_pool = device_actions(torch, env_id, (4,), n, dev, gen)
+        for k in range(burn):
+            env.step(dev_pool[k % 4])
+        torch.cuda.synchronize()
+    pipe = HostBatchPipeline(env, world, rank, tag=tag, depth=PIPE_DEPTH, mode=mode)
+    host_actions = host_action_pool(np, env_id, 16, n, rank)
+    check = {}
+
+    def run(count):
+        last = -1
+        for _ in range(count):
+            t = pipe.submit(host_actions[pipe.k % 16])
+            if pipe.is_consumer and t >= 1:
+                pipe.consume(t - 1)
+            last = t
+        if pipe.is_consumer and last >= 0:
+            check["batch"] = pipe.consume(last)
+        pipe.drain()
+
+    warm = max(5, min(args.warmup, 50))
+    sync_all(cx)
+    t0 = time.perf_counter()
+    run(warm)
+    sync_all(cx)
+    t_est = max_over_ranks(cx, (time.perf_counter() - t0) / warm)
+    Ke = int(min(args.e2e_steps, max(20, math.ceil(0.3 / t_est))))
+    Ke = int(max_over_ranks(cx, float(Ke)))
+    with clock_window(cx):
+        sync_all(cx)
+        t0 = time.perf_counter()
+        run(Ke)
+        sync_all(cx)
+        elapsed = max_over_ranks(cx, time.perf_counter() - t0)
+    ok = None
+    if pipe.is_consumer:  # the landed batch is the real thing: right shapes, finite observations from every rank
+        bt = check["batch"]
+        ok = bool(bt["obs"].shape[0] == n * world and np.isfinite(np.asarray(bt["obs"], dtype=np.float64)).all())
+    pipe.close()
+    del env
+    return {"value": world * Ke * n / elapsed, "unit": UNIT, "h2d_bytes_per_step": n * facts["act_bytes"],
+            "d2h_bytes_per_step": n * facts["out_bytes"], "steps": Ke, "ms_per_step": elapsed / Ke * 1e3,
+            "host_batch_ok": ok, "pipeline_depth": PIPE_DEPTH,
+            "path": ("gymnasium_b200.distributed.HostBatchPipeline(make_vec(...)).submit(host numpy actions) / .consume(): pinned "
+                     "H2D of the actions + fused step launch + " +
+                     ("D2H of every rank's rows over its own PCIe link into ONE page-locked host batch shared by all ranks"
+                      if mode == "dma" else
+                      "ONE NCCL gather of all shards' packed outputs to rank 0 (NVLink) + rank 0's D2H of the gathered batch") +
+                     "; the copies of step k overlap the kernel of step k+1")}
+
+
+def measure_e2e_sync(cx, args, env_id, n):
+    """The blocking call: env.step(host numpy actions) -> host numpy arrays (H2D + launch + one D2H + stream sync per call)."""
+    import gymnasium_b200
+
+    torch, np, dev = cx.torch, cx.np, cx.dev
+    env = gymnasium_b200.make_vec(env_id, num_envs=n, device=dev, copy=False, output="numpy", **env_kwargs(env_id))
+    env.reset(seed=0)
+    burn = BURN_IN.get(env_id, 0)
+    if burn:
+        gen = torch.Generator(device=dev).manual_seed(7)
+        dev_pool = device_actions(torch, env_id, (4,), n, dev, gen)
+        env.output = "torch"
+        for k in range(burn):
+            env.step(dev_pool[k % 4])
+        env.output = "numpy"
+        torch.cuda.synchronize()
+    host_actions = host_action_pool(np, env_id, 16, n, 0)
+    for k in range(5):
+        env.step(host_actions[k % 16])
+    t0 = time.perf_counter()
+    for k in range(5):
+        env.step(host_actions[k % 16])
+    t_est = (time.perf_counter() - t0) / 5
+    Ke = int(min(args.e2e_steps, max(20, math.ceil(0.3 / t_est))))
+    with clock_window(cx):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            env.step(host_actions[k % 16])
+        torch.cuda.synchronize()
+        elapsed = time.perf_counter() - t0
+    return {"value": Ke * n / elapsed, "unit": UNIT, "steps": Ke, "ms_per_step": elapsed / Ke * 1e3,
+            "path": "gymnasium_b200.make_vec(..., output='numpy').step(host numpy actions) -> host numpy arrays (blocking)"}
+
+
+def family_block(cx, args, env_id, n, K, W, with_sync_e2e, fma_cache, cpu_baseline=None):
+    """Everything measured for one family at this world size: device-timed value, roofline, pipelined e2e (+ NCCL variant)."""
+    facts = ENV_FACTS[env_id]
+    res = measure_device(cx, args, env_id, n, K, W, args.ring if env_id == args.env else 0)
+    envs, acts = res.pop("envs"), res.pop("acts")
+    per_gpu = res["value"] / cx.world
+    kernel_s = res["elapsed_s"] / res["timed_steps"]
+    if env_id in FLOP_BOUND:
+        fp64 = env_id == "Humanoid-v5"
+        if fp64 not in fma_cache:
+            fma_cache[fp64] = measure_fma_peak(cx.torch, cx.dev, fp64=fp64)
+        roof = flop_roofline(env_id, per_gpu, fma_cache[fp64], cpu_baseline)
+        roof["kernel"] = facts["kernel"]
+        roof["avg_launch_us"] = kernel_s * 1e6
+        roof["traffic"] = load_ncu_traffic(facts["kernel"])
+        hbm = facts["step_bytes"] * n / kernel_s / 1e9
+        roof["hbm"] = {"achieved_GBs": hbm, "frac_of_hbm_peak": hbm / cx.hbm_peak,
+                       "algorithmic_bytes_per_env_step": facts["step_bytes"]}
+    else:
+        achieved = facts["step_bytes"] * n / kernel_s / 1e9
+        roof = {"kernel": facts["kernel"], "bound": "hbm", "achieved": achieved, "peak": cx.hbm_peak, "unit": "GB/s",
+                "frac": achieved / cx.hbm_peak, "peak_source": cx.peak_src,
+                "algorithmic_bytes_per_env_step": facts["step_bytes"], "avg_launch_us": kernel_s * 1e6,
+                "traffic": load_ncu_traffic(facts["kernel"])}
+    block = {k: res[k] for k in ("value", "ms_per_step", "ms_per_step_p50", "ms_per_step_p95", "ms_per_step_min",
+                                 "timed_steps", "graph_launches", "replays", "reps_of_K", "l2_policy")}
+    block["timed_region_ms"] = res["elapsed_s"] * 1e3
+    block["value_excluding_reset_calls"] = res["value"] * (1 - res["reset_frac"])
+    block["reset_call_fraction"] = res["reset_frac"]
+    block["roofline"] = roof
+    block["gpu_launches"] = res["timed_steps"] * facts.get("launches_per_step", 1)
+    return block, envs, acts
+
+
+def run_b200(args):
+    import gymnasium_b200
+
+    cx = make_ctx(args)
+    torch, rank, world, dev = cx.torch, cx.rank, cx.world, cx.dev
+    facts = ENV_FACTS[args.env]
+    n = args.num_envs or facts["default_n"]
+    args.num_envs = n
     K, W = args.steps, args.warmup
-    g_main = capture(min(K, G)) if K > 0 else None
-    g_tail = capture(K % G) if (K > G and K % G) else None
-    g_warm = capture(max(1, min(W, G)))
+    fma_cache = {}
 
-    def run_steps(count, gm, gt):
-        if count <= G:
-            gm.replay()
-        else:
-            for _ in range(count // G):
-                gm.replay()
-            if gt is not None:
-                gt.replay()
+    # CPU baselines first (rank 0, N = 1 only): the Humanoid oracle sample also feeds the FLOP model
+    cpu_baseline = None
+    cpu_other = {}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_subprocess(args, args.env, n, 12)
 
-    # warm-up (>= W launches), then the timed region
-    for _ in range(max(1, math.ceil(W / max(1, min(W, G))))):
-        g_warm.replay()
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ctx = sampler.window() if sampler else None
-    if ctx:
-        ctx.__enter__()
-    sync_all()
-    e0.record()
-    run_steps(K, g_main, g_tail)
-    e1.record()
-    sync_all()
-    if ctx:
-        ctx.__exit__()
-    elapsed = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    value = world * K * n / elapsed
-    kernel_s = elapsed / K
-    achieved = step_bytes * n / kernel_s / 1e9
-
-    fma_peak = measure_fma_peak(torch, dev, fp64=args.env == "Humanoid-v5") if args.env in FLOP_BOUND and rank == 0 else None
-
-    # reference counting rule (performance.py:88-90): NEXT_STEP reset calls are not env steps
-    import torch as _t
-    reset_frac = float(_t.stack([(e._ctrl < 0).float().mean() for e in envs]).mean().item())
+    block, envs, acts = family_block(cx, args, args.env, n, K, W, True, fma_cache, cpu_baseline)
     extras = {}
     if not args.no_extras and rank == 0 and world == 1:  # supporting numbers belong to the 1-GPU line
-        extras = run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, envs[0], acts[0])
+        extras = run_extras(args, cx, gymnasium_b200, envs[0], acts[0], fma_cache)
+    del envs, acts
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the public API ----------------------------------------------------------------------------
-    del g_main, g_tail, g_warm
-    e2e_env = gymnasium_b200.make_vec(args.env, num_envs=n, device=dev, copy=False, env_offset=rank * n,
-                                      output="numpy" if world == 1 else "torch", **kw)
-    e2e_env.reset(seed=0)
-    host_actions = host_action_pool(np, args.env, 16, n, rank)
-    if burn_in:  # same steady-state mix as the device-resident batches (untimed set-up)
-        dev_pool = device_actions(torch, args.env, (4,), n, dev, gen)
-        keep = e2e_env.output
-        e2e_env.output = "torch"
-        for k in range(burn_in):
-            e2e_env.step(dev_pool[k % 4])
-        e2e_env.output = keep
-        torch.cuda.synchronize()
-    pinned = {}
-    gathered = {}
+    e2e = measure_e2e(cx, args, args.env, n, "dma", "main")
+    if world > 1:
+        e2e["nccl_gather_variant"] = measure_e2e(cx, args, args.env, n, "nccl", "main")
+    else:
+        e2e["blocking_step_variant"] = measure_e2e_sync(cx, args, args.env, n)
 
-    def e2e_step(k):
-        out = e2e_env.step(host_actions[k % 16])
-        if world == 1:
-            return out  # numpy arrays on the host (pinned H2D of actions + one D2H of the packed result inside step())
-        # N > 1: ONE NCCL gather of every shard's packed step outputs (obs | reward | flags) to rank 0, then one D2H of
-        # the gathered batch into pinned host memory ("a single host-side batch")
-        wire, _layout = e2e_env.packed_outputs()
-        if "buf" not in gathered:
-            gathered["buf"] = torch.empty((world, wire.numel()), dtype=torch.uint8, device=dev) if rank == 0 else None
-            pinned["buf"] = torch.empty((world, wire.numel()), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
-        dist.gather(wire, list(gathered["buf"].unbind(0)) if rank == 0 else None, dst=0)
-        if rank == 0:
-            pinned["buf"].copy_(gathered["buf"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return pinned
+    # BASELINE configs[4] / north_star: Humanoid-v5, 8192 envs per GPU, at EVERY world size (SCALE carries the curve)
+    humanoid = None
+    if args.env.startswith("CartPole") and not args.no_humanoid:
+        hn = ENV_FACTS["Humanoid-v5"]["default_n"]
+        hcpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            hcpu = cpu_baseline_subprocess(args, "Humanoid-v5", hn, 10)
+        humanoid, henvs, hacts = family_block(cx, args, "Humanoid-v5", hn, K, W, False, fma_cache, hcpu)
+        del henvs, hacts
+        torch.cuda.empty_cache()
+        humanoid["e2e"] = measure_e2e(cx, args, "Humanoid-v5", hn, "dma", "hum")
+        if world > 1:
+            humanoid["e2e"]["nccl_gather_variant"] = measure_e2e(cx, args, "Humanoid-v5", hn, "nccl", "hum")
+        humanoid["cpu_baseline"] = hcpu
+        humanoid["config"] = {"workload": f"Humanoid-v5 {hn} envs per GPU (BASELINE configs[4]), random actions U[-0.4,0.4]^17, "
+                                          f"NEXT_STEP autoreset, TimeLimit 1000, steady state after {BURN_IN['Humanoid-v5']} burn-in steps",
+                              "num_envs_per_gpu": hn, "dtype": "f64"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_extras and args.env.startswith("CartPole"):
+        cpu_other["FrozenLake-v1"] = cpu_baseline_subprocess(args, "FrozenLake-v1", 1 << 20, 8)
+        cpu_other["LunarLander-v3"] = cpu_baseline_subprocess(args, "LunarLander-v3", 16384, 8)
+        if "frozenlake_8x8_1M" in extras:
+            extras["frozenlake_8x8_1M"]["cpu_baseline"] = cpu_other["FrozenLake-v1"]
+        if "lunarlander_16384" in extras:
+            extras["lunarlander_16384"]["cpu_baseline"] = cpu_other["LunarLander-v3"]
 
-    Ke = max(1, min(K, args.e2e_steps))
-    for k in range(max(3, min(W, 20))):
-        e2e_step(k)
-    ctx = sampler.window() if sampler else None
-    if ctx:
-        ctx.__enter__()
-    sync_all()
-    t0 = time.perf_counter()
-    for k in range(Ke):
-        e2e_step(k)
-    sync_all()
-    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
-    if ctx:
-        ctx.__exit__()
-    e2e_value = world * Ke * n / e2e_elapsed
-    out_bytes = n * facts["out_bytes"]
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * facts["act_bytes"], "d2h_bytes_per_step": out_bytes,
-           "steps": Ke, "ms_per_step": e2e_elapsed / Ke * 1e3,
-           "path": "gymnasium_b200.make_vec(...).step(host numpy actions) -> host numpy arrays"
-                   + ("" if world == 1 else " + NCCL gather of every shard's outputs to rank 0 + D2H of the gathered batch")}
-
-    clocks = sampler.stop() if sampler else None
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_subprocess(args)
-
+    clocks = cx.sampler.stop() if cx.sampler else None
     if rank == 0:
-        kname = facts["kernel"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": block["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": block["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": facts["dtype"], "data": "synthetic",
             "config": {
                 "workload": f"{args.env} {n} envs per GPU, fused step+auto-reset kernel, random actions, NEXT_STEP "
                             f"autoreset, TimeLimit, numpy-parity PCG64 streams",
                 "num_envs_per_gpu": n, "parallelism": f"env-shards x{world} (no data-path collective)",
-                "l2_policy": (f"inputs larger than L2: ring of {ring} independent {n}-env batches "
-                              f"({ring * foot / 1e6:.0f} MB > 2 x {info['l2_bytes'] / 1e6:.0f} MB L2), round-robin"
-                              if ring * foot > 2 * info["l2_bytes"] else
-                              f"ring of {ring} independent {n}-env batches ({ring * foot / 1e6:.0f} MB); this family is "
-                              f"latency/FLOP-bound, not HBM-bound, so L2 residency does not affect the timing"),
-                "launch": "CUDA graphs of one step launch per batch, CUDA-event timing on the launch stream",
+                "l2_policy": block["l2_policy"],
+                "launch": (f"one CUDA graph of {block['graph_launches']} step launches (= {block['graph_launches'] / K:g} x the "
+                           f"K={K} steps asked for) replayed {block['replays']} times: {block['timed_steps']} timed steps, "
+                           f"{block['timed_region_ms']:.1f} ms region, CUDA events on the launch stream around every replay"),
                 "counting": "calls x N (reset calls included); see value_excluding_reset_calls",
-                "steady_state": {"LunarLander-v3": "120 untimed burn-in steps per batch before warm-up",
-                                 "Humanoid-v5": "60 untimed burn-in steps per batch before warm-up"}.get(args.env),
+                "steady_state": (f"{BURN_IN[args.env]} untimed burn-in steps per batch before warm-up" if args.env in BURN_IN else None),
             },
-            "value_excluding_reset_calls": value * (1 - reset_frac), "reset_call_fraction": reset_frac,
-            "gpu_launches": K * ENV_FACTS[args.env].get("launches_per_step", 1),
-            "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": step_bytes, "avg_launch_us": kernel_s * 1e6,
-                         "traffic": load_ncu_traffic(kname)},
+            "timing": {k: block[k] for k in ("timed_steps", "graph_launches", "replays", "reps_of_K", "timed_region_ms",
+                                             "ms_per_step_p50", "ms_per_step_p95", "ms_per_step_min")},
+            "value_excluding_reset_calls": block["value_excluding_reset_calls"],
+            "reset_call_fraction": block["reset_call_fraction"],
+            "gpu_launches": block["gpu_launches"],
+            "roofline": block["roofline"],
             "e2e": e2e,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
-            **({"roofline_flop": flop_roofline(args.env, value / world, fma_peak, cpu_baseline)} if fma_peak else {}),
             "device": torch.cuda.get_device_name(dev),
         }
+        if humanoid is not None:
+            line["humanoid_8192_per_gpu"] = humanoid
         line.update(extras)
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        cx.dist.destroy_process_group()
     return 0
 
 
-def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0):
-    """Supporting measurements (rank 0): the same kernel at a DRAM-sized batch, the fused-K rollout kernel, the
-    L2-resident single-batch rate, FrozenLake at its BASELINE size, and the reset-call fraction."""
+def run_extras(args, cx, gymnasium_b200, env0, acts0, fma_cache):
+    """Supporting measurements (rank 0, N = 1): the same kernel at a DRAM-sized batch, the fused-K rollout kernel, the
+    L2-resident single-batch rate, the launch floor, FrozenLake and LunarLander at their BASELINE sizes."""
+    torch, dev, sampler, hbm_peak = cx.torch, cx.dev, cx.sampler, cx.hbm_peak
     out = {}
     is_cartpole = args.env.startswith("CartPole")
     facts = ENV_FACTS[args.env]
@@ -623,28 +833,45 @@ def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0)
     if not nact or args.env == "LunarLander-v3":
         return out  # the supporting numbers below are for the HBM-bound discrete families
 
-    def timed(fn, iters, warm=3):
+    def timed(fn, iters, warm=3, min_s=0.05):
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with sampler.window():
-            a.record()
-            for _ in range(iters):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-        return a.elapsed_time(b) * 1e-3 / iters
+        total, count = 0.0, 0
+        with clock_window(cx):
+            while total < min_s and count < 200 * iters:
+                a.record()
+                for _ in range(iters):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                total += a.elapsed_time(b) * 1e-3
+                count += iters
+        return total / count
 
     step_bytes = CARTPOLE_STEP_BYTES if is_cartpole else FROZENLAKE_STEP_BYTES
+    # (0) launch floor of this part: a graph-replayed chain of the cheapest possible kernel (32-env step launches)
+    tiny = gymnasium_b200.make_vec(args.env, num_envs=32, device=dev, copy=False, **kw)
+    tiny.reset(seed=0)
+    ta = torch.zeros(32, dtype=torch.int64, device=dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(512):
+            tiny.step(ta)
+    t = timed(g.replay, 10) / 512
+    out["launch_floor"] = {"us_per_graph_node": t * 1e6,
+                           "note": "the same step kernel over 32 envs, 512 launches per CUDA graph: what one graph node costs "
+                                   "on this part with no data to move; N=65536 moves 6.9 MB = 1.06 us at the HBM peak on top"}
+    del g, tiny
     # (1) L2-resident: one batch stepped back to back (what a single training loop sees)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        for t in range(64):
-            env0.step(acts0[t % acts0.shape[0]])
-    t = timed(g.replay, 50) / 64
+        for t_ in range(256):
+            env0.step(acts0[t_ % acts0.shape[0]])
+    t = timed(g.replay, 10) / 256
     out["l2_resident"] = {"steps_per_s": args.num_envs / t, "us_per_launch": t * 1e6,
-                          "note": "single 65536-env batch, state stays in L2 (not HBM-cold)"}
+                          "note": f"single {args.num_envs}-env batch, state stays in L2 (not HBM-cold)"}
     del g
     # (2) same step kernel, DRAM-sized batch: kernel quality away from the launch-latency floor
     big = 1 << 24
@@ -658,7 +885,7 @@ def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0)
                                    "steps_per_s": big / t, "us_per_launch": t * 1e6}
     del e, a
     torch.cuda.empty_cache()
-    # (4) fused K-step rollout kernel with on-device Philox actions, trajectory streamed to HBM
+    # (3) fused K-step rollout kernel with on-device Philox actions, trajectory streamed to HBM
     Kf = 64
     e = gymnasium_b200.make_vec(args.env, num_envs=args.num_envs, device=dev, **kw)
     e.reset(seed=0)
@@ -670,8 +897,8 @@ def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0)
                             "bytes_per_env_step": rb, "gpu_launches": 1,
                             "note": f"{Kf} steps per launch, state in registers, [K,N] trajectory written once"}
     del e
-    # (5) the other BASELINE single-GPU config: FrozenLake-v1 8x8, 1,048,576 envs
     if is_cartpole:
+        # (4) BASELINE configs[2]: FrozenLake-v1 8x8, 1,048,576 envs
         nfl = 1 << 20
         ringf = 4  # 4 x 103 MB > 2 x L2
         fls = []
@@ -689,12 +916,14 @@ def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0)
 
         t = timed(fstep, 40, warm=8)
         bw = FROZENLAKE_STEP_BYTES * nfl / t / 1e9
-        out["frozenlake_8x8_1M"] = {"steps_per_s": nfl / t, "us_per_launch": t * 1e6, "achieved_GBs": bw,
-                                    "frac_of_hbm_peak": bw / hbm_peak,
-                                    "algorithmic_bytes_per_env_step": FROZENLAKE_STEP_BYTES,
+        out["frozenlake_8x8_1M"] = {"steps_per_s": nfl / t, "us_per_launch": t * 1e6,
+                                    "roofline": {"kernel": "frozenlake_step_kernel<int64>", "bound": "hbm", "achieved": bw,
+                                                 "peak": hbm_peak, "unit": "GB/s", "frac": bw / hbm_peak,
+                                                 "algorithmic_bytes_per_env_step": FROZENLAKE_STEP_BYTES},
                                     "l2_policy": f"ring of {ringf} batches of 1,048,576 envs (inputs larger than L2)"}
-        # (6) BASELINE config 4: LunarLander-v3, 16384 envs (latency-bound rigid-body solve; reported against its own
-        #     state traffic, not as an HBM-roofline claim)
+        del fls
+        torch.cuda.empty_cache()
+        # (5) BASELINE configs[3]: LunarLander-v3, 16384 envs (latency-bound rigid-body solve: FLOP roofline, not HBM)
         nl = 16384
         ll = gymnasium_b200.make_vec("LunarLander-v3", num_envs=nl, device=dev, copy=False)
         ll.reset(seed=0)
@@ -705,24 +934,29 @@ def run_extras(args, torch, gymnasium_b200, dev, sampler, hbm_peak, env0, acts0)
             ll.step(la[k[0] % 8])
             k[0] += 1
 
-        t = timed(lstep, 200, warm=20)
+        t = timed(lstep, 100, warm=BURN_IN["LunarLander-v3"])
+        if False not in fma_cache:
+            fma_cache[False] = measure_fma_peak(torch, dev, fp64=False)
         out["lunarlander_16384"] = {"steps_per_s": nl / t, "us_per_launch": t * 1e6,
-                                    "note": "one fused step+autoreset launch per call, random actions, 1 thread/env; "
-                                            "bit-exact vs oracle/lunar_lander.c (Box2D parity unpinned)"}
+                                    "roofline": flop_roofline("LunarLander-v3", nl / t, fma_cache[False], None),
+                                    "note": "one fused step+autoreset launch per call, random actions, steady state after 120 "
+                                            "burn-in steps; bit-exact vs oracle/lunar_lander.c (Box2D parity unpinned)"}
         for big in (131072, 1048576):
             ll = gymnasium_b200.make_vec("LunarLander-v3", num_envs=big, device=dev, copy=False)
             ll.reset(seed=0)
             la2 = torch.randint(0, 4, (big,), device=dev, dtype=torch.int64)
-            t = timed(lambda: ll.step(la2), 30, warm=60)
+            t = timed(lambda: ll.step(la2), 10, warm=60)
             out[f"lunarlander_{big}"] = {"steps_per_s": big / t, "us_per_launch": t * 1e6}
         del ll
     return out
 
 
-def cpu_baseline_subprocess(args):
+def cpu_baseline_subprocess(args, env_id, num_envs, budget_s):
     """Times the reference arm in a fresh process (AsyncVectorEnv forks workers; keep that away from the CUDA context)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "20", "--warmup", "3",
-           "--env", args.env, "--num-envs", str(args.num_envs), "--ref-budget", "12"]
+           "--env", env_id, "--num-envs", str(num_envs), "--ref-budget", str(budget_s)]
+    if env_id != args.env:
+        cmd.append("--no-extras")
     try:
         env = dict(os.environ)
         for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
@@ -742,8 +976,8 @@ def cpu_baseline_subprocess(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--env", default="CartPole-v1", choices=sorted(ENV_FACTS))
     ap.add_argument("--num-envs", type=int, default=0, help="envs per GPU (0 = the BASELINE size of --env)")
@@ -752,6 +986,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=20.0, help="seconds of CPU work for the reference arm")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-humanoid", action="store_true", help="skip the Humanoid-v5 8192-envs/GPU block of the default line")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

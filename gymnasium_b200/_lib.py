@@ -99,6 +99,13 @@ class HumanoidState(C.Structure):
                                            "order")]
 
 
+class CopySeg(C.Structure):
+    """``b2e_copy_seg``."""
+
+    _fields_ = [("host_dst", c_void_p), ("dev_src", c_void_p), ("dst_pitch", C.c_size_t), ("src_pitch", C.c_size_t),
+                ("width", C.c_size_t), ("height", C.c_size_t)]
+
+
 P = c_void_p
 _BP = C.POINTER(Batch)
 
@@ -108,6 +115,9 @@ SIGNATURES = {
     "b2e_last_error": (C.c_char_p, []),
     "b2e_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_size_t)]),
+    "b2e_host_register": (C.c_int, [P, C.c_size_t]),
+    "b2e_host_unregister": (C.c_int, [P]),
+    "b2e_copy_to_host_async": (C.c_int, [P, c_i32, P]),
     "b2e_rng_seed": (C.c_int, [_BP, c_u64, P, P, P, P]),
     "b2e_rng_random": (C.c_int, [_BP, P, c_i32, P, P]),
     "b2e_cartpole_reset": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P]),

@@ -137,3 +137,42 @@ extern "C" int b2e_rng_random(const b2e_batch* b, uint64_t* rng, int32_t k, doub
   rng_random_kernel<<<grid_for(b->n), kBlock, 0, (cudaStream_t)stream>>>(b->n, rng, k, out);
   return cuda_status(cudaGetLastError(), "b2e_rng_random");
 }
+
+// ---- single host-side batch (multi-GPU): every rank DMAs its shard's packed step outputs over its own PCIe link into one
+// page-locked host buffer that all ranks of the node map (gymnasium_b200/distributed.py: HostBatch)
+extern "C" int b2e_host_register(void* host, size_t bytes) {
+  if (!host || bytes == 0) {
+    set_error("b2e_host_register: null pointer or zero size");
+    return B2E_EINVAL;
+  }
+  return cuda_status(cudaHostRegister(host, bytes, cudaHostRegisterPortable), "b2e_host_register");
+}
+
+extern "C" int b2e_host_unregister(void* host) {
+  if (!host) {
+    set_error("b2e_host_unregister: null pointer");
+    return B2E_EINVAL;
+  }
+  return cuda_status(cudaHostUnregister(host), "b2e_host_unregister");
+}
+
+extern "C" int b2e_copy_to_host_async(const b2e_copy_seg* segs, int32_t count, void* stream) {
+  if (!segs || count < 0) {
+    set_error("b2e_copy_to_host_async: null segment list or count < 0");
+    return B2E_EINVAL;
+  }
+  for (int32_t i = 0; i < count; ++i) {
+    const b2e_copy_seg& g = segs[i];
+    if (!g.host_dst || !g.dev_src) {
+      set_error("b2e_copy_to_host_async: segment %d has a null pointer", i);
+      return B2E_EINVAL;
+    }
+    if (g.width == 0 || g.height == 0) continue;
+    cudaError_t e = g.height == 1
+                        ? cudaMemcpyAsync(g.host_dst, g.dev_src, g.width, cudaMemcpyDeviceToHost, (cudaStream_t)stream)
+                        : cudaMemcpy2DAsync(g.host_dst, g.dst_pitch, g.dev_src, g.src_pitch, g.width, g.height,
+                                            cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (int st = cuda_status(e, "b2e_copy_to_host_async")) return st;
+  }
+  return 0;
+}

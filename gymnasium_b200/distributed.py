@@ -84,3 +84,300 @@ class BatchGather:
                     full[s0:s0 + c] = stage[r * maxc:r * maxc + c]
             out[key] = full.view(torch.bool) if as_u8 else full
         return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _np_dtype(dt):
+    import numpy as np
+
+    return np.dtype(np.bool_) if dt == torch.bool else torch.empty((), dtype=dt).numpy().dtype
+
+
+class HostBatch:
+    """ONE host-side batch shared by every rank of a node.
+
+    ``depth`` slots, each holding the step outputs of ALL envs key by key -- ``obs [N_total, ...]``, ``reward [N_total]``,
+    ... (struct-of-arrays keys such as Humanoid's ``info [13][n]`` become ``[13][N_total]``) -- in a shared-memory file that
+    each rank maps and page-locks in its own CUDA context, so every GPU DMAs its shard's rows into place over its OWN PCIe
+    link (8 links in parallel instead of a gather to rank 0 followed by one copy over rank 0's link).  It plays the role of
+    ``AsyncVectorEnv``'s shared-memory observation buffer (gymnasium/vector/async_vector_env.py:234-245; the workers write
+    their slice at :849-852).
+
+    Header (one cache line per counter): ``seq[r]`` = number of steps whose rows rank r has landed (written by the GPU: an
+    8-byte copy queued behind the data copies on the same stream; by the host in the CPU tests), ``ack`` = number of steps
+    the consumer has released.  Step k lives in slot ``k % depth``; a producer may overwrite it once ``ack >= k-depth+1``.
+
+    ``layout``: ``[(key, shape, torch dtype, ...)]`` of ONE shard's outputs (``B200VectorEnv.packed_outputs()[1]``);
+    ``bounds``: ``[(start, count)]`` per rank (``shard_bounds``); ``soa_keys``: keys laid out ``[c][n]`` instead of ``[n][...]``.
+    """
+
+    LINE = 64
+
+    def __init__(self, layout, bounds, rank: int, tag: str = "0", depth: int = 3, soa_keys=(), barrier=None,
+                 register: bool = True, directory: str | None = None):
+        import mmap
+
+        import numpy as np
+
+        self.world, self.rank, self.depth = len(bounds), int(rank), int(depth)
+        self.bounds = [(int(s), int(c)) for s, c in bounds]
+        self.total = sum(c for _, c in self.bounds)
+        n_mine = self.bounds[self.rank][1]
+        self.keys = []  # (key, global shape, numpy dtype, slot offset, row bytes, soa rows)
+        off = 0
+        for entry in layout:
+            key, shape, dt = entry[0], tuple(entry[1]), entry[2]
+            npdt = _np_dtype(dt)
+            if key in soa_keys:
+                if len(shape) != 2 or shape[1] != n_mine:
+                    raise ValueError(f"{key}: a struct-of-arrays key must have shape (c, n), got {shape}")
+                gshape, rowb, rows = (shape[0], self.total), npdt.itemsize, shape[0]
+            else:
+                if shape[0] != n_mine:
+                    raise ValueError(f"{key}: leading dim {shape[0]} is not this rank's shard size {n_mine}")
+                gshape, rowb, rows = (self.total,) + shape[1:], int(np.prod(shape[1:], dtype=np.int64)) * npdt.itemsize, 0
+            self.keys.append((key, gshape, npdt, off, rowb, rows))
+            off = (off + int(np.prod(gshape, dtype=np.int64)) * npdt.itemsize + 255) // 256 * 256
+        self.slot_bytes = max(off, 256)
+        self.header_bytes = (self.LINE * (self.world + 1) + 4095) // 4096 * 4096
+        self.total_bytes = self.header_bytes + self.depth * self.slot_bytes
+        if barrier is None:
+            barrier = dist.barrier if (dist.is_available() and dist.is_initialized() and self.world > 1) else (lambda: None)
+        name = f"b2e_hostbatch_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}_{tag}"
+        self.path = os.path.join(directory or self._pick_dir(self.total_bytes), name)
+        if rank == 0:
+            try:
+                os.unlink(self.path)
+            except FileNotFoundError:
+                pass
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_EXCL, 0o600)
+            os.ftruncate(fd, self.total_bytes)
+            barrier()
+        else:
+            barrier()
+            fd = os.open(self.path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, self.total_bytes)
+        os.close(fd)
+        barrier()  # everybody has it mapped: the name can go (the pages live as long as a mapping does)
+        if rank == 0:
+            os.unlink(self.path)
+        self._np = np.frombuffer(self._mm, dtype=np.uint8)
+        self._hdr = self._np[: self.header_bytes].view(np.int64)
+        self._addr = self._np.ctypes.data
+        self._registered = False
+        if rank == 0:
+            self._np[:] = 0  # also faults every page in before it is page-locked
+        barrier()
+        if register:
+            from . import _lib
+
+            self._lib = _lib.load()
+            _lib.check(self._lib.b2e_host_register(self._addr, self.total_bytes), "b2e_host_register")
+            self._registered = True
+        barrier()
+
+    @staticmethod
+    def _pick_dir(nbytes: int) -> str:
+        for d in (os.environ.get("B2E_HOSTBATCH_DIR"), "/dev/shm", "/tmp"):
+            if d and os.path.isdir(d):
+                try:
+                    st = os.statvfs(d)
+                    if st.f_bavail * st.f_frsize > nbytes + (64 << 20):
+                        return d
+                except OSError:
+                    continue
+        return "/tmp"
+
+    # ---- addressing ------------------------------------------------------------------------------------------------
+    def views(self, k: int) -> dict:
+        """numpy views ``{key: global array}`` of the slot step k lives in."""
+        import numpy as np
+
+        base = self.header_bytes + (k % self.depth) * self.slot_bytes
+        out = {}
+        for key, gshape, npdt, off, _rowb, _rows in self.keys:
+            nb = int(np.prod(gshape, dtype=np.int64)) * npdt.itemsize
+            out[key] = self._np[base + off: base + off + nb].view(npdt).reshape(gshape)
+        return out
+
+    def segments(self, k: int, src_rank: int, dev_ptrs: dict) -> list[tuple]:
+        """Copy segments ``(host_dst, dev_src, dst_pitch, src_pitch, width, height)`` that land rank `src_rank`'s shard of
+        step k: one contiguous run per row-major key, one pitched copy per struct-of-arrays key."""
+        base = self._addr + self.header_bytes + (k % self.depth) * self.slot_bytes
+        start, count = self.bounds[src_rank]
+        segs = []
+        for key, _gshape, npdt, off, rowb, rows in self.keys:
+            if rows:
+                w = count * npdt.itemsize
+                segs.append((base + off + start * npdt.itemsize, dev_ptrs[key], self.total * npdt.itemsize, w, w, rows))
+            else:
+                segs.append((base + off + start * rowb, dev_ptrs[key], 0, 0, count * rowb, 1))
+        return segs
+
+    def seq_addr(self, rank: int | None = None) -> int:
+        r = self.rank if rank is None else rank
+        return self._addr + r * self.LINE
+
+    # ---- protocol --------------------------------------------------------------------------------------------------
+    def _seq(self, r: int) -> int:
+        return int(self._hdr[r * self.LINE // 8])
+
+    def acked(self) -> int:
+        return int(self._hdr[self.world * self.LINE // 8])
+
+    def publish_host(self, k: int) -> None:
+        """Host-side publication of step k (CPU tests; on a GPU the copy stream writes the counter itself)."""
+        self._hdr[self.rank * self.LINE // 8] = k + 1
+
+    def wait_writable(self, k: int, timeout: float = 120.0) -> None:
+        """Blocks until the slot of step k has been released by the consumer (always true for the first `depth` steps)."""
+        need = k - self.depth + 1
+        if need <= 0 or self.acked() >= need:
+            return
+        self._spin(lambda: self.acked() >= need, timeout, f"ack of step {need - 1}")
+
+    def wait_ready(self, k: int, ranks=None, timeout: float = 120.0) -> dict:
+        """Consumer: blocks until the rows of step k from every rank (or from `ranks`) have landed; returns `views(k)`."""
+        ranks = range(self.world) if ranks is None else ranks
+        if not all(self._seq(r) > k for r in ranks):
+            self._spin(lambda: all(self._seq(r) > k for r in ranks), timeout, f"step {k} from ranks {list(ranks)}")
+        return self.views(k)
+
+    def ack(self, k: int) -> None:
+        self._hdr[self.world * self.LINE // 8] = k + 1
+
+    @staticmethod
+    def _spin(cond, timeout, what):
+        import time
+
+        t0 = time.perf_counter()
+        spins = 0
+        while not cond():
+            spins += 1
+            if spins > 2000:
+                time.sleep(0)  # yield: several ranks may share a core in a small container
+                if time.perf_counter() - t0 > timeout:
+                    raise TimeoutError(f"HostBatch: timed out waiting for {what}")
+
+    def close(self) -> None:
+        if self._registered:
+            self._lib.b2e_host_unregister(self._addr)
+            self._registered = False
+        self._hdr = self._np = None
+        try:
+            self._mm.close()
+        except (BufferError, ValueError):
+            pass
+
+
+class HostBatchPipeline:
+    """Pipelined end-to-end stepping of one shard.  ``submit(host_actions)`` enqueues the pinned H2D copy of the actions and
+    the fused step launch on the caller's stream and, on a copy stream, the D2H copies of the step outputs into this rank's
+    rows of the shared :class:`HostBatch` followed by its 8-byte sequence word -- no host synchronisation.  ``consume(k)``
+    (consumer rank) waits until every rank's rows of step k have landed and returns numpy views of the whole batch.  The
+    copies of step k overlap the kernel of step k+1 (the env rotates over `depth` output buffers).
+
+    ``mode="nccl"`` gathers the packed outputs of all ranks to the consumer with ONE NCCL gather on the side stream (NVLink),
+    overlapped with the next step the same way; the consumer alone copies the gathered shards to the host (one PCIe link).
+    """
+
+    def __init__(self, env, world_size: int, rank: int, total_envs: int | None = None, tag: str = "0", depth: int = 3,
+                 mode: str = "dma", consumer: int = 0):
+        if env.output != "torch" or env.copy or env.out_buffers < depth:
+            raise ValueError("HostBatchPipeline needs an env made with output='torch', copy=False, out_buffers >= depth")
+        if mode not in ("dma", "nccl"):
+            raise ValueError(f"mode must be 'dma' or 'nccl', got {mode!r}")
+        import ctypes as C
+
+        from . import _lib
+
+        self.env, self.world, self.rank, self.depth, self.mode, self.consumer = env, world_size, rank, depth, mode, consumer
+        self._C, self._lib_mod, self._lib = C, _lib, _lib.load()
+        dev = env.device
+        total = env.num_envs * world_size if total_envs is None else int(total_envs)
+        bounds = [shard_bounds(total, world_size, r) for r in range(world_size)]
+        if bounds[rank][1] != env.num_envs:
+            raise ValueError(f"env has {env.num_envs} sub-envs but rank {rank}'s shard of {total} is {bounds[rank][1]}")
+        self.is_consumer = rank == consumer
+        self._rings = [env._outputs() for _ in range(env.out_buffers)]  # allocates the ring; the layout is fixed now
+        wire, layout = env.packed_outputs()
+        self.layout, self.wire_bytes = layout, int(wire.numel())
+        soa = tuple(getattr(env, "soa_output_keys", ()))
+        if mode == "dma":
+            self.host = HostBatch(layout, bounds, rank, tag=f"{tag}_dma", depth=depth, soa_keys=soa)
+        else:
+            if len({c for _, c in bounds}) != 1:
+                raise ValueError("mode='nccl' needs equal shards")
+            # private to the consumer: nobody else writes it, so its "world" for the seq/ack protocol is 1 rank
+            self.host = (HostBatch(layout, bounds, rank, tag=f"{tag}_nccl", depth=depth, soa_keys=soa, barrier=lambda: None)
+                         if self.is_consumer else None)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.k = 0
+        self._ev_step = [torch.cuda.Event() for _ in range(depth)]
+        self._ev_copy = [None] * depth
+        self._seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._gathered = ([torch.empty((world_size, self.wire_bytes), dtype=torch.uint8, device=dev) for _ in range(depth)]
+                          if mode == "nccl" and self.is_consumer else None)
+        self._seg_cache: dict = {}
+
+    def _segments(self, k: int, out: dict):
+        """ctypes array of the copy segments of step k (cached per (slot, output set))."""
+        key = (k % self.depth, out["_wire"].data_ptr())
+        hit = self._seg_cache.get(key)
+        if hit is not None:
+            return hit
+        segs = []
+        if self.mode == "dma":
+            segs += self.host.segments(k, self.rank, {e[0]: out[e[0]].data_ptr() for e in self.layout})
+        else:
+            g = self._gathered[k % self.depth]
+            for r in range(self.world):
+                base = g[r].data_ptr()
+                segs += self.host.segments(k, r, {e[0]: base + e[3] for e in self.layout})
+        segs.append((self.host.seq_addr(), self._seq_dev.data_ptr(), 0, 0, 8, 1))
+        arr = (self._lib_mod.CopySeg * len(segs))(*[self._lib_mod.CopySeg(*s) for s in segs])
+        self._seg_cache[key] = (arr, len(segs))
+        return self._seg_cache[key]
+
+    def submit(self, actions) -> int:
+        k, j = self.k, self.k % self.depth
+        env, dev = self.env, self.env.device
+        main = torch.cuda.current_stream(dev)
+        if self._ev_copy[j] is not None:
+            main.wait_event(self._ev_copy[j])  # the kernel of step k re-uses the output set step k-depth was copied from
+        env.step(actions)
+        out = env._out
+        self._ev_step[j].record(main)
+        cs = self.copy_stream
+        cs.wait_event(self._ev_step[j])
+        with torch.cuda.stream(cs):
+            if self.mode == "nccl":
+                dst = list(self._gathered[j].unbind(0)) if self.is_consumer else None
+                dist.gather(out["_wire"], dst, dst=self.consumer)
+            if self.host is not None:
+                self.host.wait_writable(k)
+                self._seq_dev.add_(1)
+                arr, cnt = self._segments(k, out)
+                self._lib_mod.check(self._lib.b2e_copy_to_host_async(arr, cnt, cs.cuda_stream), "b2e_copy_to_host_async")
+        ev = self._ev_copy[j] or torch.cuda.Event()
+        ev.record(cs)
+        self._ev_copy[j] = ev
+        self.k += 1
+        return k
+
+    def consume(self, k: int, ack: bool = True) -> dict:
+        """Consumer rank: numpy views ``{key: [N_total, ...]}`` of step k's batch (valid until the slot is re-used, i.e. until
+        `depth - 1` further steps have been acknowledged)."""
+        ranks = None if self.mode == "dma" else [self.rank]
+        out = self.host.wait_ready(k, ranks=ranks)
+        if ack:
+            self.host.ack(k)
+        return out
+
+    def drain(self) -> None:
+        self.copy_stream.synchronize()
+
+    def close(self) -> None:
+        self.drain()
+        if self.host is not None:
+            self.host.close()

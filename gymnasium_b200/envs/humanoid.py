@@ -29,6 +29,7 @@ class HumanoidVectorEnv(B200VectorEnv):
 
     metadata = {"render_modes": [], "render_fps": 67, "autoreset_mode": AutoresetMode.NEXT_STEP}
     discrete_actions = False
+    soa_output_keys = ("info",)  # outputs laid out [c][n] rather than [n][...] (distributed.HostBatch lands them pitched)
 
     def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 1000, xml_file: str = "humanoid.xml",
                  frame_skip: int = 5, forward_reward_weight: float = 1.25, ctrl_cost_weight: float = 0.1,

@@ -64,6 +64,7 @@ class B200VectorEnv(VectorEnv):
         output: str = "torch",
         copy: bool = True,
         validate_actions: bool = False,
+        out_buffers: int = 1,
         render_mode: str | None = None,
     ):
         if render_mode is not None:
@@ -87,6 +88,11 @@ class B200VectorEnv(VectorEnv):
         self.env_offset = int(env_offset)
         self.output = output
         self.copy = bool(copy)
+        # copy=False only: rotate over this many preallocated output sets, so that a consumer (a D2H copy or a gather on
+        # another stream) may still be reading step k's outputs while the kernel of step k+1 writes the next set
+        self.out_buffers = max(1, int(out_buffers))
+        self._out_ring: list[dict[str, torch.Tensor]] = []
+        self._out_pos = 0
         # opt-in: the reference asserts `action_space.contains(action)` per sub-env (e.g. cartpole.py:165-167); checking
         # on the device costs a reduction + a host sync per step, so by default the kernels clamp instead
         self.validate_actions = bool(validate_actions)
@@ -124,12 +130,11 @@ class B200VectorEnv(VectorEnv):
         self._seed_list: list[int] | None = None
         self._has_reset = False
         self._pending: tuple | None = None  # ("reset" | "step", result, reset mask) between *_async and *_wait
-        self._pinned_actions: torch.Tensor | None = None
+        self._pinned_actions: list | None = None  # ring of (pinned tensor, numpy view, event of the last H2D out of it)
+        self._pinned_pos = 0
         self._out: dict[str, torch.Tensor] = {}
         self._pinned_wire: torch.Tensor | None = None
         self._pinned_np: np.ndarray | None = None
-        self._pinned_actions_np: np.ndarray | None = None
-        self._h2d_event: torch.cuda.Event | None = None
 
     # ------------------------------------------------------------------------------------------------------------
     # hooks for families
@@ -154,8 +159,17 @@ class B200VectorEnv(VectorEnv):
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _outputs(self) -> dict[str, torch.Tensor]:
-        if self.copy or not self._out:
+        if self.copy:
             self._out = self._alloc_outputs()  # fresh tensors from the caching allocator; kernels write in place
+        elif self.out_buffers > 1:
+            if len(self._out_ring) < self.out_buffers:
+                self._out_ring.append(self._alloc_outputs())
+                self._out = self._out_ring[-1]
+            else:
+                self._out = self._out_ring[self._out_pos % self.out_buffers]
+            self._out_pos += 1
+        elif not self._out:
+            self._out = self._alloc_outputs()
         return self._out
 
     def _alloc_packed(self, layout: dict[str, tuple[tuple, torch.dtype]]) -> dict[str, torch.Tensor]:
@@ -322,18 +336,23 @@ class B200VectorEnv(VectorEnv):
                 raise ValueError(f"expected {n} actions (one per sub-environment), got {a.shape[0]}")
             if self.discrete_actions and a.ndim != 1:
                 raise ValueError(f"discrete actions must have shape ({n},), got {a.shape}")
-            # stage through a cached pinned buffer with a plain single-threaded memcpy, then one async H2D copy
-            pa = self._pinned_actions
-            if pa is None or tuple(pa.shape) != a.shape or self._pinned_actions_np.dtype != a.dtype:
-                pa = self._pinned_actions = torch.from_numpy(np.empty(a.shape, dtype=a.dtype)).pin_memory()
-                self._pinned_actions_np = pa.numpy()
-            if self._h2d_event is not None:
-                self._h2d_event.synchronize()  # the previous step's DMA out of this buffer must have finished
-            np.copyto(self._pinned_actions_np, a)
-            t = pa.to(self.device, non_blocking=True)
-            if self._h2d_event is None:
-                self._h2d_event = torch.cuda.Event()
-            self._h2d_event.record(torch.cuda.current_stream(self.device))
+            # stage through a small ring of cached pinned buffers with a plain single-threaded memcpy, then one async
+            # H2D copy (a ring, so that the host may run ahead of the stream by a few steps without waiting for a DMA)
+            ring = self._pinned_actions
+            if ring is None or tuple(ring[0][0].shape) != a.shape or ring[0][1].dtype != a.dtype:
+                ring = self._pinned_actions = []
+                for _ in range(4):
+                    pt = torch.from_numpy(np.empty(a.shape, dtype=a.dtype)).pin_memory()
+                    ring.append([pt, pt.numpy(), None])
+            slot = ring[self._pinned_pos % len(ring)]
+            self._pinned_pos += 1
+            if slot[2] is not None:
+                slot[2].synchronize()  # the DMA that last read this staging buffer must have finished
+            np.copyto(slot[1], a)
+            t = slot[0].to(self.device, non_blocking=True)
+            if slot[2] is None:
+                slot[2] = torch.cuda.Event()
+            slot[2].record(torch.cuda.current_stream(self.device))
             return t
         if t.dim() == 0:
             raise TypeError(f"actions must have a leading dimension of num_envs={n}, got a scalar tensor")
@@ -410,6 +429,7 @@ class B200VectorEnv(VectorEnv):
 
     def close_extras(self, **kwargs):
         self._out = {}
+        self._out_ring = []
         self._rng = None
         self._ctrl = None
 

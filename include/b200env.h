@@ -67,6 +67,25 @@ const char* b2e_last_error(void);
 /* sm_count / cc may be NULL. Returns B2E_ENODEV when no device. */
 int b2e_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
 
+/* ---- single host-side batch: what AsyncVectorEnv's shared-memory observations are on the reference side (one buffer all
+ * workers write their slice of, gymnasium/vector/async_vector_env.py:234-245, :849-852 `write_to_shared_memory`).  Here
+ * every GPU rank of a node maps ONE host buffer, page-locks it in its own CUDA context (b2e_host_register) and DMAs its
+ * shard's packed step outputs into its slice over its own PCIe link (b2e_copy_to_host_async on the caller's copy stream);
+ * see gymnasium_b200/distributed.py: HostBatch.  `host` is a HOST pointer (the only ones in this ABI). */
+int b2e_host_register(void* host, size_t bytes);
+int b2e_host_unregister(void* host);
+/* One segment of a step's outputs: `height` rows of `width` bytes (height 1 = a contiguous run; struct-of-arrays outputs such as
+ * Humanoid's info[13][n] land in the global [13][N_total] array as a pitched copy). */
+typedef struct b2e_copy_seg {
+  void* host_dst;      /* inside a b2e_host_register'ed buffer */
+  const void* dev_src;
+  size_t dst_pitch, src_pitch; /* bytes between rows (ignored when height == 1) */
+  size_t width, height;
+} b2e_copy_seg;
+/* Enqueues the device->host copies of `count` segments on `stream`, in order (a trailing 8-byte segment is how a rank publishes
+ * its sequence word behind the data). */
+int b2e_copy_to_host_async(const b2e_copy_seg* segs, int32_t count, void* stream);
+
 /* ---- RNG: gymnasium/utils/seeding.py:39-41 -> numpy SeedSequence -> PCG64 ---------------------------------------
  * rng   : uint64 [2][n][2]  = {state(lo,hi)}[n] then {inc(lo,hi)}[n]
  * seeds : uint64 [n] device, or NULL => seed_i = base_seed + env_offset + i  (SyncVectorEnv.reset seed+i, :205-208)

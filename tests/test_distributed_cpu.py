@@ -68,3 +68,74 @@ def test_gather_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[-1] for r in res), res
+
+
+# ---- HostBatch: the single host-side batch every rank lands its rows in (CPU: memmove stands in for the DMA engine) ------
+def _apply_segments(segs):
+    import ctypes
+
+    for dst, src, dpitch, spitch, width, height in segs:
+        for row in range(height):
+            ctypes.memmove(dst + row * dpitch, src + row * spitch, width)
+
+
+def _hostbatch_worker(rank, world, port, q):
+    from gymnasium_b200.distributed import HostBatch
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        total, depth, steps = 11, 2, 7  # ragged shards (6 + 5), fewer slots than steps: exercises the ack protocol
+        bounds = [shard_bounds(total, world, r) for r in range(world)]
+        start, n = bounds[rank]
+        layout = [("obs", (n, 3), torch.float64), ("info", (4, n), torch.float64), ("reward", (n,), torch.float64),
+                  ("terminated", (n,), torch.bool)]
+        hb = HostBatch(layout, bounds, rank, tag="cpu_test", depth=depth, soa_keys=("info",), register=False)
+        ok = True
+        gi = np.arange(start, start + n)
+        for k in range(steps):
+            # this rank's "device" outputs of step k: values encode (step, global env index)
+            obs = np.ascontiguousarray(np.stack([gi + 100.0 * k, gi * 2.0, gi * 3.0 + k], axis=1))
+            info = np.ascontiguousarray(np.stack([gi + 0.25 * c + k for c in range(4)]))
+            reward = gi * 0.5 + k
+            term = ((gi + k) % 3 == 0)
+            src = {"obs": obs, "info": info, "reward": reward, "terminated": term}
+            hb.wait_writable(k)
+            _apply_segments(hb.segments(k, rank, {key: a.ctypes.data for key, a in src.items()}))
+            hb.publish_host(k)
+            if rank == 0:  # the consumer lags one step behind, as the bench loop does
+                if k >= 1:
+                    ok = ok and _check_hostbatch(hb, k - 1, total)
+        if rank == 0:
+            ok = ok and _check_hostbatch(hb, steps - 1, total)
+        dist.barrier()
+        hb.close()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _check_hostbatch(hb, k, total):
+    v = hb.wait_ready(k)
+    g = np.arange(total)
+    ok = (v["obs"].shape == (total, 3) and v["info"].shape == (4, total)
+          and np.array_equal(v["obs"][:, 0], g + 100.0 * k) and np.array_equal(v["obs"][:, 2], g * 3.0 + k)
+          and all(np.array_equal(v["info"][c], g + 0.25 * c + k) for c in range(4))
+          and np.array_equal(v["reward"], g * 0.5 + k) and np.array_equal(v["terminated"], (g + k) % 3 == 0)
+          and v["terminated"].dtype == np.bool_)
+    hb.ack(k)
+    return ok
+
+
+def test_hostbatch_world2_lands_rows_key_major_and_throttles():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_hostbatch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[-1] for r in res), res
