@@ -169,9 +169,9 @@ extern "C" int b2e_copy_to_host_async(const b2e_copy_seg* segs, int32_t count, v
     }
     if (g.width == 0 || g.height == 0) continue;
     cudaError_t e = g.height == 1
-                        ? cudaMemcpyAsync(g.host_dst, g.dev_src, g.width, cudaMemcpyDeviceToHost, (cudaStream_t)stream)
+                        ? cudaMemcpyAsync(g.host_dst, g.dev_src, g.width, cudaMemcpyDefault, (cudaStream_t)stream)
                         : cudaMemcpy2DAsync(g.host_dst, g.dst_pitch, g.dev_src, g.src_pitch, g.width, g.height,
-                                            cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+                                            cudaMemcpyDefault, (cudaStream_t)stream);
     if (int st = cuda_status(e, "b2e_copy_to_host_async")) return st;
   }
   return 0;

@@ -21,6 +21,7 @@
 // Jacobian, A = J M^-1 J^T + R): thread-local memory (~36 KB/env) in the thread mapping, 24 KB of shared memory in the warp
 // mapping; persistent state is 74 doubles per env in struct-of-arrays layout.  ~0.9 MFLOP fp64 per env-step; both
 // mappings are bound by dependent-issue latency, not by FLOP/s or HBM.
+#include <atomic>
 #include <assert.h>
 #include <string.h>
 
@@ -1166,12 +1167,15 @@ __global__ void __launch_bounds__(kHumanoidBlock) humanoid_step_kernel(const Hum
 
 template <typename ActT, int W>
 int launch_warp_step(const HumanoidArgs& a, cudaStream_t s) {
-  static bool configured = false;  // opt in to > 48 KB of dynamic shared memory once per instantiation
+  // opt in to > 48 KB of dynamic shared memory once per instantiation AND device (the attribute is per device/context)
+  static std::atomic<bool> configured[64];
   const int smem = (int)sizeof(WModel) + W * (int)sizeof(WS);
-  if (!configured) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;  // slot 63 is never latched: always re-applied
+  if (dev == 63 || !configured[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(humanoid_step_warp_kernel<ActT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "b2e_humanoid_step (shared memory opt-in)");
-    configured = true;
+    if (dev != 63) configured[dev].store(true, std::memory_order_release);
   }
   if (a.order) humanoid_group_kernel<<<1, 1024, 0, s>>>(a.work, a.order, a.n);
   humanoid_step_warp_kernel<ActT, W><<<(unsigned)((a.n + W - 1) / W), 32 * W, smem, s>>>(a);

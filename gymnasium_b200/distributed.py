@@ -139,7 +139,12 @@ class HostBatch:
             self.keys.append((key, gshape, npdt, off, rowb, rows))
             off = (off + int(np.prod(gshape, dtype=np.int64)) * npdt.itemsize + 255) // 256 * 256
         self.slot_bytes = max(off, 256)
-        self.header_bytes = (self.LINE * (self.world + 1) + 4095) // 4096 * 4096
+        # counters (one line per rank + the ack line), then per rank a line-aligned ring of sequence-word SOURCES: the value
+        # step k publishes is written there by the host and copied behind the data by the same stream (pinned -> pinned)
+        self.src_ring = 2 * self.depth + 2
+        self._src_off = self.LINE * (self.world + 1)
+        self._src_stride = (8 * self.src_ring + self.LINE - 1) // self.LINE * self.LINE
+        self.header_bytes = (self._src_off + self._src_stride * self.world + 4095) // 4096 * 4096
         self.total_bytes = self.header_bytes + self.depth * self.slot_bytes
         if barrier is None:
             barrier = dist.barrier if (dist.is_available() and dist.is_initialized() and self.world > 1) else (lambda: None)
@@ -165,6 +170,7 @@ class HostBatch:
         self._hdr = self._np[: self.header_bytes].view(np.int64)
         self._addr = self._np.ctypes.data
         self._registered = False
+        self._views: dict = {}
         if rank == 0:
             self._np[:] = 0  # also faults every page in before it is page-locked
         barrier()
@@ -193,11 +199,16 @@ class HostBatch:
         """numpy views ``{key: global array}`` of the slot step k lives in."""
         import numpy as np
 
-        base = self.header_bytes + (k % self.depth) * self.slot_bytes
+        j = k % self.depth
+        hit = self._views.get(j)
+        if hit is not None:
+            return hit
+        base = self.header_bytes + j * self.slot_bytes
         out = {}
         for key, gshape, npdt, off, _rowb, _rows in self.keys:
             nb = int(np.prod(gshape, dtype=np.int64)) * npdt.itemsize
             out[key] = self._np[base + off: base + off + nb].view(npdt).reshape(gshape)
+        self._views[j] = out
         return out
 
     def segments(self, k: int, src_rank: int, dev_ptrs: dict) -> list[tuple]:
@@ -217,6 +228,12 @@ class HostBatch:
     def seq_addr(self, rank: int | None = None) -> int:
         r = self.rank if rank is None else rank
         return self._addr + r * self.LINE
+
+    def seq_source(self, k: int) -> int:
+        """Writes k+1 into this rank's source ring and returns its address (the last copy segment of step k reads it)."""
+        i = (self._src_off + self._src_stride * self.rank) // 8 + k % self.src_ring
+        self._hdr[i] = k + 1
+        return self._addr + 8 * i
 
     # ---- protocol --------------------------------------------------------------------------------------------------
     def _seq(self, r: int) -> int:
@@ -264,6 +281,7 @@ class HostBatch:
             self._lib.b2e_host_unregister(self._addr)
             self._registered = False
         self._hdr = self._np = None
+        self._views = {}
         try:
             self._mm.close()
         except (BufferError, ValueError):
@@ -315,7 +333,8 @@ class HostBatchPipeline:
         self.k = 0
         self._ev_step = [torch.cuda.Event() for _ in range(depth)]
         self._ev_copy = [None] * depth
-        self._seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._cs_handle = self.copy_stream.cuda_stream
+        self._seq_dev = torch.zeros(2 * depth + 2, dtype=torch.int64, device=dev)
         self._gathered = ([torch.empty((world_size, self.wire_bytes), dtype=torch.uint8, device=dev) for _ in range(depth)]
                           if mode == "nccl" and self.is_consumer else None)
         self._seg_cache: dict = {}
@@ -334,7 +353,11 @@ class HostBatchPipeline:
             for r in range(self.world):
                 base = g[r].data_ptr()
                 segs += self.host.segments(k, r, {e[0]: base + e[3] for e in self.layout})
-        segs.append((self.host.seq_addr(), self._seq_dev.data_ptr(), 0, 0, 8, 1))
+        # publication: the sequence word goes pinned source -> device scratch -> seq word, two DMAs queued behind the data (a
+        # host->host cudaMemcpyAsync is NOT stream-ordered: the runtime copies on the calling thread, ahead of the data)
+        bounce = self._seq_dev[k % self._seq_dev.numel():].data_ptr()
+        segs.append((bounce, 0, 0, 0, 8, 1))  # source patched per step: HostBatch.seq_source(k)
+        segs.append((self.host.seq_addr(), bounce, 0, 0, 8, 1))
         arr = (self._lib_mod.CopySeg * len(segs))(*[self._lib_mod.CopySeg(*s) for s in segs])
         self._seg_cache[key] = (arr, len(segs))
         return self._seg_cache[key]
@@ -350,15 +373,17 @@ class HostBatchPipeline:
         self._ev_step[j].record(main)
         cs = self.copy_stream
         cs.wait_event(self._ev_step[j])
-        with torch.cuda.stream(cs):
-            if self.mode == "nccl":
+        if self.mode == "nccl":
+            with torch.cuda.stream(cs):
                 dst = list(self._gathered[j].unbind(0)) if self.is_consumer else None
                 dist.gather(out["_wire"], dst, dst=self.consumer)
-            if self.host is not None:
-                self.host.wait_writable(k)
-                self._seq_dev.add_(1)
-                arr, cnt = self._segments(k, out)
-                self._lib_mod.check(self._lib.b2e_copy_to_host_async(arr, cnt, cs.cuda_stream), "b2e_copy_to_host_async")
+        if self.host is not None:
+            self.host.wait_writable(k)
+            arr, cnt = self._segments(k, out)
+            arr[cnt - 2].dev_src = self.host.seq_source(k)
+            st = self._lib.b2e_copy_to_host_async(arr, cnt, self._cs_handle)
+            if st:
+                self._lib_mod.check(st, "b2e_copy_to_host_async")
         ev = self._ev_copy[j] or torch.cuda.Event()
         ev.record(cs)
         self._ev_copy[j] = ev

@@ -228,8 +228,13 @@ class B200VectorEnv(VectorEnv):
                 raise ValueError(f"Seed must be a non-negative integer, got {base}")  # seeding.py:28-34
             if base + self.env_offset + n - 1 > _U64:
                 raise ValueError("gymnasium_b200 supports seeds below 2**64")
-            if mask is None or self._base_seed is None:
+            if mask is None or not self._seeded:
                 self._base_seed, self._seed_list = base, None
+            else:  # masked re-seed: only those lanes change their seed (np_random_seed stays per-lane exact)
+                seeds = list(self.np_random_seed)
+                for i in torch.nonzero(mask).flatten().tolist():
+                    seeds[i] = base + self.env_offset + i
+                self._seed_list, self._base_seed = seeds, None
         else:
             seed = list(seed)
             if len(seed) != n:
@@ -249,8 +254,22 @@ class B200VectorEnv(VectorEnv):
                 raise ValueError("gymnasium_b200 supports seeds in [0, 2**64)")
             arr = np.array([int(s) for s in seed], dtype=np.uint64).view(np.int64)
             seeds_dev = torch.from_numpy(arr).to(self.device)
-            self._seed_list, self._base_seed = [int(s) for s in seed], None
+            if mask is not None and self._seeded:  # only the masked lanes take their new seed
+                old, m = list(self.np_random_seed), mask.cpu().tolist()
+                self._seed_list, self._base_seed = [int(s) if m[i] else old[i] for i, s in enumerate(seed)], None
+            else:
+                self._seed_list, self._base_seed = [int(s) for s in seed], None
         if self.rng_mode == "numpy":
+            if not self._seeded:
+                # first seeding of this batch: EVERY lane gets its stream, whatever the reset mask says -- an unmasked lane
+                # is an env whose np_random self-seeds lazily at its first draw (gymnasium/core.py:226-235); all-zero PCG64
+                # words would make every later autoreset of that lane draw u = 0.0
+                if mask is not None and seeds_dev is None:
+                    mask = None
+                elif mask is not None:
+                    lazy = torch.from_numpy(np.array([secrets.randbits(62) for _ in range(n)], dtype=np.int64)).to(self.device)
+                    seeds_dev = torch.where(mask, seeds_dev, lazy)
+                    mask = None
             mask_u8 = None if mask is None else mask.view(torch.uint8)
             _lib.check(
                 self._lib.b2e_rng_seed(C.byref(self._batch), base & _U64, ptr(seeds_dev), ptr(mask_u8),
@@ -393,6 +412,10 @@ class B200VectorEnv(VectorEnv):
                 self._check_actions(t)
             out = self._outputs()
             self._batch.action_dtype = _ACT_DTYPES[t.dtype]
+            if self.rng_mode == "philox" and torch.cuda.is_current_stream_capturing():
+                # the call counter that keys this call's Philox draws is a kernel ARGUMENT: a graph replay would re-use it
+                raise RuntimeError("rng='philox' cannot be captured in a CUDA graph (every replay would repeat the captured "
+                                   "call counter and with it the reset draws); use rng='numpy' (per-env PCG64 state in HBM)")
             self._step_kernel(t, out)
             self._batch.call_counter += 1
         if self.output == "numpy":

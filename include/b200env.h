@@ -78,7 +78,7 @@ int b2e_host_unregister(void* host);
  * Humanoid's info[13][n] land in the global [13][N_total] array as a pitched copy). */
 typedef struct b2e_copy_seg {
   void* host_dst;      /* inside a b2e_host_register'ed buffer */
-  const void* dev_src;
+  const void* dev_src; /* device memory, or page-locked host memory (the sequence word's source) */
   size_t dst_pitch, src_pitch; /* bytes between rows (ignored when height == 1) */
   size_t width, height;
 } b2e_copy_seg;

@@ -752,3 +752,32 @@ def test_async_call_api_and_attr_access():
     cp.close()
     with pytest.raises(errors.ClosedEnvironmentError):
         cp.reset(seed=0)
+
+
+@pytest.mark.gpu
+def test_first_reset_with_mask_seeds_every_lane_and_np_random_seed_tracks_masked_reseeds():
+    """A first reset() that carries a reset_mask must not leave the other lanes on all-zero PCG64 words (their autoresets
+    would all draw u = 0.0), and np_random_seed must follow masked int / list re-seeds lane by lane."""
+    mask = np.array([True, False, True, False, False, True])
+    env = gymnasium_b200.make_vec("CartPole-v1", num_envs=6, output="numpy")
+    env.reset(seed=100, options={"reset_mask": mask})
+    words = env.rng_state()  # [2][n][2]
+    assert (words[0].any(axis=1)).all() and (words[1].any(axis=1)).all()
+    assert env.np_random_seed == tuple(100 + i for i in range(6))
+    # masked lanes follow numpy exactly
+    for i in np.nonzero(mask)[0]:
+        st = np.random.PCG64(np.random.SeedSequence(100 + int(i))).state["state"]
+        # four uniform draws were taken by the reset: advance the reference stream the same way
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(100 + int(i))))
+        g.uniform(-0.05, 0.05, size=4)
+        s = g.bit_generator.state["state"]["state"]
+        assert int(words[0][i][0]) | (int(words[0][i][1]) << 64) == s and st is not None
+    env.reset(seed=500, options={"reset_mask": np.array([False, True, False, False, False, False])})
+    assert env.np_random_seed == (100, 501, 102, 103, 104, 105)
+    env.reset(seed=[1, 2, 3, 4, 5, 6], options={"reset_mask": np.array([False, False, False, True, False, False])})
+    assert env.np_random_seed == (100, 501, 102, 4, 104, 105)
+    # seed=None on a never-seeded batch with a mask: every lane still gets a (lazy) stream
+    env2 = gymnasium_b200.make_vec("CartPole-v1", num_envs=6, output="numpy")
+    env2.reset(options={"reset_mask": mask})
+    w2 = env2.rng_state()
+    assert (w2[0].any(axis=1)).all() and (w2[1].any(axis=1)).all()
