@@ -10,8 +10,12 @@
 // intrinsics so ptxas can never contract a*b+c into an FMA: apart from sin/cos (CUDA libdevice vs the host libm,
 // <= 1-2 ulp) the op sequence is the reference's, which keeps whole trajectories inside the 1e-5 tolerance.
 //
-// Memory: struct-of-arrays float64 state [4][n] (four fully coalesced 8-byte streams), one packed int32 control word,
-// float4 observation store, RNG state touched only by lanes that reset.  HBM-bound: 106 B/env-step with int64 actions.
+// Memory: float64 state as two 16-byte streams, [2][n] double2 = (x, x_dot)[n] then (theta, theta_dot)[n] (two fully
+// coalesced LDG.128 / STG.128 per env instead of four 8-byte accesses), one packed int32 control word, float4 observation
+// store, RNG state touched only by lanes that reset.  HBM-bound: 106 B/env-step with int64 actions.
+// Code layout: the step kernel's hot path is straight-line (loads -> Euler step -> stores); everything rare -- the
+// autoreset draws (PCG64 128-bit arithmetic / Philox), libdevice's sincos for |theta| >= 0.3 -- lives in __noinline__
+// functions so that the instruction stream an SM has to fetch for a cold launch stays short.
 #include "common.cuh"
 
 namespace b2e {
@@ -53,6 +57,13 @@ __device__ __forceinline__ double div_total_mass(double x) {
   return __fma_rn(__fma_rn(-q, d, x), r, q);
 }
 
+// libdevice's sincos (Payne-Hanek reduction and all), out of line and returning in registers
+__device__ __noinline__ double2 sincos_cold(double x) {
+  double sn, cs;
+  sincos(x, &sn, &cs);
+  return make_double2(sn, cs);
+}
+
 // sin/cos for |x| < 0.3 (every non-terminated CartPole angle: |theta| <= 12 deg = 0.2094): the classic fdlibm kernel
 // polynomials (k_sin.c / k_cos.c coefficients), no range reduction, < 1 ulp; larger arguments (custom reset bounds,
 // DISABLED-mode steps past termination) take libdevice's sincos.
@@ -78,7 +89,9 @@ __device__ __forceinline__ void sincos_pole(double x, double* sn, double* cs) {
     q = __dmul_rn(z, q);
     *cs = __dsub_rn(1.0, __fma_rn(-z, q, __dmul_rn(0.5, z)));
   } else {
-    sincos(x, sn, cs);
+    const double2 r = sincos_cold(x);
+    *sn = r.x;
+    *cs = r.y;
   }
 }
 
@@ -106,13 +119,12 @@ __device__ __forceinline__ bool is_terminated(const State4& s) {  // cartpole.py
 }
 
 __device__ __forceinline__ State4 load_state(const double* __restrict__ st, int64_t n, int64_t i) {
-  return State4{st[i], st[n + i], st[2 * n + i], st[3 * n + i]};
+  const double2 a = reinterpret_cast<const double2*>(st)[i], b = reinterpret_cast<const double2*>(st)[n + i];
+  return State4{a.x, a.y, b.x, b.y};
 }
 __device__ __forceinline__ void store_state(double* __restrict__ st, int64_t n, int64_t i, const State4& s) {
-  st[i] = s.x;
-  st[n + i] = s.xd;
-  st[2 * n + i] = s.th;
-  st[3 * n + i] = s.thd;
+  reinterpret_cast<double2*>(st)[i] = make_double2(s.x, s.xd);
+  reinterpret_cast<double2*>(st)[n + i] = make_double2(s.th, s.thd);
 }
 __device__ __forceinline__ float4 to_obs(const State4& s) {
   return make_float4((float)s.x, (float)s.xd, (float)s.th, (float)s.thd);
@@ -151,20 +163,76 @@ __global__ void __launch_bounds__(kBlock) cartpole_reset_kernel(const CartPoleAr
   reinterpret_cast<float4*>(a.obs)[i] = to_obs(s);
 }
 
-// one env's step given its preloaded inputs
-__device__ __forceinline__ void step_env(const CartPoleArgs& a, int64_t i, int32_t c, const State4& s0, int action) {
+// The autoreset path of the step kernel, out of line (see the file header): CartPoleEnv.reset for one env -- draws, state,
+// cleared control word, observation.  Scalar arguments only, so that the call costs the hot path nothing (a reference to
+// the kernel's argument struct would make ptxas copy all of it to local memory in the kernel prologue).  `g` carries the
+// env's PCG64 words when the caller has already loaded them (numpy mode, kSpecRng).
+__device__ __noinline__ void reset_env_cold(double* __restrict__ state, int32_t* __restrict__ ctrl, uint64_t* __restrict__ rng,
+                                            float* __restrict__ obs, int64_t n, int64_t i, double low, double range,
+                                            int32_t rng_mode, uint64_t philox_seed, uint64_t env, uint64_t counter,
+                                            bool have_words, ulonglong2 w_state, ulonglong2 w_inc) {
+  State4 s;
+  if (rng_mode == B2E_RNG_NUMPY) {
+    Pcg64 g;
+    if (have_words) {
+      g.state = u128{w_state.x, w_state.y};
+      g.inc = u128{w_inc.x, w_inc.y};
+    } else {
+      g = pcg64_load(rng, n, i);
+    }
+    s.x = g.uniform(low, range);  // cartpole.py:236-241: x, x_dot, theta, theta_dot in this order
+    s.xd = g.uniform(low, range);
+    s.th = g.uniform(low, range);
+    s.thd = g.uniform(low, range);
+    pcg64_store_state(rng, i, g);
+  } else {
+    const uint4 r0 = philox_block(philox_seed, env, counter, 1u), r1 = philox_block(philox_seed, env, counter, 2u);
+    s.x = __dadd_rn(low, __dmul_rn(range, u53_to_double(r0.x, r0.y)));
+    s.xd = __dadd_rn(low, __dmul_rn(range, u53_to_double(r0.z, r0.w)));
+    s.th = __dadd_rn(low, __dmul_rn(range, u53_to_double(r1.x, r1.y)));
+    s.thd = __dadd_rn(low, __dmul_rn(range, u53_to_double(r1.z, r1.w)));
+  }
+  store_state(state, n, i, s);
+  ctrl[i] = 0;
+  __stcs(reinterpret_cast<float4*>(obs) + i, to_obs(s));
+}
+
+// One thread per env.  All loads are issued before the first use (one memory round trip).  kSpecRng: the PCG64 words of
+// EVERY lane are loaded up front together with the state (+32 B/env of reads, ~5 % of the lanes need them) -- with ~5 % of
+// the lanes on an autoreset call, 4 warps out of 5 contain one, and a load that depends on the control word would put a
+// second DRAM round trip (~0.8 us) on the critical path of a launch that lasts 3 us.  Used for batches up to 2^21 envs,
+// where the launch is latency-bound; DRAM-sized batches are bandwidth-bound and take the dependent load instead.
+// Launch geometry was swept on a B200 at N=65536 (graph-chained launches, us per launch, L2-resident / HBM-cold ring):
+// CTA 64: 3.01 / 3.91, 128: 3.21 / 4.05, 256: 3.33 / 4.08, 448 (one CTA per SM): 3.28 / 4.01, 1024: 4.65 / 5.29; 2 or 4
+// envs per thread were slower (4.10 / 6.3 us L2-resident); programmatic dependent launch made N >= 65536 slower (4.07 vs
+// 3.27 us) and is opt-in (B2E_PDL=1).  b2e_cartpole_cfg.step_block overrides the CTA size.
+constexpr int kStepBlock = 64;
+constexpr int64_t kSpecRngMaxEnvs = 1 << 21;
+
+template <typename ActT, bool kSpecRng>
+__global__ void __launch_bounds__(1024) cartpole_step_kernel(const CartPoleArgs a) {
+  pdl_prologue();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const int32_t c = a.ctrl[i];
+  const State4 s0 = load_state(a.state, a.n, i);
+  const int action = load_action<ActT>(a.actions, i);
+  ulonglong2 w_state = make_ulonglong2(0, 0), w_inc = make_ulonglong2(0, 0);
+  const bool have_words = kSpecRng && a.rng_mode == B2E_RNG_NUMPY;
+  if (have_words) {
+    w_state = reinterpret_cast<const ulonglong2*>(a.rng)[i];
+    w_inc = __ldg(reinterpret_cast<const ulonglong2*>(a.rng) + a.n + i);
+  }
   if (a.mode == B2E_AUTORESET_NEXT_STEP && ctrl_pending(c)) {
     // sync_vector_env.py:279-284: the call after a done is the reset; reward 0, flags False, action ignored
-    const State4 s = sample_reset(a, i, a.call_counter);
-    store_state(a.state, a.n, i, s);
-    a.ctrl[i] = 0;
-    __stcs(reinterpret_cast<float4*>(a.obs) + i, to_obs(s));
+    reset_env_cold(a.state, a.ctrl, a.rng, a.obs, a.n, i, a.low, a.range, a.rng_mode, a.philox_seed,
+                   (uint64_t)(a.env_offset + i), a.call_counter, have_words, w_state, w_inc);
     __stcs(a.reward + i, 0.0);
     a.term[i] = 0;
     a.trunc[i] = 0;
     return;
   }
-  State4 s = euler_step(s0, action);
+  const State4 s = euler_step(s0, action);
   const bool term = is_terminated(s);
   const int32_t elapsed = ctrl_elapsed(c) + 1;
   const bool trunc = a.max_steps > 0 && elapsed >= a.max_steps;  // wrappers/common.py:130-133
@@ -177,8 +245,9 @@ __device__ __forceinline__ void step_env(const CartPoleArgs& a, int64_t i, int32
       cn |= kPending;
     } else if (a.mode == B2E_AUTORESET_SAME_STEP) {  // sync_vector_env.py:302-319
       reinterpret_cast<float4*>(a.final_obs)[i] = to_obs(s);
-      s = sample_reset(a, i, a.call_counter);
-      cn = 0;
+      reset_env_cold(a.state, a.ctrl, a.rng, a.obs, a.n, i, a.low, a.range, a.rng_mode, a.philox_seed,
+                     (uint64_t)(a.env_offset + i), a.call_counter, have_words, w_state, w_inc);
+      return;
     }
   }
   store_state(a.state, a.n, i, s);
@@ -186,28 +255,12 @@ __device__ __forceinline__ void step_env(const CartPoleArgs& a, int64_t i, int32
   __stcs(reinterpret_cast<float4*>(a.obs) + i, to_obs(s));
 }
 
-// One thread per env.  All loads are issued before the first use (one memory round trip).  Launch geometry was swept
-// on a B200 at N=65536 (graph-chained launches, us per launch, L2-resident / HBM-cold ring): CTA 64: 3.01 / 3.91,
-// 128: 3.21 / 4.05, 256: 3.33 / 4.08, 448 (one CTA per SM): 3.28 / 4.01, 1024: 4.65 / 5.29; 2 or 4 envs per thread
-// were slower (4.10 / 6.3 us L2-resident); programmatic dependent launch made N >= 65536 slower (4.07 vs 3.27 us) and
-// is opt-in (B2E_PDL=1).  b2e_cartpole_cfg.step_block overrides the CTA size.
-constexpr int kStepBlock = 64;
-
-template <typename ActT>
-__global__ void __launch_bounds__(1024) cartpole_step_kernel(const CartPoleArgs a) {
-  pdl_prologue();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const int32_t c = a.ctrl[i];
-  const State4 s0 = load_state(a.state, a.n, i);
-  const int action = load_action<ActT>(a.actions, i);
-  step_env(a, i, c, s0, action);
-}
-
 template <typename ActT>
 cudaError_t launch_step(const CartPoleArgs& a, cudaStream_t st, int block) {
   if (block < 32 || block > 1024 || (block & 31)) block = kStepBlock;
-  return launch_pdl(cartpole_step_kernel<ActT>, grid_for(a.n, block), block, 0, st, a);
+  static const bool no_spec = getenv("B2E_CARTPOLE_NO_SPEC_RNG") != nullptr;  // measurement switch (scripts/block_sweep.py)
+  if (a.n <= kSpecRngMaxEnvs && !no_spec) return launch_pdl(cartpole_step_kernel<ActT, true>, grid_for(a.n, block), block, 0, st, a);
+  return launch_pdl(cartpole_step_kernel<ActT, false>, grid_for(a.n, block), block, 0, st, a);
 }
 
 struct RolloutArgs {

@@ -40,6 +40,11 @@ class ClassicVectorEnv(B200VectorEnv):
     def state(self) -> torch.Tensor:
         return self._state.t().contiguous()
 
+    def set_state(self, state) -> None:
+        """Overwrites the per-env float64 state from a ``(N, state_size)`` array."""
+        t = torch.as_tensor(state, dtype=torch.float64).to(self.device).reshape(self.num_envs, self.state_size)
+        self._state.copy_(t.t())
+
     def _alloc_outputs(self):
         n = self.num_envs
         layout = {"obs": ((n, self.obs_size), torch.float32), "reward": ((n,), torch.float64),

@@ -97,7 +97,7 @@ int b2e_rng_seed(const b2e_batch* b, uint64_t base_seed, const uint64_t* seeds, 
 int b2e_rng_random(const b2e_batch* b, uint64_t* rng, int32_t k, double* out, void* stream);
 
 /* ---- CartPole-v1: gymnasium/envs/classic_control/cartpole.py:164-247 ---------------------------------------------
- * state  : float64 [4][n]  (x, x_dot, theta, theta_dot) struct-of-arrays
+ * state  : float64 [2][n][2]  two 16-byte streams: (x, x_dot)[n] then (theta, theta_dot)[n]
  * ctrl   : int32 [n]       bits 0..30 elapsed steps (TimeLimit), bit 31 = autoreset pending (NEXT_STEP)
  * obs    : float32 [n][4]
  */

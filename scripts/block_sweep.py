@@ -13,7 +13,7 @@ def chain(envs, acts, L=60, reps=40):
         with torch.cuda.graph(g, stream=s):
             for k in range(L):
                 envs[k % len(envs)].step(acts)
-    for _ in range(5): g.replay()
+    for _ in range(30): g.replay()   # also walks every batch into its steady state (~5 % of the lanes on an autoreset call)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -25,6 +25,7 @@ n = 65536
 acts = torch.randint(0, 2, (n,), device="cuda")
 ring = [gymnasium_b200.make_vec("CartPole-v1", num_envs=n, copy=False, env_offset=j * n) for j in range(30)]
 for e in ring: e.reset(seed=0)
-for blk in [64, 128, 192, 256, 320, 384, 448, 512, 640, 768, 1024]:
+print("speculative RNG load:", "off" if os.environ.get("B2E_CARTPOLE_NO_SPEC_RNG") else "on", " PDL:", "on" if os.environ.get("B2E_PDL") else "off")
+for blk in [32, 64, 96, 128, 192, 256, 448, 1024]:
     for e in ring: e._cfg.step_block = blk
     print(f"block {blk:5d}: L2-resident {chain(ring[:1], acts):.3f} us   HBM-cold ring {chain(ring, acts):.3f} us")

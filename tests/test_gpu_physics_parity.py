@@ -1,0 +1,197 @@
+"""Parity hardening for the two physics families whose third-party engines (Box2D, MuJoCo) cannot be installed here.
+
+* config-size runs: LunarLander-v3 at BASELINE's N=16384 and Humanoid-v5 at N=8192 on the GPU, with a sampled set of 256
+  GLOBAL env indices checked bit for bit against the C oracle (envs are independent: the oracle gets those indices as a seed
+  list), through at least one autoreset per family;
+* sharding invariance of Humanoid (env_offset), which the 8-GPU configuration depends on;
+* analytic known-answer tests that do NOT depend on the repo's own oracle: closed forms of the engines' integrators in free
+  flight (total-momentum balance), the numpy RNG draw order of reset(), zero actuation for zero control;
+* the reference's own reward identity with its exact grouping and `==` (tests/envs/mujoco/test_mujoco_v5.py:248-254).
+"""
+import numpy as np
+import pytest
+
+import gymnasium_b200
+
+pytestmark = pytest.mark.gpu
+
+
+def make(env_id, n, **kw):
+    kw.setdefault("output", "numpy")
+    return gymnasium_b200.make_vec(env_id, num_envs=n, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_lunarlander_config_size_sampled_lanes_match_oracle():
+    """BASELINE configs[3]: 16384 envs.  256 sampled global indices vs oracle/lunar_lander.c, bit-exact, through autoresets."""
+    from oracle.lunar_lander import OracleLunarLander
+
+    n, T, seed = 16384, 320, 77
+    rs = np.random.default_rng(10)
+    idx = np.sort(rs.choice(n, size=256, replace=False))
+    idx[0], idx[-1] = 0, n - 1
+    env = make("LunarLander-v3", n)
+    ora = OracleLunarLander(len(idx))
+    o1, _ = env.reset(seed=seed)
+    o2, _ = ora.reset(seed=[seed + int(i) for i in idx])
+    np.testing.assert_array_equal(o1[idx], o2)
+    resets = np.zeros(len(idx), dtype=np.int64)
+    for t in range(T):
+        a = rs.integers(0, 4, n)
+        x, y = env.step(a), ora.step(a[idx])
+        np.testing.assert_array_equal(x[0][idx], y[0], err_msg=f"obs differ at step {t}")
+        np.testing.assert_array_equal(x[1][idx], y[1], err_msg=f"reward differs at step {t}")
+        np.testing.assert_array_equal(x[2][idx], y[2])
+        np.testing.assert_array_equal(x[3][idx], y[3])
+        resets += y[2] | y[3]
+    assert (resets >= 1).mean() > 0.95 and resets.sum() > len(idx)  # (almost) every sampled lane went through an autoreset
+    assert not env.contact_overflow()
+
+
+def test_humanoid_config_size_sampled_lanes_match_oracle():
+    """BASELINE configs[4]: 8192 envs per GPU.  256 sampled global indices vs oracle/humanoid.c, bit-exact, through autoresets."""
+    from oracle.humanoid import OracleHumanoid
+
+    n, T, seed = 8192, 110, 5
+    rs = np.random.default_rng(12)
+    idx = np.sort(rs.choice(n, size=256, replace=False))
+    idx[0], idx[-1] = 0, n - 1
+    env = make("Humanoid-v5", n)
+    ora = OracleHumanoid(len(idx))
+    o1, _ = env.reset(seed=seed)
+    o2, _ = ora.reset(seed=[seed + int(i) for i in idx])
+    np.testing.assert_array_equal(o1[idx], o2)
+    resets = np.zeros(len(idx), dtype=np.int64)
+    for t in range(T):
+        a = rs.uniform(-0.4, 0.4, size=(n, 17)).astype(np.float32)
+        x, y = env.step(a), ora.step(a[idx])
+        np.testing.assert_array_equal(x[0][idx], y[0], err_msg=f"obs differ at step {t}")
+        np.testing.assert_array_equal(x[1][idx], y[1], err_msg=f"reward differs at step {t}")
+        np.testing.assert_array_equal(x[2][idx], y[2])
+        np.testing.assert_array_equal(x[3][idx], y[3])
+        for k in ("x_velocity", "reward_forward", "reward_contact"):
+            np.testing.assert_array_equal(x[4][k][idx], y[4][k], err_msg=k)
+        resets += y[2] | y[3]
+    assert (resets >= 1).mean() > 0.9  # random actions make the humanoid fall within ~40-80 steps: autoresets were crossed
+    assert not env.buffer_overflow()
+
+
+def test_humanoid_sharding_is_invariant():
+    """One 96-env batch == shards of 40 + 56 envs with env_offset (seeds use the GLOBAL env index), through autoresets."""
+    whole = make("Humanoid-v5", 96, max_episode_steps=25)
+    parts = [make("Humanoid-v5", 40, env_offset=0, max_episode_steps=25), make("Humanoid-v5", 56, env_offset=40, max_episode_steps=25)]
+    ow, iw = whole.reset(seed=123)
+    op = [p.reset(seed=123) for p in parts]
+    np.testing.assert_array_equal(ow, np.concatenate([o for o, _ in op]))
+    np.testing.assert_array_equal(iw["x_position"], np.concatenate([i["x_position"] for _, i in op]))
+    rs = np.random.default_rng(8)
+    for t in range(60):
+        a = rs.uniform(-0.4, 0.4, size=(96, 17)).astype(np.float32)
+        xw = whole.step(a)
+        xp = [parts[0].step(a[:40]), parts[1].step(a[40:])]
+        for k in range(4):
+            np.testing.assert_array_equal(xw[k], np.concatenate([xp[0][k], xp[1][k]]), err_msg=f"output {k} at step {t}")
+        for key in ("x_velocity", "reward_ctrl", "distance_from_origin"):
+            np.testing.assert_array_equal(xw[4][key], np.concatenate([xp[0][4][key], xp[1][4][key]]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# analytic known answers (independent of oracle/*.c)
+def _humanoid_momentum(obs):
+    """Total linear momentum per unit mass from the observation alone: cinert rows carry (.., m*(xipos - com), m) and cvel rows
+    the spatial velocity at the subtree COM, so a body's COM velocity is v + w x (xipos - com) (humanoid_v5.py:436-470)."""
+    cin = obs[:, 45:175].reshape(-1, 13, 10)
+    cvel = obs[:, 175:253].reshape(-1, 13, 6)
+    m = cin[:, :, 9]
+    off = cin[:, :, 6:9] / m[:, :, None]
+    v = cvel[:, :, 3:6] + np.cross(cvel[:, :, 0:3], off)
+    return (m[:, :, None] * v).sum(axis=1) / m.sum(axis=1)[:, None], m
+
+
+def test_humanoid_free_fall_known_answer():
+    """Noise-free reset, zero control: until the first contact the only external force is gravity, so the mass centre obeys
+    v_com(t) = (0, 0, -9.81 t) whatever the limbs do (RK4 is exact for constant acceleration).  The stock model's joint
+    armature (1.0, humanoid.xml:4) is rotor inertia outside the body masses, which limits the identity to ~1e-7; an error in
+    kinematics, composite inertia, the factorisation, the bias forces or the integrator shows up at 1e-2.  Zero control must
+    give exactly zero actuator forces (gear * ctrl), and the body masses must be the stock model's (mjModel.body_mass)."""
+    n = 8
+    env = make("Humanoid-v5", n, reset_noise_scale=0.0)
+    obs, _ = env.reset(seed=0)
+    np.testing.assert_array_equal(obs[:, 0], 1.4)
+    act = np.zeros((n, 17), dtype=np.float32)
+    free = 0
+    for k in range(12):
+        obs, r, te, tr, info = env.step(act)
+        if np.abs(obs[:, 270:348]).max() > 0:  # cfrc_ext: the first contact has happened
+            break
+        t = (k + 1) * 5 * 0.003  # frame_skip 5 x timestep 0.003 (humanoid.xml:8, humanoid_v5.py:268)
+        p, m = _humanoid_momentum(obs)
+        np.testing.assert_allclose(p[:, 2], -9.81 * t, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(p[:, :2], 0.0, rtol=0, atol=1e-7)
+        np.testing.assert_array_equal(obs[:, 253:270], 0.0)            # qfrc_actuator[6:] with zero ctrl
+        np.testing.assert_array_equal(info["reward_ctrl"], 0.0)
+        np.testing.assert_allclose(info["x_velocity"], 0.0, atol=1e-7)  # the COM does not move sideways in free fall
+        assert (info["reward_survive"] == 5.0).all() and not te.any()
+        free += 1
+    assert free >= 8, f"only {free} free-fall steps before the first contact"
+    # well-known mjModel.body_mass of the stock humanoid.xml (inertiafromgeom): torso 8.907, lwaist 2.262, pelvis 6.616, ...
+    known = [8.90746237, 2.26194671, 6.61619413, 4.75175093, 2.75569617, 1.76714587, 4.75175093, 2.75569617, 1.76714587,
+             1.66108048, 1.22954019, 1.66108048, 1.22954019]
+    np.testing.assert_allclose(m[0], known, rtol=1e-7)
+
+
+def test_lunarlander_free_flight_known_answer():
+    """reset() then no-op steps: before any contact the only external forces on (lander + 2 legs) are gravity and the initial
+    random force on the lander, applied during the world.Step embedded in reset() (lunar_lander.py:393-399, :447).  Box2D's
+    semi-implicit Euler then gives the total momentum in closed form, P_k = h F + M h g (k + 1), with F read from numpy's own
+    stream in the reference's draw order (12 terrain heights, then fx, fy).  Checked from the engine's body states; masses
+    from the shoelace areas of the fixtures (density 5 / 1)."""
+    n, seed = 64, 2024
+    env = make("LunarLander-v3", n)
+    obs, _ = env.reset(seed=seed)
+    h, g = 1.0 / 50.0, -10.0
+    poly = np.array([(-14, 17), (-17, 0), (-17, -10), (17, -10), (17, 0), (14, 17)], dtype=np.float64) / 30.0
+    x, y = poly[:, 0], poly[:, 1]
+    area = 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+    m_lander, m_leg = 5.0 * area, 1.0 * (2 * 2 / 30.0) * (2 * 8 / 30.0)
+    M = m_lander + 2 * m_leg
+    F = np.zeros((n, 2))
+    for i in range(n):
+        gen = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed + i)))
+        gen.uniform(0, 400 / 30.0 / 2, size=(12,))       # terrain heights (lunar_lander.py:344)
+        F[i] = [gen.uniform(-1000.0, 1000.0), gen.uniform(-1000.0, 1000.0)]
+    masses = np.array([m_lander, m_leg, m_leg])
+
+    def momentum():
+        b = env.body_state().cpu().numpy().astype(np.float64)  # (n, 3, 7): c.x c.y angle v.x v.y w sleep
+        return (masses[None, :, None] * b[:, :, 3:5]).sum(axis=1)
+
+    p = momentum()
+    np.testing.assert_allclose(p[:, 0], h * F[:, 0], rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(p[:, 1], h * F[:, 1] + M * h * g, rtol=2e-5, atol=2e-4)
+    # the observation's velocity entries are the lander's (vel * (W/2 or H/2) / FPS, lunar_lander.py:627-628); right after
+    # reset the legs have barely pulled on it
+    b = env.body_state().cpu().numpy()
+    np.testing.assert_allclose(obs[:, 2], b[:, 0, 3] * (600 / 30.0 / 2) / 50, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(obs[:, 3], b[:, 0, 4] * (400 / 30.0 / 2) / 50, rtol=1e-6, atol=1e-7)
+    a = np.zeros(n, dtype=np.int64)
+    for k in range(1, 25):  # the lander starts at the top of the viewport: ~1 s of flight before anything can touch
+        o, r, te, tr, _ = env.step(a)
+        assert not te.any() and (o[:, 6:8] == 0).all()
+        p = momentum()
+        np.testing.assert_allclose(p[:, 0], h * F[:, 0], rtol=5e-5, atol=5e-4, err_msg=f"step {k}")
+        np.testing.assert_allclose(p[:, 1], h * F[:, 1] + M * h * g * (k + 1), rtol=5e-5, atol=5e-4, err_msg=f"step {k}")
+
+
+def test_humanoid_reward_identity_is_exact_with_the_reference_grouping():
+    """tests/envs/mujoco/test_mujoco_v5.py:248-254 asserts `reward == (forward + survive) + (ctrl + contact)` with ==."""
+    env = make("Humanoid-v5", 256)
+    env.reset(seed=3)
+    rs = np.random.default_rng(2)
+    for _ in range(100):
+        a = rs.uniform(-0.4, 0.4, size=(256, 17)).astype(np.float32)
+        _, reward, te, tr, info = env.step(a)
+        live = ~(info["reward_survive"] == 0) | te  # autoreset calls return reward 0 and zeroed terms: identity holds too
+        total = (info["reward_forward"] + info["reward_survive"]) + (info["reward_ctrl"] + info["reward_contact"])
+        assert (reward == total).all(), np.abs(reward - total).max()
+        assert live.any()
