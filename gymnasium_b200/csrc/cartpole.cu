@@ -200,8 +200,8 @@ __device__ __noinline__ void reset_env_cold(double* __restrict__ state, int32_t*
 // One thread per env.  All loads are issued before the first use (one memory round trip).  kSpecRng: the PCG64 words of
 // EVERY lane are loaded up front together with the state (+32 B/env of reads, ~5 % of the lanes need them) -- with ~5 % of
 // the lanes on an autoreset call, 4 warps out of 5 contain one, and a load that depends on the control word would put a
-// second DRAM round trip (~0.8 us) on the critical path of a launch that lasts 3 us.  Used for batches up to 2^21 envs,
-// where the launch is latency-bound; DRAM-sized batches are bandwidth-bound and take the dependent load instead.
+// second memory round trip on the critical path of a launch that lasts 3 us.  Opt-in (B2E_CARTPOLE_SPEC_RNG=1, batches up
+// to 2^21 envs): it pays off only while the batch is L2-resident, see launch_step.
 // Launch geometry was swept on a B200 at N=65536 (graph-chained launches, us per launch, L2-resident / HBM-cold ring):
 // CTA 64: 3.01 / 3.91, 128: 3.21 / 4.05, 256: 3.33 / 4.08, 448 (one CTA per SM): 3.28 / 4.01, 1024: 4.65 / 5.29; 2 or 4
 // envs per thread were slower (4.10 / 6.3 us L2-resident); programmatic dependent launch made N >= 65536 slower (4.07 vs
@@ -258,8 +258,10 @@ __global__ void __launch_bounds__(1024) cartpole_step_kernel(const CartPoleArgs 
 template <typename ActT>
 cudaError_t launch_step(const CartPoleArgs& a, cudaStream_t st, int block) {
   if (block < 32 || block > 1024 || (block & 31)) block = kStepBlock;
-  static const bool no_spec = getenv("B2E_CARTPOLE_NO_SPEC_RNG") != nullptr;  // measurement switch (scripts/block_sweep.py)
-  if (a.n <= kSpecRngMaxEnvs && !no_spec) return launch_pdl(cartpole_step_kernel<ActT, true>, grid_for(a.n, block), block, 0, st, a);
+  // opt-in: measured on B200 at N=65536 (profiles/r2_notes.md) the up-front load wins when the batch is L2-resident (3.03 vs
+  // 3.13 us per launch) but loses on the HBM-cold ring (3.84 vs 3.66 us: +30 % DRAM reads outweigh the saved round trip)
+  static const bool spec = getenv("B2E_CARTPOLE_SPEC_RNG") != nullptr;
+  if (a.n <= kSpecRngMaxEnvs && spec) return launch_pdl(cartpole_step_kernel<ActT, true>, grid_for(a.n, block), block, 0, st, a);
   return launch_pdl(cartpole_step_kernel<ActT, false>, grid_for(a.n, block), block, 0, st, a);
 }
 

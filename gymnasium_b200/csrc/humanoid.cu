@@ -32,7 +32,7 @@ namespace {
 
 #define HD __host__ __device__ inline
 
-constexpr int NB = 14, NQ = 24, NV = 23, NU = 17, NJ = 18, NG = 18, MAXCON = 12, MAXEFC = 32, MAXPAIR = 160;
+constexpr int NB = 14, NQ = 24, NV = 23, NU = 17, NJ = 18, NG = 18, MAXCON = 12, MAXEFC = 24, MAXPAIR = 160;
 constexpr double MINVAL = 1e-15, PI = 3.14159265358979323846;
 constexpr int G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3;
 
@@ -1165,6 +1165,8 @@ __global__ void __launch_bounds__(kHumanoidBlock) humanoid_step_kernel(const Hum
 
 #include "humanoid_warp.cuh"  // warp-per-env mapping of the same physics (shares every HD helper above)
 
+static_assert(sizeof(WModel) + 10 * sizeof(WS) <= 227 * 1024, "10 envs per CTA must fit the 227 KB of shared memory an sm_100a CTA can opt in to");
+
 template <typename ActT, int W>
 int launch_warp_step(const HumanoidArgs& a, cudaStream_t s) {
   // opt in to > 48 KB of dynamic shared memory once per instantiation AND device (the attribute is per device/context)
@@ -1276,7 +1278,8 @@ extern "C" int b2e_humanoid_step(const b2e_batch* b, const b2e_humanoid_cfg* cfg
       case 2: return f64 ? launch_warp_step<double, 2>(a, s) : launch_warp_step<float, 2>(a, s);
       case 4: return f64 ? launch_warp_step<double, 4>(a, s) : launch_warp_step<float, 4>(a, s);
       case 8: return f64 ? launch_warp_step<double, 8>(a, s) : launch_warp_step<float, 8>(a, s);
-      default: set_error("b2e_humanoid_step: warp mapping supports 1, 2, 4 or 8 envs per CTA, got %d", W); return B2E_EINVAL;
+      case 10: return f64 ? launch_warp_step<double, 10>(a, s) : launch_warp_step<float, 10>(a, s);
+      default: set_error("b2e_humanoid_step: warp mapping supports 1, 2, 4, 8 or 10 envs per CTA, got %d", W); return B2E_EINVAL;
     }
     return cuda_status(cudaGetLastError(), "b2e_humanoid_step");
   }

@@ -619,15 +619,39 @@ struct VC {
   float k00, k01, k11, n00, n10, n01, n11, friction;
 };
 
-// Static dispatch on a body index: the solver keeps the three bodies' positions/velocities in registers, so every
-// access must use a compile-time index; the (divergent) runtime index of a contact's body selects one of three inlined
-// instantiations instead of forcing the arrays into local memory.
-template <class F>
-DI void with_body(int ib, F&& f) {
-  switch (ib) {
-    case 0: f(std::integral_constant<int, 0>{}); break;
-    case 1: f(std::integral_constant<int, 1>{}); break;
-    default: f(std::integral_constant<int, 2>{}); break;
+// Body access by a RUNTIME index without control flow: the solver keeps the three bodies' positions / velocities in
+// registers, and a contact's body index differs lane to lane.  Selecting the operands (and writing the result back) with
+// predicated moves lets lanes that touch different bodies execute the same instructions together; a switch on the index
+// (three inlined copies of every contact routine, the round-1 version) serialised them for all 180 + 60 iterations.
+DI float sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
+DI Pos get_pos(const Pos (&P)[kND], int ib) {
+  Pos r;
+  r.c.x = sel3(ib, P[0].c.x, P[1].c.x, P[2].c.x);
+  r.c.y = sel3(ib, P[0].c.y, P[1].c.y, P[2].c.y);
+  r.a = sel3(ib, P[0].a, P[1].a, P[2].a);
+  return r;
+}
+DI void put_pos(Pos (&P)[kND], int ib, V2 c, float a) {
+#pragma unroll
+  for (int i = 0; i < kND; ++i) {
+    P[i].c.x = ib == i ? c.x : P[i].c.x;
+    P[i].c.y = ib == i ? c.y : P[i].c.y;
+    P[i].a = ib == i ? a : P[i].a;
+  }
+}
+DI Vel get_vel(const Vel (&V)[kND], int ib) {
+  Vel r;
+  r.v.x = sel3(ib, V[0].v.x, V[1].v.x, V[2].v.x);
+  r.v.y = sel3(ib, V[0].v.y, V[1].v.y, V[2].v.y);
+  r.w = sel3(ib, V[0].w, V[1].w, V[2].w);
+  return r;
+}
+DI void put_vel(Vel (&V)[kND], int ib, V2 v, float w) {
+#pragma unroll
+  for (int i = 0; i < kND; ++i) {
+    V[i].v.x = ib == i ? v.x : V[i].v.x;
+    V[i].v.y = ib == i ? v.y : V[i].v.y;
+    V[i].w = ib == i ? w : V[i].w;
   }
 }
 
@@ -676,13 +700,17 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
     }
   for (int k = 0; k < nvc; ++k) {  // InitializeVelocityConstraints (bodyA = static moon at the origin)
     VC& vc = vcs[k];
-    with_body(vc.ib, [&](auto IB) {
-      constexpr int ib = decltype(IB)::value;
-      const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
-      const V2 cB = P[ib].c;
+    {
+      const int ib = vc.ib;
+      const float mB = sel3(ib, M.inv_mass[0], M.inv_mass[1], M.inv_mass[2]);
+      const float iB = sel3(ib, M.inv_I[0], M.inv_I[1], M.inv_I[2]);
+      const V2 lcB = mk(sel3(ib, M.local_center[0].x, M.local_center[1].x, M.local_center[2].x),
+                        sel3(ib, M.local_center[0].y, M.local_center[1].y, M.local_center[2].y));
+      const Pos pB = get_pos(P, ib);
+      const V2 cB = pB.c;
       Xf xfB;
-      xfB.q = rot_set(P[ib].a);
-      xfB.p = cB - rmul(xfB.q, M.local_center[ib]);
+      xfB.q = rot_set(pB.a);
+      xfB.p = cB - rmul(xfB.q, lcB);
       V2 pts[2];
       if (vc.type == 1) {  // b2WorldManifold::Initialize, e_faceA
         vc.normal = vc.local_normal;
@@ -727,22 +755,23 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
           vc.count = 1;
         }
       }
-    });
+    }
   }
   for (int k = 0; k < nvc; ++k) {  // WarmStart
     VC& vc = vcs[k];
-    with_body(vc.ib, [&](auto IB) {
-      constexpr int ib = decltype(IB)::value;
-      V2 vB = Vv[ib].v;
-      float wB = Vv[ib].w;
-      const V2 tangent = cross_vs(vc.normal, 1.0f);
-      for (int j = 0; j < vc.count; ++j) {
-        const V2 Pi = (vc.p[j].ni * vc.normal) + (vc.p[j].ti * tangent);
-        wB += M.inv_I[ib] * cross(vc.p[j].rB, Pi);
-        vB = vB + M.inv_mass[ib] * Pi;
-      }
-      Vv[ib].v = vB; Vv[ib].w = wB;
-    });
+    const int ib = vc.ib;
+    const float mB = sel3(ib, M.inv_mass[0], M.inv_mass[1], M.inv_mass[2]);
+    const float iB = sel3(ib, M.inv_I[0], M.inv_I[1], M.inv_I[2]);
+    const Vel vel = get_vel(Vv, ib);
+    V2 vB = vel.v;
+    float wB = vel.w;
+    const V2 tangent = cross_vs(vc.normal, 1.0f);
+    for (int j = 0; j < vc.count; ++j) {
+      const V2 Pi = (vc.p[j].ni * vc.normal) + (vc.p[j].ti * tangent);
+      wB += iB * cross(vc.p[j].rB, Pi);
+      vB = vB + mB * Pi;
+    }
+    put_vel(Vv, ib, vB, wB);
   }
   joint_init_velocity(j1, 1, P[0], P[2], Vv[0], Vv[2], dt_ratio);
   joint_init_velocity(j0, 0, P[0], P[1], Vv[0], Vv[1], dt_ratio);
@@ -751,11 +780,13 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
     joint_solve_velocity(j0, 0, Vv[0], Vv[1], h);
     for (int k = 0; k < nvc; ++k) {
       VC& vc = vcs[k];
-      with_body(vc.ib, [&](auto IB) {
-        constexpr int ib = decltype(IB)::value;
-        const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
-        V2 vB = Vv[ib].v;
-        float wB = Vv[ib].w;
+      {
+        const int ib = vc.ib;
+        const float mB = sel3(ib, M.inv_mass[0], M.inv_mass[1], M.inv_mass[2]);
+        const float iB = sel3(ib, M.inv_I[0], M.inv_I[1], M.inv_I[2]);
+        const Vel vel = get_vel(Vv, ib);
+        V2 vB = vel.v;
+        float wB = vel.w;
         const V2 normal = vc.normal, tangent = cross_vs(normal, 1.0f);
         for (int j = 0; j < vc.count; ++j) {
           VCP& p = vc.p[j];
@@ -820,8 +851,8 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
             c2.ni = xy;
           }
         }
-        Vv[ib].v = vB; Vv[ib].w = wB;
-      });
+        put_vel(Vv, ib, vB, wB);
+      }
     }
   }
   for (int k = 0; k < nvc; ++k)  // StoreImpulses
@@ -852,15 +883,19 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
     float min_sep = 0.0f;
     for (int k = 0; k < nvc; ++k) {
       const VC& vc = vcs[k];
-      with_body(vc.ib, [&](auto IB) {
-        constexpr int ib = decltype(IB)::value;
-        const float mB = M.inv_mass[ib], iB = M.inv_I[ib];
-        V2 cB = P[ib].c;
-        float aB = P[ib].a;
+      {
+        const int ib = vc.ib;
+        const float mB = sel3(ib, M.inv_mass[0], M.inv_mass[1], M.inv_mass[2]);
+        const float iB = sel3(ib, M.inv_I[0], M.inv_I[1], M.inv_I[2]);
+        const V2 lcB = mk(sel3(ib, M.local_center[0].x, M.local_center[1].x, M.local_center[2].x),
+                          sel3(ib, M.local_center[0].y, M.local_center[1].y, M.local_center[2].y));
+        const Pos pB = get_pos(P, ib);
+        V2 cB = pB.c;
+        float aB = pB.a;
         for (int j = 0; j < vc.pos_count; ++j) {
           Xf xfB;
           xfB.q = rot_set(aB);
-          xfB.p = cB - rmul(xfB.q, M.local_center[ib]);
+          xfB.p = cB - rmul(xfB.q, lcB);
           V2 normal, point;
           float sep;
           if (vc.type == 1) {
@@ -885,8 +920,8 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
           cB = cB + mB * Pi;
           aB += iB * cross(rB, Pi);
         }
-        P[ib].c = cB; P[ib].a = aB;
-      });
+        put_pos(P, ib, cB, aB);
+      }
     }
     const bool contacts_ok = min_sep >= -3.0f * kLinearSlop;
     const bool ok1 = joint_solve_position(j1, 1, P[0], P[2]);

@@ -159,5 +159,5 @@ class HumanoidVectorEnv(B200VectorEnv):
         return self._s["qvel"].t().contiguous()
 
     def buffer_overflow(self) -> bool:
-        """True if any env ever exhausted the per-env contact (12) or constraint-row (32) buffers."""
+        """True if any env ever exhausted the per-env contact (12) or constraint-row (24) buffers."""
         return bool(self._s["overflow"].item())

@@ -278,7 +278,7 @@ typedef struct b2e_humanoid_cfg {
   int32_t frame_skip;                  /* 5 */
   int32_t lanes_per_warp;              /* thread-per-env mapping: envs per warp (1..32); 0 = library default */
   int32_t impl;                        /* 0 = library default, 1 = thread per env, 2 = warp per env (shared memory) */
-  int32_t envs_per_cta;                /* warp mapping: 1, 2, 4 or 8 envs (warps) per CTA; 0 = library default (8) */
+  int32_t envs_per_cta;                /* warp mapping: 1, 2, 4, 8 or 10 envs (warps) per CTA; 0 = library default */
   int32_t schedule;                    /* warp mapping, bit 0: no CTA barrier before each mj_forward evaluation,
                                           bit 1: do not group envs by solver work (both only affect speed) */
 } b2e_humanoid_cfg;

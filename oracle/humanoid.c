@@ -36,7 +36,7 @@
 #define NJ 18
 #define NG 18
 #define MAXCON 12
-#define MAXEFC 32
+#define MAXEFC 24
 #define MINVAL 1e-15
 #define PI 3.14159265358979323846
 

@@ -22,8 +22,10 @@ for lanes in [32, 16, 8, 4, 2]:
     k = [0]
     def f():
         e.step(a[k[0] % 8]); k[0] += 1
-    t = timed(f, 150, 80)
+    t = timed(f, 150, 150)
     print(f"LunarLander n={n} lanes/warp {lanes:2d}: {t*1e6:8.1f} us/step  {n/t:.3e} steps/s")
+if os.environ.get("B2E_LANDER_ONLY"):
+    sys.exit(0)
 n = 8192
 for lanes in [32, 16, 8, 4, 2]:
     e = gymnasium_b200.make_vec("Humanoid-v5", num_envs=n, copy=False, impl="thread")

@@ -759,7 +759,7 @@ def test_first_reset_with_mask_seeds_every_lane_and_np_random_seed_tracks_masked
     """A first reset() that carries a reset_mask must not leave the other lanes on all-zero PCG64 words (their autoresets
     would all draw u = 0.0), and np_random_seed must follow masked int / list re-seeds lane by lane."""
     mask = np.array([True, False, True, False, False, True])
-    env = gymnasium_b200.make_vec("CartPole-v1", num_envs=6, output="numpy")
+    env = make("CartPole-v1", 6)
     env.reset(seed=100, options={"reset_mask": mask})
     words = env.rng_state()  # [2][n][2]
     assert (words[0].any(axis=1)).all() and (words[1].any(axis=1)).all()
@@ -777,7 +777,7 @@ def test_first_reset_with_mask_seeds_every_lane_and_np_random_seed_tracks_masked
     env.reset(seed=[1, 2, 3, 4, 5, 6], options={"reset_mask": np.array([False, False, False, True, False, False])})
     assert env.np_random_seed == (100, 501, 102, 4, 104, 105)
     # seed=None on a never-seeded batch with a mask: every lane still gets a (lazy) stream
-    env2 = gymnasium_b200.make_vec("CartPole-v1", num_envs=6, output="numpy")
+    env2 = make("CartPole-v1", 6)
     env2.reset(options={"reset_mask": mask})
     w2 = env2.rng_state()
     assert (w2[0].any(axis=1)).all() and (w2[1].any(axis=1)).all()
