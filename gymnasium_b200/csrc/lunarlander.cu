@@ -9,11 +9,12 @@
 // and, below the reference, the part of the third-party Box2D 2.3.x engine (pybox2d, pyproject.toml:38-43 -- not
 // vendored in the reference tree) that this scene exercises: b2PolygonShape mass/hull, fat-AABB broad phase,
 // b2CollideEdgeAndPolygon manifolds with feature ids (warm starting), b2ContactSolver (friction, 2-point block
-// solver, Baumgarte position correction), b2RevoluteJoint (motor + limit), island sleep.  Written against Box2D's
+// solver, Baumgarte position correction), b2RevoluteJoint (motor + limit), island sleep, b2World::SolveTOI.  Written against Box2D's
 // published algorithm; numeric parity with the real wheel is UNPINNED (it is not installable here) -- the checker is
 // oracle/lunar_lander.c, which this kernel matches bit for bit, and the reference's heuristic-landing test.
-// Not restated: b2World::SolveTOI (continuous collision), wind (enable_wind=False is the registered default),
-// continuous actions.
+// b2World::SolveTOI (continuous collision against the static terrain: b2TimeOfImpact with its b2Distance / GJK core and
+// separation-function root finder, the TOI sub-step island) is restated as well.  Not restated: wind
+// (enable_wind=False is the registered default), continuous actions.
 //
 // Arithmetic: float32 for everything Box2D does, one IEEE rounding per operation (the library is built with
 // --fmad=false); float64 for the Python-side glue.  sin/cos come from one fixed double-precision sequence shared with
@@ -155,7 +156,7 @@ struct Body {
   float w, sleep;
   Xf xf;  // derived
   V2 c0;
-  float a0;
+  float a0, alpha0;  // b2Sweep: pose at the start of the step / of the current TOI interval, its time fraction
 };
 struct Joint {
   float ix, iy, iz, motor;
@@ -171,6 +172,8 @@ struct MPoint {
 };
 struct Contact {
   int pair, touching, type, count;
+  int enabled, toi_flag, toi_count;  // b2Contact e_enabledFlag (kept across steps), e_toiFlag / m_toiCount (per step)
+  float toi;                         // m_toi: cached time of impact of this step
   float friction;
   V2 local_normal, local_point;
   MPoint pt[2];
@@ -389,6 +392,7 @@ __device__ __noinline__ void collide(Lander& L) {
     }
     MPoint old[2] = {c.pt[0], c.pt[1]};
     const int old_count = c.count, was = c.touching;
+    c.enabled = 1;  // b2Contact::Update re-enables the contact
     collide_edge_polygon(c, edge_v1(L, e), edge_v2(L, e), g_model.poly[dyn], L.b[dyn].xf);
     const int touching = c.count > 0;
     for (int i = 0; i < c.count; ++i) {
@@ -432,6 +436,10 @@ DI void find_new_contacts(Lander& L, const bool moved[kND]) {
       c.touching = 0;
       c.type = 0;
       c.count = 0;
+      c.enabled = 1;
+      c.toi_flag = 0;
+      c.toi_count = 0;
+      c.toi = 1.0f;
       c.friction = sqrtf(g_model.edge_friction[e] * g_model.poly_friction[d]);
       L.awake = 1;
     }
@@ -958,33 +966,670 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
   }
 }
 
-// b2World::Step(1/50, 180, 60) without SolveTOI
+// ---- continuous collision: b2Distance (GJK), b2TimeOfImpact, b2World::SolveTOI / b2Island::SolveTOI --------------------
+// Proxy A is always a terrain edge (2 vertices; its body, the static moon, has the identity transform, so b2Mul / b2MulT
+// by it are exact no-ops and are written as such), proxy B the polygon of a dynamic body; both have radius b2_polygonRadius.
+constexpr float kEpsilon = 1.192092896e-07f;
+constexpr int kMaxSubSteps = 8;
+constexpr float kToiBaumgarte = 0.75f;
+constexpr int kMaxPolyVerts = 8;
+
+struct Sweep {
+  V2 lc, c0, c;
+  float a0, a, alpha0;
+};
+DI Xf sweep_xf(const Sweep& s, float beta) {  // b2Sweep::GetTransform
+  Xf xf;
+  xf.p = ((1.0f - beta) * s.c0) + (beta * s.c);
+  const float angle = (1.0f - beta) * s.a0 + beta * s.a;
+  xf.q = rot_set(angle);
+  xf.p = xf.p - rmul(xf.q, s.lc);
+  return xf;
+}
+DI void sweep_advance(Sweep& s, float alpha) {  // b2Sweep::Advance
+  const float beta = (alpha - s.alpha0) / (1.0f - s.alpha0);
+  s.c0 = s.c0 + beta * (s.c - s.c0);
+  s.a0 += beta * (s.a - s.a0);
+  s.alpha0 = alpha;
+}
+DI Sweep body_sweep(const Body& b, V2 lc) { return Sweep{lc, b.c0, b.c, b.a0, b.a, b.alpha0}; }
+DI void body_set_sweep(Body& b, const Sweep& s) {
+  b.c0 = s.c0; b.c = s.c; b.a0 = s.a0; b.a = s.a; b.alpha0 = s.alpha0;
+}
+DI V2 rmulT(Rot q, V2 v) { return mk(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
+
+struct Proxy {
+  V2 v[6];
+  int count;
+};
+DI int proxy_support(const Proxy& p, V2 d) {  // b2DistanceProxy::GetSupport
+  int best = 0;
+  float bestv = dot(p.v[0], d);
+  for (int i = 1; i < p.count; ++i) {
+    const float v = dot(p.v[i], d);
+    if (v > bestv) {
+      best = i;
+      bestv = v;
+    }
+  }
+  return best;
+}
+
+struct SV {  // b2SimplexVertex
+  V2 wA, wB, w;
+  float a;
+  int iA, iB;
+};
+struct SCache {  // b2SimplexCache
+  float metric;
+  int count, iA[3], iB[3];
+};
+struct Simplex {
+  SV v[3];
+  int count;
+};
+DI float simplex_metric(const Simplex& s) {
+  if (s.count == 2) return len(s.v[0].w - s.v[1].w);
+  if (s.count == 3) return cross(s.v[1].w - s.v[0].w, s.v[2].w - s.v[0].w);
+  return 0.0f;
+}
+DI void simplex_solve2(Simplex& s) {
+  const V2 w1 = s.v[0].w, w2 = s.v[1].w, e12 = w2 - w1;
+  const float d12_2 = -dot(w1, e12);
+  if (d12_2 <= 0.0f) { s.v[0].a = 1.0f; s.count = 1; return; }
+  const float d12_1 = dot(w2, e12);
+  if (d12_1 <= 0.0f) { s.v[1].a = 1.0f; s.count = 1; s.v[0] = s.v[1]; return; }
+  const float inv = 1.0f / (d12_1 + d12_2);
+  s.v[0].a = d12_1 * inv;
+  s.v[1].a = d12_2 * inv;
+  s.count = 2;
+}
+DI void simplex_solve3(Simplex& s) {
+  const V2 w1 = s.v[0].w, w2 = s.v[1].w, w3 = s.v[2].w;
+  const V2 e12 = w2 - w1;
+  const float w1e12 = dot(w1, e12), w2e12 = dot(w2, e12), d12_1 = w2e12, d12_2 = -w1e12;
+  const V2 e13 = w3 - w1;
+  const float w1e13 = dot(w1, e13), w3e13 = dot(w3, e13), d13_1 = w3e13, d13_2 = -w1e13;
+  const V2 e23 = w3 - w2;
+  const float w2e23 = dot(w2, e23), w3e23 = dot(w3, e23), d23_1 = w3e23, d23_2 = -w2e23;
+  const float n123 = cross(e12, e13);
+  const float d123_1 = n123 * cross(w2, w3), d123_2 = n123 * cross(w3, w1), d123_3 = n123 * cross(w1, w2);
+  if (d12_2 <= 0.0f && d13_2 <= 0.0f) { s.v[0].a = 1.0f; s.count = 1; return; }
+  if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) {
+    const float inv = 1.0f / (d12_1 + d12_2);
+    s.v[0].a = d12_1 * inv; s.v[1].a = d12_2 * inv; s.count = 2; return;
+  }
+  if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) {
+    const float inv = 1.0f / (d13_1 + d13_2);
+    s.v[0].a = d13_1 * inv; s.v[2].a = d13_2 * inv; s.count = 2; s.v[1] = s.v[2]; return;
+  }
+  if (d12_1 <= 0.0f && d23_2 <= 0.0f) { s.v[1].a = 1.0f; s.count = 1; s.v[0] = s.v[1]; return; }
+  if (d13_1 <= 0.0f && d23_1 <= 0.0f) { s.v[2].a = 1.0f; s.count = 1; s.v[0] = s.v[2]; return; }
+  if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) {
+    const float inv = 1.0f / (d23_1 + d23_2);
+    s.v[1].a = d23_1 * inv; s.v[2].a = d23_2 * inv; s.count = 2; s.v[0] = s.v[2]; return;
+  }
+  const float inv = 1.0f / (d123_1 + d123_2 + d123_3);
+  s.v[0].a = d123_1 * inv; s.v[1].a = d123_2 * inv; s.v[2].a = d123_3 * inv; s.count = 3;
+}
+
+// b2Distance with useRadii = false: returns the distance and updates the simplex cache
+__device__ __noinline__ float gjk_distance(SCache& cache, const Proxy& pA, const Proxy& pB, Xf xfB) {
+  Simplex s;
+  s.count = cache.count;
+  for (int i = 0; i < s.count; ++i) {  // b2Simplex::ReadCache
+    SV& v = s.v[i];
+    v.iA = cache.iA[i];
+    v.iB = cache.iB[i];
+    v.wA = pA.v[v.iA];
+    v.wB = xmul(xfB, pB.v[v.iB]);
+    v.w = v.wB - v.wA;
+    v.a = 0.0f;
+  }
+  if (s.count > 1) {
+    const float metric1 = cache.metric, metric2 = simplex_metric(s);
+    if (metric2 < 0.5f * metric1 || 2.0f * metric1 < metric2 || metric2 < kEpsilon) s.count = 0;
+  }
+  if (s.count == 0) {
+    SV& v = s.v[0];
+    v.iA = 0;
+    v.iB = 0;
+    v.wA = pA.v[0];
+    v.wB = xmul(xfB, pB.v[0]);
+    v.w = v.wB - v.wA;
+    v.a = 1.0f;
+    s.count = 1;
+  }
+  int saveA[3], saveB[3], iter = 0;
+  while (iter < 20) {
+    const int save_count = s.count;
+    for (int i = 0; i < save_count; ++i) {
+      saveA[i] = s.v[i].iA;
+      saveB[i] = s.v[i].iB;
+    }
+    if (s.count == 2) simplex_solve2(s);
+    else if (s.count == 3) simplex_solve3(s);
+    if (s.count == 3) break;
+    V2 d;  // b2Simplex::GetSearchDirection
+    if (s.count == 1) {
+      d = -s.v[0].w;
+    } else {
+      const V2 e12 = s.v[1].w - s.v[0].w;
+      const float sgn = cross(e12, -s.v[0].w);
+      d = sgn > 0.0f ? cross_sv(1.0f, e12) : cross_vs(e12, 1.0f);
+    }
+    if (dot(d, d) < kEpsilon * kEpsilon) break;
+    SV& v = s.v[s.count];
+    v.iA = proxy_support(pA, -d);
+    v.wA = pA.v[v.iA];
+    v.iB = proxy_support(pB, rmulT(xfB.q, d));
+    v.wB = xmul(xfB, pB.v[v.iB]);
+    v.w = v.wB - v.wA;
+    ++iter;
+    bool duplicate = false;
+    for (int i = 0; i < save_count; ++i)
+      if (v.iA == saveA[i] && v.iB == saveB[i]) {
+        duplicate = true;
+        break;
+      }
+    if (duplicate) break;
+    ++s.count;
+  }
+  V2 a, b;  // GetWitnessPoints
+  if (s.count == 1) {
+    a = s.v[0].wA;
+    b = s.v[0].wB;
+  } else if (s.count == 2) {
+    a = (s.v[0].a * s.v[0].wA) + (s.v[1].a * s.v[1].wA);
+    b = (s.v[0].a * s.v[0].wB) + (s.v[1].a * s.v[1].wB);
+  } else {
+    a = ((s.v[0].a * s.v[0].wA) + (s.v[1].a * s.v[1].wA)) + (s.v[2].a * s.v[2].wA);
+    b = a;
+  }
+  cache.metric = simplex_metric(s);  // WriteCache
+  cache.count = s.count;
+  for (int i = 0; i < s.count; ++i) {
+    cache.iA[i] = s.v[i].iA;
+    cache.iB[i] = s.v[i].iB;
+  }
+  return len(a - b);
+}
+
+// b2SeparationFunction (sweep A is the identity for every t)
+struct SepFn {
+  Sweep sB;
+  int type;  // 0 points, 1 faceA, 2 faceB
+  V2 local_point, axis;
+};
+DI void sep_init(SepFn& f, const SCache& cache, const Proxy& pA, const Proxy& pB, const Sweep& sB, float t1) {
+  f.sB = sB;
+  const Xf xfB = sweep_xf(sB, t1);
+  if (cache.count == 1) {
+    f.type = 0;
+    const V2 pointA = pA.v[cache.iA[0]], pointB = xmul(xfB, pB.v[cache.iB[0]]);
+    f.axis = pointB - pointA;
+    normalize(f.axis);
+  } else if (cache.iA[0] == cache.iA[1]) {
+    f.type = 2;  // two points on B, one on A
+    const V2 b1 = pB.v[cache.iB[0]], b2 = pB.v[cache.iB[1]];
+    f.axis = cross_vs(b2 - b1, 1.0f);
+    normalize(f.axis);
+    const V2 normal = rmul(xfB.q, f.axis);
+    f.local_point = 0.5f * (b1 + b2);
+    const V2 pointB = xmul(xfB, f.local_point), pointA = pA.v[cache.iA[0]];
+    const float s = dot(pointA - pointB, normal);
+    if (s < 0.0f) f.axis = -f.axis;
+  } else {
+    f.type = 1;  // two points on A
+    const V2 a1 = pA.v[cache.iA[0]], a2 = pA.v[cache.iA[1]];
+    f.axis = cross_vs(a2 - a1, 1.0f);
+    normalize(f.axis);
+    const V2 normal = f.axis;
+    f.local_point = 0.5f * (a1 + a2);
+    const V2 pointA = f.local_point, pointB = xmul(xfB, pB.v[cache.iB[0]]);
+    const float s = dot(pointB - pointA, normal);
+    if (s < 0.0f) f.axis = -f.axis;
+  }
+}
+DI float sep_find_min(const SepFn& f, const Proxy& pA, const Proxy& pB, int& iA, int& iB, float t) {
+  const Xf xfB = sweep_xf(f.sB, t);
+  if (f.type == 0) {
+    iA = proxy_support(pA, f.axis);
+    iB = proxy_support(pB, rmulT(xfB.q, -f.axis));
+    const V2 pointA = pA.v[iA], pointB = xmul(xfB, pB.v[iB]);
+    return dot(pointB - pointA, f.axis);
+  } else if (f.type == 1) {
+    const V2 normal = f.axis, pointA = f.local_point;
+    iA = -1;
+    iB = proxy_support(pB, rmulT(xfB.q, -normal));
+    const V2 pointB = xmul(xfB, pB.v[iB]);
+    return dot(pointB - pointA, normal);
+  } else {
+    const V2 normal = rmul(xfB.q, f.axis), pointB = xmul(xfB, f.local_point);
+    iB = -1;
+    iA = proxy_support(pA, -normal);
+    const V2 pointA = pA.v[iA];
+    return dot(pointA - pointB, normal);
+  }
+}
+DI float sep_evaluate(const SepFn& f, const Proxy& pA, const Proxy& pB, int iA, int iB, float t) {
+  const Xf xfB = sweep_xf(f.sB, t);
+  if (f.type == 0) {
+    const V2 pointA = pA.v[iA], pointB = xmul(xfB, pB.v[iB]);
+    return dot(pointB - pointA, f.axis);
+  } else if (f.type == 1) {
+    const V2 normal = f.axis, pointA = f.local_point, pointB = xmul(xfB, pB.v[iB]);
+    return dot(pointB - pointA, normal);
+  } else {
+    const V2 normal = rmul(xfB.q, f.axis), pointB = xmul(xfB, f.local_point), pointA = pA.v[iA];
+    return dot(pointA - pointB, normal);
+  }
+}
+
+// b2TimeOfImpact with tMax = 1: returns the state (1 failed, 2 overlapped, 3 touching, 4 separated) and t
+__device__ __noinline__ int time_of_impact(const Proxy& pA, const Proxy& pB, Sweep sB, float& t_out) {
+  const float tMax = 1.0f;
+  {  // b2Sweep::Normalize
+    const float two_pi = 2.0f * kPi;
+    const float d = two_pi * floorf(sB.a0 / two_pi);
+    sB.a0 -= d;
+    sB.a -= d;
+  }
+  const float total_radius = kPolyRadius + kPolyRadius;
+  const float target = fmaxf(kLinearSlop, total_radius - 3.0f * kLinearSlop), tolerance = 0.25f * kLinearSlop;
+  float t1 = 0.0f;
+  int iter = 0, state = 0;
+  t_out = tMax;
+  SCache cache;
+  cache.count = 0;
+  for (;;) {
+    const Xf xfB = sweep_xf(sB, t1);
+    const float distance = gjk_distance(cache, pA, pB, xfB);
+    if (distance <= 0.0f) { state = 2; t_out = 0.0f; break; }
+    if (distance < target + tolerance) { state = 3; t_out = t1; break; }
+    SepFn fcn;
+    sep_init(fcn, cache, pA, pB, sB, t1);
+    bool done = false;
+    int push_back = 0;
+    float t2 = tMax;
+    for (;;) {
+      int iA, iB;
+      float s2 = sep_find_min(fcn, pA, pB, iA, iB, t2);
+      if (s2 > target + tolerance) { state = 4; t_out = tMax; done = true; break; }
+      if (s2 > target - tolerance) { t1 = t2; break; }
+      float s1 = sep_evaluate(fcn, pA, pB, iA, iB, t1);
+      if (s1 < target - tolerance) { state = 1; t_out = t1; done = true; break; }
+      if (s1 <= target + tolerance) { state = 3; t_out = t1; done = true; break; }
+      int root_iters = 0;
+      float a1 = t1, a2 = t2;
+      for (;;) {
+        float t;
+        if (root_iters & 1) t = a1 + (target - s1) * (a2 - a1) / (s2 - s1);
+        else t = 0.5f * (a1 + a2);
+        ++root_iters;
+        const float s = sep_evaluate(fcn, pA, pB, iA, iB, t);
+        if (fabsf(s - target) < tolerance) { t2 = t; break; }
+        if (s > target) { a1 = t; s1 = s; } else { a2 = t; s2 = s; }
+        if (root_iters == 50) break;
+      }
+      ++push_back;
+      if (push_back == kMaxPolyVerts) break;
+    }
+    ++iter;
+    if (done) break;
+    if (iter == 20) { state = 1; t_out = t1; break; }
+  }
+  return state;
+}
+
+// b2Contact::Update of list slot k: re-enable, evaluate the manifold at the body's current transform, carry the impulses of
+// matching feature ids, Begin/EndContact
+DI void contact_update(Lander& L, int k) {
+  Contact& c = L.ct[k];
+  const int dyn = c.pair / kNE, e = c.pair % kNE;
+  MPoint old[2] = {c.pt[0], c.pt[1]};
+  const int old_count = c.count, was = c.touching;
+  c.enabled = 1;
+  collide_edge_polygon(c, edge_v1(L, e), edge_v2(L, e), g_model.poly[dyn], L.b[dyn].xf);
+  const int touching = c.count > 0;
+  for (int i = 0; i < c.count; ++i) {
+    MPoint& mp = c.pt[i];
+    mp.ni = 0.0f;
+    mp.ti = 0.0f;
+    for (int j = 0; j < old_count; ++j)
+      if (old[j].id == mp.id) {
+        mp.ni = old[j].ni;
+        mp.ti = old[j].ti;
+        break;
+      }
+  }
+  c.touching = touching;
+  if (!was && touching) begin_contact(L, dyn);
+  if (was && !touching) end_contact(L, dyn);
+}
+
+// b2Body::SynchronizeFixtures + b2DynamicTree::MoveProxy of dynamic body d; true if its fat AABB moved
+DI bool sync_fixtures(Lander& L, int d) {
+  const Body& b = L.b[d];
+  Xf xf1;
+  xf1.q = rot_set(b.a0);
+  xf1.p = b.c0 - rmul(xf1.q, g_model.local_center[d]);
+  const Aabb a1 = poly_aabb(g_model.poly[d], xf1), a2 = poly_aabb(g_model.poly[d], b.xf);
+  const Aabb comb{vmin(a1.lo, a2.lo), vmax(a1.hi, a2.hi)};
+  const V2 disp = b.xf.p - xf1.p;
+  if (aabb_contains(L.fat[d], comb)) return false;
+  Aabb fb = fatten(comb);
+  const V2 dd = kAabbMul * disp;
+  if (dd.x < 0.0f) fb.lo.x += dd.x; else fb.hi.x += dd.x;
+  if (dd.y < 0.0f) fb.lo.y += dd.y; else fb.hi.y += dd.y;
+  L.fat[d] = fb;
+  return true;
+}
+
+// b2Island::SolveTOI for the island {moon, body dyn} with the contact slots isl[0..n) (isl[0] is the TOI contact): TOI position
+// solve (<= 20 iterations, Baumgarte 0.75), leap of faith, 180 velocity iterations without warm starting and without
+// joints, position integration over the rest of the step
+__device__ __noinline__ void solve_toi_island(Lander& L, int dyn, const int* isl, int n, float h) {
+  const Model& M = g_model;
+  Body& B = L.b[dyn];
+  const float mB = M.inv_mass[dyn], iB = M.inv_I[dyn];
+  const V2 lcB = M.local_center[dyn];
+  V2 cB = B.c, vB = B.v;
+  float aB = B.a, wB = B.w;
+  VC vcs[kMaxContacts];
+  for (int k = 0; k < n; ++k) {  // b2ContactSolver constructor, warmStarting = false
+    VC& vc = vcs[k];
+    const Contact& c = L.ct[isl[k]];
+    vc.slot = isl[k];
+    vc.ib = dyn;
+    vc.friction = c.friction;
+    vc.count = vc.pos_count = c.count;
+    vc.type = c.type;
+    vc.local_normal = c.local_normal;
+    vc.local_point = c.local_point;
+    for (int j = 0; j < 2; ++j) {
+      vc.p[j].ni = 0.0f;
+      vc.p[j].ti = 0.0f;
+      vc.lpts[j] = c.pt[j].lp;
+    }
+  }
+  for (int it = 0; it < 20; ++it) {  // SolveTOIPositionConstraints
+    float min_sep = 0.0f;
+    for (int k = 0; k < n; ++k) {
+      const VC& vc = vcs[k];
+      for (int j = 0; j < vc.pos_count; ++j) {
+        Xf xfB;
+        xfB.q = rot_set(aB);
+        xfB.p = cB - rmul(xfB.q, lcB);
+        V2 normal, point;
+        float sep;
+        if (vc.type == 1) {
+          normal = vc.local_normal;
+          const V2 clip = xmul(xfB, vc.lpts[j]);
+          sep = dot(clip - vc.local_point, normal) - kPolyRadius - kPolyRadius;
+          point = clip;
+        } else {
+          normal = rmul(xfB.q, vc.local_normal);
+          const V2 plane = xmul(xfB, vc.local_point), clip = vc.lpts[j];
+          sep = dot(clip - plane, normal) - kPolyRadius - kPolyRadius;
+          point = clip;
+          normal = -normal;
+        }
+        const V2 rB = point - cB;
+        min_sep = fminf(min_sep, sep);
+        const float C = clampf(kToiBaumgarte * (sep + kLinearSlop), -kMaxLinCorr, 0.0f);
+        const float rnB = cross(rB, normal);
+        const float K = mB + iB * rnB * rnB;
+        const float impulse = K > 0.0f ? -C / K : 0.0f;
+        const V2 Pi = impulse * normal;
+        cB = cB + mB * Pi;
+        aB += iB * cross(rB, Pi);
+      }
+    }
+    if (min_sep >= -1.5f * kLinearSlop) break;
+  }
+  B.c0 = cB;  // leap of faith to the new safe state (the moon's sweep does not change)
+  B.a0 = aB;
+  for (int k = 0; k < n; ++k) {  // InitializeVelocityConstraints
+    VC& vc = vcs[k];
+    Xf xfB;
+    xfB.q = rot_set(aB);
+    xfB.p = cB - rmul(xfB.q, lcB);
+    V2 pts[2];
+    if (vc.type == 1) {
+      vc.normal = vc.local_normal;
+      const V2 plane = vc.local_point;
+      for (int j = 0; j < vc.count; ++j) {
+        const V2 clip = xmul(xfB, vc.lpts[j]);
+        const V2 cA = clip + (kPolyRadius - dot(clip - plane, vc.normal)) * vc.normal;
+        const V2 cBp = clip - kPolyRadius * vc.normal;
+        pts[j] = 0.5f * (cA + cBp);
+      }
+    } else {
+      const V2 nrm = rmul(xfB.q, vc.local_normal);
+      const V2 plane = xmul(xfB, vc.local_point);
+      for (int j = 0; j < vc.count; ++j) {
+        const V2 clip = vc.lpts[j];
+        const V2 cBp = clip + (kPolyRadius - dot(clip - plane, nrm)) * nrm;
+        const V2 cA = clip - kPolyRadius * nrm;
+        pts[j] = 0.5f * (cA + cBp);
+      }
+      vc.normal = -nrm;
+    }
+    for (int j = 0; j < vc.count; ++j) {
+      VCP& p = vc.p[j];
+      p.rB = pts[j] - cB;
+      const float rnB = cross(p.rB, vc.normal);
+      const float kN = mB + iB * rnB * rnB;
+      p.normal_mass = kN > 0.0f ? 1.0f / kN : 0.0f;
+      const V2 tangent = cross_vs(vc.normal, 1.0f);
+      const float rtB = cross(p.rB, tangent);
+      const float kT = mB + iB * rtB * rtB;
+      p.tangent_mass = kT > 0.0f ? 1.0f / kT : 0.0f;
+    }
+    if (vc.count == 2) {
+      const float rn1B = cross(vc.p[0].rB, vc.normal), rn2B = cross(vc.p[1].rB, vc.normal);
+      const float k11 = mB + iB * rn1B * rn1B, k22 = mB + iB * rn2B * rn2B, k12 = mB + iB * rn1B * rn2B;
+      if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+        vc.k00 = k11; vc.k01 = k12; vc.k11 = k22;
+        float det = k11 * k22 - k12 * k12;
+        if (det != 0.0f) det = 1.0f / det;
+        vc.n00 = det * k22; vc.n10 = -det * k12; vc.n01 = -det * k12; vc.n11 = det * k11;
+      } else {
+        vc.count = 1;
+      }
+    }
+  }
+  for (int it = 0; it < 180; ++it)  // SolveVelocityConstraints: contacts only
+    for (int k = 0; k < n; ++k) {
+      VC& vc = vcs[k];
+      const V2 normal = vc.normal, tangent = cross_vs(normal, 1.0f);
+      for (int j = 0; j < vc.count; ++j) {
+        VCP& p = vc.p[j];
+        const V2 dv = vB + cross_sv(wB, p.rB);
+        const float vt = dot(dv, tangent) - 0.0f;
+        float lambda = p.tangent_mass * (-vt);
+        const float maxf = vc.friction * p.ni;
+        const float newi = clampf(p.ti + lambda, -maxf, maxf);
+        lambda = newi - p.ti;
+        p.ti = newi;
+        const V2 Pi = lambda * tangent;
+        vB = vB + mB * Pi;
+        wB += iB * cross(p.rB, Pi);
+      }
+      if (vc.count == 1) {
+        VCP& p = vc.p[0];
+        const V2 dv = vB + cross_sv(wB, p.rB);
+        const float vn = dot(dv, normal);
+        float lambda = -p.normal_mass * (vn - 0.0f);
+        const float newi = fmaxf(p.ni + lambda, 0.0f);
+        lambda = newi - p.ni;
+        p.ni = newi;
+        const V2 Pi = lambda * normal;
+        vB = vB + mB * Pi;
+        wB += iB * cross(p.rB, Pi);
+      } else {
+        VCP &c1 = vc.p[0], &c2 = vc.p[1];
+        const float ax = c1.ni, ay = c2.ni;
+        const V2 dv1 = vB + cross_sv(wB, c1.rB), dv2 = vB + cross_sv(wB, c2.rB);
+        float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+        float bx = vn1 - 0.0f, by = vn2 - 0.0f;
+        bx -= vc.k00 * ax + vc.k01 * ay;
+        by -= vc.k01 * ax + vc.k11 * ay;
+        float xx, xy;
+        bool solved = false;
+        xx = -(vc.n00 * bx + vc.n10 * by);
+        xy = -(vc.n01 * bx + vc.n11 * by);
+        if (xx >= 0.0f && xy >= 0.0f) solved = true;
+        if (!solved) {
+          xx = -c1.normal_mass * bx;
+          xy = 0.0f;
+          vn2 = vc.k01 * xx + by;
+          if (xx >= 0.0f && vn2 >= 0.0f) solved = true;
+        }
+        if (!solved) {
+          xx = 0.0f;
+          xy = -c2.normal_mass * by;
+          vn1 = vc.k01 * xy + bx;
+          if (xy >= 0.0f && vn1 >= 0.0f) solved = true;
+        }
+        if (!solved) {
+          xx = 0.0f;
+          xy = 0.0f;
+          if (bx >= 0.0f && by >= 0.0f) solved = true;
+        }
+        if (solved) {
+          const float dx = xx - ax, dy = xy - ay;
+          const V2 P1 = dx * normal, P2 = dy * normal;
+          vB = vB + mB * (P1 + P2);
+          wB += iB * (cross(c1.rB, P1) + cross(c2.rB, P2));
+          c1.ni = xx;
+          c2.ni = xy;
+        }
+      }
+    }
+  // the TOI impulses are not stored for warm starting; integrate positions over the rest of the step
+  const V2 tr = h * vB;
+  if (dot(tr, tr) > kMaxTranslation * kMaxTranslation) {
+    const float ratio = kMaxTranslation / len(tr);
+    vB = ratio * vB;
+  }
+  const float rotn = h * wB;
+  if (rotn * rotn > kMaxRotation * kMaxRotation) {
+    const float ratio = kMaxRotation / fabsf(rotn);
+    wB *= ratio;
+  }
+  cB = cB + h * vB;
+  aB += h * wB;
+  B.c = cB; B.a = aB; B.v = vB; B.w = wB;
+  sync_transform(B, lcB);
+}
+
+// b2World::SolveTOI(step) with m_stepComplete = true on entry (no sub-stepping mode); the island is awake
+__device__ __noinline__ void solve_toi(Lander& L, float dt) {
+  for (int d = 0; d < kND; ++d) L.b[d].alpha0 = 0.0f;
+  float moon_alpha0 = 0.0f;
+  for (int k = 0; k < L.nct; ++k) {
+    L.ct[k].toi_flag = 0;
+    L.ct[k].toi_count = 0;
+    L.ct[k].toi = 1.0f;
+  }
+  for (;;) {
+    int min_k = -1;
+    float min_alpha = 1.0f;
+    for (int k = 0; k < L.nct; ++k) {  // world contact list, most recent first
+      Contact& c = L.ct[k];
+      if (!c.enabled) continue;
+      if (c.toi_count > kMaxSubSteps) continue;
+      float alpha = 1.0f;
+      if (c.toi_flag) {
+        alpha = c.toi;
+      } else {
+        const int dyn = c.pair / kNE, e = c.pair % kNE;
+        Body& bB = L.b[dyn];
+        float alpha0 = moon_alpha0;  // put the sweeps onto the same time interval
+        if (moon_alpha0 < bB.alpha0) {
+          alpha0 = bB.alpha0;
+          moon_alpha0 = alpha0;  // b2Sweep::Advance of a sweep with c0 == c, a0 == a
+        } else if (bB.alpha0 < moon_alpha0) {
+          alpha0 = moon_alpha0;
+          Sweep s = body_sweep(bB, g_model.local_center[dyn]);
+          sweep_advance(s, alpha0);
+          body_set_sweep(bB, s);
+        }
+        Proxy pA, pB;
+        pA.v[0] = edge_v1(L, e);
+        pA.v[1] = edge_v2(L, e);
+        pA.count = 2;
+        pB.count = g_model.poly[dyn].count;
+        for (int i = 0; i < pB.count; ++i) pB.v[i] = g_model.poly[dyn].v[i];
+        float beta;
+        const int state = time_of_impact(pA, pB, body_sweep(bB, g_model.local_center[dyn]), beta);
+        alpha = state == 3 ? fminf(alpha0 + (1.0f - alpha0) * beta, 1.0f) : 1.0f;
+        c.toi = alpha;
+        c.toi_flag = 1;
+      }
+      if (alpha < min_alpha) {
+        min_k = k;
+        min_alpha = alpha;
+      }
+    }
+    if (min_k < 0 || 1.0f - 10.0f * kEpsilon < min_alpha) break;  // no more TOI events
+    Contact& mc = L.ct[min_k];
+    const int dyn = mc.pair / kNE;
+    Body& bB = L.b[dyn];
+    const V2 lcB = g_model.local_center[dyn];
+    const float moon_backup = moon_alpha0;
+    const Sweep backup = body_sweep(bB, lcB);
+    moon_alpha0 = min_alpha;  // bA->Advance(minAlpha) on the static body
+    {                         // b2Body::Advance
+      Sweep s = backup;
+      sweep_advance(s, min_alpha);
+      s.c = s.c0;
+      s.a = s.a0;
+      body_set_sweep(bB, s);
+      sync_transform(bB, lcB);
+    }
+    contact_update(L, min_k);  // the TOI contact likely has some new contact points
+    mc.toi_flag = 0;
+    ++mc.toi_count;
+    if (!mc.enabled || !mc.touching) {  // not solid: restore the sweeps
+      mc.enabled = 0;
+      moon_alpha0 = moon_backup;
+      body_set_sweep(bB, backup);
+      sync_transform(bB, lcB);
+      continue;
+    }
+    // island: the TOI contact, then the other contacts of bB (most recent first) that touch at the advanced pose
+    int isl[kMaxContacts], ni = 0;
+    isl[ni++] = min_k;
+    for (int k = 0; k < L.nct; ++k) {
+      if (k == min_k || L.ct[k].pair / kNE != dyn) continue;
+      contact_update(L, k);  // other = the moon, already in the island: not advanced
+      if (!L.ct[k].enabled || !L.ct[k].touching) continue;
+      isl[ni++] = k;
+    }
+    solve_toi_island(L, dyn, isl, ni, (1.0f - min_alpha) * dt);
+    bool moved[kND] = {false, false, false};
+    moved[dyn] = sync_fixtures(L, dyn);
+    for (int k = 0; k < L.nct; ++k)  // invalidate all contact TOIs on this displaced body
+      if (L.ct[k].pair / kNE == dyn) L.ct[k].toi_flag = 0;
+    find_new_contacts(L, moved);
+  }
+}
+
+// b2World::Step(1/50, 180, 60): new-fixture pairs, Collide, Solve (+ SynchronizeFixtures / FindNewContacts), SolveTOI,
+// ClearForces
 DI void world_step(Lander& L, float dt, float dt_ratio, float gravity, bool first_step) {
   bool moved[kND] = {true, true, true};
   if (first_step) find_new_contacts(L, moved);  // e_newFixture
   collide(L);
   if (L.awake) {
     solve_island(L, dt, dt_ratio, gravity);
-    for (int d = kND - 1; d >= 0; --d) {  // SynchronizeFixtures + b2DynamicTree::MoveProxy
-      const Body& b = L.b[d];
-      Xf xf1;
-      xf1.q = rot_set(b.a0);
-      xf1.p = b.c0 - rmul(xf1.q, g_model.local_center[d]);
-      const Aabb a1 = poly_aabb(g_model.poly[d], xf1), a2 = poly_aabb(g_model.poly[d], b.xf);
-      const Aabb comb{vmin(a1.lo, a2.lo), vmax(a1.hi, a2.hi)};
-      const V2 disp = b.xf.p - xf1.p;
-      moved[d] = false;
-      if (!aabb_contains(L.fat[d], comb)) {
-        Aabb fb = fatten(comb);
-        const V2 dd = kAabbMul * disp;
-        if (dd.x < 0.0f) fb.lo.x += dd.x; else fb.hi.x += dd.x;
-        if (dd.y < 0.0f) fb.lo.y += dd.y; else fb.hi.y += dd.y;
-        L.fat[d] = fb;
-        moved[d] = true;
-      }
-    }
+    for (int d = kND - 1; d >= 0; --d) moved[d] = sync_fixtures(L, d);
     find_new_contacts(L, moved);
   }
+  if (L.awake) solve_toi(L, dt);  // m_continuousPhysics; a sleeping island has no active body
   L.force = mk(0.0f, 0.0f);  // ClearForces
 }
 
@@ -1059,6 +1704,7 @@ DI void load_state(const LanderArgs& a, int64_t i, Lander& L) {
     c.touching = (hd >> 8) & 1;
     c.type = (hd >> 9) & 3;
     c.count = (hd >> 11) & 3;
+    c.enabled = (hd >> 13) & 1;
     c.friction = __uint_as_float(w[1 * n]);
     c.local_normal = mk(__uint_as_float(w[2 * n]), __uint_as_float(w[3 * n]));
     c.local_point = mk(__uint_as_float(w[4 * n]), __uint_as_float(w[5 * n]));
@@ -1107,7 +1753,8 @@ DI void store_state(const LanderArgs& a, int64_t i, const Lander& L) {
   for (int k = 0; k < L.nct; ++k) {
     uint32_t* w = a.contacts + (int64_t)k * kSlotWords * n + i;
     const Contact& c = L.ct[k];
-    w[0] = (uint32_t)c.pair | ((uint32_t)c.touching << 8) | ((uint32_t)c.type << 9) | ((uint32_t)c.count << 11);
+    w[0] = (uint32_t)c.pair | ((uint32_t)c.touching << 8) | ((uint32_t)c.type << 9) | ((uint32_t)c.count << 11) |
+           ((uint32_t)c.enabled << 13);
     w[1 * n] = __float_as_uint(c.friction);
     w[2 * n] = __float_as_uint(c.local_normal.x);
     w[3 * n] = __float_as_uint(c.local_normal.y);

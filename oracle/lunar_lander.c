@@ -15,9 +15,9 @@
  * The only behavioural pin the reference offers for this boundary is the heuristic landing test
  * (tests/envs/test_env_implementation.py:12-16 with the policy at lunar_lander.py:791-842); tests/test_oracle_lunar.py
  * runs it against this file.
- * Known deviation: b2World::SolveTOI (continuous collision vs the static terrain) is NOT restated; the discrete
- * solver alone runs.  It matters only on the frames of a high-speed first impact, which end the episode anyway when
- * the lander hull is involved (game_over).
+ * b2World::SolveTOI (continuous collision of the three dynamic bodies against the static terrain: b2TimeOfImpact with its
+ * b2Distance / GJK core and b2SeparationFunction root finder, the TOI sub-step island with its own position and velocity
+ * solve) IS restated -- world.Step runs it after the discrete solve on every call (lunar_lander.py:619).
  *
  * All Box2D arithmetic is float32 with one rounding per operation (compile with -ffp-contract=off); the Python-side
  * glue (dispersion, impulses, observation scaling, shaping reward) is float64 as in the reference.
@@ -177,6 +177,7 @@ typedef struct {
   v2 force;
   float torque, mass, inv_mass, I, inv_I, sleep_time;
   int awake;
+  float alpha0;               /* b2Sweep::alpha0 (continuous collision) */
 } body_t;
 
 typedef struct { uint8_t indexA, indexB, typeA, typeB; } cid_t; /* b2ContactFeature */
@@ -187,6 +188,8 @@ typedef struct { mpoint_t points[2]; v2 local_normal, local_point; int type /*1 
 
 typedef struct {
   int exists, touching;
+  int enabled, toi_flag, toi_count; /* b2Contact e_enabledFlag / e_toiFlag / m_toiCount */
+  float toi;                        /* m_toi: cached time of impact of this step */
   long seq;          /* creation order: lists are walked most-recent-first like Box2D's intrusive lists */
   float friction;
   manifold_t m;
@@ -217,6 +220,7 @@ typedef struct {
   int new_fixture;
   /* env */
   int game_over, leg_contact[2], has_prev_shaping;
+  long toi_calls, toi_events;  /* statistics: b2TimeOfImpact evaluations / solid TOI events (sub-steps) since reset */
   double prev_shaping, helipad_y;
   float gravity;
   pcg64_t rng;
@@ -484,7 +488,34 @@ static int contacts_sorted(const lander_t* L, int* idx, int dyn_filter /* -1 = a
   return n;
 }
 
-/* b2ContactManager::Collide + b2Contact::Update */
+/* b2Contact::Update: re-enable, evaluate the manifold at the bodies' current transforms, carry the impulses of matching
+ * feature ids, wake on a change of the touching state, Begin/EndContact */
+static void contact_update(lander_t* L, int k) {
+  contact_t* c = &L->contact[k];
+  int dyn = k / NEDGE, e = k % NEDGE;
+  body_t* bB = &L->b[1 + dyn];
+  manifold_t old = c->m;
+  c->enabled = 1;
+  int was = c->touching;
+  collide_edge_polygon(&c->m, L->edge_v1[e], L->edge_v2[e], &L->poly[dyn], bB->xf);
+  int touching = c->m.count > 0;
+  for (int i = 0; i < c->m.count; ++i) {
+    mpoint_t* mp2 = &c->m.points[i];
+    mp2->normal_impulse = 0.0f; mp2->tangent_impulse = 0.0f;
+    for (int j = 0; j < old.count; ++j)
+      if (cid_key(old.points[j].id) == cid_key(mp2->id)) {
+        mp2->normal_impulse = old.points[j].normal_impulse;
+        mp2->tangent_impulse = old.points[j].tangent_impulse;
+        break;
+      }
+  }
+  if (touching != was) set_awake(bB, 1);
+  c->touching = touching;
+  if (!was && touching) begin_contact(L, dyn);
+  if (was && !touching) end_contact(L, dyn);
+}
+
+/* b2ContactManager::Collide */
 static void collide(lander_t* L) {
   int idx[NPAIR];
   int n = contacts_sorted(L, idx, -1);
@@ -498,24 +529,7 @@ static void collide(lander_t* L) {
       c->exists = 0;
       continue;
     }
-    manifold_t old = c->m;
-    int was = c->touching;
-    collide_edge_polygon(&c->m, L->edge_v1[e], L->edge_v2[e], &L->poly[dyn], bB->xf);
-    int touching = c->m.count > 0;
-    for (int i = 0; i < c->m.count; ++i) {
-      mpoint_t* mp2 = &c->m.points[i];
-      mp2->normal_impulse = 0.0f; mp2->tangent_impulse = 0.0f;
-      for (int j = 0; j < old.count; ++j)
-        if (cid_key(old.points[j].id) == cid_key(mp2->id)) {
-          mp2->normal_impulse = old.points[j].normal_impulse;
-          mp2->tangent_impulse = old.points[j].tangent_impulse;
-          break;
-        }
-    }
-    if (touching != was) set_awake(bB, 1);
-    c->touching = touching;
-    if (!was && touching) begin_contact(L, dyn);
-    if (was && !touching) end_contact(L, dyn);
+    contact_update(L, idx[t]);
   }
 }
 
@@ -529,6 +543,7 @@ static void find_new_contacts(lander_t* L, const int moved[NDYN]) {
       if (!aabb_overlap(L->edge_fat[e], L->poly_fat[d])) continue;
       memset(c, 0, sizeof(*c));
       c->exists = 1;
+      c->enabled = 1;      /* b2Contact constructor: m_flags = e_enabledFlag, m_toiCount = 0 */
       c->seq = ++L->seq;
       c->friction = sqrtf(L->edge_friction[e] * L->poly_friction[d]); /* b2MixFriction */
       set_awake(&L->b[1 + d], 1);
@@ -990,7 +1005,563 @@ static void solve_island(lander_t* L, float h, float dt_ratio, int vel_iters, in
     for (int i = 1; i < NBODY; ++i) set_awake(&L->b[i], 0);
 }
 
-/* b2World::Step(dt, 180, 60) without SolveTOI */
+/* ------------------------------------------------------------------------------------------------------------------
+ * Continuous collision: b2Distance (GJK), b2TimeOfImpact, b2World::SolveTOI / b2Island::SolveTOI.
+ * Proxy A is always a terrain edge (2 vertices, body = the static moon whose transform is the identity: b2Mul / b2MulT by
+ * it are exact no-ops and are written as such), proxy B a polygon of a dynamic body.  Radii: b2_polygonRadius each. */
+#define B2_EPSILON 1.192092896e-07f
+#define B2_MAXFLOAT 3.402823466e+38f
+#define MAX_SUB_STEPS 8
+#define TOI_BAUMGARTE 0.75f
+#define MAX_POLY_VERTS 8
+
+typedef struct { v2 lc, c0, c; float a0, a, alpha0; } sweep_t;
+static xf_t sweep_xf(const sweep_t* s, float beta) { /* b2Sweep::GetTransform */
+  xf_t xf;
+  xf.p = vadd(vscale(1.0f - beta, s->c0), vscale(beta, s->c));
+  float angle = (1.0f - beta) * s->a0 + beta * s->a;
+  xf.q = rot_set(angle);
+  xf.p = vsub(xf.p, rmul(xf.q, s->lc));
+  return xf;
+}
+static void sweep_advance(sweep_t* s, float alpha) { /* b2Sweep::Advance */
+  float beta = (alpha - s->alpha0) / (1.0f - s->alpha0);
+  s->c0 = vadd(s->c0, vscale(beta, vsub(s->c, s->c0)));
+  s->a0 += beta * (s->a - s->a0);
+  s->alpha0 = alpha;
+}
+static sweep_t body_sweep(const body_t* b) {
+  sweep_t s = {b->local_center, b->c0, b->c, b->a0, b->a, b->alpha0};
+  return s;
+}
+static void body_set_sweep(body_t* b, const sweep_t* s) { b->c0 = s->c0; b->c = s->c; b->a0 = s->a0; b->a = s->a; b->alpha0 = s->alpha0; }
+static void body_advance(body_t* b, float alpha) { /* b2Body::Advance */
+  sweep_t s = body_sweep(b);
+  sweep_advance(&s, alpha);
+  s.c = s.c0;
+  s.a = s.a0;
+  body_set_sweep(b, &s);
+  sync_transform(b);
+}
+
+typedef struct { const v2* v; int count; } proxy_t;
+static int proxy_support(const proxy_t* p, v2 d) { /* b2DistanceProxy::GetSupport */
+  int best = 0;
+  float bestv = vdot(p->v[0], d);
+  for (int i = 1; i < p->count; ++i) {
+    float v = vdot(p->v[i], d);
+    if (v > bestv) { best = i; bestv = v; }
+  }
+  return best;
+}
+
+typedef struct { v2 wA, wB, w; float a; int iA, iB; } sv_t;        /* b2SimplexVertex */
+typedef struct { float metric; int count; int iA[3], iB[3]; } scache_t; /* b2SimplexCache */
+typedef struct { sv_t v[3]; int count; } simplex_t;
+
+static float simplex_metric(const simplex_t* s) {
+  switch (s->count) {
+    case 1: return 0.0f;
+    case 2: return vlen(vsub(s->v[0].w, s->v[1].w));
+    case 3: return vcross(vsub(s->v[1].w, s->v[0].w), vsub(s->v[2].w, s->v[0].w));
+    default: return 0.0f;
+  }
+}
+static void simplex_solve2(simplex_t* s) {
+  v2 w1 = s->v[0].w, w2 = s->v[1].w, e12 = vsub(w2, w1);
+  float d12_2 = -vdot(w1, e12);
+  if (d12_2 <= 0.0f) { s->v[0].a = 1.0f; s->count = 1; return; }
+  float d12_1 = vdot(w2, e12);
+  if (d12_1 <= 0.0f) { s->v[1].a = 1.0f; s->count = 1; s->v[0] = s->v[1]; return; }
+  float inv = 1.0f / (d12_1 + d12_2);
+  s->v[0].a = d12_1 * inv;
+  s->v[1].a = d12_2 * inv;
+  s->count = 2;
+}
+static void simplex_solve3(simplex_t* s) {
+  v2 w1 = s->v[0].w, w2 = s->v[1].w, w3 = s->v[2].w;
+  v2 e12 = vsub(w2, w1);
+  float w1e12 = vdot(w1, e12), w2e12 = vdot(w2, e12), d12_1 = w2e12, d12_2 = -w1e12;
+  v2 e13 = vsub(w3, w1);
+  float w1e13 = vdot(w1, e13), w3e13 = vdot(w3, e13), d13_1 = w3e13, d13_2 = -w1e13;
+  v2 e23 = vsub(w3, w2);
+  float w2e23 = vdot(w2, e23), w3e23 = vdot(w3, e23), d23_1 = w3e23, d23_2 = -w2e23;
+  float n123 = vcross(e12, e13);
+  float d123_1 = n123 * vcross(w2, w3), d123_2 = n123 * vcross(w3, w1), d123_3 = n123 * vcross(w1, w2);
+  if (d12_2 <= 0.0f && d13_2 <= 0.0f) { s->v[0].a = 1.0f; s->count = 1; return; }
+  if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) {
+    float inv = 1.0f / (d12_1 + d12_2);
+    s->v[0].a = d12_1 * inv; s->v[1].a = d12_2 * inv; s->count = 2; return;
+  }
+  if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) {
+    float inv = 1.0f / (d13_1 + d13_2);
+    s->v[0].a = d13_1 * inv; s->v[2].a = d13_2 * inv; s->count = 2; s->v[1] = s->v[2]; return;
+  }
+  if (d12_1 <= 0.0f && d23_2 <= 0.0f) { s->v[1].a = 1.0f; s->count = 1; s->v[0] = s->v[1]; return; }
+  if (d13_1 <= 0.0f && d23_1 <= 0.0f) { s->v[2].a = 1.0f; s->count = 1; s->v[0] = s->v[2]; return; }
+  if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) {
+    float inv = 1.0f / (d23_1 + d23_2);
+    s->v[1].a = d23_1 * inv; s->v[2].a = d23_2 * inv; s->count = 2; s->v[0] = s->v[2]; return;
+  }
+  float inv = 1.0f / (d123_1 + d123_2 + d123_3);
+  s->v[0].a = d123_1 * inv; s->v[1].a = d123_2 * inv; s->v[2].a = d123_3 * inv; s->count = 3;
+}
+
+/* b2Distance with useRadii = false; returns the distance, updates the cache */
+static float gjk_distance(scache_t* cache, const proxy_t* pA, const proxy_t* pB, xf_t xfB) {
+  simplex_t s;
+  s.count = cache->count;
+  for (int i = 0; i < s.count; ++i) { /* b2Simplex::ReadCache */
+    sv_t* v = &s.v[i];
+    v->iA = cache->iA[i]; v->iB = cache->iB[i];
+    v->wA = pA->v[v->iA];
+    v->wB = xmul(xfB, pB->v[v->iB]);
+    v->w = vsub(v->wB, v->wA);
+    v->a = 0.0f;
+  }
+  if (s.count > 1) {
+    float metric1 = cache->metric, metric2 = simplex_metric(&s);
+    if (metric2 < 0.5f * metric1 || 2.0f * metric1 < metric2 || metric2 < B2_EPSILON) s.count = 0;
+  }
+  if (s.count == 0) {
+    sv_t* v = &s.v[0];
+    v->iA = 0; v->iB = 0;
+    v->wA = pA->v[0];
+    v->wB = xmul(xfB, pB->v[0]);
+    v->w = vsub(v->wB, v->wA);
+    v->a = 1.0f;
+    s.count = 1;
+  }
+  int saveA[3], saveB[3], iter = 0;
+  while (iter < 20) {
+    int save_count = s.count;
+    for (int i = 0; i < save_count; ++i) { saveA[i] = s.v[i].iA; saveB[i] = s.v[i].iB; }
+    if (s.count == 2) simplex_solve2(&s);
+    else if (s.count == 3) simplex_solve3(&s);
+    if (s.count == 3) break;
+    v2 d; /* b2Simplex::GetSearchDirection */
+    if (s.count == 1) d = vneg(s.v[0].w);
+    else {
+      v2 e12 = vsub(s.v[1].w, s.v[0].w);
+      float sgn = vcross(e12, vneg(s.v[0].w));
+      d = sgn > 0.0f ? vcross_sv(1.0f, e12) : vcross_vs(e12, 1.0f);
+    }
+    if (vdot(d, d) < B2_EPSILON * B2_EPSILON) break;
+    sv_t* v = &s.v[s.count];
+    v->iA = proxy_support(pA, vneg(d));               /* b2MulT(identity, -d) */
+    v->wA = pA->v[v->iA];
+    v->iB = proxy_support(pB, rmulT(xfB.q, d));
+    v->wB = xmul(xfB, pB->v[v->iB]);
+    v->w = vsub(v->wB, v->wA);
+    ++iter;
+    int duplicate = 0;
+    for (int i = 0; i < save_count; ++i)
+      if (v->iA == saveA[i] && v->iB == saveB[i]) { duplicate = 1; break; }
+    if (duplicate) break;
+    ++s.count;
+  }
+  v2 a, b; /* GetWitnessPoints */
+  if (s.count == 1) { a = s.v[0].wA; b = s.v[0].wB; }
+  else if (s.count == 2) {
+    a = vadd(vscale(s.v[0].a, s.v[0].wA), vscale(s.v[1].a, s.v[1].wA));
+    b = vadd(vscale(s.v[0].a, s.v[0].wB), vscale(s.v[1].a, s.v[1].wB));
+  } else {
+    a = vadd(vadd(vscale(s.v[0].a, s.v[0].wA), vscale(s.v[1].a, s.v[1].wA)), vscale(s.v[2].a, s.v[2].wA));
+    b = a;
+  }
+  cache->metric = simplex_metric(&s); /* WriteCache */
+  cache->count = s.count;
+  for (int i = 0; i < s.count; ++i) { cache->iA[i] = s.v[i].iA; cache->iB[i] = s.v[i].iB; }
+  return vlen(vsub(a, b));
+}
+
+/* b2SeparationFunction (sweep A is the identity for all t) */
+typedef struct { const proxy_t *pA, *pB; sweep_t sB; int type /*0 points, 1 faceA, 2 faceB*/; v2 local_point, axis; } sepfn_t;
+static void sep_init(sepfn_t* f, const scache_t* cache, const proxy_t* pA, const proxy_t* pB, const sweep_t* sB, float t1) {
+  f->pA = pA; f->pB = pB; f->sB = *sB;
+  xf_t xfB = sweep_xf(sB, t1);
+  if (cache->count == 1) {
+    f->type = 0;
+    v2 pointA = pA->v[cache->iA[0]], pointB = xmul(xfB, pB->v[cache->iB[0]]);
+    f->axis = vsub(pointB, pointA);
+    vnormalize(&f->axis);
+  } else if (cache->iA[0] == cache->iA[1]) {
+    f->type = 2; /* two points on B, one on A */
+    v2 b1 = pB->v[cache->iB[0]], b2 = pB->v[cache->iB[1]];
+    f->axis = vcross_vs(vsub(b2, b1), 1.0f);
+    vnormalize(&f->axis);
+    v2 normal = rmul(xfB.q, f->axis);
+    f->local_point = vscale(0.5f, vadd(b1, b2));
+    v2 pointB = xmul(xfB, f->local_point), pointA = pA->v[cache->iA[0]];
+    float s = vdot(vsub(pointA, pointB), normal);
+    if (s < 0.0f) f->axis = vneg(f->axis);
+  } else {
+    f->type = 1; /* two points on A */
+    v2 a1 = pA->v[cache->iA[0]], a2 = pA->v[cache->iA[1]];
+    f->axis = vcross_vs(vsub(a2, a1), 1.0f);
+    vnormalize(&f->axis);
+    v2 normal = f->axis;
+    f->local_point = vscale(0.5f, vadd(a1, a2));
+    v2 pointA = f->local_point, pointB = xmul(xfB, pB->v[cache->iB[0]]);
+    float s = vdot(vsub(pointB, pointA), normal);
+    if (s < 0.0f) f->axis = vneg(f->axis);
+  }
+}
+static float sep_find_min(const sepfn_t* f, int* iA, int* iB, float t) {
+  xf_t xfB = sweep_xf(&f->sB, t);
+  if (f->type == 0) {
+    *iA = proxy_support(f->pA, f->axis);
+    *iB = proxy_support(f->pB, rmulT(xfB.q, vneg(f->axis)));
+    v2 pointA = f->pA->v[*iA], pointB = xmul(xfB, f->pB->v[*iB]);
+    return vdot(vsub(pointB, pointA), f->axis);
+  } else if (f->type == 1) {
+    v2 normal = f->axis, pointA = f->local_point;
+    *iA = -1;
+    *iB = proxy_support(f->pB, rmulT(xfB.q, vneg(normal)));
+    v2 pointB = xmul(xfB, f->pB->v[*iB]);
+    return vdot(vsub(pointB, pointA), normal);
+  } else {
+    v2 normal = rmul(xfB.q, f->axis), pointB = xmul(xfB, f->local_point);
+    *iB = -1;
+    *iA = proxy_support(f->pA, vneg(normal));
+    v2 pointA = f->pA->v[*iA];
+    return vdot(vsub(pointA, pointB), normal);
+  }
+}
+static float sep_evaluate(const sepfn_t* f, int iA, int iB, float t) {
+  xf_t xfB = sweep_xf(&f->sB, t);
+  if (f->type == 0) {
+    v2 pointA = f->pA->v[iA], pointB = xmul(xfB, f->pB->v[iB]);
+    return vdot(vsub(pointB, pointA), f->axis);
+  } else if (f->type == 1) {
+    v2 normal = f->axis, pointA = f->local_point, pointB = xmul(xfB, f->pB->v[iB]);
+    return vdot(vsub(pointB, pointA), normal);
+  } else {
+    v2 normal = rmul(xfB.q, f->axis), pointB = xmul(xfB, f->local_point), pointA = f->pA->v[iA];
+    return vdot(vsub(pointA, pointB), normal);
+  }
+}
+
+/* b2TimeOfImpact with tMax = 1: returns the state (1 failed, 2 overlapped, 3 touching, 4 separated) and *t_out */
+static int time_of_impact(const proxy_t* pA, const proxy_t* pB, sweep_t sB, float* t_out) {
+  const float tMax = 1.0f;
+  { /* b2Sweep::Normalize */
+    const float two_pi = 2.0f * B2_PI;
+    float d = two_pi * floorf(sB.a0 / two_pi);
+    sB.a0 -= d;
+    sB.a -= d;
+  }
+  const float total_radius = POLYGON_RADIUS + POLYGON_RADIUS;
+  const float target = fmaxf(LINEAR_SLOP, total_radius - 3.0f * LINEAR_SLOP), tolerance = 0.25f * LINEAR_SLOP;
+  float t1 = 0.0f;
+  int iter = 0, state = 0;
+  *t_out = tMax;
+  scache_t cache;
+  cache.count = 0;
+  for (;;) {
+    xf_t xfB = sweep_xf(&sB, t1);
+    float distance = gjk_distance(&cache, pA, pB, xfB);
+    if (distance <= 0.0f) { state = 2; *t_out = 0.0f; break; }
+    if (distance < target + tolerance) { state = 3; *t_out = t1; break; }
+    sepfn_t fcn;
+    sep_init(&fcn, &cache, pA, pB, &sB, t1);
+    int done = 0, push_back = 0;
+    float t2 = tMax;
+    for (;;) {
+      int iA, iB;
+      float s2 = sep_find_min(&fcn, &iA, &iB, t2);
+      if (s2 > target + tolerance) { state = 4; *t_out = tMax; done = 1; break; }
+      if (s2 > target - tolerance) { t1 = t2; break; }
+      float s1 = sep_evaluate(&fcn, iA, iB, t1);
+      if (s1 < target - tolerance) { state = 1; *t_out = t1; done = 1; break; }
+      if (s1 <= target + tolerance) { state = 3; *t_out = t1; done = 1; break; }
+      int root_iters = 0;
+      float a1 = t1, a2 = t2;
+      for (;;) {
+        float t;
+        if (root_iters & 1) t = a1 + (target - s1) * (a2 - a1) / (s2 - s1);
+        else t = 0.5f * (a1 + a2);
+        ++root_iters;
+        float s = sep_evaluate(&fcn, iA, iB, t);
+        if (fabsf(s - target) < tolerance) { t2 = t; break; }
+        if (s > target) { a1 = t; s1 = s; } else { a2 = t; s2 = s; }
+        if (root_iters == 50) break;
+      }
+      ++push_back;
+      if (push_back == MAX_POLY_VERTS) break;
+    }
+    ++iter;
+    if (done) break;
+    if (iter == 20) { state = 1; *t_out = t1; break; }
+  }
+  return state;
+}
+
+/* b2Body::SynchronizeFixtures + b2DynamicTree::MoveProxy for dynamic body d; returns 1 if the fat AABB moved */
+static int sync_fixtures(lander_t* L, int d) {
+  body_t* b = &L->b[1 + d];
+  xf_t xf1;
+  xf1.q = rot_set(b->a0);
+  xf1.p = vsub(b->c0, rmul(xf1.q, b->local_center));
+  aabb_t a1 = poly_aabb(&L->poly[d], xf1), a2 = poly_aabb(&L->poly[d], b->xf);
+  aabb_t comb = {vmin(a1.lo, a2.lo), vmax(a1.hi, a2.hi)};
+  v2 disp = vsub(b->xf.p, xf1.p);
+  if (aabb_contains(L->poly_fat[d], comb)) return 0;
+  aabb_t fb = fatten(comb);
+  v2 dd = vscale(AABB_MULTIPLIER, disp);
+  if (dd.x < 0.0f) fb.lo.x += dd.x; else fb.hi.x += dd.x;
+  if (dd.y < 0.0f) fb.lo.y += dd.y; else fb.hi.y += dd.y;
+  L->poly_fat[d] = fb;
+  return 1;
+}
+
+/* b2Island::SolveTOI for the island {moon, body 1 + dyn} with the contacts idx[0..n) (idx[0] is the TOI contact): TOI
+ * position solve (<= 20 iterations, Baumgarte 0.75), leap of faith, 180 velocity iterations without warm starting and
+ * without joints, position integration over the rest of the step */
+static void solve_toi_island(lander_t* L, int dyn, const int* idx, int n, float h, int vel_iters) {
+  body_t* B = &L->b[1 + dyn];
+  const float mB = B->inv_mass, iB = B->inv_I;
+  const v2 lcB = B->local_center;
+  v2 cB = B->c, vB = B->vel;
+  float aB = B->a, wB = B->w;
+  vc_t vcs[NPAIR];
+  for (int k = 0; k < n; ++k) { /* b2ContactSolver constructor, warmStarting = false */
+    vc_t* vc = &vcs[k];
+    contact_t* c = &L->contact[idx[k]];
+    memset(vc, 0, sizeof(*vc));
+    vc->c = c;
+    vc->friction = c->friction;
+    vc->count = vc->pos_count = c->m.count;
+    vc->type = c->m.type;
+    vc->local_normal = c->m.local_normal; vc->local_point = c->m.local_point;
+    for (int j = 0; j < vc->count; ++j) vc->local_points[j] = c->m.points[j].local_point;
+  }
+  for (int it = 0; it < 20; ++it) { /* SolveTOIPositionConstraints */
+    float min_sep = 0.0f;
+    for (int k = 0; k < n; ++k) {
+      vc_t* vc = &vcs[k];
+      for (int j = 0; j < vc->pos_count; ++j) {
+        xf_t xfB;
+        xfB.q = rot_set(aB);
+        xfB.p = vsub(cB, rmul(xfB.q, lcB));
+        v2 normal, point;
+        float sep;
+        if (vc->type == 1) {
+          normal = vc->local_normal;
+          v2 plane = vc->local_point, clip = xmul(xfB, vc->local_points[j]);
+          sep = vdot(vsub(clip, plane), normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+          point = clip;
+        } else {
+          normal = rmul(xfB.q, vc->local_normal);
+          v2 plane = xmul(xfB, vc->local_point), clip = vc->local_points[j];
+          sep = vdot(vsub(clip, plane), normal) - POLYGON_RADIUS - POLYGON_RADIUS;
+          point = clip;
+          normal = vneg(normal);
+        }
+        v2 rB = vsub(point, cB);
+        min_sep = fminf(min_sep, sep);
+        float C = fclamp(TOI_BAUMGARTE * (sep + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
+        float rnB = vcross(rB, normal);
+        float K = mB + iB * rnB * rnB;
+        float impulse = K > 0.0f ? -C / K : 0.0f;
+        v2 Pi = vscale(impulse, normal);
+        cB = vadd(cB, vscale(mB, Pi));
+        aB += iB * vcross(rB, Pi);
+      }
+    }
+    if (min_sep >= -1.5f * LINEAR_SLOP) break;
+  }
+  B->c0 = cB; B->a0 = aB; /* leap of faith to the new safe state (the moon's sweep does not change) */
+  for (int k = 0; k < n; ++k) { /* InitializeVelocityConstraints */
+    vc_t* vc = &vcs[k];
+    xf_t xfB;
+    xfB.q = rot_set(aB);
+    xfB.p = vsub(cB, rmul(xfB.q, lcB));
+    v2 pts[2];
+    manifold_t m = vc->c->m;
+    world_manifold(&m, xfB, &vc->normal, pts);
+    for (int j = 0; j < vc->count; ++j) {
+      vcp_t* p = &vc->p[j];
+      p->rB = vsub(pts[j], cB);
+      float rnB = vcross(p->rB, vc->normal);
+      float kN = mB + iB * rnB * rnB;
+      p->normal_mass = kN > 0.0f ? 1.0f / kN : 0.0f;
+      v2 tangent = vcross_vs(vc->normal, 1.0f);
+      float rtB = vcross(p->rB, tangent);
+      float kT = mB + iB * rtB * rtB;
+      p->tangent_mass = kT > 0.0f ? 1.0f / kT : 0.0f;
+      p->velocity_bias = 0.0f;
+    }
+    if (vc->count == 2) {
+      float rn1B = vcross(vc->p[0].rB, vc->normal), rn2B = vcross(vc->p[1].rB, vc->normal);
+      float k11 = mB + iB * rn1B * rn1B, k22 = mB + iB * rn2B * rn2B, k12 = mB + iB * rn1B * rn2B;
+      if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+        vc->K[0][0] = k11; vc->K[0][1] = k12; vc->K[1][0] = k12; vc->K[1][1] = k22;
+        float a = k11, b = k12, c = k12, d = k22, det = a * d - b * c;
+        if (det != 0.0f) det = 1.0f / det;
+        vc->NM[0][0] = det * d; vc->NM[1][0] = -det * b; vc->NM[0][1] = -det * c; vc->NM[1][1] = det * a;
+      } else vc->count = 1;
+    }
+  }
+  for (int it = 0; it < vel_iters; ++it) /* SolveVelocityConstraints: contacts only */
+    for (int k = 0; k < n; ++k) {
+      vc_t* vc = &vcs[k];
+      v2 normal = vc->normal, tangent = vcross_vs(normal, 1.0f);
+      for (int j = 0; j < vc->count; ++j) {
+        vcp_t* p = &vc->p[j];
+        v2 dv = vadd(vB, vcross_sv(wB, p->rB));
+        float vt = vdot(dv, tangent) - 0.0f;
+        float lambda = p->tangent_mass * (-vt);
+        float maxf = vc->friction * p->normal_impulse;
+        float newi = fclamp(p->tangent_impulse + lambda, -maxf, maxf);
+        lambda = newi - p->tangent_impulse;
+        p->tangent_impulse = newi;
+        v2 Pi = vscale(lambda, tangent);
+        vB = vadd(vB, vscale(mB, Pi));
+        wB += iB * vcross(p->rB, Pi);
+      }
+      if (vc->count == 1) {
+        vcp_t* p = &vc->p[0];
+        v2 dv = vadd(vB, vcross_sv(wB, p->rB));
+        float vn = vdot(dv, normal);
+        float lambda = -p->normal_mass * (vn - p->velocity_bias);
+        float newi = fmaxf(p->normal_impulse + lambda, 0.0f);
+        lambda = newi - p->normal_impulse;
+        p->normal_impulse = newi;
+        v2 Pi = vscale(lambda, normal);
+        vB = vadd(vB, vscale(mB, Pi));
+        wB += iB * vcross(p->rB, Pi);
+      } else {
+        vcp_t *c1 = &vc->p[0], *c2 = &vc->p[1];
+        float ax = c1->normal_impulse, ay = c2->normal_impulse;
+        v2 dv1 = vadd(vB, vcross_sv(wB, c1->rB)), dv2 = vadd(vB, vcross_sv(wB, c2->rB));
+        float vn1 = vdot(dv1, normal), vn2 = vdot(dv2, normal);
+        float bx = vn1 - c1->velocity_bias, by = vn2 - c2->velocity_bias;
+        bx -= vc->K[0][0] * ax + vc->K[1][0] * ay;
+        by -= vc->K[0][1] * ax + vc->K[1][1] * ay;
+        float xx, xy;
+        int solved = 0;
+        xx = -(vc->NM[0][0] * bx + vc->NM[1][0] * by);
+        xy = -(vc->NM[0][1] * bx + vc->NM[1][1] * by);
+        if (xx >= 0.0f && xy >= 0.0f) solved = 1;
+        if (!solved) {
+          xx = -c1->normal_mass * bx; xy = 0.0f;
+          vn2 = vc->K[0][1] * xx + by;
+          if (xx >= 0.0f && vn2 >= 0.0f) solved = 1;
+        }
+        if (!solved) {
+          xx = 0.0f; xy = -c2->normal_mass * by;
+          vn1 = vc->K[1][0] * xy + bx;
+          if (xy >= 0.0f && vn1 >= 0.0f) solved = 1;
+        }
+        if (!solved) {
+          xx = 0.0f; xy = 0.0f;
+          if (bx >= 0.0f && by >= 0.0f) solved = 1;
+        }
+        if (solved) {
+          float dx = xx - ax, dy = xy - ay;
+          v2 P1 = vscale(dx, normal), P2 = vscale(dy, normal);
+          vB = vadd(vB, vscale(mB, vadd(P1, P2)));
+          wB += iB * (vcross(c1->rB, P1) + vcross(c2->rB, P2));
+          c1->normal_impulse = xx; c2->normal_impulse = xy;
+        }
+      }
+    }
+  /* the TOI impulses are not stored for warm starting; integrate positions over the rest of the step */
+  v2 tr = vscale(h, vB);
+  if (vdot(tr, tr) > MAX_TRANSLATION * MAX_TRANSLATION) { float ratio = MAX_TRANSLATION / vlen(tr); vB = vscale(ratio, vB); }
+  float rotn = h * wB;
+  if (rotn * rotn > MAX_ROTATION * MAX_ROTATION) { float ratio = MAX_ROTATION / fabsf(rotn); wB *= ratio; }
+  cB = vadd(cB, vscale(h, vB));
+  aB += h * wB;
+  B->c = cB; B->a = aB; B->vel = vB; B->w = wB;
+  sync_transform(B);
+}
+
+/* b2World::SolveTOI(step) with m_stepComplete = true on entry (no sub-stepping mode) */
+static void solve_toi(lander_t* L, float dt, int vel_iters) {
+  for (int i = 0; i < NBODY; ++i) L->b[i].alpha0 = 0.0f;
+  for (int k = 0; k < NPAIR; ++k) { L->contact[k].toi_flag = 0; L->contact[k].toi_count = 0; L->contact[k].toi = 1.0f; }
+  body_t* moon = &L->b[0];
+  for (;;) {
+    int idx[NPAIR], n = contacts_sorted(L, idx, -1), min_k = -1;
+    float min_alpha = 1.0f;
+    for (int t = 0; t < n; ++t) {
+      contact_t* c = &L->contact[idx[t]];
+      if (!c->enabled) continue;
+      if (c->toi_count > MAX_SUB_STEPS) continue;
+      float alpha = 1.0f;
+      if (c->toi_flag) alpha = c->toi;
+      else {
+        int dyn = idx[t] / NEDGE, e = idx[t] % NEDGE;
+        body_t* bB = &L->b[1 + dyn];
+        if (!bB->awake) continue; /* activeA is false (static), activeB = awake; collideA is true (not dynamic) */
+        float alpha0 = moon->alpha0; /* put the sweeps onto the same time interval */
+        if (moon->alpha0 < bB->alpha0) {
+          alpha0 = bB->alpha0;
+          moon->alpha0 = alpha0; /* b2Sweep::Advance of a sweep with c0 == c, a0 == a */
+        } else if (bB->alpha0 < moon->alpha0) {
+          alpha0 = moon->alpha0;
+          sweep_t s = body_sweep(bB);
+          sweep_advance(&s, alpha0);
+          body_set_sweep(bB, &s);
+        }
+        v2 ev[2] = {L->edge_v1[e], L->edge_v2[e]};
+        proxy_t pA = {ev, 2}, pB = {L->poly[dyn].v, L->poly[dyn].count};
+        float beta;
+        int state = time_of_impact(&pA, &pB, body_sweep(bB), &beta);
+        ++L->toi_calls;
+        alpha = state == 3 ? fminf(alpha0 + (1.0f - alpha0) * beta, 1.0f) : 1.0f;
+        c->toi = alpha;
+        c->toi_flag = 1;
+      }
+      if (alpha < min_alpha) { min_k = idx[t]; min_alpha = alpha; }
+    }
+    if (min_k < 0 || 1.0f - 10.0f * B2_EPSILON < min_alpha) break; /* no more TOI events */
+    contact_t* mc = &L->contact[min_k];
+    const int dyn = min_k / NEDGE;
+    body_t* bB = &L->b[1 + dyn];
+    const float moon_backup = moon->alpha0;
+    const sweep_t backup = body_sweep(bB);
+    moon->alpha0 = min_alpha; /* bA->Advance(minAlpha) on the static body */
+    body_advance(bB, min_alpha);
+    contact_update(L, min_k); /* the TOI contact likely has some new contact points */
+    mc->toi_flag = 0;
+    ++mc->toi_count;
+    if (!mc->enabled || !mc->touching) { /* not solid: restore the sweeps */
+      mc->enabled = 0;
+      moon->alpha0 = moon_backup;
+      body_set_sweep(bB, &backup);
+      sync_transform(bB);
+      continue;
+    }
+    set_awake(bB, 1);
+    ++L->toi_events;
+    /* island: the TOI contact, then the other contacts of bB (most recent first) that touch at the advanced pose */
+    int isl[NPAIR], ni = 0;
+    isl[ni++] = min_k;
+    {
+      int bidx[NPAIR], bn = contacts_sorted(L, bidx, dyn);
+      for (int t = 0; t < bn; ++t) {
+        if (bidx[t] == min_k) continue;
+        contact_update(L, bidx[t]); /* other = the moon, already in the island: not advanced */
+        if (!L->contact[bidx[t]].enabled || !L->contact[bidx[t]].touching) continue;
+        isl[ni++] = bidx[t];
+      }
+    }
+    solve_toi_island(L, dyn, isl, ni, (1.0f - min_alpha) * dt, vel_iters);
+    int moved[NDYN] = {0, 0, 0};
+    moved[dyn] = sync_fixtures(L, dyn);
+    { /* invalidate all contact TOIs on this displaced body */
+      int bidx[NPAIR], bn = contacts_sorted(L, bidx, dyn);
+      for (int t = 0; t < bn; ++t) L->contact[bidx[t]].toi_flag = 0;
+    }
+    find_new_contacts(L, moved);
+  }
+}
+
+/* b2World::Step(dt, 180, 60): new-fixture pairs, Collide, Solve (+ SynchronizeFixtures / FindNewContacts), SolveTOI,
+ * ClearForces */
 static void world_step(lander_t* L, float dt, int vel_iters, int pos_iters) {
   int moved[NDYN] = {1, 1, 1};
   if (L->new_fixture) { find_new_contacts(L, moved); L->new_fixture = 0; }
@@ -1001,26 +1572,10 @@ static void world_step(lander_t* L, float dt, int vel_iters, int pos_iters) {
   solve_island(L, dt, dt_ratio, vel_iters, pos_iters);
   if (was_awake) {
     /* SynchronizeFixtures for island bodies (most recently created first) + FindNewContacts */
-    for (int d = NDYN - 1; d >= 0; --d) {
-      body_t* b = &L->b[1 + d];
-      xf_t xf1;
-      xf1.q = rot_set(b->a0);
-      xf1.p = vsub(b->c0, rmul(xf1.q, b->local_center));
-      aabb_t a1 = poly_aabb(&L->poly[d], xf1), a2 = poly_aabb(&L->poly[d], b->xf);
-      aabb_t comb = {vmin(a1.lo, a2.lo), vmax(a1.hi, a2.hi)};
-      v2 disp = vsub(b->xf.p, xf1.p);
-      moved[d] = 0;
-      if (!aabb_contains(L->poly_fat[d], comb)) { /* b2DynamicTree::MoveProxy */
-        aabb_t fb = fatten(comb);
-        v2 dd = vscale(AABB_MULTIPLIER, disp);
-        if (dd.x < 0.0f) fb.lo.x += dd.x; else fb.hi.x += dd.x;
-        if (dd.y < 0.0f) fb.lo.y += dd.y; else fb.hi.y += dd.y;
-        L->poly_fat[d] = fb;
-        moved[d] = 1;
-      }
-    }
+    for (int d = NDYN - 1; d >= 0; --d) moved[d] = sync_fixtures(L, d);
     find_new_contacts(L, moved);
   }
+  if (dt > 0.0f) solve_toi(L, dt, vel_iters); /* m_continuousPhysics && step.dt > 0 */
   if (dt > 0.0f) L->inv_dt0 = inv_dt;
   for (int i = 1; i < NBODY; ++i) { L->b[i].force = V(0, 0); L->b[i].torque = 0.0f; } /* ClearForces */
 }
@@ -1236,6 +1791,19 @@ void ll_debug_state(const ll_vec_t* v, int i, float* bodies, float* misc) {
   int nc = 0, nt = 0;
   for (int k = 0; k < NPAIR; ++k) { nc += L->contact[k].exists; nt += L->contact[k].touching; }
   misc[6] = (float)nc; misc[7] = (float)nt;
+}
+void ll_toi_stats(const ll_vec_t* v, int i, long* out /* [2]: b2TimeOfImpact calls, solid TOI events since reset */) {
+  out[0] = v->env[i].toi_calls; out[1] = v->env[i].toi_events;
+}
+/* Direct probe of the restated b2TimeOfImpact: a box with half extents (hx, hy) (body origin = centroid) swept from
+ * (c0, a0) to (c1, a1) against the edge e1-e2; returns the b2TOIOutput state (1 failed, 2 overlapped, 3 touching,
+ * 4 separated) and writes t. */
+int ll_toi_probe(const float* e, float hx, float hy, const float* c0, float a0, const float* c1, float a1, float* t) {
+  v2 ev[2] = {V(e[0], e[1]), V(e[2], e[3])};
+  v2 bv[4] = {V(-hx, -hy), V(hx, -hy), V(hx, hy), V(-hx, hy)};
+  proxy_t pA = {ev, 2}, pB = {bv, 4};
+  sweep_t s = {V(0, 0), V(c0[0], c0[1]), V(c1[0], c1[1]), a0, a1, 0.0f};
+  return time_of_impact(&pA, &pB, s, t);
 }
 void ll_terrain(const ll_vec_t* v, int i, float* xy /* [11][4] */) {
   const lander_t* L = &v->env[i];

@@ -27,6 +27,9 @@ def lib():
         l.ll_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         l.ll_debug_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         l.ll_terrain.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        l.ll_toi_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        l.ll_toi_probe.restype = C.c_int
+        l.ll_toi_probe.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
         _lib = l
     return _lib
 
@@ -83,6 +86,12 @@ class OracleLunarLander:
         lib().ll_debug_state(self._h, i, bodies.ctypes.data, misc.ctypes.data)
         return bodies, misc
 
+    def toi_stats(self, i=0):
+        """(b2TimeOfImpact evaluations, solid TOI events) of env i since its last reset."""
+        out = (C.c_long * 2)()
+        lib().ll_toi_stats(self._h, i, out)
+        return int(out[0]), int(out[1])
+
     def terrain(self, i=0):
         xy = np.zeros((11, 4), dtype=np.float32)
         lib().ll_terrain(self._h, i, xy.ctypes.data)
@@ -107,3 +116,13 @@ def heuristic(s):
     elif angle_todo > +0.05:
         a = 1
     return a
+
+
+def toi_probe(edge, half_extents, c0, a0, c1, a1):
+    """The oracle's restated b2TimeOfImpact for a box swept from (c0, a0) to (c1, a1) against an edge -> (state, t)."""
+    e = np.asarray(edge, dtype=np.float32).reshape(4)
+    p0, p1 = np.asarray(c0, dtype=np.float32), np.asarray(c1, dtype=np.float32)
+    t = C.c_float(0)
+    st = lib().ll_toi_probe(e.ctypes.data, float(half_extents[0]), float(half_extents[1]), p0.ctypes.data, float(a0),
+                            p1.ctypes.data, float(a1), C.byref(t))
+    return int(st), float(t.value)
