@@ -71,6 +71,8 @@ class HumanoidVectorEnv(B200VectorEnv):
             "work": torch.zeros(n, dtype=torch.int32, device=dev),    # solver work of the last step (scheduling hint)
             "order": torch.zeros(n, dtype=torch.int32, device=dev),   # scratch: envs grouped by that work
         }
+        self._last_done = None  # terminated | truncated of the previous step() (NEXT_STEP: those lanes are on their reset call)
+        self._info_sid, self._info_prev = -1, None
         self._state = _lib.HumanoidState(ctrl=self._ctrl.data_ptr(), rng=ptr(self._rng),
                                          **{k: v.data_ptr() for k, v in self._s.items()})
 
@@ -142,12 +144,37 @@ class HumanoidVectorEnv(B200VectorEnv):
 
     def _reset_info(self, out, mask):
         # HumanoidEnv._get_reset_info (humanoid_v5.py:534-541): the five state keys
+        if mask is None:
+            self._last_done = None
+        elif self._last_done is not None:  # lanes reset by hand are no longer waiting for their autoreset call
+            self._last_done = self._same_kind(self._last_done, mask) & ~mask
+        self._info_sid = -1
         return self._info_dict(out, mask, INFO_KEYS[:5])
 
+    def _same_kind(self, x, like):
+        """x as a numpy array / torch tensor, whichever `like` is (the output kind may be switched between calls)."""
+        if isinstance(x, np.ndarray) == isinstance(like, np.ndarray):
+            return x
+        return x.cpu().numpy() if isinstance(x, torch.Tensor) else torch.as_tensor(x, device=self.device)
+
     def _step_info(self, out):
-        info = self._info_dict(out, None, INFO_KEYS)
+        """Info of a step call.  In NEXT_STEP mode a lane whose previous step ended its episode is on its reset call
+        (sync_vector_env.py:279-284) and reports only the five keys of ``_get_reset_info``; in SAME_STEP mode a lane that
+        ends its episode has its step info replaced by the reset info (:302-319).  The masks of the six step-only keys
+        (velocities, reward terms) are therefore False on those lanes, as ``SyncVectorEnv._add_info`` leaves them."""
+        done = out["terminated"] | out["truncated"]
+        sid = int(self._batch.call_counter)
+        if sid != self._info_sid:  # step_wait() asks again for the same step (host arrays): keep that step's predecessor
+            self._info_sid, self._info_prev = sid, self._last_done
+        info = self._info_dict(out, None, INFO_KEYS[:5])
+        step_mask = None
+        if self.autoreset_mode == AutoresetMode.NEXT_STEP and self._info_prev is not None:
+            step_mask = ~self._same_kind(self._info_prev, done)
+        elif self.autoreset_mode == AutoresetMode.SAME_STEP:
+            step_mask = ~done
+        info.update(self._info_dict(out, step_mask, INFO_KEYS[5:]))
+        self._last_done = done.copy() if isinstance(done, np.ndarray) else done
         if self.autoreset_mode == AutoresetMode.SAME_STEP:
-            done = out["terminated"] | out["truncated"]
             info.update({"final_obs": out["final_obs"], "_final_obs": done})
         return info
 

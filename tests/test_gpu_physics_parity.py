@@ -195,3 +195,30 @@ def test_humanoid_reward_identity_is_exact_with_the_reference_grouping():
         total = (info["reward_forward"] + info["reward_survive"]) + (info["reward_ctrl"] + info["reward_contact"])
         assert (reward == total).all(), np.abs(reward - total).max()
         assert live.any()
+
+
+@pytest.mark.parametrize("output", ["numpy", "torch"])
+def test_humanoid_info_masks_follow_syncvectorenv(output):
+    """NEXT_STEP: the call after a done is that lane's reset() -- SyncVectorEnv merges only the 5 reset-info keys for it, so
+    the masks of the 6 step-only keys are False there (vector_env.py:277-338 `_add_info`); SAME_STEP: lanes that end an
+    episode report their reset info as well."""
+    env = gymnasium_b200.make_vec("Humanoid-v5", num_envs=32, max_episode_steps=4, output=output)
+    env.reset(seed=0)
+    a = np.zeros((32, 17), dtype=np.float32)
+    prev = np.zeros(32, dtype=bool)
+    for t in range(11):
+        _, _, te, tr, info = env.step(a)
+        te, tr = np.asarray(te.cpu() if output == "torch" else te), np.asarray(tr.cpu() if output == "torch" else tr)
+        for k in ("x_position", "tendon_length", "distance_from_origin"):
+            assert bool(np.asarray(info["_" + k].cpu() if output == "torch" else info["_" + k]).all())
+        for k in ("x_velocity", "reward_survive", "reward_contact"):
+            m = np.asarray(info["_" + k].cpu() if output == "torch" else info["_" + k])
+            np.testing.assert_array_equal(m, ~prev, err_msg=f"{k} at step {t}")
+        prev = te | tr
+    assert prev.any() or t > 4
+    same = gymnasium_b200.make_vec("Humanoid-v5", num_envs=8, max_episode_steps=3, autoreset_mode="SameStep", output="numpy")
+    same.reset(seed=0)
+    for t in range(4):
+        _, _, te, tr, info = same.step(a[:8])
+        np.testing.assert_array_equal(info["_reward_forward"], ~(te | tr))
+        np.testing.assert_array_equal(info["_final_obs"], te | tr)
