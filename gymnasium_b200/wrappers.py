@@ -105,8 +105,11 @@ class RecordEpisodeStatistics(_Base):
         return int(self._count.item())
 
     def _queue(self, key):
-        c = min(self.episode_count, self._buffer_length)
-        return self._ring[key][:c] if self.episode_count <= self._buffer_length else self._ring[key]
+        """The reference's ``deque(maxlen=buffer_length)`` (wrappers/vector/common.py:103-105): oldest first."""
+        count, B = self.episode_count, self._buffer_length
+        if count <= B:
+            return self._ring[key][:count]
+        return torch.roll(self._ring[key], -(count % B))  # the ring's write position is the oldest entry
 
     @property
     def return_queue(self):
@@ -163,12 +166,14 @@ class RecordEpisodeStatistics(_Base):
         infos[f"_{self._stats_key}"] = dones
         # ring buffers of finished episodes (the reference's deques), written at count + rank-among-dones
         rank = torch.cumsum(dones.to(torch.int64), 0) - 1
-        slot = torch.where(dones, (self._count + rank) % self._buffer_length, torch.full_like(rank, self._buffer_length))
+        n_done = dones.sum()
+        keep = dones & (rank >= n_done - self._buffer_length)  # more finishers than slots: only the last ones survive (deque)
+        slot = torch.where(keep, (self._count + rank) % self._buffer_length, torch.full_like(rank, self._buffer_length))
         for key, src in (("r", self.episode_returns), ("l", self.episode_lengths), ("t", elapsed)):
             padded = torch.cat([self._ring[key], self._ring[key].new_zeros(1)])
             padded[slot] = src.to(padded.dtype)
             self._ring[key] = padded[:-1]
-        self._count = self._count + dones.sum()
+        self._count = self._count + n_done
         if self._autoreset_mode == AutoresetMode.SAME_STEP:
             self.episode_returns = torch.where(dones, torch.zeros_like(self.episode_returns), self.episode_returns)
             self.episode_lengths = torch.where(dones, torch.zeros_like(self.episode_lengths), self.episode_lengths)

@@ -70,6 +70,15 @@ def test_record_episode_statistics_matches_reference(mode):
     assert mine.episode_count == ref.episode_count
     np.testing.assert_allclose(np.sort(mine.return_queue.numpy()), np.sort(np.array(ref.return_queue)), atol=1e-12)
     np.testing.assert_array_equal(np.sort(mine.length_queue.numpy()), np.sort(np.array(ref.length_queue)))
+    # a buffer smaller than the number of episodes (and than the finishers of one step): same entries, same (chronological)
+    # order as the reference's deques
+    ref = Ref(ScriptedEnv(n, T, 1, False, mode), buffer_length=4)
+    mine = W.RecordEpisodeStatistics(ScriptedEnv(n, T, 1, True, mode), buffer_length=4)
+    ref.reset(); mine.reset()
+    for t in range(T):
+        ref.step(np.zeros(n, dtype=np.int64)); mine.step(np.zeros(n, dtype=np.int64))
+        np.testing.assert_allclose(mine.return_queue.numpy(), np.array(ref.return_queue), atol=1e-12, err_msg=f"step {t}")
+        np.testing.assert_array_equal(mine.length_queue.numpy(), np.array(ref.length_queue))
 
 
 def test_normalize_observation_and_reward_match_reference():
