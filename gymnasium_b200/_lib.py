@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200env.so")
+# B2E_LIB_PATH: load another build of the same library (A/B measurements of kernel variants, scripts/lanes_sweep.py)
+LIB_PATH = os.environ.get("B2E_LIB_PATH") or os.path.join(_HERE, "libb200env.so")
 
 # enums (include/b200env.h)
 AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP, AUTORESET_DISABLED = 0, 1, 2
@@ -72,14 +73,14 @@ class LunarLanderCfg(C.Structure):
     """``b2e_lunarlander_cfg``."""
 
     _fields_ = [("gravity", c_double), ("enable_wind", c_i32), ("continuous", c_i32), ("lanes_per_warp", c_i32),
-                ("_pad", c_i32)]
+                ("no_grouping", c_i32)]
 
 
 class LunarLanderState(C.Structure):
     """``b2e_lunarlander_state`` (device pointers)."""
 
     _fields_ = [(k, c_void_p) for k in ("bodies", "joints", "terrain", "fat", "contacts", "flags", "prev_shaping",
-                                        "ctrl", "rng")]
+                                        "ctrl", "rng", "work", "order")]
 
 
 class HumanoidCfg(C.Structure):

@@ -1067,7 +1067,8 @@ __device__ void store_state(const HumanoidArgs& a, int64_t i, const HData& d) {
 }
 
 constexpr int kHumanoidBlock = 32;
-constexpr int kWarpEnvsPerCta = 8;  // warp mapping: envs (warps) per CTA unless b2e_humanoid_cfg.envs_per_cta says otherwise
+constexpr int kWarpEnvsPerCta = 10;  // warp mapping: envs (warps) per CTA unless b2e_humanoid_cfg.envs_per_cta says otherwise
+                                     // (10 x 20.2 KB + the 12.9 KB model = 215 KB of the 227 KB an sm_100a CTA can have)
 constexpr bool kHumanoidDefaultWarp = true;   // warp per env is the default mapping (thread per env: impl = 1)
 constexpr int kHumanoidLanes = 32;  // default envs per warp (b2e_humanoid_cfg.lanes_per_warp overrides)
 

@@ -578,7 +578,7 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane) {
     const int tri0 = lane * (lane + 1) / 2;
     for (int it = 0; it < iters; ++it) {
       double d_own = 0, r_own = 0;  // this lane's move and the residual it was computed from (for the cost change)
-      int idx = tri0;               // index of AR[lane][j] in the packed lower triangle (in bounds for every lane)
+      int idx = tri0;               // index of AR[lane][j] in the packed lower triangle (in bounds for lanes < MAXEFC)
 #pragma unroll 1
       for (int j = 0; j < n; ++j) {
         double f = f_i - r_i * ainv;
@@ -586,12 +586,12 @@ __device__ __noinline__ void w_forward(const WModel& wm, WS& w, int lane) {
         const double delta = f - f_i;
         const double dj = __shfl_sync(0xffffffffu, delta, j);
         if (lane == j) { f_i = f; d_own = delta; r_own = r_i; }
-        r_i += w.AR[idx] * dj;      // lanes >= n accumulate junk nobody reads
+        r_i += (lane < MAXEFC ? w.AR[idx] : 0.0) * dj;  // lanes >= n accumulate junk nobody reads; lanes >= MAXEFC have no row
         idx += j < lane ? 1 : j + 1;
       }
       // cost change of the sweep: the per-row gains added in row order by every lane (warp-uniform break, no broadcast)
       double* const gains = (it & 1) ? w.term : w.b;  // b_i is in registers; two buffers: no barrier after the reads
-      gains[lane] = 0.5 * d_own * d_own * aii + d_own * r_own;
+      if (lane < MAXEFC) gains[lane] = 0.5 * d_own * d_own * aii + d_own * r_own;
       WSYNC();
       double improvement = 0;
 #pragma unroll 1

@@ -1648,6 +1648,8 @@ struct LanderArgs {
   double* __restrict__ prev_shaping; // [n]
   int32_t* __restrict__ ctrl;
   uint64_t* __restrict__ rng;
+  int32_t* __restrict__ work;        // [n] or null: scheduling key of every env after its last step (see lander_key)
+  int32_t* __restrict__ order;       // [n] or null: env indices grouped by that key
   float* __restrict__ obs;           // [n][8]
   double* __restrict__ reward;
   uint8_t* __restrict__ term;
@@ -1919,6 +1921,23 @@ DI void write_obs(float* __restrict__ obs, int64_t i, const StepOut& o) {
   p[1] = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
 }
 
+// Scheduling key of an env for its NEXT step: which code paths it will walk.  A warp executes the union of its lanes' paths
+// for 180 + 60 solver iterations, so lanes that agree (no contact candidates / candidates but flying / resting on n
+// manifolds, joints at their limits or not, a reset call) should share a warp.  Scheduling only: which envs share a warp
+// never changes what an env computes.
+DI int lander_key(const Lander& L, bool pending) {
+  if (pending) return 63;
+  int touching = 0;
+  for (int k = 0; k < L.nct; ++k) touching += L.ct[k].touching;
+  const int lim = (L.j[0].limit_state != 0 ? 1 : 0) | (L.j[1].limit_state != 0 ? 2 : 0);
+  const int group = !L.awake ? 0 : L.nct == 0 ? 1 : 2 + min(touching, 12);  // asleep | free flight | near / on the ground
+  return group * 4 + lim;  // <= 59
+}
+__global__ void __launch_bounds__(1024) lunarlander_group_kernel(const int32_t* __restrict__ work, int32_t* __restrict__ order,
+                                                                 int64_t n) {
+  group_envs_by_key<64>([work](int64_t i) { return 63 - min(max(work[i], 0), 63); }, order, n);  // heaviest first
+}
+
 constexpr int kLanderBlock = 64;  // small CTAs: every SM gets work; the kernel is latency- not occupancy-bound
 constexpr int kLanderLanes = 32;  // default envs per warp (b2e_lunarlander_cfg.lanes_per_warp overrides)
 
@@ -1936,13 +1955,15 @@ __global__ void __launch_bounds__(kLanderBlock) lunarlander_reset_kernel(const L
   if (D.numpy) pcg64_store_state(a.rng, i, D.g);
   store_state(a, i, L);
   a.ctrl[i] = 0;
+  if (a.work) a.work[i] = lander_key(L, false);
   write_obs(a.obs, i, o);
 }
 
 template <typename ActT>
 __global__ void __launch_bounds__(kLanderBlock) lunarlander_step_kernel(const LanderArgs a) {
-  const int64_t i = sparse_env_index(a.lanes);
-  if (i < 0 || i >= a.n) return;
+  const int64_t slot = sparse_env_index(a.lanes);
+  if (slot < 0 || slot >= a.n) return;
+  const int64_t i = a.order ? a.order[slot] : slot;  // envs on the same code paths share a warp
   const int32_t c = a.ctrl[i];
   int action = load_action<ActT>(a.actions, i);
   action = min(max(action, 0), 3);
@@ -1988,6 +2009,7 @@ __global__ void __launch_bounds__(kLanderBlock) lunarlander_step_kernel(const La
   if (D.numpy) pcg64_store_state(a.rng, i, D.g);
   store_state(a, i, L);
   a.ctrl[i] = cn;
+  if (a.work) a.work[i] = lander_key(L, ctrl_pending(cn));
   write_obs(a.obs, i, o);
 }
 
@@ -2162,6 +2184,8 @@ int fill(const b2e_batch* b, const b2e_lunarlander_cfg* cfg, const b2e_lunarland
   a.prev_shaping = st->prev_shaping;
   a.ctrl = st->ctrl;
   a.rng = st->rng;
+  a.work = st->work;
+  a.order = (st->work && st->order && !cfg->no_grouping) ? st->order : nullptr;
   return upload_model();
 }
 
@@ -2206,6 +2230,7 @@ extern "C" int b2e_lunarlander_step(const b2e_batch* b, const b2e_lunarlander_cf
   a.final_obs = final_obs;
   const unsigned grid = sparse_grid(b->n, a.lanes, kLanderBlock);
   cudaStream_t s = (cudaStream_t)stream;
+  if (a.order) lunarlander_group_kernel<<<1, 1024, 0, s>>>(a.work, a.order, a.n);
   switch (b->action_dtype) {
     case B2E_ACT_I64: lunarlander_step_kernel<int64_t><<<grid, kLanderBlock, 0, s>>>(a); break;
     case B2E_ACT_I32: lunarlander_step_kernel<int32_t><<<grid, kLanderBlock, 0, s>>>(a); break;

@@ -47,6 +47,8 @@ class LunarLanderVectorEnv(B200VectorEnv):
             "contacts": torch.zeros((words, n), dtype=torch.int32, device=dev),
             "flags": torch.zeros(n, dtype=torch.int32, device=dev),
             "prev_shaping": torch.zeros(n, dtype=torch.float64, device=dev),
+            "work": torch.zeros(n, dtype=torch.int32, device=dev),    # scheduling key of every env after its last step
+            "order": torch.zeros(n, dtype=torch.int32, device=dev),   # scratch: envs grouped by that key
         }
         self._state = _lib.LunarLanderState(ctrl=self._ctrl.data_ptr(), rng=ptr(self._rng),
                                             **{k: v.data_ptr() for k, v in self._s.items()})

@@ -232,7 +232,7 @@ typedef struct b2e_lunarlander_cfg {
   int32_t enable_wind;   /* must be 0 */
   int32_t continuous;    /* must be 0 */
   int32_t lanes_per_warp; /* envs mapped to each warp (1..32); 0 = library default. Fewer lanes = less divergence */
-  int32_t _pad;
+  int32_t no_grouping;    /* != 0: step envs in index order even when work/order are given (scheduling only) */
 } b2e_lunarlander_cfg;
 
 typedef struct b2e_lunarlander_state {
@@ -245,6 +245,9 @@ typedef struct b2e_lunarlander_state {
   double* prev_shaping;
   int32_t* ctrl;
   uint64_t* rng;
+  int32_t* work;   /* [n] optional (may be NULL with order): scheduling key of every env after its last step */
+  int32_t* order;  /* [n] optional scratch: env indices grouped by `work`; the step kernel then puts envs that walk the
+                      same code paths into the same warp (scheduling only: results do not depend on it) */
 } b2e_lunarlander_state;
 
 int b2e_lunarlander_state_words(void);

@@ -222,3 +222,26 @@ def test_humanoid_info_masks_follow_syncvectorenv(output):
         _, _, te, tr, info = same.step(a[:8])
         np.testing.assert_array_equal(info["_reward_forward"], ~(te | tr))
         np.testing.assert_array_equal(info["_final_obs"], te | tr)
+
+
+def test_lunarlander_grouping_is_scheduling_only():
+    """Envs are regrouped into warps by their contact / joint-limit state; that must never change results, and `order` must
+    be a permutation of the env indices."""
+    n, T = 3000, 260
+    envs = []
+    for no_grouping, lanes in ((0, 0), (1, 0), (0, 8)):
+        e = make("LunarLander-v3", n)
+        e._cfg.no_grouping, e._cfg.lanes_per_warp = no_grouping, lanes
+        e.reset(seed=17)
+        envs.append(e)
+    rs = np.random.default_rng(6)
+    for t in range(T):
+        a = rs.integers(0, 4, n)
+        outs = [e.step(a) for e in envs]
+        for o in outs[1:]:
+            for k in range(4):
+                np.testing.assert_array_equal(outs[0][k], o[k], err_msg=f"output {k} differs at step {t}")
+    order = envs[0]._s["order"].cpu().numpy()
+    assert sorted(order.tolist()) == list(range(n))
+    work = envs[0]._s["work"].cpu().numpy()
+    assert work.min() >= 0 and work.max() <= 63 and len(np.unique(work)) > 3
