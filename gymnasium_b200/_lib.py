@@ -107,6 +107,21 @@ class CopySeg(C.Structure):
                 ("width", C.c_size_t), ("height", C.c_size_t)]
 
 
+class Call(C.Structure):
+    """``b2e_call``."""
+
+    _fields_ = [("fn", c_void_p), ("nargs", c_i32), ("_pad", c_i32), ("args", c_u64 * 16)]
+
+
+class PipeSlot(C.Structure):
+    """``b2e_pipe_slot``."""
+
+    _fields_ = [("staging_host", c_void_p), ("actions_dev", c_void_p), ("action_bytes", C.c_size_t),
+                ("calls", C.POINTER(Call)), ("segs", C.POINTER(CopySeg)), ("ncalls", c_i32), ("nsegs", c_i32),
+                ("ev_h2d", c_void_p), ("ev_step", c_void_p), ("ev_copy", c_void_p), ("h2d_pending", c_i32),
+                ("copy_pending", c_i32)]
+
+
 P = c_void_p
 _BP = C.POINTER(Batch)
 
@@ -119,6 +134,9 @@ SIGNATURES = {
     "b2e_host_register": (C.c_int, [P, C.c_size_t]),
     "b2e_host_unregister": (C.c_int, [P]),
     "b2e_copy_to_host_async": (C.c_int, [P, c_i32, P]),
+    "b2e_pipe_slot_init": (C.c_int, [C.POINTER(PipeSlot)]),
+    "b2e_pipe_slot_destroy": (C.c_int, [C.POINTER(PipeSlot)]),
+    "b2e_pipe_submit": (C.c_int, [C.POINTER(PipeSlot), P, P, P, P, c_i64, P, c_double]),
     "b2e_rng_seed": (C.c_int, [_BP, c_u64, P, P, P, P]),
     "b2e_rng_random": (C.c_int, [_BP, P, c_i32, P, P]),
     "b2e_cartpole_reset": (C.c_int, [_BP, C.POINTER(CartPoleCfg), P, P, P, P, P, P]),

@@ -1,6 +1,8 @@
 // api.cu -- library-wide C-ABI entry points (version, errors, device query) and the numpy-parity RNG seeding kernel.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
+#include <time.h>
 
 #include "common.cuh"
 
@@ -175,4 +177,95 @@ extern "C" int b2e_copy_to_host_async(const b2e_copy_seg* segs, int32_t count, v
     if (int st = cuda_status(e, "b2e_copy_to_host_async")) return st;
   }
   return 0;
+}
+
+// ---- pipelined end-to-end step in ONE host call (gymnasium_b200/distributed.py: HostBatchPipeline) ----------------------
+extern "C" int b2e_pipe_slot_init(b2e_pipe_slot* s) {
+  if (!s) {
+    set_error("b2e_pipe_slot_init: slot is NULL");
+    return B2E_EINVAL;
+  }
+  cudaEvent_t ev[3];
+  for (int i = 0; i < 3; ++i)
+    if (int st = cuda_status(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming), "b2e_pipe_slot_init")) return st;
+  s->ev_h2d = ev[0];
+  s->ev_step = ev[1];
+  s->ev_copy = ev[2];
+  s->h2d_pending = s->copy_pending = 0;
+  return 0;
+}
+
+extern "C" int b2e_pipe_slot_destroy(b2e_pipe_slot* s) {
+  if (!s) return 0;
+  void** ev[3] = {&s->ev_h2d, &s->ev_step, &s->ev_copy};
+  for (int i = 0; i < 3; ++i)
+    if (*ev[i]) {
+      cudaEventDestroy((cudaEvent_t)*ev[i]);
+      *ev[i] = nullptr;
+    }
+  return 0;
+}
+
+typedef int (*b2e_anyfn)(uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
+                         uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t);
+
+extern "C" int b2e_pipe_submit(b2e_pipe_slot* s, const void* host_actions, void* main_stream, void* copy_stream,
+                               const int64_t* ack_word, int64_t need_ack, const void* seq_src, double timeout_s) {
+  if (!s || !host_actions || !s->staging_host || !s->actions_dev || !s->calls || !s->segs || s->nsegs < 2 || !seq_src) {
+    set_error("b2e_pipe_submit: null pointer in the slot or its arguments");
+    return B2E_EINVAL;
+  }
+  cudaStream_t ms = (cudaStream_t)main_stream, cs = (cudaStream_t)copy_stream;
+  // (1) stage this step's actions: the DMA that last read the staging buffer must be done
+  if (s->h2d_pending)
+    if (int st = cuda_status(cudaEventSynchronize((cudaEvent_t)s->ev_h2d), "b2e_pipe_submit (staging)")) return st;
+  memcpy(s->staging_host, host_actions, s->action_bytes);
+  // (2) the kernel re-uses the output set whose last landing copies must have drained
+  if (s->copy_pending)
+    if (int st = cuda_status(cudaStreamWaitEvent(ms, (cudaEvent_t)s->ev_copy, 0), "b2e_pipe_submit (output set)")) return st;
+  if (int st = cuda_status(cudaMemcpyAsync(s->actions_dev, s->staging_host, s->action_bytes, cudaMemcpyHostToDevice, ms),
+                           "b2e_pipe_submit (H2D)"))
+    return st;
+  cudaEventRecord((cudaEvent_t)s->ev_h2d, ms);
+  s->h2d_pending = 1;
+  // (3) the family's fused step: the recorded C-ABI call(s), every argument a pointer or an integer
+  for (int32_t c = 0; c < s->ncalls; ++c) {
+    const b2e_call& k = s->calls[c];
+    if (!k.fn || k.nargs < 0 || k.nargs > 16) {
+      set_error("b2e_pipe_submit: bad recorded call %d", c);
+      return B2E_EINVAL;
+    }
+    const uint64_t* a = k.args;
+    const int st = ((b2e_anyfn)k.fn)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13],
+                                     a[14], a[15]);
+    if (st) return st;  // the callee has set the error text
+  }
+  cudaEventRecord((cudaEvent_t)s->ev_step, ms);
+  cudaStreamWaitEvent(cs, (cudaEvent_t)s->ev_step, 0);
+  // (4) the consumer must have released the slot this step lands in
+  if (ack_word) {
+    const volatile int64_t* ack = ack_word;
+    if (*ack < need_ack) {
+      struct timespec t0, t1;
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      unsigned spins = 0;
+      while (*ack < need_ack) {
+        if ((++spins & 0x3ffu) == 0) {
+          clock_gettime(CLOCK_MONOTONIC, &t1);
+          if ((double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec) > timeout_s) {
+            set_error("b2e_pipe_submit: timed out waiting for the consumer to release step %lld", (long long)(need_ack - 1));
+            return B2E_ETIMEOUT;
+          }
+          struct timespec nap = {0, 2000};
+          nanosleep(&nap, nullptr);  // several ranks may share a core
+        }
+      }
+    }
+  }
+  // (5) land the outputs + the sequence word (its source is the second-to-last segment's)
+  s->segs[s->nsegs - 2].dev_src = seq_src;
+  if (int st = b2e_copy_to_host_async(s->segs, s->nsegs, copy_stream)) return st;
+  cudaEventRecord((cudaEvent_t)s->ev_copy, cs);
+  s->copy_pending = 1;
+  return cuda_status(cudaGetLastError(), "b2e_pipe_submit");
 }

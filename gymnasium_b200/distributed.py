@@ -288,6 +288,43 @@ class HostBatch:
             pass
 
 
+class _CallRecorder:
+    """Stands in for the ctypes library while a family's ``_step_kernel`` runs: instead of launching, every ``b2e_*`` call is
+    recorded as (function address, machine-word arguments) -- what ``b2e_pipe_submit`` replays from C."""
+
+    def __init__(self, lib):
+        self._lib, self.calls = lib, []
+
+    def __getattr__(self, name):
+        import ctypes as C
+
+        fn = getattr(self._lib, name)
+        if not name.startswith("b2e_"):
+            return fn
+
+        def record(*args):
+            words = []
+            for a in args:
+                if a is None:
+                    words.append(0)
+                elif isinstance(a, int):
+                    words.append(a & ((1 << 64) - 1))
+                elif hasattr(a, "_obj"):  # ctypes.byref(struct): the struct lives as long as the env does
+                    words.append(C.addressof(a._obj))
+                elif isinstance(a, C._SimpleCData):
+                    words.append(int(a.value or 0))
+                elif isinstance(a, float):
+                    raise TypeError(f"{name}: floating-point arguments cannot be replayed as machine words")
+                else:
+                    words.append(C.cast(a, C.c_void_p).value or 0)
+            if len(words) > 16:
+                raise TypeError(f"{name}: more than 16 arguments")
+            self.calls.append((C.cast(fn, C.c_void_p).value, words))
+            return 0
+
+        return record
+
+
 class HostBatchPipeline:
     """Pipelined end-to-end stepping of one shard.  ``submit(host_actions)`` enqueues the pinned H2D copy of the actions and
     the fused step launch on the caller's stream and, on a copy stream, the D2H copies of the step outputs into this rank's
@@ -300,7 +337,7 @@ class HostBatchPipeline:
     """
 
     def __init__(self, env, world_size: int, rank: int, total_envs: int | None = None, tag: str = "0", depth: int = 3,
-                 mode: str = "dma", consumer: int = 0):
+                 mode: str = "dma", consumer: int = 0, fast: bool = True):
         if env.output != "torch" or env.copy or env.out_buffers < depth:
             raise ValueError("HostBatchPipeline needs an env made with output='torch', copy=False, out_buffers >= depth")
         if mode not in ("dma", "nccl"):
@@ -338,6 +375,10 @@ class HostBatchPipeline:
         self._gathered = ([torch.empty((world_size, self.wire_bytes), dtype=torch.uint8, device=dev) for _ in range(depth)]
                           if mode == "nccl" and self.is_consumer else None)
         self._seg_cache: dict = {}
+        # fast path (mode 'dma', numpy-parity RNG): the whole submit is ONE C call, b2e_pipe_submit, replaying the family's
+        # recorded step call(s) -- set up lazily at the first submit, when the action dtype / shape is known
+        self._fast = None if (mode == "dma" and fast and env.rng_mode == "numpy") else False
+        self._slots = None
 
     def _segments(self, k: int, out: dict):
         """ctypes array of the copy segments of step k (cached per (slot, output set))."""
@@ -362,7 +403,87 @@ class HostBatchPipeline:
         self._seg_cache[key] = (arr, len(segs))
         return self._seg_cache[key]
 
+    def _setup_fast(self, a) -> bool:
+        """Builds the b2e_pipe_slot of every (staging buffer, output set, landing slot) triple for host actions shaped and
+        typed like `a`.  Returns False (slow path) if the family's step cannot be replayed from C."""
+        import numpy as np
+
+        C, L = self._C, self._lib_mod
+        env, dev, depth = self.env, self.env.device, self.depth
+        if not isinstance(a, np.ndarray) or a.shape[0] != env.num_envs or a.dtype.kind not in "iuf":
+            return False
+        if not getattr(env, "replayable_step", True):  # the family's step is more than C-ABI calls (e.g. Taxi's fickle passenger)
+            return False
+        if env.discrete_actions and (a.ndim != 1 or a.dtype not in (np.int64, np.int32, np.uint8)):
+            return False
+        if not env.discrete_actions and a.dtype not in (np.float32, np.float64):
+            return False
+        from .vector_env import _ACT_DTYPES
+
+        self._fast_shape, self._fast_dtype = a.shape, a.dtype
+        self._main_handle = torch.cuda.current_stream(dev).cuda_stream
+        self._keep = []  # buffers the slots point into
+        slots = (L.PipeSlot * depth)()
+        for j in range(depth):
+            out = self._rings[j]
+            staging = torch.from_numpy(np.empty(a.shape, dtype=a.dtype)).pin_memory()
+            act_dev = torch.empty(a.shape, dtype=staging.dtype, device=dev)
+            rec = _CallRecorder(env._lib)
+            real = env._lib
+            env._batch.action_dtype = _ACT_DTYPES[act_dev.dtype]
+            env._lib = rec
+            try:
+                with torch.cuda.device(dev):
+                    env._step_kernel(act_dev, out)
+            except TypeError:
+                return False
+            finally:
+                env._lib = real
+            if not rec.calls:
+                return False
+            calls = (L.Call * len(rec.calls))()
+            for c, (fn, words) in zip(calls, rec.calls):
+                c.fn, c.nargs = fn, len(words)
+                for i, wd in enumerate(words):
+                    c.args[i] = wd
+            seg_list = self.host.segments(j, self.rank, {e[0]: out[e[0]].data_ptr() for e in self.layout})
+            bounce = self._seq_dev[j:].data_ptr()
+            seg_list.append((bounce, 0, 0, 0, 8, 1))  # source patched per step by b2e_pipe_submit
+            seg_list.append((self.host.seq_addr(), bounce, 0, 0, 8, 1))
+            segs = (L.CopySeg * len(seg_list))(*[L.CopySeg(*sg) for sg in seg_list])
+            sl = slots[j]
+            sl.staging_host, sl.actions_dev, sl.action_bytes = staging.data_ptr(), act_dev.data_ptr(), a.nbytes
+            sl.calls, sl.ncalls = calls, len(rec.calls)
+            sl.segs, sl.nsegs = segs, len(seg_list)
+            L.check(self._lib.b2e_pipe_slot_init(C.byref(sl)), "b2e_pipe_slot_init")
+            self._keep += [staging, act_dev, calls, segs]
+        self._slots = slots
+        self._ack_addr = self.host._addr + self.host.world * self.host.LINE
+        return True
+
     def submit(self, actions) -> int:
+        if self._fast is None:
+            if not self.env._has_reset:
+                from . import errors
+
+                raise errors.ResetNeeded("Cannot call env.step() before calling env.reset()")
+            self._fast = self._setup_fast(actions)
+        if self._fast:
+            a = actions
+            if getattr(a, "shape", None) != self._fast_shape or a.dtype != self._fast_dtype or not a.flags.c_contiguous:
+                import numpy as np
+
+                a = np.ascontiguousarray(actions, dtype=self._fast_dtype)
+                if a.shape != self._fast_shape:
+                    raise ValueError(f"expected actions of shape {self._fast_shape}, got {a.shape}")
+            k, j = self.k, self.k % self.depth
+            st = self._lib.b2e_pipe_submit(self._C.byref(self._slots[j]), a.ctypes.data, self._main_handle, self._cs_handle,
+                                           self._ack_addr, k - self.depth + 1, self.host.seq_source(k), 120.0)
+            if st:
+                self._lib_mod.check(st, "b2e_pipe_submit")
+            self.env._out = self._rings[j]
+            self.k += 1
+            return k
         k, j = self.k, self.k % self.depth
         env, dev = self.env, self.env.device
         main = torch.cuda.current_stream(dev)
@@ -404,5 +525,10 @@ class HostBatchPipeline:
 
     def close(self) -> None:
         self.drain()
+        if self._slots is not None:
+            torch.cuda.synchronize(self.env.device)
+            for sl in self._slots:
+                self._lib.b2e_pipe_slot_destroy(self._C.byref(sl))
+            self._slots = None
         if self.host is not None:
             self.host.close()

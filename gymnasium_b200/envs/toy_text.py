@@ -187,6 +187,11 @@ class TaxiVectorEnv(TabularVectorEnv):
                 "b2e_taxi_fickle_reset",
             )
 
+    @property
+    def replayable_step(self) -> bool:
+        """False when the step is more than C-ABI calls (distributed.HostBatchPipeline then keeps to the Python path)."""
+        return not self.fickle_passenger
+
     def _step_kernel(self, actions, out):
         if self.fickle_passenger:
             self._prev_state.copy_(self._pstate)

@@ -33,6 +33,7 @@ extern "C" {
 /* error codes */
 #define B2E_EINVAL (-1)  /* bad argument (null pointer, bad enum, n < 0) */
 #define B2E_ENODEV (-2)  /* no CUDA device / wrong architecture */
+#define B2E_ETIMEOUT (-3) /* a host-side wait (b2e_pipe_submit: consumer acknowledgement) timed out */
 
 /* autoreset modes: gymnasium/vector/vector_env.py:34-39 */
 #define B2E_AUTORESET_NEXT_STEP 0
@@ -85,6 +86,38 @@ typedef struct b2e_copy_seg {
 /* Enqueues the device->host copies of `count` segments on `stream`, in order (a trailing 8-byte segment is how a rank publishes
  * its sequence word behind the data). */
 int b2e_copy_to_host_async(const b2e_copy_seg* segs, int32_t count, void* stream);
+
+/* ---- the whole pipelined step in ONE host call: what AsyncVectorEnv.step_async (gymnasium/vector/async_vector_env.py:440-
+ * 475: send the actions to the workers) plus the workers' write of their results into the shared buffer (:849-852) are on
+ * the reference side.  A slot bundles everything that is fixed for one (staging buffer, output set, landing slot) triple:
+ *   staging_host / actions_dev / action_bytes : page-locked staging buffer and the device buffer the step reads actions from
+ *   calls / ncalls : the family's step for this output set, recorded as C-ABI calls of THIS header (function address + its
+ *                    arguments; every argument of every step entry point is a pointer or an integer, i.e. one machine word)
+ *   segs / nsegs   : the landing copies (b2e_copy_seg) of this output set; the last two publish the sequence word
+ *   ev_*           : cudaEvent_t, owned by the slot (b2e_pipe_slot_init / _destroy)
+ * b2e_pipe_submit(slot, host_actions, ...): memcpy into the staging buffer, async H2D on main_stream, the recorded step,
+ * then on copy_stream (ordered after the step) the landing copies -- after the consumer's acknowledgement word *ack_word has
+ * reached need_ack (spin, timeout_s).  Never synchronises a stream; returns B2E_ETIMEOUT if the consumer stalls. */
+typedef struct b2e_call {
+  void* fn;
+  int32_t nargs;
+  int32_t _pad;
+  uint64_t args[16];
+} b2e_call;
+typedef struct b2e_pipe_slot {
+  void* staging_host;
+  void* actions_dev;
+  size_t action_bytes;
+  const b2e_call* calls;
+  b2e_copy_seg* segs;
+  int32_t ncalls, nsegs;
+  void *ev_h2d, *ev_step, *ev_copy;
+  int32_t h2d_pending, copy_pending;
+} b2e_pipe_slot;
+int b2e_pipe_slot_init(b2e_pipe_slot* slot);
+int b2e_pipe_slot_destroy(b2e_pipe_slot* slot);
+int b2e_pipe_submit(b2e_pipe_slot* slot, const void* host_actions, void* main_stream, void* copy_stream,
+                    const int64_t* ack_word, int64_t need_ack, const void* seq_src, double timeout_s);
 
 /* ---- RNG: gymnasium/utils/seeding.py:39-41 -> numpy SeedSequence -> PCG64 ---------------------------------------
  * rng   : uint64 [2][n][2]  = {state(lo,hi)}[n] then {inc(lo,hi)}[n]

@@ -12,8 +12,10 @@ from gymnasium_b200.distributed import HostBatchPipeline
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("env_id,n,steps", [("CartPole-v1", 4096, 40), ("Humanoid-v5", 64, 12), ("FrozenLake-v1", 2048, 30)])
-def test_pipeline_batches_equal_blocking_step(env_id, n, steps):
+@pytest.mark.parametrize("fast", [True, False])
+@pytest.mark.parametrize("env_id,n,steps", [("CartPole-v1", 4096, 40), ("Humanoid-v5", 64, 12), ("FrozenLake-v1", 2048, 30),
+                                            ("LunarLander-v3", 512, 30)])
+def test_pipeline_batches_equal_blocking_step(env_id, n, steps, fast):
     kw = {"map_name": "8x8"} if env_id.startswith("FrozenLake") else {}
     ref = gymnasium_b200.make_vec(env_id, num_envs=n, output="numpy", **kw)
     env = gymnasium_b200.make_vec(env_id, num_envs=n, copy=False, out_buffers=3, **kw)
@@ -24,7 +26,7 @@ def test_pipeline_batches_equal_blocking_step(env_id, n, steps):
         acts = rs.uniform(-0.4, 0.4, size=(steps, n, 17)).astype(np.float32)
     else:
         acts = rs.integers(0, ref.single_action_space.n, size=(steps, n))
-    pipe = HostBatchPipeline(env, 1, 0, tag=f"test_{env_id}", depth=3)
+    pipe = HostBatchPipeline(env, 1, 0, tag=f"test_{env_id}_{int(fast)}", depth=3, fast=fast)
     expect = [ref.step(a) for a in acts]
     got = []
     for k in range(steps):
@@ -32,6 +34,7 @@ def test_pipeline_batches_equal_blocking_step(env_id, n, steps):
         if t >= 1:  # consume one step behind, as the bench loop does
             got.append({key: v.copy() for key, v in pipe.consume(t - 1).items()})
     got.append({key: v.copy() for key, v in pipe.consume(steps - 1).items()})
+    assert bool(pipe._fast) == fast  # fast: every submit was ONE b2e_pipe_submit call replaying the recorded step
     pipe.close()
     for k in range(steps):
         o, r, te, tr, info = expect[k]
