@@ -73,7 +73,7 @@ class LunarLanderCfg(C.Structure):
     """``b2e_lunarlander_cfg``."""
 
     _fields_ = [("gravity", c_double), ("enable_wind", c_i32), ("continuous", c_i32), ("lanes_per_warp", c_i32),
-                ("no_grouping", c_i32)]
+                ("grouping", c_i32)]
 
 
 class LunarLanderState(C.Structure):

@@ -48,7 +48,7 @@ class LunarLanderVectorEnv(B200VectorEnv):
             "flags": torch.zeros(n, dtype=torch.int32, device=dev),
             "prev_shaping": torch.zeros(n, dtype=torch.float64, device=dev),
             "work": torch.zeros(n, dtype=torch.int32, device=dev),    # scheduling key of every env after its last step
-            "order": torch.zeros(n, dtype=torch.int32, device=dev),   # scratch: envs grouped by that key
+            "order": torch.zeros(9 * n + 64, dtype=torch.int32, device=dev),  # scratch: thread slot -> env of a grouped launch
         }
         self._state = _lib.LunarLanderState(ctrl=self._ctrl.data_ptr(), rng=ptr(self._rng),
                                             **{k: v.data_ptr() for k, v in self._s.items()})

@@ -265,7 +265,8 @@ typedef struct b2e_lunarlander_cfg {
   int32_t enable_wind;   /* must be 0 */
   int32_t continuous;    /* must be 0 */
   int32_t lanes_per_warp; /* envs mapped to each warp (1..32); 0 = library default. Fewer lanes = less divergence */
-  int32_t no_grouping;    /* != 0: step envs in index order even when work/order are given (scheduling only) */
+  int32_t grouping;       /* h > 0: envs in free flight share dense warps, envs near the ground get sparse warps of h lanes (clamped to 4..32)
+                             (needs work/order; scheduling only); 0 = off */
 } b2e_lunarlander_cfg;
 
 typedef struct b2e_lunarlander_state {
@@ -279,8 +280,8 @@ typedef struct b2e_lunarlander_state {
   int32_t* ctrl;
   uint64_t* rng;
   int32_t* work;   /* [n] optional (may be NULL with order): scheduling key of every env after its last step */
-  int32_t* order;  /* [n] optional scratch: env indices grouped by `work`; the step kernel then puts envs that walk the
-                      same code paths into the same warp (scheduling only: results do not depend on it) */
+  int32_t* order;  /* [9 * n + 64] optional scratch: env index (or -1) of every thread slot of a grouped launch
+                      (scheduling only: results do not depend on it) */
 } b2e_lunarlander_state;
 
 int b2e_lunarlander_state_words(void);

@@ -15,10 +15,11 @@ def timed(fn, iters, warm):
 
 n = 16384
 for lanes in [int(x) for x in os.environ.get("B2E_LANES", "32,16,8,4,2").split(",")]:
+    print("grouping", os.environ.get("B2E_GROUPING", "0"), end=" ")
     e = gymnasium_b200.make_vec("LunarLander-v3", num_envs=n, copy=False)
     e._cfg.lanes_per_warp = lanes
-    if hasattr(e._cfg, "no_grouping"):
-        e._cfg.no_grouping = int(os.environ.get("B2E_NO_GROUPING", "0"))
+    if hasattr(e._cfg, "grouping"):
+        e._cfg.grouping = int(os.environ.get("B2E_GROUPING", "0"))
     e.reset(seed=0)
     a = torch.randint(0, 4, (8, n), device="cuda")
     k = [0]
