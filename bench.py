@@ -338,7 +338,7 @@ ENV_FACTS = {
     "LunarLander-v3": dict(step_bytes=2 * (41 * 4 + 4 + 8 + 4) + 32 + 8 + 32 + 8 + 2, kernel="lunarlander_step_kernel<int64>",
                            dtype="f32+f64", nact=4, out_bytes=32 + 8 + 1 + 1, act_bytes=8, default_n=16384),
     # qpos/qvel/warmstart/com r+w (72 doubles x 2) + action 17 f32 + obs 348 f64 + reward + info 13 f64 + flags
-    "Humanoid-v5": dict(step_bytes=2 * 72 * 8 + 68 + 348 * 8 + 8 + 13 * 8 + 2 + 8, kernel="humanoid_step_warp_kernel<float, 8>", launches_per_step=2,
+    "Humanoid-v5": dict(step_bytes=2 * 72 * 8 + 68 + 348 * 8 + 8 + 13 * 8 + 2 + 8, kernel="humanoid_step_warp_kernel<float, 10>", launches_per_step=2,
                         dtype="f64", nact=0, out_bytes=348 * 8 + 8 + 13 * 8 + 2, act_bytes=68, default_n=8192),
 }
 

@@ -1440,7 +1440,14 @@ __device__ __noinline__ void solve_toi_island(Lander& L, int dyn, const int* isl
       }
     }
   }
-  for (int it = 0; it < 180; ++it)  // SolveVelocityConstraints: contacts only
+  for (int it = 0; it < 180; ++it) {  // SolveVelocityConstraints: contacts only
+    // Exact early exit: one sweep is a deterministic function of (vB, wB, accumulated impulses).  If a sweep leaves all of
+    // them bit-identical, every later sweep would too -- the remaining iterations are no-ops and can be skipped without
+    // changing a single bit (checked against the oracle, which always runs all 180).  Most TOI sub-steps (one body, one or
+    // two manifolds, no joints, no warm start) reach that fixed point within ~10 sweeps.
+    const V2 v_before = vB;
+    const float w_before = wB;
+    bool impulses_changed = false;
     for (int k = 0; k < n; ++k) {
       VC& vc = vcs[k];
       const V2 normal = vc.normal, tangent = cross_vs(normal, 1.0f);
@@ -1452,6 +1459,7 @@ __device__ __noinline__ void solve_toi_island(Lander& L, int dyn, const int* isl
         const float maxf = vc.friction * p.ni;
         const float newi = clampf(p.ti + lambda, -maxf, maxf);
         lambda = newi - p.ti;
+        impulses_changed |= newi != p.ti;
         p.ti = newi;
         const V2 Pi = lambda * tangent;
         vB = vB + mB * Pi;
@@ -1464,6 +1472,7 @@ __device__ __noinline__ void solve_toi_island(Lander& L, int dyn, const int* isl
         float lambda = -p.normal_mass * (vn - 0.0f);
         const float newi = fmaxf(p.ni + lambda, 0.0f);
         lambda = newi - p.ni;
+        impulses_changed |= newi != p.ni;
         p.ni = newi;
         const V2 Pi = lambda * normal;
         vB = vB + mB * Pi;
@@ -1503,11 +1512,14 @@ __device__ __noinline__ void solve_toi_island(Lander& L, int dyn, const int* isl
           const V2 P1 = dx * normal, P2 = dy * normal;
           vB = vB + mB * (P1 + P2);
           wB += iB * (cross(c1.rB, P1) + cross(c2.rB, P2));
+          impulses_changed |= (xx != c1.ni) | (xy != c2.ni);
           c1.ni = xx;
           c2.ni = xy;
         }
       }
     }
+    if (!impulses_changed && vB.x == v_before.x && vB.y == v_before.y && wB == w_before) break;
+  }
   // the TOI impulses are not stored for warm starting; integrate positions over the rest of the step
   const V2 tr = h * vB;
   if (dot(tr, tr) > kMaxTranslation * kMaxTranslation) {

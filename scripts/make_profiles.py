@@ -12,7 +12,7 @@ src = os.path.join("gpurun_out", tag)
 os.makedirs("profiles", exist_ok=True)
 KEYS = {"step": "cartpole_step_kernel<int64>", "big": "cartpole_step_kernel<int64> N=16M",
         "rollout": "cartpole_rollout_kernel<philox>", "lake": "frozenlake_step_kernel<int64>",
-        "lander": "lunarlander_step_kernel<int64>", "humanoid": "humanoid_step_warp_kernel<float, 8>"}
+        "lander": "lunarlander_step_kernel<int64>", "humanoid": "humanoid_step_warp_kernel<float, 10>"}
 summary, lines = {}, []
 for name, key in KEYS.items():
     p = os.path.join(src, f"ncu_{name}.ncu-rep")
@@ -48,6 +48,14 @@ for name, key in KEYS.items():
         "warp_instructions": r0.get("smsp__inst_executed.sum"),
         "kernel_name": r0.get("Kernel Name"),
         "threads_active_per_instruction": r0.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "tensor_pipe_cycles_active_pct": r0.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+        "tensor_pipe_instructions": r0.get("sm__inst_executed_pipe_tensor.sum"),
+        "fp64_pipe_instructions": r0.get("sm__inst_executed_pipe_fp64.sum"),
+        "fma_pipe_pct": r0.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+        "local_load_sectors": r0.get("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum"),
+        "local_store_sectors": r0.get("l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum"),
+        "l1_hit_rate_pct": r0.get("l1tex__t_sector_hit_rate.pct"),
+        "shared_mem_per_block_dynamic": r0.get("launch__shared_mem_per_block_dynamic"),
         "stall_cycles_per_issue": {k: r0.get(f"smsp__average_warps_issue_stalled_{k}_per_issue_active.ratio")
                                    for k in ("long_scoreboard", "barrier", "wait", "no_instruction", "short_scoreboard",
                                              "branch_resolving", "math_pipe_throttle")},

@@ -15,7 +15,13 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__shared_mem_per_block_dynamic",
-        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers"] + [
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_fp64.sum",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "l1tex__t_sector_hit_rate.pct"] + [
     f"smsp__average_warps_issue_stalled_{k}_per_issue_active.ratio"
     for k in ("barrier", "wait", "no_instruction", "short_scoreboard", "branch_resolving", "math_pipe_throttle")]
 

@@ -241,7 +241,8 @@ def test_lunarlander_grouping_is_scheduling_only():
         for o in outs[1:]:
             for k in range(4):
                 np.testing.assert_array_equal(outs[0][k], o[k], err_msg=f"output {k} differs at step {t}")
-    order = envs[0]._s["order"].cpu().numpy()
+    slots = 32 * ((n + 31) // 32 + (n + 3) // 4)  # dense warps + sparse warps of 4 lanes (lander_group_slots)
+    order = envs[0]._s["order"].cpu().numpy()[:slots]
     assert sorted(order[order >= 0].tolist()) == list(range(n))  # every env owns exactly one thread slot
     work = envs[0]._s["work"].cpu().numpy()
     assert work.min() >= 0 and work.max() <= 63 and len(np.unique(work)) > 3
