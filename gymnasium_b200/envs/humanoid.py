@@ -44,12 +44,24 @@ class HumanoidVectorEnv(B200VectorEnv):
             raise ValueError(f"impl must be one of {sorted(_IMPLS)}, got {impl!r}")
         if xml_file != "humanoid.xml":
             raise NotImplementedError("gymnasium_b200 compiles the stock humanoid.xml only")
-        if not (exclude_current_positions_from_observation and include_cinert_in_observation and include_cvel_in_observation
-                and include_qfrc_actuator_in_observation and include_cfrc_ext_in_observation):
-            raise NotImplementedError("only the default 348-dimensional observation layout is implemented")
+        # observation layout (humanoid_v5.py:376-393, :436-470): the kernel always writes the full 348 columns
+        # qpos[2:] (22) | qvel (23) | cinert[1:] (130) | cvel[1:] (78) | qfrc_actuator[6:] (17) | cfrc_ext[1:] (78); the
+        # non-default flags select columns of it (and prepend qpos[0:2], which the info block carries) on the way out
+        keep = [(0, 45, True), (45, 175, include_cinert_in_observation), (175, 253, include_cvel_in_observation),
+                (253, 270, include_qfrc_actuator_in_observation), (270, 348, include_cfrc_ext_in_observation)]
+        cols = np.concatenate([np.arange(a, b) for a, b, on in keep if on])
+        self._prepend_xy = not exclude_current_positions_from_observation
+        self._obs_cols = None if len(cols) == OBS_SIZE else cols
+        obs_size = len(cols) + (2 if self._prepend_xy else 0)
+        self.observation_structure = {  # humanoid_v5.py:399-407
+            "skipped_qpos": 2 * bool(exclude_current_positions_from_observation),
+            "qpos": 24 - 2 * bool(exclude_current_positions_from_observation), "qvel": 23,
+            "cinert": 130 * bool(include_cinert_in_observation), "cvel": 78 * bool(include_cvel_in_observation),
+            "qfrc_actuator": 17 * bool(include_qfrc_actuator_in_observation),
+            "cfrc_ext": 78 * bool(include_cfrc_ext_in_observation), "ten_length": 0, "ten_velocity": 0}
         if contact_cost_range[0] > 0 or not np.isneginf(contact_cost_range[0]) and contact_cost_range[0] != 0:
             raise NotImplementedError("contact_cost_range lower bounds other than -inf/0 are not implemented")
-        obs_space = Box(low=-np.inf, high=np.inf, shape=(OBS_SIZE,), dtype=np.float64)  # humanoid_v5.py:395-397
+        obs_space = Box(low=-np.inf, high=np.inf, shape=(obs_size,), dtype=np.float64)  # humanoid_v5.py:395-397
         act_space = Box(low=-0.4, high=0.4, shape=(17,), dtype=np.float32)             # ctrlrange, mujoco_env.py:105-110
         super().__init__(num_envs, obs_space, act_space, max_episode_steps=max_episode_steps, render_mode=render_mode,
                          **engine_kwargs)
@@ -177,6 +189,54 @@ class HumanoidVectorEnv(B200VectorEnv):
         if self.autoreset_mode == AutoresetMode.SAME_STEP:
             info.update({"final_obs": out["final_obs"], "_final_obs": done})
         return info
+
+    # ---- non-default observation layouts: column selection on the way out ----------------------------------------------
+    def _shape_obs(self, obs, info_block):
+        if self._obs_cols is None and not self._prepend_xy:
+            return obs
+        host = isinstance(obs, np.ndarray)
+        if self._obs_cols is not None:
+            if host:
+                obs = obs[:, self._obs_cols]
+            else:
+                if not hasattr(self, "_obs_cols_dev"):
+                    self._obs_cols_dev = torch.as_tensor(self._obs_cols, device=self.device)
+                obs = obs.index_select(1, self._obs_cols_dev)
+        if self._prepend_xy:
+            xy = info_block[0:2].T
+            obs = np.concatenate([xy, obs], axis=1) if host else torch.cat([xy, obs], dim=1)
+        return obs
+
+    def _custom_layout(self) -> bool:
+        return self._obs_cols is not None or self._prepend_xy
+
+    def _host_obs(self, host):
+        return self._shape_obs(host["obs"], host["info"])
+
+    def reset(self, *, seed=None, options=None):
+        obs, info = super().reset(seed=seed, options=options)
+        if self._custom_layout():
+            raw = self._pinned_np_info() if isinstance(obs, np.ndarray) else self._out["info"]
+            obs = self._shape_obs(obs, raw)
+        return obs, info
+
+    def step(self, actions):
+        obs, reward, terminated, truncated, info = super().step(actions)
+        if self._custom_layout():
+            if self.autoreset_mode == AutoresetMode.SAME_STEP and self._prepend_xy:
+                raise NotImplementedError("exclude_current_positions_from_observation=False is not available in SAME_STEP mode")
+            raw = self._pinned_np_info() if isinstance(obs, np.ndarray) else self._out["info"]
+            obs = self._shape_obs(obs, raw)
+            if "final_obs" in info:
+                info["final_obs"] = self._shape_obs(info["final_obs"], raw)
+        return obs, reward, terminated, truncated, info
+
+    def _pinned_np_info(self):
+        """The info block [13][n] of the last host copy (output='numpy')."""
+        for k, shape, dt, off, nbytes in self._wire_layout:
+            if k == "info":
+                return self._pinned_np[off:off + nbytes].view(np.float64).reshape(shape)
+        raise KeyError("info")
 
     # introspection -------------------------------------------------------------------------------------------------
     def qpos(self) -> torch.Tensor:

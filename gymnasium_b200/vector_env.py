@@ -434,11 +434,26 @@ class B200VectorEnv(VectorEnv):
         return tuple(self._base_seed + self.env_offset + i for i in range(self.num_envs))
 
     @property
-    def np_random(self):
-        raise AttributeError(
-            "B200VectorEnv keeps its per-env PCG64 streams on the device; read `rng_state()` for the raw "
-            "(state, inc) words (they equal numpy's bit_generator.state for the same seed)."
-        )
+    def np_random(self) -> tuple:
+        """``SyncVectorEnv.np_random`` (sync_vector_env.py:182-185): one ``numpy.random.Generator`` per sub-env.  The live
+        streams are the PCG64 words on the device; these Generators are SNAPSHOTS of them (same state and increment, so they
+        produce exactly the draws the env would make next) -- drawing from them does not advance the env's streams."""
+        words = self.rng_state()
+        if words is None:
+            raise AttributeError("rng='philox' keeps no per-env generator state (stateless counter-based draws)")
+        if not self._seeded:
+            with torch.cuda.device(self.device):
+                self._seed_streams(None, None)
+            words = self.rng_state()
+        gens = []
+        for i in range(self.num_envs):
+            bg = np.random.PCG64()
+            bg.state = {"bit_generator": "PCG64",
+                        "state": {"state": int(words[0, i, 0]) | (int(words[0, i, 1]) << 64),
+                                  "inc": int(words[1, i, 0]) | (int(words[1, i, 1]) << 64)},
+                        "has_uint32": 0, "uinteger": 0}
+            gens.append(np.random.Generator(bg))
+        return tuple(gens)
 
     def rng_state(self) -> np.ndarray | None:
         """uint64 [2][n][2] host copy of the PCG64 (state, inc) words; None in philox mode."""

@@ -781,3 +781,52 @@ def test_first_reset_with_mask_seeds_every_lane_and_np_random_seed_tracks_masked
     env2.reset(options={"reset_mask": mask})
     w2 = env2.rng_state()
     assert (w2[0].any(axis=1)).all() and (w2[1].any(axis=1)).all()
+
+
+@pytest.mark.gpu
+def test_np_random_snapshots_continue_the_device_streams():
+    """SyncVectorEnv.np_random (sync_vector_env.py:182-185): the Generators handed out reproduce the draws the env makes next."""
+    env = make("CartPole-v1", 5)
+    env.reset(seed=40)
+    gens = env.np_random
+    assert len(gens) == 5 and all(isinstance(g, np.random.Generator) for g in gens)
+    for i, g in enumerate(gens):
+        ref = np.random.Generator(np.random.PCG64(np.random.SeedSequence(40 + i)))
+        ref.uniform(-0.05, 0.05, size=4)  # the reset's draws
+        assert g.random() == ref.random()
+    nxt = [g.uniform(-0.05, 0.05, size=4) for g in env.np_random]  # what the next reset of every lane will draw
+    obs, _ = env.reset()
+    np.testing.assert_array_equal(obs, np.asarray(nxt, dtype=np.float64).astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_humanoid_observation_flags_select_columns():
+    """include_*_in_observation / exclude_current_positions_from_observation (humanoid_v5.py:281-300, :436-470)."""
+    full = make("Humanoid-v5", 6)
+    o_full, i_full = full.reset(seed=9)
+    a = np.random.default_rng(0).uniform(-0.4, 0.4, size=(3, 6, 17)).astype(np.float32)
+    small = make("Humanoid-v5", 6, include_cinert_in_observation=False, include_cfrc_ext_in_observation=False)
+    xy = make("Humanoid-v5", 6, exclude_current_positions_from_observation=False, include_cvel_in_observation=False,
+              include_qfrc_actuator_in_observation=False)
+    o_small, _ = small.reset(seed=9)
+    o_xy, _ = xy.reset(seed=9)
+    assert small.single_observation_space.shape == (348 - 130 - 78,) and xy.single_observation_space.shape == (348 - 78 - 17 + 2,)
+    assert small.observation_structure["cinert"] == 0 and xy.observation_structure["skipped_qpos"] == 0
+
+    def check(of, info, os_, ox):
+        np.testing.assert_array_equal(os_, np.concatenate([of[:, :45], of[:, 175:270]], axis=1))
+        np.testing.assert_array_equal(ox[:, 0], info["x_position"])
+        np.testing.assert_array_equal(ox[:, 1], info["y_position"])
+        np.testing.assert_array_equal(ox[:, 2:], np.concatenate([of[:, :175], of[:, 270:]], axis=1))
+
+    check(o_full, i_full, o_small, o_xy)
+    for t in range(3):
+        of, rf, _, _, info = full.step(a[t])
+        os_, rs_, _, _, _ = small.step(a[t])
+        ox, rx, _, _, _ = xy.step(a[t])
+        check(of, info, os_, ox)
+        np.testing.assert_array_equal(rf, rs_)
+        np.testing.assert_array_equal(rf, rx)
+    t_env = make("Humanoid-v5", 4, include_cinert_in_observation=False, output="torch")
+    o, _ = t_env.reset(seed=1)
+    assert tuple(o.shape) == (4, 218) and o.is_cuda
