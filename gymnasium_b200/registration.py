@@ -44,6 +44,7 @@ ENVS = {
                        "gymnasium.envs.box2d.lunar_lander:LunarLander", 1000, 200, {}),
     "Humanoid-v5": ("gymnasium_b200.envs.humanoid:HumanoidVectorEnv",
                     "gymnasium.envs.mujoco.humanoid_v5:HumanoidEnv", 1000, None, {}),
+    "Hopper-v5": ("gymnasium_b200.envs.hopper:HopperVectorEnv", "gymnasium.envs.mujoco.hopper_v5:HopperEnv", 1000, 3800.0, {}),
 }
 NAMESPACE = "B200"
 

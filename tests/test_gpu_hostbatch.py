@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("fast", [True, False])
 @pytest.mark.parametrize("env_id,n,steps", [("CartPole-v1", 4096, 40), ("Humanoid-v5", 64, 12), ("FrozenLake-v1", 2048, 30),
-                                            ("LunarLander-v3", 512, 30)])
+                                            ("LunarLander-v3", 512, 30), ("Hopper-v5", 256, 30)])
 def test_pipeline_batches_equal_blocking_step(env_id, n, steps, fast):
     kw = {"map_name": "8x8"} if env_id.startswith("FrozenLake") else {}
     ref = gymnasium_b200.make_vec(env_id, num_envs=n, output="numpy", **kw)
@@ -24,6 +24,8 @@ def test_pipeline_batches_equal_blocking_step(env_id, n, steps, fast):
     rs = np.random.default_rng(5)
     if env_id == "Humanoid-v5":
         acts = rs.uniform(-0.4, 0.4, size=(steps, n, 17)).astype(np.float32)
+    elif env_id == "Hopper-v5":
+        acts = rs.uniform(-1.0, 1.0, size=(steps, n, 3)).astype(np.float32)
     else:
         acts = rs.integers(0, ref.single_action_space.n, size=(steps, n))
     pipe = HostBatchPipeline(env, 1, 0, tag=f"test_{env_id}_{int(fast)}", depth=3, fast=fast)

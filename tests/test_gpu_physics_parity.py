@@ -246,3 +246,72 @@ def test_lunarlander_grouping_is_scheduling_only():
     assert sorted(order[order >= 0].tolist()) == list(range(n))  # every env owns exactly one thread slot
     work = envs[0]._s["work"].cpu().numpy()
     assert work.min() >= 0 and work.max() <= 63 and len(np.unique(work)) > 3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Hopper-v5 (the Humanoid solver generalised to another MuJoCo robot); checker = oracle/hopper.c
+@pytest.mark.parametrize("n,T,dtype", [(512, 130, np.float32), (8192, 70, np.float32), (64, 60, np.float64)])
+def test_hopper_matches_oracle_bit_exact(n, T, dtype):
+    from oracle.hopper import OracleHopper
+
+    seed = 21
+    rs = np.random.default_rng(3)
+    idx = np.arange(n) if n <= 512 else np.sort(rs.choice(n, size=256, replace=False))
+    env = make("Hopper-v5", n)
+    ora = OracleHopper(len(idx))
+    o1, i1 = env.reset(seed=seed)
+    o2, i2 = ora.reset(seed=[seed + int(i) for i in idx])
+    assert o1.shape == (n, 11) and o1.dtype == np.float64
+    np.testing.assert_array_equal(o1[idx], o2)
+    np.testing.assert_array_equal(i1["z_distance_from_origin"][idx], i2["z_distance_from_origin"])
+    resets = np.zeros(len(idx), dtype=np.int64)
+    for t in range(T):
+        a = rs.uniform(-1.0, 1.0, size=(n, 3)).astype(dtype)
+        x = env.step(a)
+        if dtype == np.float64:  # the oracle's control cost is the float32 one; compare everything but reward_ctrl / reward
+            y = ora.step(a[idx].astype(np.float32))
+            if (a[idx].astype(np.float32).astype(np.float64) != a[idx]).any():
+                np.testing.assert_array_equal(x[2][idx], y[2])
+                break  # float64 actions that are not float32-representable drive a (slightly) different trajectory
+        else:
+            y = ora.step(a[idx])
+        np.testing.assert_array_equal(x[0][idx], y[0], err_msg=f"obs differ at step {t}")
+        np.testing.assert_array_equal(x[1][idx], y[1], err_msg=f"reward differs at step {t}")
+        np.testing.assert_array_equal(x[2][idx], y[2])
+        np.testing.assert_array_equal(x[3][idx], y[3])
+        for k in ("x_position", "x_velocity", "reward_forward", "reward_ctrl", "reward_survive"):
+            np.testing.assert_array_equal(x[4][k][idx], y[4][k], err_msg=k)
+        total = x[4]["reward_forward"] + x[4]["reward_survive"] + x[4]["reward_ctrl"]
+        assert (x[1] == total).all()  # tests/envs/mujoco/test_mujoco_v5.py:236-241, exact
+        resets += y[2] | y[3]
+    if dtype == np.float32:
+        assert (resets >= 1).mean() > 0.9  # random policies fall within ~25 steps: autoresets were crossed
+    assert not env.buffer_overflow()
+
+
+def test_hopper_sharding_and_api():
+    import torch
+
+    whole = make("Hopper-v5", 96, max_episode_steps=30)
+    parts = [make("Hopper-v5", 40, env_offset=0, max_episode_steps=30), make("Hopper-v5", 56, env_offset=40, max_episode_steps=30)]
+    ow, _ = whole.reset(seed=8)
+    np.testing.assert_array_equal(ow, np.concatenate([p.reset(seed=8)[0] for p in parts]))
+    rs = np.random.default_rng(2)
+    for t in range(70):
+        a = rs.uniform(-1, 1, size=(96, 3)).astype(np.float32)
+        xw = whole.step(a)
+        xp = [parts[0].step(a[:40]), parts[1].step(a[40:])]
+        for k in range(4):
+            np.testing.assert_array_equal(xw[k], np.concatenate([xp[0][k], xp[1][k]]), err_msg=f"output {k} at step {t}")
+    t_env = make("Hopper-v5", 4, output="torch")
+    o, info = t_env.reset(seed=1)
+    assert o.dtype == torch.float64 and tuple(o.shape) == (4, 11) and set(info) >= {"x_position", "_x_position"}
+    assert t_env.single_action_space.shape == (3,) and float(t_env.single_action_space.high[0]) == 1.0
+    with pytest.raises(ValueError, match="Action dimension mismatch"):
+        t_env.step(np.zeros((4, 2), dtype=np.float32))
+    same = make("Hopper-v5", 16, autoreset_mode="SameStep", max_episode_steps=9)
+    same.reset(seed=0)
+    for t in range(12):
+        _, _, te, tr, info = same.step(np.zeros((16, 3), dtype=np.float32))
+        np.testing.assert_array_equal(info["_final_obs"], te | tr)
+        np.testing.assert_array_equal(info["_x_velocity"], ~(te | tr))

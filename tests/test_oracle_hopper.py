@@ -1,0 +1,95 @@
+"""Hopper-v5 oracle (oracle/hopper.c, MuJoCo-subset restatement; PARITY UNPINNED -- mujoco is not installable here).  What CAN
+be pinned: the reference's structural checks for this boundary, analytic known answers, self-consistency."""
+import numpy as np
+
+from oracle.hopper import NB, OracleHopper
+
+
+def test_model_sizes_and_masses():
+    """nq = nv = 6, nu = 3, nbody = 5 (world + 4), observation 11 (tests/envs/mujoco/test_mujoco_v5.py:538-547 lists the
+    model sizes of every v5 env; hopper_v5.py:232-236 the observation).  Body masses = capsule volumes x density 1000."""
+    env = OracleHopper(2)
+    obs, info = env.reset(seed=3)
+    assert obs.shape == (2, 11) and set(info) >= {"x_position", "z_distance_from_origin"}
+    mass, misc, inv = env.model_info()
+    assert len(mass) == NB == 5 and mass[0] == 0
+
+    def capsule(r, half):
+        return 1000.0 * (np.pi * r * r * 2 * half + 4.0 / 3.0 * np.pi * r ** 3)
+
+    np.testing.assert_allclose(mass[1:], [capsule(0.05, 0.2), capsule(0.05, 0.225), capsule(0.04, 0.25), capsule(0.06, 0.195)],
+                               rtol=1e-12)
+    assert misc[1] == 7  # floor x 4 body geoms + torso-leg, torso-foot, thigh-foot
+
+
+def test_noise_free_reset_is_the_init_state_and_free_fall_known_answer():
+    """reset_noise_scale = 0 => qpos = qpos0 = (0, 1.25, 0, 0, 0, 0) (the `ref` of rootz), qvel = 0.  Until the foot reaches the
+    floor the only external force is gravity: the mass centre falls with z(t) = z0 - g t^2 / 2 exactly under RK4 (the joint
+    armature of 1 kg m^2 on the three leg hinges is rotor inertia outside the body masses: identity to ~1e-6)."""
+    env = OracleHopper(1, reset_noise_scale=0.0)
+    obs, info = env.reset(seed=0)
+    np.testing.assert_array_equal(obs[0], [1.25] + [0.0] * 10)
+    mass, _, _ = env.model_info()
+    M = mass.sum()
+    xipos0 = env.debug(0)[4]
+    z0 = (mass * xipos0[:, 2]).sum() / M
+    free = 0
+    for k in range(12):
+        obs, r, te, tr, info = env.step(np.zeros((1, 3), dtype=np.float32))
+        qpos, qvel, qacc, counts, xipos = env.debug(0)
+        if counts[0] > 0:
+            break
+        t = (k + 1) * 4 * 0.002
+        # xipos is from the last mj_forward of the step = RK4 stage 4 of the last sub-step, evaluated at time t
+        zc = (mass * xipos[:, 2]).sum() / M
+        assert abs(zc - (z0 - 0.5 * 9.81 * t * t)) < 5e-6, (k, zc)
+        assert abs((mass * xipos[:, 0]).sum() / M - (mass * xipos0[:, 0]).sum() / M) < 1e-9
+        assert r[0] == 1.0 and info["reward_ctrl"][0] == 0.0  # healthy, zero control
+        free += 1
+    assert free >= 8
+
+
+def test_reward_identity_health_and_termination():
+    """reward == reward_forward + reward_survive + reward_ctrl (tests/envs/mujoco/test_mujoco_v5.py:236-241, exact ==);
+    unhealthy (z <= 0.7 or |angle| >= 0.2) terminates with reward_survive 0; random policies fall within ~20-30 steps."""
+    n = 48
+    env = OracleHopper(n)
+    env.reset(seed=5)
+    rs = np.random.default_rng(1)
+    lens, cur, nterm = [], np.zeros(n, int), 0
+    prev_done = np.zeros(n, bool)
+    for t in range(150):
+        a = rs.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+        obs, r, te, tr, info = env.step(a)
+        live = ~prev_done
+        total = info["reward_forward"] + info["reward_survive"] + info["reward_ctrl"]
+        assert (r[live] == total[live]).all()
+        assert (r[prev_done] == 0).all() and not te[prev_done].any()
+        assert (info["reward_survive"][live & te] == 0).all() and (info["reward_survive"][live & ~te] == 1.0).all()
+        z, ang = obs[:, 0], obs[:, 1]
+        assert ((z[live & ~te] > 0.7) & (np.abs(ang[live & ~te]) < 0.2)).all()
+        # float32 control cost of the float32 action (NumPy 2 / NEP 50): -1e-3 * sum(a^2) in float32
+        want = -(np.float32(1e-3) * (a[:, 0] * a[:, 0] + a[:, 1] * a[:, 1] + a[:, 2] * a[:, 2])).astype(np.float64)
+        np.testing.assert_array_equal(info["reward_ctrl"][live], want[live])
+        assert np.abs(obs[:, 5:]).max() <= 10.0
+        cur += 1
+        for i in np.nonzero(te | tr)[0]:
+            lens.append(cur[i]); cur[i] = 0
+        nterm += int(te.sum())
+        prev_done = te | tr
+    assert nterm > n and 8 < np.mean(lens) < 60
+
+
+def test_determinism_and_seeding():
+    a, b, c = OracleHopper(3), OracleHopper(3), OracleHopper(3)
+    oa, _ = a.reset(seed=11)
+    ob, _ = b.reset(seed=11)
+    oc, _ = c.reset(seed=12)
+    np.testing.assert_array_equal(oa, ob)
+    assert not np.array_equal(oa, oc)
+    np.testing.assert_array_equal(oa[1], oc[0])  # sub-env i is seeded seed + i
+    # reset noise: qpos0 + U(-5e-3, 5e-3) from numpy's stream, 6 qpos draws then 6 qvel draws (hopper_v5.py:322-337)
+    g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(11)))
+    qpos = np.array([0, 1.25, 0, 0, 0, 0]) + g.uniform(-5e-3, 5e-3, size=6)
+    qvel = g.uniform(-5e-3, 5e-3, size=6)
+    np.testing.assert_array_equal(oa[0], np.concatenate([qpos[1:], np.clip(qvel, -10, 10)]))
