@@ -160,7 +160,7 @@ def run_reference(args):
         have_ref, why = False, repr(e)
 
     alternatives = {}
-    if have_ref and args.env in ("LunarLander-v3", "Humanoid-v5"):
+    if have_ref and args.env in ("LunarLander-v3", "Humanoid-v5", "Hopper-v5"):
         have_ref, why = False, "Box2D / mujoco wheels are not installable here (no runnable reference for this env)"
     if have_ref:
         import warnings
@@ -241,18 +241,22 @@ def run_reference(args):
             from oracle.humanoid import OracleHumanoid
 
             n, env = 64, OracleHumanoid(64)
+        elif args.env == "Hopper-v5":
+            from oracle.hopper import OracleHopper
+
+            n, env = 256, OracleHopper(256)
         elif args.env.startswith("CartPole"):
             n = args.num_envs or 65536
             env = OracleCartPole(n)
         else:
             n, env = 4096, OracleFrozenLake(4096, map_name="8x8")
-        if args.env in ("LunarLander-v3", "Humanoid-v5"):
+        if args.env in ("LunarLander-v3", "Humanoid-v5", "Hopper-v5"):
             # the C restatement releases the GIL inside its ctypes call: one env batch per host thread, all host cores
             import threading
 
             T = max(1, min(cores, 256))
             cls = type(env)
-            n = {"LunarLander-v3": 2048, "Humanoid-v5": 128}[args.env]  # long calls: the GIL-held wrapper code stays < 1 %
+            n = {"LunarLander-v3": 2048, "Humanoid-v5": 128, "Hopper-v5": 1024}[args.env]  # long calls: the GIL-held wrapper code stays < 1 %
             pool = host_action_pool(np, args.env, 8, n, 0)
             envs = [cls(n) for _ in range(T)]
             for t, e in enumerate(envs):
@@ -340,6 +344,9 @@ ENV_FACTS = {
     # qpos/qvel/warmstart/com r+w (72 doubles x 2) + action 17 f32 + obs 348 f64 + reward + info 13 f64 + flags
     "Humanoid-v5": dict(step_bytes=2 * 72 * 8 + 68 + 348 * 8 + 8 + 13 * 8 + 2 + 8, kernel="humanoid_step_warp_kernel<float, 10>", launches_per_step=2,
                         dtype="f64", nact=0, out_bytes=348 * 8 + 8 + 13 * 8 + 2, act_bytes=68, default_n=8192),
+    # qpos/qvel/warmstart r+w (18 doubles x 2) + action 3 f32 + obs 11 f64 + reward + info 6 f64 + flags + ctrl
+    "Hopper-v5": dict(step_bytes=2 * 18 * 8 + 12 + 11 * 8 + 8 + 6 * 8 + 2 + 8, kernel="hopper_step_kernel<float>", dtype="f64",
+                      nact=0, act_dim=3, act_range=1.0, out_bytes=11 * 8 + 8 + 6 * 8 + 2, act_bytes=12, default_n=16384),
 }
 
 
@@ -347,10 +354,11 @@ def device_actions(torch, env_id, shape_prefix, n, dev, gen=None):
     f = ENV_FACTS[env_id]
     if f["nact"]:
         return torch.randint(0, f["nact"], (*shape_prefix, n), device=dev, dtype=torch.int64, generator=gen)
-    return (torch.rand((*shape_prefix, n, 17), device=dev, generator=gen) * 0.8 - 0.4).float()
+    k, r = f.get("act_dim", 17), f.get("act_range", 0.4)
+    return (torch.rand((*shape_prefix, n, k), device=dev, generator=gen) * (2 * r) - r).float()
 
 
-FLOP_BOUND = ("Humanoid-v5", "LunarLander-v3")  # families whose bound is SIMT arithmetic latency/throughput, not HBM
+FLOP_BOUND = ("Humanoid-v5", "LunarLander-v3", "Hopper-v5")  # families whose bound is SIMT arithmetic latency/throughput, not HBM
 
 
 def measure_fma_peak(torch, dev, fp64):
@@ -387,6 +395,12 @@ def flop_roofline(env_id, steps_per_s_per_gpu, peak_tflops, cpu_baseline):
         model = (f"20 x (30k smooth + 10k collision + nefc(2 nv^2 + 2 nefc nv) + sweeps 2 nefc^2) + 2k, nv=23, "
                  f"nefc={nefc:.2f}, sweeps={sweeps:.2f} ({'measured on the oracle sample of this run' if st else 'oracle sample of ' + HUMANOID_NOMINAL_STATS['source']})")
         dtype = "f64"
+    elif env_id == "Hopper-v5":
+        nv, nefc, sweeps = 6, 5.0, 20.0
+        f_fwd = 4e3 + 1e3 + nefc * (2 * nv * nv + 2 * nefc * nv) + sweeps * 2 * nefc * nefc
+        flops = 16 * f_fwd  # frame_skip 4 x RK4
+        model, dtype = ("16 x (4k smooth + 1k collision + nefc(2 nv^2 + 2 nefc nv) + sweeps 2 nefc^2), nv=6, nominal nefc=5, "
+                        "sweeps=20 (SURVEY 8d formula scaled to the 6-dof model)"), "f64"
     else:
         flops, model, dtype = 47.5e3, "nominal 45-50 kflop per Box2D step (180 velocity + 60 position iterations)", "f32"
     achieved = flops * steps_per_s_per_gpu / 1e12
@@ -427,11 +441,12 @@ def host_action_pool(np, env_id, count, n, seed):
     rs = np.random.default_rng(seed)
     if f["nact"]:
         return rs.integers(0, f["nact"], size=(count, n)).astype(np.int64)
-    return rs.uniform(-0.4, 0.4, size=(count, n, 17)).astype(np.float32)
+    k, r = f.get("act_dim", 17), f.get("act_range", 0.4)
+    return rs.uniform(-r, r, size=(count, n, k)).astype(np.float32)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-BURN_IN = {"LunarLander-v3": 120, "Humanoid-v5": 60}  # untimed steps per batch that bring a physics family to its steady mix
+BURN_IN = {"LunarLander-v3": 120, "Humanoid-v5": 60, "Hopper-v5": 40}  # untimed steps per batch that bring a physics family to its steady mix
 PIPE_DEPTH = 3
 # constraint rows / PGS sweeps per mj_forward of the random-action steady state (oracle sample, profiles/r1_bench_humanoid.json);
 # used for the FLOP model when the run has no fresh oracle sample (N > 1)
@@ -704,7 +719,7 @@ def family_block(cx, args, env_id, n, K, W, with_sync_e2e, fma_cache, cpu_baseli
     per_gpu = res["value"] / cx.world
     kernel_s = res["elapsed_s"] / res["timed_steps"]
     if env_id in FLOP_BOUND:
-        fp64 = env_id == "Humanoid-v5"
+        fp64 = env_id in ("Humanoid-v5", "Hopper-v5")
         if fp64 not in fma_cache:
             fma_cache[fp64] = measure_fma_peak(cx.torch, cx.dev, fp64=fp64)
         roof = flop_roofline(env_id, per_gpu, fma_cache[fp64], cpu_baseline)
@@ -784,6 +799,8 @@ def run_b200(args):
             extras["frozenlake_8x8_1M"]["cpu_baseline"] = cpu_other["FrozenLake-v1"]
         if "lunarlander_16384" in extras:
             extras["lunarlander_16384"]["cpu_baseline"] = cpu_other["LunarLander-v3"]
+        if "hopper_16384" in extras:
+            extras["hopper_16384"]["cpu_baseline"] = cpu_baseline_subprocess(args, "Hopper-v5", 16384, 6)
 
     clocks = cx.sampler.stop() if cx.sampler else None
     if rank == 0:
@@ -942,6 +959,25 @@ def run_extras(args, cx, gymnasium_b200, env0, acts0, fma_cache):
                                     "roofline": flop_roofline("LunarLander-v3", nl / t, fma_cache[False], None),
                                     "note": "one fused step+autoreset launch per call, random actions, steady state after 120 "
                                             "burn-in steps; bit-exact vs oracle/lunar_lander.c (Box2D parity unpinned)"}
+        # (6) SURVEY 8f rank 4: Hopper-v5 (the Humanoid solver on another MuJoCo robot), 16384 envs
+        nh = 16384
+        hp = gymnasium_b200.make_vec("Hopper-v5", num_envs=nh, device=dev, copy=False)
+        hp.reset(seed=0)
+        ha = (torch.rand((8, nh, 3), device=dev) * 2 - 1).float()
+        k = [0]
+
+        def hstep():
+            hp.step(ha[k[0] % 8])
+            k[0] += 1
+
+        t = timed(hstep, 20, warm=BURN_IN["Hopper-v5"])
+        if True not in fma_cache:
+            fma_cache[True] = measure_fma_peak(torch, dev, fp64=True)
+        out["hopper_16384"] = {"steps_per_s": nh / t, "us_per_launch": t * 1e6,
+                               "roofline": flop_roofline("Hopper-v5", nh / t, fma_cache[True], None),
+                               "note": "Hopper-v5, one thread per env, random actions U[-1,1]^3, steady state after 40 burn-in "
+                                       "steps; bit-exact vs oracle/hopper.c (MuJoCo parity unpinned)"}
+        del hp
         for big in (131072, 1048576):
             ll = gymnasium_b200.make_vec("LunarLander-v3", num_envs=big, device=dev, copy=False)
             ll.reset(seed=0)
