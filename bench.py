@@ -447,7 +447,13 @@ def host_action_pool(np, env_id, count, n, seed):
 
 # ----------------------------------------------------------------------------------------------------------------------
 BURN_IN = {"LunarLander-v3": 120, "Humanoid-v5": 60, "Hopper-v5": 40}  # untimed steps per batch that bring a physics family to its steady mix
-PIPE_DEPTH = 3
+PIPE_DEPTH = 3  # output sets / host slots in flight (see pipe_depth())
+
+
+def pipe_depth(env_id):
+    """Deeper for the families whose step is much shorter than the host's per-step work: the ranks then run ahead of the
+    consumer by several steps and per-step jitter (scheduling, the consumer's own submit) averages out instead of stalling all ranks."""
+    return 8 if env_id in ("CartPole-v1", "FrozenLake-v1") else PIPE_DEPTH
 # constraint rows / PGS sweeps per mj_forward of the random-action steady state (oracle sample, profiles/r1_bench_humanoid.json);
 # used for the FLOP model when the run has no fresh oracle sample (N > 1)
 HUMANOID_NOMINAL_STATS = {"mean_nefc": 2.71, "mean_pgs_sweeps": 12.29, "source": "profiles/r1_bench_humanoid.json"}
@@ -620,7 +626,8 @@ def measure_e2e(cx, args, env_id, n, mode, tag):
     torch, np, dev, rank, world = cx.torch, cx.np, cx.dev, cx.rank, cx.world
     facts = ENV_FACTS[env_id]
     kw = env_kwargs(env_id)
-    env = gymnasium_b200.make_vec(env_id, num_envs=n, device=dev, copy=False, out_buffers=PIPE_DEPTH, env_offset=rank * n, **kw)
+    depth = pipe_depth(env_id)
+    env = gymnasium_b200.make_vec(env_id, num_envs=n, device=dev, copy=False, out_buffers=depth, env_offset=rank * n, **kw)
     env.reset(seed=0)
     burn = BURN_IN.get(env_id, 0)
     if burn:  # same steady-state mix as the device-resident batches (untimed set-up)
@@ -629,7 +636,7 @@ def measure_e2e(cx, args, env_id, n, mode, tag):
         for k in range(burn):
             env.step(dev_pool[k % 4])
         torch.cuda.synchronize()
-    pipe = HostBatchPipeline(env, world, rank, tag=tag, depth=PIPE_DEPTH, mode=mode)
+    pipe = HostBatchPipeline(env, world, rank, tag=tag, depth=depth, mode=mode)
     host_actions = host_action_pool(np, env_id, 16, n, rank)
     check = {}
 
@@ -667,7 +674,7 @@ def measure_e2e(cx, args, env_id, n, mode, tag):
     del env
     return {"value": world * Ke * n / elapsed, "unit": UNIT, "h2d_bytes_per_step": n * facts["act_bytes"],
             "d2h_bytes_per_step": n * facts["out_bytes"], "steps": Ke, "ms_per_step": elapsed / Ke * 1e3,
-            "host_batch_ok": ok, "pipeline_depth": PIPE_DEPTH,
+            "host_batch_ok": ok, "pipeline_depth": depth,
             "path": ("gymnasium_b200.distributed.HostBatchPipeline(make_vec(...)).submit(host numpy actions) / .consume(): pinned "
                      "H2D of the actions + fused step launch + " +
                      ("D2H of every rank's rows over its own PCIe link into ONE page-locked host batch shared by all ranks"

@@ -100,8 +100,8 @@ class HumanoidState(C.Structure):
                                            "order")]
 
 
-class HopperCfg(C.Structure):
-    """``b2e_hopper_cfg``."""
+class MjPlanarCfg(C.Structure):
+    """``b2e_mjplanar_cfg`` (Hopper-v5, Walker2d-v5)."""
 
     _fields_ = [(k, c_double) for k in ("reset_noise_scale", "forward_reward_weight", "ctrl_cost_weight", "healthy_reward",
                                         "healthy_z_min", "healthy_z_max", "healthy_angle_min", "healthy_angle_max",
@@ -109,8 +109,8 @@ class HopperCfg(C.Structure):
         ("terminate_when_unhealthy", c_i32), ("frame_skip", c_i32), ("lanes_per_warp", c_i32), ("_pad", c_i32)]
 
 
-class HopperState(C.Structure):
-    """``b2e_hopper_state`` (device pointers)."""
+class MjPlanarState(C.Structure):
+    """``b2e_mjplanar_state`` (device pointers)."""
 
     _fields_ = [(k, c_void_p) for k in ("qpos", "qvel", "qacc_warmstart", "ctrl", "rng", "overflow")]
 
@@ -173,8 +173,11 @@ SIGNATURES = {
     "b2e_humanoid_reset": (C.c_int, [_BP, C.POINTER(HumanoidCfg), C.POINTER(HumanoidState), P, P, P, P]),
     "b2e_humanoid_step": (C.c_int, [_BP, C.POINTER(HumanoidCfg), C.POINTER(HumanoidState), P, P, P, P, P, P, P, P]),
     "b2e_hopper_model_info": (C.c_int, [P, P, P]),
-    "b2e_hopper_reset": (C.c_int, [_BP, C.POINTER(HopperCfg), C.POINTER(HopperState), P, P, P, P]),
-    "b2e_hopper_step": (C.c_int, [_BP, C.POINTER(HopperCfg), C.POINTER(HopperState), P, P, P, P, P, P, P, P]),
+    "b2e_hopper_reset": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P]),
+    "b2e_hopper_step": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P, P, P, P, P]),
+    "b2e_walker2d_model_info": (C.c_int, [P, P, P]),
+    "b2e_walker2d_reset": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P]),
+    "b2e_walker2d_step": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P, P, P, P, P]),
     "b2e_frozenlake_reset": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P]),
     "b2e_frozenlake_step": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), P, P, P, P, P, P, P, P, P, P, P, P]),
     "b2e_frozenlake_rollout": (C.c_int, [_BP, C.POINTER(FrozenLakeCfg), c_i32, P, P, P, P, P, P, P, P, P, P]),

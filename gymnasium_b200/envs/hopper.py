@@ -1,10 +1,10 @@
-"""Hopper-v5 on the B200 engine.
+"""Hopper-v5 and Walker2d-v5 on the B200 engine.
 
-Mirrors ``HopperEnv`` v5 (gymnasium/envs/mujoco/hopper_v5.py:24-343) and the ``MujocoEnv`` plumbing it uses
-(gymnasium/envs/mujoco/mujoco_env.py:35-229) behind the vector API with SyncVectorEnv's conventions; the multibody dynamics
-the reference delegates to the MuJoCo wheel run in ``gymnasium_b200/csrc/hopper.cu`` (the articulated-body / PGS core of the
-Humanoid kernel generalised to slide + hinge joints).  Numeric parity with the real MuJoCo wheel is unpinned (it cannot be
-installed here); see DESIGN.md.
+Mirror ``HopperEnv`` v5 (gymnasium/envs/mujoco/hopper_v5.py:24-343) and ``Walker2dEnv`` v5 (walker2d_v5.py:24-342) and the
+``MujocoEnv`` plumbing they use (gymnasium/envs/mujoco/mujoco_env.py:35-229) behind the vector API with SyncVectorEnv's
+conventions; the multibody dynamics the reference delegates to the MuJoCo wheel run in ``gymnasium_b200/csrc/mjc_planar.cuh``
+(the articulated-body / PGS core of the Humanoid kernel generalised to slide + hinge joints).  Numeric parity with the real
+MuJoCo wheel is unpinned (it cannot be installed here); see DESIGN.md.
 """
 from __future__ import annotations
 
@@ -18,36 +18,38 @@ from .._api import AutoresetMode, Box
 from ..vector_env import B200VectorEnv, ptr
 
 INFO_KEYS = ("x_position", "z_distance_from_origin", "x_velocity", "reward_forward", "reward_ctrl", "reward_survive")
-OBS_SIZE = 5 + 6  # qpos[1:] | clip(qvel, -10, 10)  (hopper_v5.py:232-236, :253-261)
 
 
-class HopperVectorEnv(B200VectorEnv):
-    """N Hopper-v5 envs.  Observation ``(N, 11) float64``, action ``(N, 3) float32`` in [-1, 1], reward float64, info = the
-    keys of ``HopperEnv.step`` as ``(N,)`` arrays with their ``_key`` masks."""
+class _MjPlanarVectorEnv(B200VectorEnv):
+    """Shared host logic of the planar MuJoCo robots: observation ``(N, 2 nq - 1) float64`` = qpos[1:] | clip(qvel, -10, 10),
+    action ``(N, nu) float32`` in [-1, 1], reward float64, info = the keys of the env's ``step`` as ``(N,)`` arrays with
+    their ``_key`` masks."""
 
     metadata = {"render_modes": [], "render_fps": 125, "autoreset_mode": AutoresetMode.NEXT_STEP}
     discrete_actions = False
     soa_output_keys = ("info",)
+    robot, xml, NQ, NU = "hopper", "hopper.xml", 6, 3
 
-    def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 1000, xml_file: str = "hopper.xml",
-                 frame_skip: int = 4, forward_reward_weight: float = 1.0, ctrl_cost_weight: float = 1e-3,
-                 healthy_reward: float = 1.0, terminate_when_unhealthy: bool = True,
-                 healthy_state_range=(-100.0, 100.0), healthy_z_range=(0.7, float("inf")),
-                 healthy_angle_range=(-0.2, 0.2), reset_noise_scale: float = 5e-3,
-                 exclude_current_positions_from_observation: bool = True, render_mode: str | None = None, **engine_kwargs):
-        if xml_file != "hopper.xml":
-            raise NotImplementedError("gymnasium_b200 compiles the stock hopper.xml only")
+    def __init__(self, num_envs, max_episode_steps, xml_file, frame_skip, forward_reward_weight, ctrl_cost_weight,
+                 healthy_reward, terminate_when_unhealthy, healthy_state_range, healthy_z_range, healthy_angle_range,
+                 reset_noise_scale, exclude_current_positions_from_observation, render_mode, engine_kwargs):
+        if xml_file != self.xml:
+            raise NotImplementedError(f"gymnasium_b200 compiles the stock {self.xml} only")
         if not exclude_current_positions_from_observation:
-            raise NotImplementedError("only the default 11-dimensional observation layout is implemented")
-        obs_space = Box(low=-np.inf, high=np.inf, shape=(OBS_SIZE,), dtype=np.float64)  # hopper_v5.py:237-239
-        act_space = Box(low=-1.0, high=1.0, shape=(3,), dtype=np.float32)               # ctrlrange, mujoco_env.py:105-110
+            raise NotImplementedError("only the default observation layout (x position excluded) is implemented")
+        nq, nu = self.NQ, self.NU
+        self.obs_size = 2 * nq - 1
+        obs_space = Box(low=-np.inf, high=np.inf, shape=(self.obs_size,), dtype=np.float64)  # hopper_v5.py:237-239
+        act_space = Box(low=-1.0, high=1.0, shape=(nu,), dtype=np.float32)                   # ctrlrange, mujoco_env.py:105-110
         super().__init__(num_envs, obs_space, act_space, max_episode_steps=max_episode_steps, render_mode=render_mode,
                          **engine_kwargs)
         n, dev = self.num_envs, self.device
         self.frame_skip = int(frame_skip)
         self.dt = 0.002 * self.frame_skip  # mujoco_env.py:189-191
-        self.observation_structure = {"skipped_qpos": 1, "qpos": 5, "qvel": 6}  # hopper_v5.py:241-246
-        self._cfg = _lib.HopperCfg(
+        self.observation_structure = {"skipped_qpos": 1, "qpos": nq - 1, "qvel": nq}  # hopper_v5.py:241-246
+        self._reset_fn = getattr(self._lib, f"b2e_{self.robot}_reset")
+        self._step_fn = getattr(self._lib, f"b2e_{self.robot}_step")
+        self._cfg = _lib.MjPlanarCfg(
             reset_noise_scale=float(reset_noise_scale), forward_reward_weight=float(forward_reward_weight),
             ctrl_cost_weight=float(ctrl_cost_weight), healthy_reward=float(healthy_reward),
             healthy_z_min=float(healthy_z_range[0]), healthy_z_max=float(healthy_z_range[1]),
@@ -55,23 +57,23 @@ class HopperVectorEnv(B200VectorEnv):
             healthy_state_min=float(healthy_state_range[0]), healthy_state_max=float(healthy_state_range[1]),
             terminate_when_unhealthy=int(bool(terminate_when_unhealthy)), frame_skip=self.frame_skip)
         self._s = {
-            "qpos": torch.zeros((6, n), dtype=torch.float64, device=dev),
-            "qvel": torch.zeros((6, n), dtype=torch.float64, device=dev),
-            "qacc_warmstart": torch.zeros((6, n), dtype=torch.float64, device=dev),
+            "qpos": torch.zeros((nq, n), dtype=torch.float64, device=dev),
+            "qvel": torch.zeros((nq, n), dtype=torch.float64, device=dev),
+            "qacc_warmstart": torch.zeros((nq, n), dtype=torch.float64, device=dev),
             "overflow": torch.zeros(1, dtype=torch.int32, device=dev),
         }
         self._last_done = None
         self._info_sid, self._info_prev = -1, None
-        self._state = _lib.HopperState(ctrl=self._ctrl.data_ptr(), rng=ptr(self._rng),
+        self._state = _lib.MjPlanarState(ctrl=self._ctrl.data_ptr(), rng=ptr(self._rng),
                                        **{k: v.data_ptr() for k, v in self._s.items()})
 
     def _alloc_outputs(self):
         n = self.num_envs
-        layout = {"obs": ((n, OBS_SIZE), torch.float64), "reward": ((n,), torch.float64),
+        layout = {"obs": ((n, self.obs_size), torch.float64), "reward": ((n,), torch.float64),
                   "info": ((len(INFO_KEYS), n), torch.float64), "terminated": ((n,), torch.bool),
                   "truncated": ((n,), torch.bool)}
         if self.autoreset_mode == AutoresetMode.SAME_STEP:
-            layout["final_obs"] = ((n, OBS_SIZE), torch.float64)
+            layout["final_obs"] = ((n, self.obs_size), torch.float64)
         out = self._alloc_packed(layout)
         if "final_obs" in out:
             out["final_obs"].zero_()
@@ -81,16 +83,16 @@ class HopperVectorEnv(B200VectorEnv):
         n = self.num_envs
         if isinstance(actions, torch.Tensor):
             t = actions
-            if t.dim() != 2 or tuple(t.shape) != (n, 3):
-                raise ValueError(f"Action dimension mismatch. Expected {(n, 3)}, found {tuple(t.shape)}")  # mujoco_env.py:198-201
+            if t.dim() != 2 or tuple(t.shape) != (n, self.NU):
+                raise ValueError(f"Action dimension mismatch. Expected {(n, self.NU)}, found {tuple(t.shape)}")  # mujoco_env.py:198-201
             if t.dtype not in (torch.float32, torch.float64):
                 t = t.to(torch.float32)
             return t.to(self.device).contiguous()
         a = np.asarray(actions)
         if a.ndim == 0:
             raise TypeError(f"actions must have a leading dimension of num_envs={n}, got a scalar")
-        if a.shape != (n, 3):
-            raise ValueError(f"Action dimension mismatch. Expected {(n, 3)}, found {a.shape}")
+        if a.shape != (n, self.NU):
+            raise ValueError(f"Action dimension mismatch. Expected {(n, self.NU)}, found {a.shape}")
         if a.dtype not in (np.float32, np.float64):
             a = a.astype(np.float32)
         return super()._prepare_actions(np.ascontiguousarray(a))
@@ -101,19 +103,19 @@ class HopperVectorEnv(B200VectorEnv):
                 out["obs"].copy_(self._last_obs)
             out["info"].zero_()
         _lib.check(
-            self._lib.b2e_hopper_reset(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state),
+            self._reset_fn(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state),
                                        ptr(None if mask is None else mask.view(torch.uint8)), ptr(out["obs"]),
                                        ptr(out["info"]), self._stream),
-            "b2e_hopper_reset",
+            f"b2e_{self.robot}_reset",
         )
         self._last_obs = out["obs"]
 
     def _step_kernel(self, actions, out):
         _lib.check(
-            self._lib.b2e_hopper_step(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state), ptr(actions),
+            self._step_fn(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state), ptr(actions),
                                       ptr(out["obs"]), ptr(out["reward"]), ptr(out["terminated"]), ptr(out["truncated"]),
                                       ptr(out["info"]), ptr(out.get("final_obs")), self._stream),
-            "b2e_hopper_step",
+            f"b2e_{self.robot}_step",
         )
         self._last_obs = out["obs"]
 
@@ -165,5 +167,36 @@ class HopperVectorEnv(B200VectorEnv):
         return self._s["qvel"].t().contiguous()
 
     def buffer_overflow(self) -> bool:
-        """True if any env ever exhausted the per-env contact (8) or constraint-row (16) buffers."""
+        """True if any env ever exhausted the per-env contact (8) or constraint-row (16 Hopper / 32 Walker2d) buffers."""
         return bool(self._s["overflow"].item())
+
+
+class HopperVectorEnv(_MjPlanarVectorEnv):
+    """N Hopper-v5 envs (hopper_v5.py:163-178 for the keyword arguments)."""
+
+    robot, xml, NQ, NU = "hopper", "hopper.xml", 6, 3
+
+    def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 1000, xml_file: str = "hopper.xml",
+                 frame_skip: int = 4, forward_reward_weight: float = 1.0, ctrl_cost_weight: float = 1e-3,
+                 healthy_reward: float = 1.0, terminate_when_unhealthy: bool = True,
+                 healthy_state_range=(-100.0, 100.0), healthy_z_range=(0.7, float("inf")),
+                 healthy_angle_range=(-0.2, 0.2), reset_noise_scale: float = 5e-3,
+                 exclude_current_positions_from_observation: bool = True, render_mode: str | None = None, **engine_kwargs):
+        super().__init__(num_envs, max_episode_steps, xml_file, frame_skip, forward_reward_weight, ctrl_cost_weight,
+                         healthy_reward, terminate_when_unhealthy, healthy_state_range, healthy_z_range, healthy_angle_range,
+                         reset_noise_scale, exclude_current_positions_from_observation, render_mode, engine_kwargs)
+
+
+class Walker2dVectorEnv(_MjPlanarVectorEnv):
+    """N Walker2d-v5 envs (walker2d_v5.py:172-186 for the keyword arguments)."""
+
+    robot, xml, NQ, NU = "walker2d", "walker2d_v5.xml", 9, 6
+
+    def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 1000, xml_file: str = "walker2d_v5.xml",
+                 frame_skip: int = 4, forward_reward_weight: float = 1.0, ctrl_cost_weight: float = 1e-3,
+                 healthy_reward: float = 1.0, terminate_when_unhealthy: bool = True, healthy_z_range=(0.8, 2.0),
+                 healthy_angle_range=(-1.0, 1.0), reset_noise_scale: float = 5e-3,
+                 exclude_current_positions_from_observation: bool = True, render_mode: str | None = None, **engine_kwargs):
+        super().__init__(num_envs, max_episode_steps, xml_file, frame_skip, forward_reward_weight, ctrl_cost_weight,
+                         healthy_reward, terminate_when_unhealthy, (-np.inf, np.inf), healthy_z_range, healthy_angle_range,
+                         reset_noise_scale, exclude_current_positions_from_observation, render_mode, engine_kwargs)

@@ -45,6 +45,8 @@ ENVS = {
     "Humanoid-v5": ("gymnasium_b200.envs.humanoid:HumanoidVectorEnv",
                     "gymnasium.envs.mujoco.humanoid_v5:HumanoidEnv", 1000, None, {}),
     "Hopper-v5": ("gymnasium_b200.envs.hopper:HopperVectorEnv", "gymnasium.envs.mujoco.hopper_v5:HopperEnv", 1000, 3800.0, {}),
+    "Walker2d-v5": ("gymnasium_b200.envs.hopper:Walker2dVectorEnv", "gymnasium.envs.mujoco.walker2d_v5:Walker2dEnv", 1000,
+                    None, {}),
 }
 NAMESPACE = "B200"
 

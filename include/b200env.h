@@ -342,45 +342,52 @@ int b2e_humanoid_step(const b2e_batch* b, const b2e_humanoid_cfg* cfg, const b2e
                       const void* actions, double* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
                       double* info, double* final_obs, void* stream);
 
-/* ---- Hopper-v5: gymnasium/envs/mujoco/hopper_v5.py:226-343, mujoco_env.py:132-155, assets/hopper.xml -------------------
- * (+ the MuJoCo subset of humanoid.cu generalised to slide + hinge joints; see csrc/hopper.cu)
- * Per-env state, struct-of-arrays over n envs (device, float64): qpos [6][n], qvel [6][n], qacc_warmstart [6][n];
+/* ---- Hopper-v5 / Walker2d-v5: gymnasium/envs/mujoco/hopper_v5.py:226-343, walker2d_v5.py:257-342, mujoco_env.py:132-155,
+ * assets/hopper.xml, assets/walker2d_v5.xml (+ the MuJoCo subset of humanoid.cu generalised to slide + hinge joints; see
+ * csrc/mjc_planar.cuh).  nq = nv = 6 (Hopper) / 9 (Walker2d), nu = 3 / 6.
+ * Per-env state, struct-of-arrays over n envs (device, float64): qpos [nq][n], qvel [nv][n], qacc_warmstart [nv][n];
  *   ctrl / rng as for CartPole; overflow int32 [1] (sticky: a contact/constraint buffer was exhausted)
- * actions float32 or float64 [n][3]; obs float64 [n][11] (qpos[1:], clip(qvel, -10, 10)); reward float64 [n];
+ * actions float32 or float64 [n][nu]; obs float64 [n][2 nq - 1] (qpos[1:], clip(qvel, -10, 10)); reward float64 [n];
  * info float64 [6][n]: x_position, z_distance_from_origin, x_velocity, reward_forward, reward_ctrl, reward_survive
- * final_obs float64 [n][11] (SAME_STEP only).
+ * final_obs float64 [n][2 nq - 1] (SAME_STEP only).
  */
-typedef struct b2e_hopper_cfg {
+typedef struct b2e_mjplanar_cfg {
   double reset_noise_scale;      /* 5e-3 */
   double forward_reward_weight;  /* 1.0 */
   double ctrl_cost_weight;       /* 1e-3 */
   double healthy_reward;         /* 1.0 */
-  double healthy_z_min, healthy_z_max;         /* (0.7, inf) */
-  double healthy_angle_min, healthy_angle_max; /* (-0.2, 0.2) */
-  double healthy_state_min, healthy_state_max; /* (-100, 100) */
+  double healthy_z_min, healthy_z_max;         /* Hopper (0.7, inf), Walker2d (0.8, 2.0) */
+  double healthy_angle_min, healthy_angle_max; /* Hopper (-0.2, 0.2), Walker2d (-1, 1) */
+  double healthy_state_min, healthy_state_max; /* Hopper only: (-100, 100) */
   int32_t terminate_when_unhealthy;            /* 1 */
   int32_t frame_skip;                          /* 4 */
   int32_t lanes_per_warp;                      /* envs per warp (1..32); 0 = library default */
   int32_t _pad;
-} b2e_hopper_cfg;
+} b2e_mjplanar_cfg;
 
-typedef struct b2e_hopper_state {
+typedef struct b2e_mjplanar_state {
   double* qpos;
   double* qvel;
   double* qacc_warmstart;
   int32_t* ctrl;
   uint64_t* rng;
   int32_t* overflow;
-} b2e_hopper_state;
+} b2e_mjplanar_state;
 
-/* Host-side view of the compiled model constants (no GPU needed): body_mass[5], misc[8] = {meaninertia, n collision pairs,
- * total mass, ...}, invweight[5*2 + 6] = body_invweight0 then dof_invweight0. */
+/* Host-side view of the compiled model constants (no GPU needed): body_mass[nbody], misc[8] = {meaninertia, n collision
+ * pairs, total mass, ...}, invweight[nbody*2 + nv] = body_invweight0 then dof_invweight0 (nbody = 5 / 8). */
 int b2e_hopper_model_info(double* body_mass, double* misc, double* invweight);
-int b2e_hopper_reset(const b2e_batch* b, const b2e_hopper_cfg* cfg, const b2e_hopper_state* st, const uint8_t* mask,
+int b2e_hopper_reset(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st, const uint8_t* mask,
                      double* obs, double* info, void* stream);
-int b2e_hopper_step(const b2e_batch* b, const b2e_hopper_cfg* cfg, const b2e_hopper_state* st, const void* actions,
+int b2e_hopper_step(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st, const void* actions,
                     double* obs, double* reward, uint8_t* terminated, uint8_t* truncated, double* info, double* final_obs,
                     void* stream);
+int b2e_walker2d_model_info(double* body_mass, double* misc, double* invweight);
+int b2e_walker2d_reset(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st, const uint8_t* mask,
+                       double* obs, double* info, void* stream);
+int b2e_walker2d_step(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st, const void* actions,
+                      double* obs, double* reward, uint8_t* terminated, uint8_t* truncated, double* info, double* final_obs,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ from gymnasium_b200.distributed import HostBatchPipeline, env_rank_world  # noqa
 rank, local, world = env_rank_world()
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-ok = True
+all_ok = True
 for env_id, n, steps in (("CartPole-v1", 4096, 25), ("Humanoid-v5", 64, 8)):
     total = n * world
     rs = np.random.default_rng(3)
@@ -26,10 +26,11 @@ for env_id, n, steps in (("CartPole-v1", 4096, 25), ("Humanoid-v5", 64, 8)):
         ref = gymnasium_b200.make_vec(env_id, num_envs=total, output="numpy")
         ref.reset(seed=21)
         expect = [ref.step(a) for a in acts]
-    for mode in ("dma", "nccl"):
+    for mode, fast in (("dma", True), ("dma", False), ("nccl", False)):
+        ok = True
         env = gymnasium_b200.make_vec(env_id, num_envs=n, copy=False, out_buffers=3, env_offset=rank * n)
         env.reset(seed=21)
-        pipe = HostBatchPipeline(env, world, rank, tag=f"multi_{env_id}", depth=3, mode=mode)
+        pipe = HostBatchPipeline(env, world, rank, tag=f"multi_{env_id}_{int(fast)}", depth=3, mode=mode, fast=fast)
         got = []
         for k in range(steps):
             t = pipe.submit(acts[k, rank * n:(rank + 1) * n])
@@ -45,7 +46,11 @@ for env_id, n, steps in (("CartPole-v1", 4096, 25), ("Humanoid-v5", 64, 8)):
                 for j, key in enumerate(("obs", "reward", "terminated", "truncated")):
                     if not np.array_equal(got[k][key], expect[k][j]):
                         ok = False
-                        print(f"MISMATCH {env_id} mode={mode} step {k} key {key}")
-            print(f"{env_id} world={world} mode={mode}: {'ok' if ok else 'FAILED'}")
+                        bad = np.nonzero(np.asarray(got[k][key] != expect[k][j]).reshape(total, -1).any(axis=1))[0]
+                        if k < 3:
+                            print(f"MISMATCH {env_id} mode={mode} fast={fast} step {k} key {key}: {len(bad)} rows, ranks "
+                                  f"{sorted(set((bad // n).tolist()))}, first rows {bad[:4].tolist()}", flush=True)
+            all_ok = all_ok and ok
+            print(f"{env_id} world={world} mode={mode} fast={fast}: {'ok' if ok else 'FAILED'}", flush=True)
 dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+sys.exit(0 if all_ok else 1)
