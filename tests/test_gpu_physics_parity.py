@@ -250,23 +250,26 @@ def test_lunarlander_grouping_is_scheduling_only():
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Hopper-v5 (the Humanoid solver generalised to another MuJoCo robot); checker = oracle/hopper.c
+@pytest.mark.parametrize("robot", ["Hopper-v5", "Walker2d-v5"])
 @pytest.mark.parametrize("n,T,dtype", [(512, 130, np.float32), (8192, 70, np.float32), (64, 60, np.float64)])
-def test_hopper_matches_oracle_bit_exact(n, T, dtype):
+def test_planar_robots_match_oracle_bit_exact(robot, n, T, dtype):
     from oracle.hopper import OracleHopper
+    from oracle.walker2d import OracleWalker2d
 
+    Oracle, nu, nobs = (OracleHopper, 3, 11) if robot == "Hopper-v5" else (OracleWalker2d, 6, 17)
     seed = 21
     rs = np.random.default_rng(3)
     idx = np.arange(n) if n <= 512 else np.sort(rs.choice(n, size=256, replace=False))
-    env = make("Hopper-v5", n)
-    ora = OracleHopper(len(idx))
+    env = make(robot, n)
+    ora = Oracle(len(idx))
     o1, i1 = env.reset(seed=seed)
     o2, i2 = ora.reset(seed=[seed + int(i) for i in idx])
-    assert o1.shape == (n, 11) and o1.dtype == np.float64
+    assert o1.shape == (n, nobs) and o1.dtype == np.float64
     np.testing.assert_array_equal(o1[idx], o2)
     np.testing.assert_array_equal(i1["z_distance_from_origin"][idx], i2["z_distance_from_origin"])
     resets = np.zeros(len(idx), dtype=np.int64)
     for t in range(T):
-        a = rs.uniform(-1.0, 1.0, size=(n, 3)).astype(dtype)
+        a = rs.uniform(-1.0, 1.0, size=(n, nu)).astype(dtype)
         x = env.step(a)
         if dtype == np.float64:  # the oracle's control cost is the float32 one; compare everything but reward_ctrl / reward
             y = ora.step(a[idx].astype(np.float32))
@@ -303,6 +306,9 @@ def test_hopper_sharding_and_api():
         xp = [parts[0].step(a[:40]), parts[1].step(a[40:])]
         for k in range(4):
             np.testing.assert_array_equal(xw[k], np.concatenate([xp[0][k], xp[1][k]]), err_msg=f"output {k} at step {t}")
+    w = make("Walker2d-v5", 8)
+    ow2, _ = w.reset(seed=3)
+    assert ow2.shape == (8, 17) and w.single_action_space.shape == (6,)
     t_env = make("Hopper-v5", 4, output="torch")
     o, info = t_env.reset(seed=1)
     assert o.dtype == torch.float64 and tuple(o.shape) == (4, 11) and set(info) >= {"x_position", "_x_position"}

@@ -93,3 +93,53 @@ def test_determinism_and_seeding():
     qpos = np.array([0, 1.25, 0, 0, 0, 0]) + g.uniform(-5e-3, 5e-3, size=6)
     qvel = g.uniform(-5e-3, 5e-3, size=6)
     np.testing.assert_array_equal(oa[0], np.concatenate([qpos[1:], np.clip(qvel, -10, 10)]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Walker2d-v5 on the same core (oracle/walker2d.c -> mjc_planar.h)
+def test_walker2d_model_free_fall_and_rewards():
+    from oracle.walker2d import OracleWalker2d
+
+    env = OracleWalker2d(1, reset_noise_scale=0.0)
+    obs, info = env.reset(seed=0)
+    assert obs.shape == (1, 17)  # nq = nv = 9 (tests/envs/mujoco/test_mujoco_v5.py:538-547), observation 8 + 9
+    np.testing.assert_array_equal(obs[0], [1.25] + [0.0] * 16)
+    mass, misc, inv = env.model_info()
+
+    def capsule(r, half):
+        return 1000.0 * (np.pi * r * r * 2 * half + 4.0 / 3.0 * np.pi * r ** 3)
+
+    leg = [capsule(0.05, 0.225), capsule(0.04, 0.25), capsule(0.06, 0.1)]
+    np.testing.assert_allclose(mass[1:], [capsule(0.05, 0.2)] + leg + leg, rtol=1e-12)
+    assert misc[1] == 7  # contype 1 / conaffinity 0 on the robot's geoms: floor x 7 geoms, no self-collision (walker2d_v5.xml:11)
+    M = mass.sum()
+    xipos0 = env.debug(0)[4]
+    z0 = (mass * xipos0[:, 2]).sum() / M
+    free = 0
+    for k in range(14):
+        obs, r, te, tr, info = env.step(np.zeros((1, 6), dtype=np.float32))
+        qpos, qvel, qacc, counts, xipos = env.debug(0)
+        if counts[0] > 0:
+            break
+        t = (k + 1) * 4 * 0.002
+        assert abs((mass * xipos[:, 2]).sum() / M - (z0 - 0.5 * 9.81 * t * t)) < 5e-6
+        free += 1
+    assert free >= 8
+    n = 32
+    env = OracleWalker2d(n)
+    env.reset(seed=2)
+    rs = np.random.default_rng(0)
+    prev = np.zeros(n, bool)
+    nterm = 0
+    for t in range(120):
+        a = rs.uniform(-1, 1, size=(n, 6)).astype(np.float32)
+        obs, r, te, tr, info = env.step(a)
+        live = ~prev
+        # walker2d_v5.py:305-312 and tests/envs/mujoco/test_mujoco_v5.py reward identity, exact
+        assert (r[live] == (info["reward_forward"] + info["reward_survive"] + info["reward_ctrl"])[live]).all()
+        z, ang = obs[:, 0], obs[:, 1]
+        healthy = (0.8 < z) & (z < 2.0) & (-1.0 < ang) & (ang < 1.0)  # walker2d_v5.py:261-272
+        np.testing.assert_array_equal(te[live], ~healthy[live])
+        nterm += int(te.sum())
+        prev = te | tr
+    assert nterm > n // 2
