@@ -640,15 +640,21 @@ def measure_e2e(cx, args, env_id, n, mode, tag):
     host_actions = host_action_pool(np, env_id, 16, n, rank)
     check = {}
 
+    lag = max(1, depth // 2)  # the consumer takes step k - lag after submitting step k: it rarely has to wait for the slowest rank
+    done = [0]                # steps consumed so far (consumer rank)
+
     def run(count):
         last = -1
         for _ in range(count):
             t = pipe.submit(host_actions[pipe.k % 16])
-            if pipe.is_consumer and t >= 1:
-                pipe.consume(t - 1)
+            if pipe.is_consumer and t >= lag:
+                pipe.consume(t - lag)
+                done[0] = t - lag + 1
             last = t
-        if pipe.is_consumer and last >= 0:
-            check["batch"] = pipe.consume(last)
+        if pipe.is_consumer:
+            while done[0] <= last:  # drain: every submitted step is consumed inside the timed region
+                check["batch"] = pipe.consume(done[0])
+                done[0] += 1
         pipe.drain()
 
     warm = max(5, min(args.warmup, 50))

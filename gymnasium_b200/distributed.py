@@ -512,13 +512,19 @@ class HostBatchPipeline:
         return k
 
     def consume(self, k: int, ack: bool = True) -> dict:
-        """Consumer rank: numpy views ``{key: [N_total, ...]}`` of step k's batch (valid until the slot is re-used, i.e. until
-        `depth - 1` further steps have been acknowledged)."""
+        """Consumer rank: numpy views ``{key: [N_total, ...]}`` of step k's batch.  With ``ack=True`` the slot is released to
+        the producers at once -- the views may then be overwritten as soon as `depth - 1` further steps have been submitted
+        (a fast producer rank can be that far ahead), so read them first or pass ``ack=False`` and call :meth:`release`
+        when done with them."""
         ranks = None if self.mode == "dma" else [self.rank]
         out = self.host.wait_ready(k, ranks=ranks)
         if ack:
             self.host.ack(k)
         return out
+
+    def release(self, k: int) -> None:
+        """Consumer rank: hands the slot of step k back to the producers (after ``consume(k, ack=False)``)."""
+        self.host.ack(k)
 
     def drain(self) -> None:
         self.copy_stream.synchronize()

@@ -34,10 +34,12 @@ for env_id, n, steps in (("CartPole-v1", 4096, 25), ("Humanoid-v5", 64, 8)):
         got = []
         for k in range(steps):
             t = pipe.submit(acts[k, rank * n:(rank + 1) * n])
-            if pipe.is_consumer and t >= 1:
-                got.append({key: v.copy() for key, v in pipe.consume(t - 1).items()})
+            if pipe.is_consumer and t >= 1:  # read the batch BEFORE releasing its slot: the other ranks run ahead
+                got.append({key: v.copy() for key, v in pipe.consume(t - 1, ack=False).items()})
+                pipe.release(t - 1)
         if pipe.is_consumer:
-            got.append({key: v.copy() for key, v in pipe.consume(steps - 1).items()})
+            got.append({key: v.copy() for key, v in pipe.consume(steps - 1, ack=False).items()})
+            pipe.release(steps - 1)
         pipe.drain()
         dist.barrier()
         pipe.close()

@@ -33,9 +33,11 @@ def test_pipeline_batches_equal_blocking_step(env_id, n, steps, fast):
     got = []
     for k in range(steps):
         t = pipe.submit(acts[k])
-        if t >= 1:  # consume one step behind, as the bench loop does
-            got.append({key: v.copy() for key, v in pipe.consume(t - 1).items()})
-    got.append({key: v.copy() for key, v in pipe.consume(steps - 1).items()})
+        if t >= 1:  # consume one step behind, as the bench loop does; release the slot after reading it
+            got.append({key: v.copy() for key, v in pipe.consume(t - 1, ack=False).items()})
+            pipe.release(t - 1)
+    got.append({key: v.copy() for key, v in pipe.consume(steps - 1, ack=False).items()})
+    pipe.release(steps - 1)
     assert bool(pipe._fast) == fast  # fast: every submit was ONE b2e_pipe_submit call replaying the recorded step
     pipe.close()
     for k in range(steps):
