@@ -47,8 +47,6 @@ class _MjPlanarVectorEnv(B200VectorEnv):
         self.frame_skip = int(frame_skip)
         self.dt = 0.002 * self.frame_skip  # mujoco_env.py:189-191
         self.observation_structure = {"skipped_qpos": 1, "qpos": nq - 1, "qvel": nq}  # hopper_v5.py:241-246
-        self._reset_fn = getattr(self._lib, f"b2e_{self.robot}_reset")
-        self._step_fn = getattr(self._lib, f"b2e_{self.robot}_step")
         self._cfg = _lib.MjPlanarCfg(
             reset_noise_scale=float(reset_noise_scale), forward_reward_weight=float(forward_reward_weight),
             ctrl_cost_weight=float(ctrl_cost_weight), healthy_reward=float(healthy_reward),
@@ -103,7 +101,7 @@ class _MjPlanarVectorEnv(B200VectorEnv):
                 out["obs"].copy_(self._last_obs)
             out["info"].zero_()
         _lib.check(
-            self._reset_fn(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state),
+            getattr(self._lib, f"b2e_{self.robot}_reset")(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state),
                                        ptr(None if mask is None else mask.view(torch.uint8)), ptr(out["obs"]),
                                        ptr(out["info"]), self._stream),
             f"b2e_{self.robot}_reset",
@@ -112,7 +110,7 @@ class _MjPlanarVectorEnv(B200VectorEnv):
 
     def _step_kernel(self, actions, out):
         _lib.check(
-            self._step_fn(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state), ptr(actions),
+            getattr(self._lib, f"b2e_{self.robot}_step")(C.byref(self._batch), C.byref(self._cfg), C.byref(self._state), ptr(actions),
                                       ptr(out["obs"]), ptr(out["reward"]), ptr(out["terminated"]), ptr(out["truncated"]),
                                       ptr(out["info"]), ptr(out.get("final_obs")), self._stream),
             f"b2e_{self.robot}_step",
