@@ -637,7 +637,12 @@ def measure_e2e(cx, args, env_id, n, mode, tag):
             env.step(dev_pool[k % 4])
         torch.cuda.synchronize()
     pipe = HostBatchPipeline(env, world, rank, tag=tag, depth=depth, mode=mode)
-    host_actions = host_action_pool(np, env_id, 16, n, rank)
+    pool = host_action_pool(np, env_id, 16, n, rank)
+    # this step's inputs live in page-locked host memory (16 distinct action batches, cycled): the pipeline DMAs from them;
+    # `--pageable-actions` measures the variant that takes pageable numpy arrays (one extra host copy into a staging buffer)
+    host_actions = list(pool) if args.pageable_actions else pipe.pinned_actions(16, dtype=pool.dtype)
+    for dst, src in zip(host_actions, pool):
+        dst[...] = src
     check = {}
 
     lag = max(1, depth // 2)  # the consumer takes step k - lag after submitting step k: it rarely has to wait for the slowest rank
@@ -676,11 +681,14 @@ def measure_e2e(cx, args, env_id, n, mode, tag):
     if pipe.is_consumer:  # the landed batch is the real thing: right shapes, finite observations from every rank
         bt = check["batch"]
         ok = bool(bt["obs"].shape[0] == n * world and np.isfinite(np.asarray(bt["obs"], dtype=np.float64)).all())
+    pipe_graph = bool(pipe._fast) and pipe.landing_graph
     pipe.close()
     del env
     return {"value": world * Ke * n / elapsed, "unit": UNIT, "h2d_bytes_per_step": n * facts["act_bytes"],
             "d2h_bytes_per_step": n * facts["out_bytes"], "steps": Ke, "ms_per_step": elapsed / Ke * 1e3,
             "host_batch_ok": ok, "pipeline_depth": depth,
+            "actions": "pageable numpy (staged)" if args.pageable_actions else "page-locked numpy (pipe.pinned_actions)",
+            "landing": "one CUDA graph per step" if pipe_graph else "one cudaMemcpyAsync per output key",
             "path": ("gymnasium_b200.distributed.HostBatchPipeline(make_vec(...)).submit(host numpy actions) / .consume(): pinned "
                      "H2D of the actions + fused step launch + " +
                      ("D2H of every rank's rows over its own PCIe link into ONE page-locked host batch shared by all ranks"
@@ -1034,6 +1042,8 @@ def main():
     ap.add_argument("--ring", type=int, default=0, help="batches in the L2-defeating ring (0 = auto: > 2 x L2)")
     ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--ref-budget", type=float, default=20.0, help="seconds of CPU work for the reference arm")
+    ap.add_argument("--pageable-actions", action="store_true",
+                    help="e2e: pass pageable numpy action batches (staged through one host copy) instead of page-locked ones")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-humanoid", action="store_true", help="skip the Humanoid-v5 8192-envs/GPU block of the default line")

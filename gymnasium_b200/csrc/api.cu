@@ -192,6 +192,36 @@ extern "C" int b2e_pipe_slot_init(b2e_pipe_slot* s) {
   s->ev_step = ev[1];
   s->ev_copy = ev[2];
   s->h2d_pending = s->copy_pending = 0;
+  s->copy_graph = nullptr;
+  return 0;
+}
+
+extern "C" int b2e_pipe_slot_capture(b2e_pipe_slot* s, void* copy_stream) {
+  if (!s || !s->segs || s->nsegs < 2 || !s->seq_src) {
+    set_error("b2e_pipe_slot_capture: slot, segments or seq_src missing");
+    return B2E_EINVAL;
+  }
+  if (s->copy_graph) return 0;
+  cudaStream_t cs = (cudaStream_t)copy_stream;
+  s->segs[s->nsegs - 2].dev_src = s->seq_src;  // the sequence word always travels from the slot's own page-locked word
+  if (int st = cuda_status(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed), "b2e_pipe_slot_capture (begin)")) return st;
+  const int st_copy = b2e_copy_to_host_async(s->segs, s->nsegs, copy_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e_end = cudaStreamEndCapture(cs, &graph);
+  if (st_copy) {
+    if (graph) cudaGraphDestroy(graph);
+    return st_copy;
+  }
+  if (int st = cuda_status(e_end, "b2e_pipe_slot_capture (end)")) return st;
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (int st = cuda_status(e_inst, "b2e_pipe_slot_capture (instantiate)")) return st;
+  if (int st = cuda_status(cudaGraphUpload(exec, cs), "b2e_pipe_slot_capture (upload)")) {
+    cudaGraphExecDestroy(exec);
+    return st;
+  }
+  s->copy_graph = exec;
   return 0;
 }
 
@@ -203,6 +233,10 @@ extern "C" int b2e_pipe_slot_destroy(b2e_pipe_slot* s) {
       cudaEventDestroy((cudaEvent_t)*ev[i]);
       *ev[i] = nullptr;
     }
+  if (s->copy_graph) {
+    cudaGraphExecDestroy((cudaGraphExec_t)s->copy_graph);
+    s->copy_graph = nullptr;
+  }
   return 0;
 }
 
@@ -210,24 +244,37 @@ typedef int (*b2e_anyfn)(uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint6
                          uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t);
 
 extern "C" int b2e_pipe_submit(b2e_pipe_slot* s, const void* host_actions, void* main_stream, void* copy_stream,
-                               const int64_t* ack_word, int64_t need_ack, const void* seq_src, double timeout_s) {
-  if (!s || !host_actions || !s->staging_host || !s->actions_dev || !s->calls || !s->segs || s->nsegs < 2 || !seq_src) {
+                               const int64_t* ack_word, int64_t need_ack, void* seq_src, int64_t seq_value, int32_t flags,
+                               double timeout_s) {
+  if (!s || !host_actions || !s->actions_dev || !s->calls || !s->segs || s->nsegs < 2) {
     set_error("b2e_pipe_submit: null pointer in the slot or its arguments");
     return B2E_EINVAL;
   }
+  int64_t* const seq_word = s->copy_graph ? s->seq_src : (int64_t*)seq_src;
+  const bool pinned = (flags & B2E_PIPE_ACTIONS_PINNED) != 0;
+  if (!seq_word || (!pinned && !s->staging_host)) {
+    set_error("b2e_pipe_submit: no sequence-word source, or no staging buffer for pageable actions");
+    return B2E_EINVAL;
+  }
   cudaStream_t ms = (cudaStream_t)main_stream, cs = (cudaStream_t)copy_stream;
-  // (1) stage this step's actions: the DMA that last read the staging buffer must be done
-  if (s->h2d_pending)
-    if (int st = cuda_status(cudaEventSynchronize((cudaEvent_t)s->ev_h2d), "b2e_pipe_submit (staging)")) return st;
-  memcpy(s->staging_host, host_actions, s->action_bytes);
+  const void* h2d_src = host_actions;
+  if (!pinned) {
+    // (1) stage this step's actions: the DMA that last read the staging buffer must be done
+    if (s->h2d_pending)
+      if (int st = cuda_status(cudaEventSynchronize((cudaEvent_t)s->ev_h2d), "b2e_pipe_submit (staging)")) return st;
+    memcpy(s->staging_host, host_actions, s->action_bytes);
+    h2d_src = s->staging_host;
+  }
   // (2) the kernel re-uses the output set whose last landing copies must have drained
   if (s->copy_pending)
     if (int st = cuda_status(cudaStreamWaitEvent(ms, (cudaEvent_t)s->ev_copy, 0), "b2e_pipe_submit (output set)")) return st;
-  if (int st = cuda_status(cudaMemcpyAsync(s->actions_dev, s->staging_host, s->action_bytes, cudaMemcpyHostToDevice, ms),
+  if (int st = cuda_status(cudaMemcpyAsync(s->actions_dev, h2d_src, s->action_bytes, cudaMemcpyHostToDevice, ms),
                            "b2e_pipe_submit (H2D)"))
     return st;
-  cudaEventRecord((cudaEvent_t)s->ev_h2d, ms);
-  s->h2d_pending = 1;
+  if (!pinned) {
+    cudaEventRecord((cudaEvent_t)s->ev_h2d, ms);
+    s->h2d_pending = 1;
+  }
   // (3) the family's fused step: the recorded C-ABI call(s), every argument a pointer or an integer
   for (int32_t c = 0; c < s->ncalls; ++c) {
     const b2e_call& k = s->calls[c];
@@ -262,9 +309,16 @@ extern "C" int b2e_pipe_submit(b2e_pipe_slot* s, const void* host_actions, void*
       }
     }
   }
-  // (5) land the outputs + the sequence word (its source is the second-to-last segment's)
-  s->segs[s->nsegs - 2].dev_src = seq_src;
-  if (int st = b2e_copy_to_host_async(s->segs, s->nsegs, copy_stream)) return st;
+  // (5) land the outputs + the sequence word.  Its page-locked source is written only now: once the slot has been released,
+  // the copy that published the slot's previous step has certainly read it.
+  *(volatile int64_t*)seq_word = seq_value;
+  __atomic_thread_fence(__ATOMIC_RELEASE);
+  if (s->copy_graph) {
+    if (int st = cuda_status(cudaGraphLaunch((cudaGraphExec_t)s->copy_graph, cs), "b2e_pipe_submit (landing graph)")) return st;
+  } else {
+    s->segs[s->nsegs - 2].dev_src = seq_word;
+    if (int st = b2e_copy_to_host_async(s->segs, s->nsegs, copy_stream)) return st;
+  }
   cudaEventRecord((cudaEvent_t)s->ev_copy, cs);
   s->copy_pending = 1;
   return cuda_status(cudaGetLastError(), "b2e_pipe_submit");

@@ -229,6 +229,11 @@ class HostBatch:
         r = self.rank if rank is None else rank
         return self._addr + r * self.LINE
 
+    def seq_slot_source(self, j: int) -> int:
+        """Address of the page-locked word slot j's sequence copy reads (fast path: written by ``b2e_pipe_submit`` itself once
+        the slot has been released, so one fixed word per slot is enough)."""
+        return self._addr + self._src_off + self._src_stride * self.rank + 8 * (j % self.src_ring)
+
     def seq_source(self, k: int) -> int:
         """Writes k+1 into this rank's source ring and returns its address (the last copy segment of step k reads it)."""
         i = (self._src_off + self._src_stride * self.rank) // 8 + k % self.src_ring
@@ -379,6 +384,27 @@ class HostBatchPipeline:
         # recorded step call(s) -- set up lazily at the first submit, when the action dtype / shape is known
         self._fast = None if (mode == "dma" and fast and env.rng_mode == "numpy") else False
         self._slots = None
+        self.landing_graph = os.environ.get("B2E_PIPE_NO_GRAPH", "0") in ("", "0")
+        self._pinned_ptrs: set = set()
+        self._pinned_keep: list = []
+
+    def pinned_actions(self, count: int = 1, dtype=None) -> list:
+        """`count` page-locked numpy arrays shaped like one step's action batch.  ``submit`` DMAs straight from an array
+        obtained here (no staging copy); the caller must leave it untouched until that step has been consumed."""
+        import numpy as np
+
+        env = self.env
+        if dtype is None:
+            dtype = np.int64 if env.discrete_actions else np.float32
+        shape = (env.num_envs,) if env.discrete_actions else (env.num_envs,) + tuple(env.single_action_space.shape)
+        out = []
+        for _ in range(count):
+            t = torch.from_numpy(np.zeros(shape, dtype=dtype)).pin_memory()
+            a = t.numpy()
+            self._pinned_keep.append(t)
+            self._pinned_ptrs.add(a.ctypes.data)
+            out.append(a)
+        return out
 
     def _segments(self, k: int, out: dict):
         """ctypes array of the copy segments of step k (cached per (slot, output set))."""
@@ -455,7 +481,10 @@ class HostBatchPipeline:
             sl.staging_host, sl.actions_dev, sl.action_bytes = staging.data_ptr(), act_dev.data_ptr(), a.nbytes
             sl.calls, sl.ncalls = calls, len(rec.calls)
             sl.segs, sl.nsegs = segs, len(seg_list)
+            sl.seq_src = self.host.seq_slot_source(j)
             L.check(self._lib.b2e_pipe_slot_init(C.byref(sl)), "b2e_pipe_slot_init")
+            if self.landing_graph:  # the D2H side of a step becomes ONE cudaGraphLaunch
+                L.check(self._lib.b2e_pipe_slot_capture(C.byref(sl), self._cs_handle), "b2e_pipe_slot_capture")
             self._keep += [staging, act_dev, calls, segs]
         self._slots = slots
         self._ack_addr = self.host._addr + self.host.world * self.host.LINE
@@ -477,8 +506,10 @@ class HostBatchPipeline:
                 if a.shape != self._fast_shape:
                     raise ValueError(f"expected actions of shape {self._fast_shape}, got {a.shape}")
             k, j = self.k, self.k % self.depth
-            st = self._lib.b2e_pipe_submit(self._C.byref(self._slots[j]), a.ctypes.data, self._main_handle, self._cs_handle,
-                                           self._ack_addr, k - self.depth + 1, self.host.seq_source(k), 120.0)
+            ptr = a.ctypes.data
+            st = self._lib.b2e_pipe_submit(self._C.byref(self._slots[j]), ptr, self._main_handle, self._cs_handle,
+                                           self._ack_addr, k - self.depth + 1, self._slots[j].seq_src, k + 1,
+                                           1 if ptr in self._pinned_ptrs else 0, 120.0)
             if st:
                 self._lib_mod.check(st, "b2e_pipe_submit")
             self.env._out = self._rings[j]

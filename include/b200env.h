@@ -95,7 +95,8 @@ int b2e_copy_to_host_async(const b2e_copy_seg* segs, int32_t count, void* stream
  *                    arguments; every argument of every step entry point is a pointer or an integer, i.e. one machine word)
  *   segs / nsegs   : the landing copies (b2e_copy_seg) of this output set; the last two publish the sequence word
  *   ev_*           : cudaEvent_t, owned by the slot (b2e_pipe_slot_init / _destroy)
- * b2e_pipe_submit(slot, host_actions, ...): memcpy into the staging buffer, async H2D on main_stream, the recorded step,
+ * b2e_pipe_submit(slot, host_actions, ...): memcpy into the staging buffer (skipped with B2E_PIPE_ACTIONS_PINNED: the DMA
+ * reads the caller's page-locked buffer), async H2D on main_stream, the recorded step,
  * then on copy_stream (ordered after the step) the landing copies -- after the consumer's acknowledgement word *ack_word has
  * reached need_ack (spin, timeout_s).  Never synchronises a stream; returns B2E_ETIMEOUT if the consumer stalls. */
 typedef struct b2e_call {
@@ -113,11 +114,20 @@ typedef struct b2e_pipe_slot {
   int32_t ncalls, nsegs;
   void *ev_h2d, *ev_step, *ev_copy;
   int32_t h2d_pending, copy_pending;
+  int64_t* seq_src; /* page-locked word of this slot that the landing graph's sequence copy reads (b2e_pipe_slot_capture) */
+  void* copy_graph; /* cudaGraphExec_t of the landing copies, owned by the slot; NULL = the copies are enqueued one by one */
 } b2e_pipe_slot;
+#define B2E_PIPE_ACTIONS_PINNED 1 /* host_actions is page-locked and stays untouched until the step has landed: no staging copy */
 int b2e_pipe_slot_init(b2e_pipe_slot* slot);
+/* Bakes the slot's landing copies (segs, the sequence word read from slot->seq_src) into one CUDA graph: a step's D2H side is
+ * then ONE cudaGraphLaunch instead of nsegs cudaMemcpyAsync calls. */
+int b2e_pipe_slot_capture(b2e_pipe_slot* slot, void* copy_stream);
 int b2e_pipe_slot_destroy(b2e_pipe_slot* slot);
+/* seq_value (= step index + 1) is stored to the sequence word's source -- slot->seq_src with a landing graph, else seq_src --
+ * after the wait on *ack_word, i.e. when the copy that published the slot's previous step has read it. */
 int b2e_pipe_submit(b2e_pipe_slot* slot, const void* host_actions, void* main_stream, void* copy_stream,
-                    const int64_t* ack_word, int64_t need_ack, const void* seq_src, double timeout_s);
+                    const int64_t* ack_word, int64_t need_ack, void* seq_src, int64_t seq_value, int32_t flags,
+                    double timeout_s);
 
 /* ---- RNG: gymnasium/utils/seeding.py:39-41 -> numpy SeedSequence -> PCG64 ---------------------------------------
  * rng   : uint64 [2][n][2]  = {state(lo,hi)}[n] then {inc(lo,hi)}[n]

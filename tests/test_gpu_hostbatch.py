@@ -51,6 +51,44 @@ def test_pipeline_batches_equal_blocking_step(env_id, n, steps, fast):
         np.testing.assert_array_equal(got[-1]["info"][7], expect[-1][4]["x_velocity"])
 
 
+@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("env_id,n", [("CartPole-v1", 4096), ("Humanoid-v5", 64)])
+def test_pipeline_pinned_actions_and_landing_graph(env_id, n, graph, monkeypatch):
+    """Page-locked action batches (no staging copy) and the landing copies as one CUDA graph / as single copies: same batches."""
+    monkeypatch.setenv("B2E_PIPE_NO_GRAPH", "0" if graph else "1")
+    steps, depth = 25, 4
+    ref = gymnasium_b200.make_vec(env_id, num_envs=n, output="numpy")
+    env = gymnasium_b200.make_vec(env_id, num_envs=n, copy=False, out_buffers=depth)
+    ref.reset(seed=3)
+    env.reset(seed=3)
+    rs = np.random.default_rng(8)
+    pipe = HostBatchPipeline(env, 1, 0, tag=f"pin_{env_id}_{int(graph)}", depth=depth)
+    assert pipe.landing_graph == graph
+    pool = pipe.pinned_actions(depth + 1)
+    expect, got = [], []
+    for k in range(steps):
+        a = pool[k % len(pool)]  # last used depth+1 steps ago: that step has been consumed
+        if env_id == "Humanoid-v5":
+            a[...] = rs.uniform(-0.4, 0.4, size=a.shape)
+        else:
+            a[...] = rs.integers(0, 2, size=a.shape)
+        expect.append(ref.step(a.copy()))
+        t = pipe.submit(a)
+        if t >= 2:
+            got.append({key: v.copy() for key, v in pipe.consume(t - 2, ack=False).items()})
+            pipe.release(t - 2)
+    for t in (steps - 2, steps - 1):
+        got.append({key: v.copy() for key, v in pipe.consume(t, ack=False).items()})
+        pipe.release(t)
+    assert pipe._fast and (pipe._slots[0].copy_graph is not None) == graph
+    pipe.close()
+    for k in range(steps):
+        np.testing.assert_array_equal(got[k]["obs"], expect[k][0], err_msg=f"step {k}")
+        np.testing.assert_array_equal(got[k]["reward"], expect[k][1])
+        np.testing.assert_array_equal(got[k]["terminated"], expect[k][2])
+        np.testing.assert_array_equal(got[k]["truncated"], expect[k][3])
+
+
 def test_out_buffers_rotate_without_aliasing():
     env = gymnasium_b200.make_vec("CartPole-v1", num_envs=256, copy=False, out_buffers=3)
     env.reset(seed=1)
