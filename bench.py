@@ -681,14 +681,16 @@ def measure_e2e(cx, args, env_id, n, mode, tag):
     if pipe.is_consumer:  # the landed batch is the real thing: right shapes, finite observations from every rank
         bt = check["batch"]
         ok = bool(bt["obs"].shape[0] == n * world and np.isfinite(np.asarray(bt["obs"], dtype=np.float64)).all())
-    pipe_graph = bool(pipe._fast) and pipe.landing_graph
+    landing = pipe.landing if pipe._fast else "copies (python path)"
     pipe.close()
     del env
     return {"value": world * Ke * n / elapsed, "unit": UNIT, "h2d_bytes_per_step": n * facts["act_bytes"],
             "d2h_bytes_per_step": n * facts["out_bytes"], "steps": Ke, "ms_per_step": elapsed / Ke * 1e3,
             "host_batch_ok": ok, "pipeline_depth": depth,
             "actions": "pageable numpy (staged)" if args.pageable_actions else "page-locked numpy (pipe.pinned_actions)",
-            "landing": "one CUDA graph per step" if pipe_graph else "one cudaMemcpyAsync per output key",
+            "landing": {"kernel": "landing kernel: SM stores into the mapped host batch, one launch per step",
+                        "graph": "copy engine, one CUDA graph per step",
+                        "copies": "copy engine, one cudaMemcpyAsync per output key"}.get(landing, landing),
             "path": ("gymnasium_b200.distributed.HostBatchPipeline(make_vec(...)).submit(host numpy actions) / .consume(): pinned "
                      "H2D of the actions + fused step launch + " +
                      ("D2H of every rank's rows over its own PCIe link into ONE page-locked host batch shared by all ranks"

@@ -134,7 +134,7 @@ class PipeSlot(C.Structure):
     _fields_ = [("staging_host", c_void_p), ("actions_dev", c_void_p), ("action_bytes", C.c_size_t),
                 ("calls", C.POINTER(Call)), ("segs", C.POINTER(CopySeg)), ("ncalls", c_i32), ("nsegs", c_i32),
                 ("ev_h2d", c_void_p), ("ev_step", c_void_p), ("ev_copy", c_void_p), ("h2d_pending", c_i32),
-                ("copy_pending", c_i32), ("seq_src", c_void_p), ("copy_graph", c_void_p)]
+                ("copy_pending", c_i32), ("seq_src", c_void_p), ("copy_graph", c_void_p), ("land", c_void_p)]
 
 
 P = c_void_p
@@ -152,6 +152,7 @@ SIGNATURES = {
     "b2e_pipe_slot_init": (C.c_int, [C.POINTER(PipeSlot)]),
     "b2e_pipe_slot_destroy": (C.c_int, [C.POINTER(PipeSlot)]),
     "b2e_pipe_slot_capture": (C.c_int, [C.POINTER(PipeSlot), P]),
+    "b2e_pipe_slot_land_kernel": (C.c_int, [C.POINTER(PipeSlot)]),
     "b2e_pipe_submit": (C.c_int, [C.POINTER(PipeSlot), P, P, P, P, c_i64, P, c_i64, c_i32, c_double]),
     "b2e_rng_seed": (C.c_int, [_BP, c_u64, P, P, P, P]),
     "b2e_rng_random": (C.c_int, [_BP, P, c_i32, P, P]),

@@ -147,7 +147,7 @@ extern "C" int b2e_host_register(void* host, size_t bytes) {
     set_error("b2e_host_register: null pointer or zero size");
     return B2E_EINVAL;
   }
-  return cuda_status(cudaHostRegister(host, bytes, cudaHostRegisterPortable), "b2e_host_register");
+  return cuda_status(cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped), "b2e_host_register");
 }
 
 extern "C" int b2e_host_unregister(void* host) {
@@ -179,6 +179,71 @@ extern "C" int b2e_copy_to_host_async(const b2e_copy_seg* segs, int32_t count, v
   return 0;
 }
 
+// ---- landing kernel: a step's outputs written into the page-locked host batch by the SMs (zero-copy stores over PCIe) ---
+// One launch replaces the copy engine's per-key copies (each costs a few microseconds of DMA set-up, which is what bounds a
+// microsecond-kernel family end to end) and publishes the rank's sequence word itself: every CTA fences its stores at system
+// scope, the last CTA to finish stores the word.
+namespace b2e {
+namespace {
+constexpr int kLandMaxSegs = 8;
+struct LandSeg {
+  char* dst;        // device-visible address of the host rows
+  const char* src;  // this output set, device memory
+  size_t dst_pitch, src_pitch, width, height;
+  int32_t vec;      // 1: every row starts 16-byte aligned on both sides and is a multiple of 16 bytes
+};
+struct LandArgs {
+  LandSeg seg[kLandMaxSegs];
+  int32_t count;
+  int64_t* seq;       // device-visible address of the rank's sequence word in the host batch
+  int64_t value;
+  unsigned* counter;  // CTAs done (device memory, returns to 0)
+};
+
+__global__ void __launch_bounds__(256) land_outputs_kernel(const LandArgs a) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (int s = 0; s < a.count; ++s) {
+    const LandSeg& g = a.seg[s];
+    if (g.vec) {
+      const size_t per_row = g.width / 16, n = per_row * g.height;
+      if (g.height == 1) {
+        const int4* src = reinterpret_cast<const int4*>(g.src);
+        int4* dst = reinterpret_cast<int4*>(g.dst);
+        for (size_t c = tid; c < n; c += stride) dst[c] = src[c];
+      } else {
+        for (size_t c = tid; c < n; c += stride) {
+          const size_t r = c / per_row, k = c - r * per_row;
+          reinterpret_cast<int4*>(g.dst + r * g.dst_pitch)[k] = reinterpret_cast<const int4*>(g.src + r * g.src_pitch)[k];
+        }
+      }
+    } else {
+      const size_t n = g.width * g.height;
+      for (size_t c = tid; c < n; c += stride) {
+        const size_t r = c / g.width, k = c - r * g.width;
+        g.dst[r * g.dst_pitch + k] = g.src[r * g.src_pitch + k];
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(a.counter, 1u);
+    if (prev == gridDim.x - 1) {  // every other CTA's rows are visible to the host: publish
+      *a.counter = 0;
+      __threadfence_system();
+      *reinterpret_cast<volatile int64_t*>(a.seq) = a.value;
+    }
+  }
+}
+
+struct LandPlan {
+  LandArgs args;
+  int grid;
+};
+}  // namespace
+}  // namespace b2e
+using namespace b2e;
+
 // ---- pipelined end-to-end step in ONE host call (gymnasium_b200/distributed.py: HostBatchPipeline) ----------------------
 extern "C" int b2e_pipe_slot_init(b2e_pipe_slot* s) {
   if (!s) {
@@ -193,7 +258,61 @@ extern "C" int b2e_pipe_slot_init(b2e_pipe_slot* s) {
   s->ev_copy = ev[2];
   s->h2d_pending = s->copy_pending = 0;
   s->copy_graph = nullptr;
+  s->land = nullptr;
   return 0;
+}
+
+extern "C" int b2e_pipe_slot_land_kernel(b2e_pipe_slot* s) {
+  if (!s || !s->segs || s->nsegs < 2) {
+    set_error("b2e_pipe_slot_land_kernel: slot or segments missing");
+    return B2E_EINVAL;
+  }
+  if (s->land) return 0;
+  const int nd = s->nsegs - 2;  // the last two segments publish the sequence word the copy-engine way
+  if (nd > kLandMaxSegs) {
+    set_error("b2e_pipe_slot_land_kernel: %d output keys, at most %d", nd, kLandMaxSegs);
+    return B2E_EINVAL;
+  }
+  LandPlan* p = new LandPlan();
+  memset(p, 0, sizeof(*p));
+  size_t chunks = 0;
+  for (int i = 0; i < nd; ++i) {
+    const b2e_copy_seg& g = s->segs[i];
+    LandSeg& d = p->args.seg[i];
+    void* dev = nullptr;
+    if (int st = cuda_status(cudaHostGetDevicePointer(&dev, g.host_dst, 0), "b2e_pipe_slot_land_kernel (host batch not mapped)")) {
+      delete p;
+      return st;
+    }
+    d.dst = (char*)dev;
+    d.src = (const char*)g.dev_src;
+    d.width = g.width;
+    d.height = g.height ? g.height : 1;
+    d.dst_pitch = d.height > 1 ? g.dst_pitch : g.width;
+    d.src_pitch = d.height > 1 ? g.src_pitch : g.width;
+    const uintptr_t bits = (uintptr_t)d.dst | (uintptr_t)d.src | d.width | (d.height > 1 ? (d.dst_pitch | d.src_pitch) : 0);
+    d.vec = (bits & 15) == 0;
+    chunks += (d.vec ? d.width / 16 : d.width) * d.height;
+  }
+  p->args.count = nd;
+  void* seq_dev = nullptr;
+  if (int st = cuda_status(cudaHostGetDevicePointer(&seq_dev, s->segs[s->nsegs - 1].host_dst, 0), "b2e_pipe_slot_land_kernel (seq)")) {
+    delete p;
+    return st;
+  }
+  p->args.seq = (int64_t*)seq_dev;
+  if (int st = cuda_status(cudaMalloc(&p->args.counter, sizeof(unsigned)), "b2e_pipe_slot_land_kernel (counter)")) {
+    delete p;
+    return st;
+  }
+  cudaMemset(p->args.counter, 0, sizeof(unsigned));
+  int dev_id = 0, sms = 148;
+  cudaGetDevice(&dev_id);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+  const size_t want = (chunks + 255) / 256;
+  p->grid = (int)(want < 1 ? 1 : (want > (size_t)sms * 2 ? (size_t)sms * 2 : want));
+  s->land = p;
+  return cuda_status(cudaDeviceSynchronize(), "b2e_pipe_slot_land_kernel");
 }
 
 extern "C" int b2e_pipe_slot_capture(b2e_pipe_slot* s, void* copy_stream) {
@@ -237,6 +356,12 @@ extern "C" int b2e_pipe_slot_destroy(b2e_pipe_slot* s) {
     cudaGraphExecDestroy((cudaGraphExec_t)s->copy_graph);
     s->copy_graph = nullptr;
   }
+  if (s->land) {
+    LandPlan* p = (LandPlan*)s->land;
+    if (p->args.counter) cudaFree(p->args.counter);
+    delete p;
+    s->land = nullptr;
+  }
   return 0;
 }
 
@@ -250,7 +375,7 @@ extern "C" int b2e_pipe_submit(b2e_pipe_slot* s, const void* host_actions, void*
     set_error("b2e_pipe_submit: null pointer in the slot or its arguments");
     return B2E_EINVAL;
   }
-  int64_t* const seq_word = s->copy_graph ? s->seq_src : (int64_t*)seq_src;
+  int64_t* const seq_word = s->land ? (int64_t*)s->segs[s->nsegs - 1].host_dst : s->copy_graph ? s->seq_src : (int64_t*)seq_src;
   const bool pinned = (flags & B2E_PIPE_ACTIONS_PINNED) != 0;
   if (!seq_word || (!pinned && !s->staging_host)) {
     set_error("b2e_pipe_submit: no sequence-word source, or no staging buffer for pageable actions");
@@ -311,6 +436,14 @@ extern "C" int b2e_pipe_submit(b2e_pipe_slot* s, const void* host_actions, void*
   }
   // (5) land the outputs + the sequence word.  Its page-locked source is written only now: once the slot has been released,
   // the copy that published the slot's previous step has certainly read it.
+  if (s->land) {  // the SMs store the rows and then the word itself
+    LandPlan* p = (LandPlan*)s->land;
+    p->args.value = seq_value;
+    land_outputs_kernel<<<p->grid, 256, 0, cs>>>(p->args);
+    cudaEventRecord((cudaEvent_t)s->ev_copy, cs);
+    s->copy_pending = 1;
+    return cuda_status(cudaGetLastError(), "b2e_pipe_submit (landing kernel)");
+  }
   *(volatile int64_t*)seq_word = seq_value;
   __atomic_thread_fence(__ATOMIC_RELEASE);
   if (s->copy_graph) {

@@ -342,7 +342,7 @@ class HostBatchPipeline:
     """
 
     def __init__(self, env, world_size: int, rank: int, total_envs: int | None = None, tag: str = "0", depth: int = 3,
-                 mode: str = "dma", consumer: int = 0, fast: bool = True):
+                 mode: str = "dma", consumer: int = 0, fast: bool = True, landing: str | None = None):
         if env.output != "torch" or env.copy or env.out_buffers < depth:
             raise ValueError("HostBatchPipeline needs an env made with output='torch', copy=False, out_buffers >= depth")
         if mode not in ("dma", "nccl"):
@@ -384,7 +384,11 @@ class HostBatchPipeline:
         # recorded step call(s) -- set up lazily at the first submit, when the action dtype / shape is known
         self._fast = None if (mode == "dma" and fast and env.rng_mode == "numpy") else False
         self._slots = None
-        self.landing_graph = os.environ.get("B2E_PIPE_NO_GRAPH", "0") in ("", "0")
+        # how a step's rows reach the host batch on the fast path: "kernel" (one launch, SM stores over PCIe, publishes the
+        # sequence word itself), "graph" (the copy engine's per-key copies as one CUDA graph), "copies" (one call per key)
+        self.landing = os.environ.get("B2E_PIPE_LANDING", "kernel") if landing is None else landing
+        if self.landing not in ("kernel", "graph", "copies"):
+            raise ValueError(f"landing must be 'kernel', 'graph' or 'copies', got {self.landing!r}")
         self._pinned_ptrs: set = set()
         self._pinned_keep: list = []
 
@@ -483,7 +487,9 @@ class HostBatchPipeline:
             sl.segs, sl.nsegs = segs, len(seg_list)
             sl.seq_src = self.host.seq_slot_source(j)
             L.check(self._lib.b2e_pipe_slot_init(C.byref(sl)), "b2e_pipe_slot_init")
-            if self.landing_graph:  # the D2H side of a step becomes ONE cudaGraphLaunch
+            if self.landing == "kernel":
+                L.check(self._lib.b2e_pipe_slot_land_kernel(C.byref(sl)), "b2e_pipe_slot_land_kernel")
+            elif self.landing == "graph":  # the D2H side of a step becomes ONE cudaGraphLaunch
                 L.check(self._lib.b2e_pipe_slot_capture(C.byref(sl), self._cs_handle), "b2e_pipe_slot_capture")
             self._keep += [staging, act_dev, calls, segs]
         self._slots = slots

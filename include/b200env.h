@@ -116,12 +116,17 @@ typedef struct b2e_pipe_slot {
   int32_t h2d_pending, copy_pending;
   int64_t* seq_src; /* page-locked word of this slot that the landing graph's sequence copy reads (b2e_pipe_slot_capture) */
   void* copy_graph; /* cudaGraphExec_t of the landing copies, owned by the slot; NULL = the copies are enqueued one by one */
+  void* land;       /* landing-kernel plan, owned by the slot (b2e_pipe_slot_land_kernel); takes precedence over copy_graph */
 } b2e_pipe_slot;
 #define B2E_PIPE_ACTIONS_PINNED 1 /* host_actions is page-locked and stays untouched until the step has landed: no staging copy */
 int b2e_pipe_slot_init(b2e_pipe_slot* slot);
 /* Bakes the slot's landing copies (segs, the sequence word read from slot->seq_src) into one CUDA graph: a step's D2H side is
  * then ONE cudaGraphLaunch instead of nsegs cudaMemcpyAsync calls. */
 int b2e_pipe_slot_capture(b2e_pipe_slot* slot, void* copy_stream);
+/* The landing KERNEL: the slot's output rows are stored into the page-locked host batch by the SMs (zero-copy stores over
+ * PCIe, 16 bytes per thread) in ONE launch that also publishes the sequence word (system-scope fence, last CTA stores it) --
+ * no per-key copy-engine set-up, no bounce word.  Needs the host batch mapped (b2e_host_register does) and <= 8 output keys. */
+int b2e_pipe_slot_land_kernel(b2e_pipe_slot* slot);
 int b2e_pipe_slot_destroy(b2e_pipe_slot* slot);
 /* seq_value (= step index + 1) is stored to the sequence word's source -- slot->seq_src with a landing graph, else seq_src --
  * after the wait on *ack_word, i.e. when the copy that published the slot's previous step has read it. */

@@ -51,19 +51,18 @@ def test_pipeline_batches_equal_blocking_step(env_id, n, steps, fast):
         np.testing.assert_array_equal(got[-1]["info"][7], expect[-1][4]["x_velocity"])
 
 
-@pytest.mark.parametrize("graph", [True, False])
-@pytest.mark.parametrize("env_id,n", [("CartPole-v1", 4096), ("Humanoid-v5", 64)])
-def test_pipeline_pinned_actions_and_landing_graph(env_id, n, graph, monkeypatch):
-    """Page-locked action batches (no staging copy) and the landing copies as one CUDA graph / as single copies: same batches."""
-    monkeypatch.setenv("B2E_PIPE_NO_GRAPH", "0" if graph else "1")
+@pytest.mark.parametrize("landing", ["kernel", "graph", "copies"])
+@pytest.mark.parametrize("env_id,n", [("CartPole-v1", 4096), ("Humanoid-v5", 64), ("CartPole-v1", 1001)])
+def test_pipeline_pinned_actions_and_landing_modes(env_id, n, landing):
+    """Page-locked action batches (no staging copy); rows landed by the landing kernel / a CUDA graph of copies / single
+    copies: same batches (n = 1001: rows that are not 16-byte multiples take the kernel's byte path)."""
     steps, depth = 25, 4
     ref = gymnasium_b200.make_vec(env_id, num_envs=n, output="numpy")
     env = gymnasium_b200.make_vec(env_id, num_envs=n, copy=False, out_buffers=depth)
     ref.reset(seed=3)
     env.reset(seed=3)
     rs = np.random.default_rng(8)
-    pipe = HostBatchPipeline(env, 1, 0, tag=f"pin_{env_id}_{int(graph)}", depth=depth)
-    assert pipe.landing_graph == graph
+    pipe = HostBatchPipeline(env, 1, 0, tag=f"pin_{env_id}_{landing}_{n}", depth=depth, landing=landing)
     pool = pipe.pinned_actions(depth + 1)
     expect, got = [], []
     for k in range(steps):
@@ -80,7 +79,8 @@ def test_pipeline_pinned_actions_and_landing_graph(env_id, n, graph, monkeypatch
     for t in (steps - 2, steps - 1):
         got.append({key: v.copy() for key, v in pipe.consume(t, ack=False).items()})
         pipe.release(t)
-    assert pipe._fast and (pipe._slots[0].copy_graph is not None) == graph
+    assert pipe._fast and (pipe._slots[0].copy_graph is not None) == (landing == "graph")
+    assert (pipe._slots[0].land is not None) == (landing == "kernel")
     pipe.close()
     for k in range(steps):
         np.testing.assert_array_equal(got[k]["obs"], expect[k][0], err_msg=f"step {k}")
