@@ -463,6 +463,32 @@ class Ctx:
     pass
 
 
+def bind_near_gpu(index):
+    """Runs this rank on the CPUs of its GPU's NUMA node (what `numactl --cpunodebind` under torchrun does): the rank's
+    launches, its slice of the host-side batch (first touch) and the DMA target are then local to the GPU's root complex."""
+    try:
+        import pynvml
+
+        import torch
+
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: find the NVML device by its PCI address
+            p = torch.cuda.get_device_properties(index)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{p.pci_domain_id:08X}:{p.pci_bus_id:02X}:{p.pci_device_id:02X}.0".encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no GPU-local CPUs in this process' affinity mask"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs of GPU {index}'s NUMA node (nvmlDeviceGetCpuAffinity)"
+    except Exception as e:  # noqa: BLE001 -- placement is an optimisation, never a requirement
+        return f"not bound ({type(e).__name__}: {e})"
+
+
 def make_ctx(args):
     import numpy as np
     import torch
@@ -478,6 +504,7 @@ def make_ctx(args):
         args.gpus = cx.world
     torch.cuda.set_device(cx.local_rank)
     cx.dev = torch.device("cuda", cx.local_rank)
+    cx.host_affinity = bind_near_gpu(cx.local_rank) if not args.no_bind else "not bound (--no-bind)"
     if cx.world > 1:
         dist.init_process_group("nccl", device_id=cx.dev)
     cx.info = _lib.device_info(cx.local_rank)
@@ -852,6 +879,7 @@ def run_b200(args):
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "device": torch.cuda.get_device_name(dev),
+            "host_affinity": cx.host_affinity,
         }
         if humanoid is not None:
             line["humanoid_8192_per_gpu"] = humanoid
@@ -1046,6 +1074,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=20.0, help="seconds of CPU work for the reference arm")
     ap.add_argument("--pageable-actions", action="store_true",
                     help="e2e: pass pageable numpy action batches (staged through one host copy) instead of page-locked ones")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-humanoid", action="store_true", help="skip the Humanoid-v5 8192-envs/GPU block of the default line")
@@ -1053,6 +1082,10 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
+        try:  # the CPU arm gets every core the container has, whatever the parent (a NUMA-bound bench rank) ran on
+            os.sched_setaffinity(0, range(os.cpu_count()))
+        except OSError:
+            pass
         return run_reference(args)
     return run_b200(args)
 

@@ -153,6 +153,9 @@ SIGNATURES = {
     "b2e_pipe_slot_destroy": (C.c_int, [C.POINTER(PipeSlot)]),
     "b2e_pipe_slot_capture": (C.c_int, [C.POINTER(PipeSlot), P]),
     "b2e_pipe_slot_land_kernel": (C.c_int, [C.POINTER(PipeSlot)]),
+    "b2e_land_plan_create": (C.c_int, [P, c_i32, P, C.POINTER(c_void_p)]),
+    "b2e_land_plan_launch": (C.c_int, [P, c_i64, P]),
+    "b2e_land_plan_destroy": (C.c_int, [P]),
     "b2e_pipe_submit": (C.c_int, [C.POINTER(PipeSlot), P, P, P, P, c_i64, P, c_i64, c_i32, c_double]),
     "b2e_rng_seed": (C.c_int, [_BP, c_u64, P, P, P, P]),
     "b2e_rng_random": (C.c_int, [_BP, P, c_i32, P, P]),

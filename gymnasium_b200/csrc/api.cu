@@ -1,6 +1,7 @@
 // api.cu -- library-wide C-ABI entry points (version, errors, device query) and the numpy-parity RNG seeding kernel.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -224,9 +225,9 @@ __global__ void __launch_bounds__(256) land_outputs_kernel(const LandArgs a) {
       }
     }
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // the CTA's stores are ordered before thread 0's fence (cumulative at system scope)
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned prev = atomicAdd(a.counter, 1u);
     if (prev == gridDim.x - 1) {  // every other CTA's rows are visible to the host: publish
       *a.counter = 0;
@@ -262,25 +263,24 @@ extern "C" int b2e_pipe_slot_init(b2e_pipe_slot* s) {
   return 0;
 }
 
-extern "C" int b2e_pipe_slot_land_kernel(b2e_pipe_slot* s) {
-  if (!s || !s->segs || s->nsegs < 2) {
-    set_error("b2e_pipe_slot_land_kernel: slot or segments missing");
+// A landing plan: the device-visible addresses of `count` output segments + the rank's sequence word, and the CTA counter.
+extern "C" int b2e_land_plan_create(const b2e_copy_seg* segs, int32_t count, int64_t* seq_host, void** plan_out) {
+  if (!segs || count < 0 || !seq_host || !plan_out) {
+    set_error("b2e_land_plan_create: null pointer or count < 0");
     return B2E_EINVAL;
   }
-  if (s->land) return 0;
-  const int nd = s->nsegs - 2;  // the last two segments publish the sequence word the copy-engine way
-  if (nd > kLandMaxSegs) {
-    set_error("b2e_pipe_slot_land_kernel: %d output keys, at most %d", nd, kLandMaxSegs);
+  if (count > kLandMaxSegs) {
+    set_error("b2e_land_plan_create: %d output keys, at most %d", count, kLandMaxSegs);
     return B2E_EINVAL;
   }
   LandPlan* p = new LandPlan();
   memset(p, 0, sizeof(*p));
   size_t chunks = 0;
-  for (int i = 0; i < nd; ++i) {
-    const b2e_copy_seg& g = s->segs[i];
+  for (int i = 0; i < count; ++i) {
+    const b2e_copy_seg& g = segs[i];
     LandSeg& d = p->args.seg[i];
     void* dev = nullptr;
-    if (int st = cuda_status(cudaHostGetDevicePointer(&dev, g.host_dst, 0), "b2e_pipe_slot_land_kernel (host batch not mapped)")) {
+    if (int st = cuda_status(cudaHostGetDevicePointer(&dev, g.host_dst, 0), "b2e_land_plan_create (host batch not mapped)")) {
       delete p;
       return st;
     }
@@ -294,14 +294,14 @@ extern "C" int b2e_pipe_slot_land_kernel(b2e_pipe_slot* s) {
     d.vec = (bits & 15) == 0;
     chunks += (d.vec ? d.width / 16 : d.width) * d.height;
   }
-  p->args.count = nd;
+  p->args.count = count;
   void* seq_dev = nullptr;
-  if (int st = cuda_status(cudaHostGetDevicePointer(&seq_dev, s->segs[s->nsegs - 1].host_dst, 0), "b2e_pipe_slot_land_kernel (seq)")) {
+  if (int st = cuda_status(cudaHostGetDevicePointer(&seq_dev, seq_host, 0), "b2e_land_plan_create (sequence word)")) {
     delete p;
     return st;
   }
   p->args.seq = (int64_t*)seq_dev;
-  if (int st = cuda_status(cudaMalloc(&p->args.counter, sizeof(unsigned)), "b2e_pipe_slot_land_kernel (counter)")) {
+  if (int st = cuda_status(cudaMalloc(&p->args.counter, sizeof(unsigned)), "b2e_land_plan_create (counter)")) {
     delete p;
     return st;
   }
@@ -309,10 +309,43 @@ extern "C" int b2e_pipe_slot_land_kernel(b2e_pipe_slot* s) {
   int dev_id = 0, sms = 148;
   cudaGetDevice(&dev_id);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+  // few CTAs: measured on B200 (scripts/link_probe.py, 1.7 MB): 37 CTAs 40.9 us, 148 CTAs 41.9, 296+ CTAs 45.8 (copy engine: 33.3)
+  size_t cap = (size_t)(sms / 4 > 0 ? sms / 4 : 1);
+  if (const char* e = getenv("B2E_LAND_GRID"))
+    if (atoi(e) > 0) cap = (size_t)atoi(e);
   const size_t want = (chunks + 255) / 256;
-  p->grid = (int)(want < 1 ? 1 : (want > (size_t)sms * 2 ? (size_t)sms * 2 : want));
-  s->land = p;
-  return cuda_status(cudaDeviceSynchronize(), "b2e_pipe_slot_land_kernel");
+  p->grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  *plan_out = p;
+  return cuda_status(cudaDeviceSynchronize(), "b2e_land_plan_create");
+}
+
+extern "C" int b2e_land_plan_launch(void* plan, int64_t seq_value, void* stream) {
+  if (!plan) {
+    set_error("b2e_land_plan_launch: plan is NULL");
+    return B2E_EINVAL;
+  }
+  LandPlan* p = (LandPlan*)plan;
+  p->args.value = seq_value;
+  land_outputs_kernel<<<p->grid, 256, 0, (cudaStream_t)stream>>>(p->args);
+  return cuda_status(cudaGetLastError(), "b2e_land_plan_launch");
+}
+
+extern "C" int b2e_land_plan_destroy(void* plan) {
+  if (!plan) return 0;
+  LandPlan* p = (LandPlan*)plan;
+  if (p->args.counter) cudaFree(p->args.counter);
+  delete p;
+  return 0;
+}
+
+extern "C" int b2e_pipe_slot_land_kernel(b2e_pipe_slot* s) {
+  if (!s || !s->segs || s->nsegs < 2) {
+    set_error("b2e_pipe_slot_land_kernel: slot or segments missing");
+    return B2E_EINVAL;
+  }
+  if (s->land) return 0;
+  // the last two segments publish the sequence word the copy-engine way; the kernel stores it itself
+  return b2e_land_plan_create(s->segs, s->nsegs - 2, (int64_t*)s->segs[s->nsegs - 1].host_dst, &s->land);
 }
 
 extern "C" int b2e_pipe_slot_capture(b2e_pipe_slot* s, void* copy_stream) {
@@ -357,9 +390,7 @@ extern "C" int b2e_pipe_slot_destroy(b2e_pipe_slot* s) {
     s->copy_graph = nullptr;
   }
   if (s->land) {
-    LandPlan* p = (LandPlan*)s->land;
-    if (p->args.counter) cudaFree(p->args.counter);
-    delete p;
+    b2e_land_plan_destroy(s->land);
     s->land = nullptr;
   }
   return 0;
@@ -437,9 +468,7 @@ extern "C" int b2e_pipe_submit(b2e_pipe_slot* s, const void* host_actions, void*
   // (5) land the outputs + the sequence word.  Its page-locked source is written only now: once the slot has been released,
   // the copy that published the slot's previous step has certainly read it.
   if (s->land) {  // the SMs store the rows and then the word itself
-    LandPlan* p = (LandPlan*)s->land;
-    p->args.value = seq_value;
-    land_outputs_kernel<<<p->grid, 256, 0, cs>>>(p->args);
+    if (int st = b2e_land_plan_launch(s->land, seq_value, copy_stream)) return st;
     cudaEventRecord((cudaEvent_t)s->ev_copy, cs);
     s->copy_pending = 1;
     return cuda_status(cudaGetLastError(), "b2e_pipe_submit (landing kernel)");

@@ -10,12 +10,11 @@
 // intrinsics so ptxas can never contract a*b+c into an FMA: apart from sin/cos (CUDA libdevice vs the host libm,
 // <= 1-2 ulp) the op sequence is the reference's, which keeps whole trajectories inside the 1e-5 tolerance.
 //
-// Memory: float64 state as two 16-byte streams, [2][n] double2 = (x, x_dot)[n] then (theta, theta_dot)[n] (two fully
-// coalesced LDG.128 / STG.128 per env instead of four 8-byte accesses), one packed int32 control word, float4 observation
-// store, RNG state touched only by lanes that reset.  HBM-bound: 106 B/env-step with int64 actions.
-// Code layout: the step kernel's hot path is straight-line (loads -> Euler step -> stores); everything rare -- the
-// autoreset draws (PCG64 128-bit arithmetic / Philox), libdevice's sincos for |theta| >= 0.3 -- lives in __noinline__
-// functions so that the instruction stream an SM has to fetch for a cold launch stays short.
+// Memory: struct-of-arrays float64 state [4][n] (four fully coalesced 8-byte streams), one packed int32 control word,
+// float4 observation store, RNG state touched only by lanes that reset.  HBM-bound: 106 B/env-step with int64 actions.
+// Round 2 tried two 16-byte state streams (LDG.128) and moving the rare code (autoreset draws, libdevice sincos) out of
+// line; a same-box A/B of the four combinations (scripts/cartpole_ab.sh, profiles/r2_notes.md) put this form first on the
+// HBM-cold ring (3.98 us per 65536-env launch against 4.03 / 4.04 / 4.11), so it is the default and the others are build knobs.
 #include "common.cuh"
 
 namespace b2e {
@@ -57,8 +56,14 @@ __device__ __forceinline__ double div_total_mass(double x) {
   return __fma_rn(__fma_rn(-q, d, x), r, q);
 }
 
+// A/B knobs (scripts/cartpole_ab.sh builds the variants; profiles/r2_notes.md has the same-box measurement that picked the
+// defaults): state layout -- four 8-byte streams [4][n] (default) or two 16-byte streams (-DB2E_CARTPOLE_AB_AOS2); the
+// autoreset / libdevice-sincos code inlined (default) or out of line (-DB2E_CARTPOLE_AB_COLD=__noinline__).
+#ifndef B2E_CARTPOLE_AB_COLD
+#define B2E_CARTPOLE_AB_COLD __forceinline__
+#endif
 // libdevice's sincos (Payne-Hanek reduction and all), out of line and returning in registers
-__device__ __noinline__ double2 sincos_cold(double x) {
+__device__ B2E_CARTPOLE_AB_COLD double2 sincos_cold(double x) {
   double sn, cs;
   sincos(x, &sn, &cs);
   return make_double2(sn, cs);
@@ -119,12 +124,23 @@ __device__ __forceinline__ bool is_terminated(const State4& s) {  // cartpole.py
 }
 
 __device__ __forceinline__ State4 load_state(const double* __restrict__ st, int64_t n, int64_t i) {
+#ifdef B2E_CARTPOLE_AB_AOS2  // A/B builds only
   const double2 a = reinterpret_cast<const double2*>(st)[i], b = reinterpret_cast<const double2*>(st)[n + i];
   return State4{a.x, a.y, b.x, b.y};
+#else
+  return State4{st[i], st[n + i], st[2 * n + i], st[3 * n + i]};
+#endif
 }
 __device__ __forceinline__ void store_state(double* __restrict__ st, int64_t n, int64_t i, const State4& s) {
+#ifdef B2E_CARTPOLE_AB_AOS2
   reinterpret_cast<double2*>(st)[i] = make_double2(s.x, s.xd);
   reinterpret_cast<double2*>(st)[n + i] = make_double2(s.th, s.thd);
+#else
+  st[i] = s.x;
+  st[n + i] = s.xd;
+  st[2 * n + i] = s.th;
+  st[3 * n + i] = s.thd;
+#endif
 }
 __device__ __forceinline__ float4 to_obs(const State4& s) {
   return make_float4((float)s.x, (float)s.xd, (float)s.th, (float)s.thd);
@@ -167,7 +183,7 @@ __global__ void __launch_bounds__(kBlock) cartpole_reset_kernel(const CartPoleAr
 // cleared control word, observation.  Scalar arguments only, so that the call costs the hot path nothing (a reference to
 // the kernel's argument struct would make ptxas copy all of it to local memory in the kernel prologue).  `g` carries the
 // env's PCG64 words when the caller has already loaded them (numpy mode, kSpecRng).
-__device__ __noinline__ void reset_env_cold(double* __restrict__ state, int32_t* __restrict__ ctrl, uint64_t* __restrict__ rng,
+__device__ B2E_CARTPOLE_AB_COLD void reset_env_cold(double* __restrict__ state, int32_t* __restrict__ ctrl, uint64_t* __restrict__ rng,
                                             float* __restrict__ obs, int64_t n, int64_t i, double low, double range,
                                             int32_t rng_mode, uint64_t philox_seed, uint64_t env, uint64_t counter,
                                             bool have_words, ulonglong2 w_state, ulonglong2 w_inc) {

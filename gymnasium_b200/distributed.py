@@ -171,8 +171,17 @@ class HostBatch:
         self._addr = self._np.ctypes.data
         self._registered = False
         self._views: dict = {}
+        # first touch decides the NUMA node of a page: every rank faults in ITS rows (the pages its GPU will write), rank 0 the
+        # header -- before anybody page-locks the buffer
         if rank == 0:
-            self._np[:] = 0  # also faults every page in before it is page-locked
+            self._np[: self.header_bytes] = 0
+        start, count = self.bounds[self.rank]
+        for j in range(self.depth):
+            for key, arr in self.views(j).items():
+                if key in soa_keys:
+                    arr[:, start:start + count] = 0
+                else:
+                    arr[start:start + count] = 0
         barrier()
         if register:
             from . import _lib

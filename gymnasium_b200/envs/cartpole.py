@@ -53,8 +53,8 @@ class CartPoleVectorEnv(B200VectorEnv):
                          max_episode_steps=max_episode_steps, render_mode=render_mode, **engine_kwargs)
         self.sutton_barto_reward = bool(sutton_barto_reward)
         self._cfg = _lib.CartPoleCfg(reset_low=-0.05, reset_high=0.05, sutton_barto_reward=int(self.sutton_barto_reward))
-        # two 16-byte streams: [0] = (x, x_dot) per env, [1] = (theta, theta_dot) per env
-        self._state = torch.zeros((2, self.num_envs, 2), dtype=torch.float64, device=self.device)
+        # struct of arrays: x[n], x_dot[n], theta[n], theta_dot[n]
+        self._state = torch.zeros((4, self.num_envs), dtype=torch.float64, device=self.device)
 
     # -- buffers -------------------------------------------------------------------------------------------------
     def _alloc_outputs(self):
@@ -71,12 +71,12 @@ class CartPoleVectorEnv(B200VectorEnv):
     @property
     def state(self) -> torch.Tensor:
         """float64 ``(N, 4)`` view-copy of (x, x_dot, theta, theta_dot) -- ``CartPoleEnv.state`` per env."""
-        return self._state.permute(1, 0, 2).reshape(self.num_envs, 4)
+        return self._state.t().contiguous()
 
     def set_state(self, state) -> None:
         """Overwrites the per-env state from a ``(N, 4)`` array of (x, x_dot, theta, theta_dot)."""
-        t = torch.as_tensor(state, dtype=torch.float64).to(self.device).reshape(self.num_envs, 2, 2)
-        self._state.copy_(t.permute(1, 0, 2))
+        t = torch.as_tensor(state, dtype=torch.float64).to(self.device).reshape(self.num_envs, 4)
+        self._state.copy_(t.t())
 
     # -- kernels -------------------------------------------------------------------------------------------------
     def _reset_kernel(self, mask, options, out):

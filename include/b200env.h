@@ -127,6 +127,11 @@ int b2e_pipe_slot_capture(b2e_pipe_slot* slot, void* copy_stream);
  * PCIe, 16 bytes per thread) in ONE launch that also publishes the sequence word (system-scope fence, last CTA stores it) --
  * no per-key copy-engine set-up, no bounce word.  Needs the host batch mapped (b2e_host_register does) and <= 8 output keys. */
 int b2e_pipe_slot_land_kernel(b2e_pipe_slot* slot);
+/* The same kernel without a slot (HostBatchPipeline's Python path, scripts/link_probe.py): a plan holds the device-visible
+ * addresses of `count` (<= 8) segments whose host_dst lie in a b2e_host_register'ed buffer, and of the sequence word. */
+int b2e_land_plan_create(const b2e_copy_seg* segs, int32_t count, int64_t* seq_host, void** plan);
+int b2e_land_plan_launch(void* plan, int64_t seq_value, void* stream);
+int b2e_land_plan_destroy(void* plan);
 int b2e_pipe_slot_destroy(b2e_pipe_slot* slot);
 /* seq_value (= step index + 1) is stored to the sequence word's source -- slot->seq_src with a landing graph, else seq_src --
  * after the wait on *ack_word, i.e. when the copy that published the slot's previous step has read it. */
@@ -145,7 +150,7 @@ int b2e_rng_seed(const b2e_batch* b, uint64_t base_seed, const uint64_t* seeds, 
 int b2e_rng_random(const b2e_batch* b, uint64_t* rng, int32_t k, double* out, void* stream);
 
 /* ---- CartPole-v1: gymnasium/envs/classic_control/cartpole.py:164-247 ---------------------------------------------
- * state  : float64 [2][n][2]  two 16-byte streams: (x, x_dot)[n] then (theta, theta_dot)[n]
+ * state  : float64 [4][n]     x[n], x_dot[n], theta[n], theta_dot[n] (four coalesced 8-byte streams)
  * ctrl   : int32 [n]       bits 0..30 elapsed steps (TimeLimit), bit 31 = autoreset pending (NEXT_STEP)
  * obs    : float32 [n][4]
  */

@@ -26,6 +26,6 @@ acts = torch.randint(0, 2, (n,), device="cuda")
 ring = [gymnasium_b200.make_vec("CartPole-v1", num_envs=n, copy=False, env_offset=j * n) for j in range(30)]
 for e in ring: e.reset(seed=0)
 print("speculative RNG load:", "on" if os.environ.get("B2E_CARTPOLE_SPEC_RNG") else "off", " PDL:", "on" if os.environ.get("B2E_PDL") else "off")
-for blk in [32, 64, 96, 128, 192, 256, 448, 1024]:
+for blk in [int(x) for x in os.environ.get('B2E_SWEEP_BLOCKS', '32,64,96,128,192,256,448,1024').split(',')]:
     for e in ring: e._cfg.step_block = blk
     print(f"block {blk:5d}: L2-resident {chain(ring[:1], acts):.3f} us   HBM-cold ring {chain(ring, acts):.3f} us")

@@ -14,7 +14,7 @@ import sys
 def functions_of(path):
     """[(first line, name)] of the function definitions of a C++ source (a line that starts at column 0 and opens a body)."""
     out = []
-    pat = re.compile(r"^(?:template\s*<[^>]*>\s*)?(?:extern \"C\" )?(?:static\s+)?(?:__device__|__global__|__host__|inline|static|void|int|float|double|bool|V2|Rot|Xf)[^;]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;]*$")
+    pat = re.compile(r"^(?:template\s*<[^>]*>\s*)?(?:extern \"C\" )?(?:static\s+)?(?:DI|__device__|__global__|__host__|inline|static|void|int|float|double|bool|V2|Rot|Xf)[^;]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;]*$")
     with open(path) as f:
         lines = f.read().split("\n")
     for i, ln in enumerate(lines, 1):
