@@ -221,6 +221,8 @@ typedef struct {
   /* env */
   int game_over, leg_contact[2], has_prev_shaping;
   long toi_calls, toi_events;  /* statistics: b2TimeOfImpact evaluations / solid TOI events (sub-steps) since reset */
+  long toi_clear, toi_clear_wrong; /* evaluations the CUDA engine's "clearly separated" test would skip / of those, how
+                                      many b2TimeOfImpact did NOT answer alpha = 1 (must stay 0: the skip is exact) */
   double prev_shaping, helipad_y;
   float gravity;
   pcg64_t rng;
@@ -1479,6 +1481,40 @@ static void solve_toi_island(lander_t* L, int dyn, const int* idx, int n, float 
 }
 
 /* b2World::SolveTOI(step) with m_stepComplete = true on entry (no sub-stepping mode) */
+/* The CUDA engine's shortcut around b2TimeOfImpact (gymnasium_b200/csrc/lunarlander.cu: toi_clearly_separated), restated
+ * here so that the oracle can count how often it applies and check that it never changes a result.  If every vertex of the
+ * polygon stays on one side of the edge's line by more than TOI_CLEAR_MARGIN during the whole sweep, no point of the
+ * polygon ever comes within the TOI target distance (0.005 + 0.00125) of any point of the edge, so b2TimeOfImpact cannot
+ * return e_touching and SolveTOI's alpha is 1 whatever the root finder does.  The sweep is bounded from the end pose (the
+ * body's current transform): a vertex at sweep time t lies within |c - c0| projected on the normal, plus r_max * |a - a0|
+ * for the rotation, of its end position. */
+#define TOI_CLEAR_MARGIN 0.05f
+#define TOI_CLEAR_RMAX 0.8f /* > the largest vertex distance from a body's centre of mass (lander 0.61, legs 0.28) */
+static int toi_clearly_separated(const v2* ev, const poly_t* p, const body_t* b) {
+  const v2 d = vsub(ev[1], ev[0]);
+  const float len = vlen(d);
+  if (!(len > 1e-3f)) return 0;
+  const v2 n = V(d.y / len, -d.x / len);
+  const float da = fabsf(b->a - b->a0);
+  if (!(da < 0.5f)) return 0;
+  const float slack = fabsf(vdot(n, vsub(b->c, b->c0))) + TOI_CLEAR_RMAX * da + TOI_CLEAR_MARGIN;
+  const v2 u = V(d.x / len, d.y / len);
+  const float slack_u = fabsf(vdot(u, vsub(b->c, b->c0))) + TOI_CLEAR_RMAX * da + TOI_CLEAR_MARGIN;
+  float lo = 1e30f, hi = -1e30f, ulo = 1e30f, uhi = -1e30f;
+  for (int i = 0; i < p->count; ++i) {
+    const v2 v = p->v[i];
+    const v2 w = V((b->xf.q.c * v.x - b->xf.q.s * v.y) + b->xf.p.x, (b->xf.q.s * v.x + b->xf.q.c * v.y) + b->xf.p.y);
+    const v2 r = vsub(w, ev[0]);
+    const float sd = vdot(n, r), su = vdot(u, r);
+    lo = fminf(lo, sd);
+    hi = fmaxf(hi, sd);
+    ulo = fminf(ulo, su);
+    uhi = fmaxf(uhi, su);
+  }
+  /* beside the line, or beyond one of the segment's ends along it */
+  return lo > slack || hi < -slack || ulo > len + slack_u || uhi < -slack_u;
+}
+
 static void solve_toi(lander_t* L, float dt, int vel_iters) {
   for (int i = 0; i < NBODY; ++i) L->b[i].alpha0 = 0.0f;
   for (int k = 0; k < NPAIR; ++k) { L->contact[k].toi_flag = 0; L->contact[k].toi_count = 0; L->contact[k].toi = 1.0f; }
@@ -1512,6 +1548,10 @@ static void solve_toi(lander_t* L, float dt, int vel_iters) {
         int state = time_of_impact(&pA, &pB, body_sweep(bB), &beta);
         ++L->toi_calls;
         alpha = state == 3 ? fminf(alpha0 + (1.0f - alpha0) * beta, 1.0f) : 1.0f;
+        if (toi_clearly_separated(ev, &L->poly[dyn], bB)) {
+          ++L->toi_clear;
+          if (alpha != 1.0f) ++L->toi_clear_wrong;
+        }
         c->toi = alpha;
         c->toi_flag = 1;
       }
@@ -1794,6 +1834,9 @@ void ll_debug_state(const ll_vec_t* v, int i, float* bodies, float* misc) {
 }
 void ll_toi_stats(const ll_vec_t* v, int i, long* out /* [2]: b2TimeOfImpact calls, solid TOI events since reset */) {
   out[0] = v->env[i].toi_calls; out[1] = v->env[i].toi_events;
+}
+void ll_toi_shortcut_stats(const ll_vec_t* v, int i, long* out /* [2]: evaluations the shortcut covers, of those not alpha=1 */) {
+  out[0] = v->env[i].toi_clear; out[1] = v->env[i].toi_clear_wrong;
 }
 /* Direct probe of the restated b2TimeOfImpact: a box with half extents (hx, hy) (body origin = centroid) swept from
  * (c0, a0) to (c1, a1) against the edge e1-e2; returns the b2TOIOutput state (1 failed, 2 overlapped, 3 touching,

@@ -28,6 +28,7 @@ def lib():
         l.ll_debug_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         l.ll_terrain.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.ll_toi_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        l.ll_toi_shortcut_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.ll_toi_probe.restype = C.c_int
         l.ll_toi_probe.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
         _lib = l
@@ -90,6 +91,12 @@ class OracleLunarLander:
         """(b2TimeOfImpact evaluations, solid TOI events) of env i since its last reset."""
         out = (C.c_long * 2)()
         lib().ll_toi_stats(self._h, i, out)
+        return int(out[0]), int(out[1])
+
+    def toi_shortcut_stats(self, i=0):
+        """(evaluations the CUDA engine's clearly-separated shortcut covers, of those b2TimeOfImpact did not answer alpha=1)."""
+        out = (C.c_long * 2)()
+        lib().ll_toi_shortcut_stats(self._h, i, out)
         return int(out[0]), int(out[1])
 
     def terrain(self, i=0):

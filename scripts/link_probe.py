@@ -114,7 +114,7 @@ def main():
     seq_mm = mmap.mmap(-1, 4096)
     seq_np = np.frombuffer(seq_mm, dtype=np.int64)
     _lib.check(lib.b2e_host_register(seq_np.ctypes.data, 4096), "b2e_host_register")
-    for grid in (37, 74, 148, 296, 592, 1184):
+    for grid in (8, 16, 24, 37, 74, 148, 296):
         os.environ["B2E_LAND_GRID"] = str(grid)
         seg = (_lib.CopySeg * 1)()
         seg[0].host_dst, seg[0].dev_src, seg[0].dst_pitch, seg[0].src_pitch, seg[0].width, seg[0].height = ptr, src.data_ptr(), 0, 0, nb, 1

@@ -123,3 +123,26 @@ def test_continuous_collision_runs_during_landings_and_prevents_deep_first_penet
             st = [env.toi_stats(i) for i in range(64)]
             calls, events = max(calls, sum(s[0] for s in st)), max(events, sum(s[1] for s in st))
     assert calls > 64 and events >= 16, (calls, events)
+
+
+def test_toi_clearly_separated_shortcut_never_changes_a_result():
+    """The CUDA engine skips b2TimeOfImpact for edge/polygon pairs that provably stay apart during the sweep
+    (lunarlander.cu: toi_clearly_separated).  The oracle always runs b2TimeOfImpact and records, for every evaluation the
+    predicate covers, whether the answer was alpha = 1: it must be, every time, for random and for landing trajectories."""
+    n = 96
+    covered = wrong = calls = 0
+    for policy in ("random", "heuristic"):
+        env = OracleLunarLander(n)
+        obs = env.reset(seed=31)[0]
+        rs = np.random.default_rng(11)
+        prev = np.zeros((n, 3), dtype=np.int64)
+        for _ in range(420):
+            a = rs.integers(0, 4, n) if policy == "random" else np.array([heuristic(o) for o in obs])
+            obs = env.step(a)[0]
+            cur = np.array([(env.toi_stats(i)[0],) + env.toi_shortcut_stats(i) for i in range(n)], dtype=np.int64)
+            d = cur - prev
+            d[d[:, 0] < 0] = cur[d[:, 0] < 0]  # counters restart with the episode
+            prev = cur
+            calls, covered, wrong = calls + d[:, 0].sum(), covered + d[:, 1].sum(), wrong + d[:, 2].sum()
+    assert wrong == 0
+    assert calls > 2000 and covered > 0.25 * calls, (calls, covered)
