@@ -12,7 +12,8 @@ src = os.path.join("gpurun_out", tag)
 os.makedirs("profiles", exist_ok=True)
 KEYS = {"step": "cartpole_step_kernel<int64>", "big": "cartpole_step_kernel<int64> N=16M",
         "rollout": "cartpole_rollout_kernel<philox>", "lake": "frozenlake_step_kernel<int64>",
-        "lander": "lunarlander_step_kernel<int64>", "humanoid": "humanoid_step_warp_kernel<float, 10>"}
+        "lander": "lunarlander_step_kernel<int64>", "humanoid": "humanoid_step_warp_kernel<float, 10>",
+        "land": "land_outputs_kernel (CartPole-v1 65536 envs: 1.7 MB of step outputs into the mapped host batch)"}
 summary, lines = {}, []
 for name, key in KEYS.items():
     p = os.path.join(src, f"ncu_{name}.ncu-rep")
