@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(1024) cartpole_step_kernel(const CartPoleArgs 
   const bool term = is_terminated(s);
   const int32_t elapsed = ctrl_elapsed(c) + 1;
   const bool trunc = a.max_steps > 0 && elapsed >= a.max_steps;  // wrappers/common.py:130-133
-  __stcs(a.reward + i, a.sutton ? (term ? -1.0 : 0.0) : 1.0);    // cartpole.py:205-211
+  // cartpole.py:205-220: 1.0 also on the terminating step, 0.0 on steps taken after it without a reset (only reachable with
+  // autoreset DISABLED, where bit 31 of the control word stands for `steps_beyond_terminated is not None`)
+  const bool beyond = a.mode == B2E_AUTORESET_DISABLED && ctrl_pending(c);
+  __stcs(a.reward + i, a.sutton ? (term ? -1.0 : 0.0) : (term && beyond ? 0.0 : 1.0));
   a.term[i] = term;
   a.trunc[i] = trunc;
   int32_t cn = elapsed;
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(1024) cartpole_step_kernel(const CartPoleArgs 
       return;
     }
   }
+  if (a.mode == B2E_AUTORESET_DISABLED && (term || beyond)) cn |= kPending;
   store_state(a.state, a.n, i, s);
   a.ctrl[i] = cn;
   __stcs(reinterpret_cast<float4*>(a.obs) + i, to_obs(s));

@@ -69,10 +69,12 @@ class OracleCartPole(OracleVectorEnv):
         super().__init__(num_envs, max_episode_steps, autoreset_mode)
         self.sutton_barto_reward = sutton_barto_reward
         self.state = np.zeros((num_envs, 4), dtype=np.float64)
+        self.beyond = np.zeros(num_envs, dtype=np.bool_)  # steps_beyond_terminated is not None (cartpole.py:207-220)
 
     def _reset_env(self, i, options):
         low, high = parse_reset_bounds(options)
         self.state[i] = self._rng(i).uniform(low=low, high=high, size=(4,))
+        self.beyond[i] = False  # cartpole.py:243
 
     def _step_lanes(self, lanes, actions):
         if np.any((actions < 0) | (actions > 1)):
@@ -83,8 +85,9 @@ class OracleCartPole(OracleVectorEnv):
         term = (x < -X_THRESHOLD) | (x > X_THRESHOLD) | (theta < -THETA_THRESHOLD) | (theta > THETA_THRESHOLD)
         if self.sutton_barto_reward:
             reward = np.where(term, -1.0, 0.0)
-        else:
-            reward = np.ones(len(lanes), dtype=np.float64)
+        else:  # 1.0, also on the terminating step; 0.0 on steps taken after it without a reset (DISABLED autoreset only)
+            reward = np.where(term & self.beyond[lanes], 0.0, 1.0)
+        self.beyond[lanes] |= term
         return reward, term, {}
 
     def _obs(self):

@@ -164,9 +164,34 @@ def blackjack(name, n, T, seed, mode=AutoresetMode.NEXT_STEP, **kw):
           rew.sum(), "rewards seen", sorted(set(rew.ravel().tolist())))
 
 
+def cartpole_beyond(name, n, T, seed):
+    """Single reference CartPoleEnvs (TimeLimit far away) stepped PAST termination without a reset: reward 1.0 on the
+    terminating step, 0.0 afterwards (cartpole.py:205-220).  SyncVectorEnv refuses to do this (sync_vector_env.py asserts in
+    DISABLED mode), so the tape comes from `gym.make` envs seeded seed+i like its sub-envs would be."""
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    envs = [gym.make("CartPole-v1", max_episode_steps=10 * T) for _ in range(n)]
+    obs0 = np.stack([e.reset(seed=seed + i)[0] for i, e in enumerate(envs)])
+    rs = np.random.default_rng(seed)
+    actions = (rs.random((T, n)) < 0.85).astype(np.int64)  # mostly push right: falls after ~10 steps
+    obs = np.zeros((T + 1, n, 4), np.float32)
+    obs[0] = obs0
+    rew, term = np.zeros((T, n), np.float64), np.zeros((T, n), bool)
+    for t in range(T):
+        for i, e in enumerate(envs):
+            o, r, te, _tr, _ = e.step(int(actions[t, i]))
+            obs[t + 1, i], rew[t, i], term[t, i] = o, r, te
+    np.savez_compressed(os.path.join(HERE, name), obs=obs, rew=rew, term=term, actions=actions, seed=np.int64(seed))
+    print(name, "term", term.sum(), "zero rewards", int((rew == 0).sum()))
+
+
 if __name__ == "__main__":
     assert "reference" in gym.__file__ or "_ref" in gym.__file__, gym.__file__
     print("reference:", gym.__version__, gym.__file__, "numpy", np.__version__)
+    if len(sys.argv) > 1 and sys.argv[1] == "cartpole_beyond":
+        cartpole_beyond("beyond_cartpole_n4_s5.npz", 4, 40, 5)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "blackjack":  # regenerate only the Blackjack fixtures
         blackjack("blackjack_sab_n32_s11.npz", 32, 400, 11)
         blackjack("blackjack_natural_n32_s12.npz", 32, 400, 12, natural=True, sab=False)

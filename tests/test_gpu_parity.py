@@ -315,6 +315,30 @@ def test_api_errors_and_reset_mask():
     assert env.closed
 
 
+@pytest.mark.gpu
+def test_cartpole_reward_on_steps_beyond_termination_matches_reference():
+    """Autoreset DISABLED, lanes stepped past termination without a reset (the reference's vector layer asserts instead; the
+    env itself keeps stepping): reward 1.0 on the terminating step, 0.0 afterwards (cartpole.py:205-220) -- fixture recorded
+    from single reference envs."""
+    g = golden("beyond_cartpole_n4_s5.npz")
+    n = g["actions"].shape[1]
+    env = make("CartPole-v1", n, autoreset_mode="Disabled", max_episode_steps=10_000)
+    np.testing.assert_allclose(env.reset(seed=int(g["seed"]))[0], g["obs"][0], rtol=RTOL, atol=ATOL)
+    for t, a in enumerate(g["actions"]):
+        obs, rew, term, trunc, _ = env.step(a)
+        np.testing.assert_array_equal(rew, g["rew"][t], err_msg=f"step {t}")
+        np.testing.assert_array_equal(term, g["term"][t])
+        np.testing.assert_allclose(obs, g["obs"][t + 1], rtol=1e-4, atol=1e-4)
+        assert not trunc.any()
+    # a masked reset clears the flag: the next termination pays 1.0 again
+    env.reset(options={"reset_mask": np.ones(n, dtype=bool)})
+    for _ in range(40):
+        obs, rew, term, trunc, _ = env.step(np.ones(n, dtype=np.int64))
+        if term.any():
+            break
+    assert term.any() and (rew[term] == 1.0).all()
+
+
 def test_validate_actions_mode_raises_like_the_reference():
     env = make("CartPole-v1", 4, validate_actions=True)
     env.reset(seed=0)

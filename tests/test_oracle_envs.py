@@ -151,3 +151,19 @@ def test_generator_choice_restatement_matches_numpy():
                 assert int(ref.integers(0, n)) == mine.bounded_uint32(n)
             else:
                 assert int(ref.choice(deck)) == deck[mine.bounded_uint32(13)]
+
+
+def test_cartpole_reward_on_steps_beyond_termination_matches_reference():
+    """cartpole.py:205-220: 1.0 on the terminating step, 0.0 on later steps without a reset.  SyncVectorEnv refuses to take
+    such steps, so the fixture was recorded from single reference envs and the oracle is driven below its vector layer."""
+    g = golden("beyond_cartpole_n4_s5.npz")
+    n = g["actions"].shape[1]
+    env = OracleCartPole(n, max_episode_steps=10_000, autoreset_mode="Disabled")
+    np.testing.assert_array_equal(env.reset(seed=int(g["seed"]))[0], g["obs"][0])
+    lanes = np.arange(n)
+    for t, a in enumerate(g["actions"]):
+        rew, term, _ = env._step_lanes(lanes, a)
+        np.testing.assert_array_equal(rew, g["rew"][t])
+        np.testing.assert_array_equal(term, g["term"][t])
+        np.testing.assert_array_equal(env._obs(), g["obs"][t + 1])
+    assert (g["rew"] == 0.0).sum() > 50
