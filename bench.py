@@ -1029,6 +1029,23 @@ def run_extras(args, cx, gymnasium_b200, env0, acts0, fma_cache):
                                "note": "Hopper-v5, one thread per env, random actions U[-1,1]^3, steady state after 40 burn-in "
                                        "steps; bit-exact vs oracle/hopper.c (MuJoCo parity unpinned)"}
         del hp
+        # (7) InvertedPendulum-v5 and Walker2d-v5 on the same planar kernels
+        for env_id, nn, nu, hi in (("InvertedPendulum-v5", 65536, 1, 3.0), ("Walker2d-v5", 16384, 6, 1.0)):
+            pe = gymnasium_b200.make_vec(env_id, num_envs=nn, device=dev, copy=False)
+            pe.reset(seed=0)
+            pa = ((torch.rand((8, nn, nu), device=dev) * 2 - 1) * hi).float()
+            kk = [0]
+
+            def pstep():
+                pe.step(pa[kk[0] % 8])
+                kk[0] += 1
+
+            t = timed(pstep, 20, warm=40)
+            out[env_id.split("-")[0].lower() + f"_{nn}"] = {
+                "steps_per_s": nn / t, "us_per_launch": t * 1e6,
+                "note": f"{env_id}, one thread per env, random actions, steady state after 40 burn-in steps; bit-exact vs its C "
+                        "oracle (MuJoCo parity unpinned; InvertedPendulum pinned to the cart-pole equations of motion)"}
+            del pe
         for big in (131072, 1048576):
             ll = gymnasium_b200.make_vec("LunarLander-v3", num_envs=big, device=dev, copy=False)
             ll.reset(seed=0)

@@ -30,8 +30,11 @@
 #elif defined(MJC_ROBOT_WALKER2D)
 #define MJC_API(name) b2e_walker2d_##name
 #define MJC_NAME "walker2d"
+#elif defined(MJC_ROBOT_INVPEND)
+#define MJC_API(name) b2e_inverted_pendulum_##name
+#define MJC_NAME "inverted_pendulum"
 #else
-#error "define MJC_ROBOT_HOPPER or MJC_ROBOT_WALKER2D before including mjc_planar.cuh"
+#error "define MJC_ROBOT_HOPPER, MJC_ROBOT_WALKER2D or MJC_ROBOT_INVPEND before including mjc_planar.cuh"
 #endif
 #define MJC_STR2(x) #x
 #define MJC_STR(x) MJC_STR2(x)
@@ -43,6 +46,8 @@ namespace {
 
 #if defined(MJC_ROBOT_HOPPER)
 constexpr int NB = 5, NQ = 6, NV = 6, NU = 3, NJ = 6, NG = 5, MAXCON = 8, MAXEFC = 16, MAXPAIR = 16;
+#elif defined(MJC_ROBOT_INVPEND)
+constexpr int NB = 3, NQ = 2, NV = 2, NU = 1, NJ = 2, NG = 2, MAXCON = 2, MAXEFC = 4, MAXPAIR = 2;
 #else
 constexpr int NB = 8, NQ = 9, NV = 9, NU = 6, NJ = 9, NG = 8, MAXCON = 8, MAXEFC = 32, MAXPAIR = 16;
 #endif
@@ -693,6 +698,25 @@ const GDef GEOM[NG] = {
 const int ACT_JOINT[NU] = {3, 4, 5};
 constexpr double kGear = 200.0, kMargin = 0.001;
 const double kSolimpContact[5] = {0.8, 0.8, 0.01, 0.5, 2.0};
+#elif defined(MJC_ROBOT_INVPEND)
+// inverted_pendulum.xml: defaults joint armature 0 damping 1 limited (:4), geom contype 0 (:5: nothing collides), motor
+// ctrlrange -3 3 gear 100 (:7, :27); RK4, timestep 0.02 (:9); the rail (a world geom, :13) takes part in nothing and is left
+// out.  Slide ranges are lengths, hinge ranges degrees.  The pole's capsule is given by fromto (:19): see build_model.
+const BDef BODY[NB] = {{0, {0, 0, 0}}, {0, {0, 0, 0}}, {1, {0, 0, 0}}};
+const JDef JOINT[NJ] = {
+    {2, 1, {0, 0, 0}, {1, 0, 0}, 1, -1, 1, 0, 1, 0},    // slider
+    {3, 2, {0, 0, 0}, {0, 1, 0}, 1, -90, 90, 0, 1, 0},  // hinge
+};
+const double kPoleFromTo[6] = {0, 0, 0, 0.001, 0, 0.6};
+const GDef GEOM[NG] = {
+    {G_CAPSULE, 1, {0, 0, 0}, {0.707, 0, 0.707, 0}, 0.1, 0.1, 1.0, 3, 0, 1},  // cart
+    {G_CAPSULE, 2, {0, 0, 0}, {1, 0, 0, 0}, 0.049, 0.3, 1.0, 3, 0, 1},         // cpole: pos / quat / half length from fromto
+};
+const int ACT_JOINT[NU] = {0};
+constexpr double kGear = 100.0, kMargin = 0.0;
+const double kSolimpContact[5] = {0.9, 0.95, 0.001, 0.5, 2.0};
+#define MJC_TIMESTEP 0.02
+#define MJC_CTRLRANGE 3.0
 #else
 // walker2d_v5.xml: defaults joint armature 0.01 damping .1 limited (:10), geom condim 3 contype 1 conaffinity 0 friction .7
 // (:11: the robot's geoms collide with the floor only); floor conaffinity 1 (:16); RK4, timestep 0.002 (:13); gear 100 (:57-62)
@@ -727,10 +751,15 @@ constexpr double kGear = 100.0, kMargin = 0.0;
 const double kSolimpContact[5] = {0.9, 0.95, 0.001, 0.5, 2.0};
 #endif
 
+#ifndef MJC_TIMESTEP
+#define MJC_TIMESTEP 0.002
+#define MJC_CTRLRANGE 1.0
+#endif
+
 void build_model(HModel& m) {
   const double DEG = PI / 180.0;
   memset(&m, 0, sizeof(m));
-  m.timestep = 0.002; m.gravity[2] = -9.81; m.margin = kMargin; m.tolerance = 1e-8; m.iterations = 100;
+  m.timestep = MJC_TIMESTEP; m.gravity[2] = -9.81; m.margin = kMargin; m.tolerance = 1e-8; m.iterations = 100;
   m.solref[0] = 0.02; m.solref[1] = 1.0;
   m.solimp[0] = 0.9; m.solimp[1] = 0.95; m.solimp[2] = 0.001; m.solimp[3] = 0.5; m.solimp[4] = 2.0;
   for (int k = 0; k < 5; ++k) m.solimp_contact[k] = kSolimpContact[k];
@@ -747,7 +776,8 @@ void build_model(HModel& m) {
     cp3(m.jnt_axis[j], J.axis);
     normalize3(m.jnt_axis[j]);
     m.jnt_limited[j] = J.limited;
-    m.jnt_range[j][0] = J.lo * DEG; m.jnt_range[j][1] = J.hi * DEG;
+    const double unit = J.type == 3 ? DEG : 1.0;  // compiler angle="degree" applies to hinges only
+    m.jnt_range[j][0] = J.lo * unit; m.jnt_range[j][1] = J.hi * unit;
     m.jnt_stiffness[j] = 0.0;
     m.dof_armature[j] = J.armature; m.dof_damping[j] = J.damping;
     m.qpos0[j] = J.ref;
@@ -772,15 +802,30 @@ void build_model(HModel& m) {
     m.geom_type[g] = G.type; m.geom_body[g] = G.body; m.geom_condim[g] = G.condim;
     m.geom_contype[g] = G.contype; m.geom_conaffinity[g] = G.conaffinity;
     m.geom_friction[g] = G.friction;
-    double I[3] = {0, 0, 0}, q[4] = {G.quat[0], G.quat[1], G.quat[2], G.quat[3]};
+    double I[3] = {0, 0, 0}, q[4] = {G.quat[0], G.quat[1], G.quat[2], G.quat[3]}, gpos[3], ghalf = G.half;
+    cp3(gpos, G.pos);
+#if defined(MJC_ROBOT_INVPEND)
+    if (g == 1) {  // capsule from `fromto`: centre = midpoint, half length = |to - from| / 2, frame = the rotation taking z
+                   // onto the segment about z x segment (user_objects.cc mjCGeom::Compile / mjuu_z2quat)
+      const double* ft = kPoleFromTo;
+      double vec[3] = {ft[3] - ft[0], ft[4] - ft[1], ft[5] - ft[2]}, z[3] = {0, 0, 1}, axis[3];
+      for (int k = 0; k < 3; ++k) gpos[k] = 0.5 * (ft[k] + ft[3 + k]);
+      ghalf = 0.5 * normalize3(vec);
+      cross3(axis, z, vec);
+      const double sn = norm3(axis);
+      if (sn < 1e-10) { axis[0] = 1; axis[1] = 0; axis[2] = 0; } else { axis[0] /= sn; axis[1] /= sn; axis[2] /= sn; }
+      const double ang = atan2(sn, vec[2]);
+      q[0] = cos(0.5 * ang); q[1] = axis[0] * sin(0.5 * ang); q[2] = axis[1] * sin(0.5 * ang); q[3] = axis[2] * sin(0.5 * ang);
+    }
+#endif
     quat_normalize(q);
     quat2mat(m.geom_mat[g], q);
-    cp3(m.geom_pos[g], G.pos);
+    cp3(m.geom_pos[g], gpos);
     gmass[g] = 0;
     if (G.type == G_PLANE) {
       m.geom_rbound[g] = 0;
     } else {
-      const double r = G.r, half = G.half, h = 2.0 * half;
+      const double r = G.r, half = ghalf, h = 2.0 * half;
       m.geom_size[g][0] = r; m.geom_size[g][1] = half;
       m.geom_rbound[g] = r + half;
       const double ms = 1000.0 * (4.0 / 3.0) * PI * r * r * r, mc = 1000.0 * PI * r * r * h;
@@ -800,8 +845,9 @@ void build_model(HModel& m) {
     m.body_mass[b] = bm[b];
     for (int k = 0; k < 3; ++k) m.body_ipos[b][k] = bcom[b][k] / bm[b];
   }
-  for (int g = 1; g < NG; ++g) {  // parallel-axis accumulation about the body com
+  for (int g = 0; g < NG; ++g) {  // parallel-axis accumulation about the body com
     const int b = GEOM[g].body;
+    if (b == 0) continue;  // world geoms (the floor) carry no inertia
     const double dv[3] = {m.geom_pos[g][0] - m.body_ipos[b][0], m.geom_pos[g][1] - m.body_ipos[b][1],
                           m.geom_pos[g][2] - m.body_ipos[b][2]};
     const double d2 = dot3(dv, dv);
@@ -813,7 +859,7 @@ void build_model(HModel& m) {
   for (int b = NB - 1; b >= 1; --b) m.subtree_mass[m.parent[b]] += m.subtree_mass[b];
   for (int u = 0; u < NU; ++u) {
     m.act_dof[u] = m.jnt_dofadr[ACT_JOINT[u]]; m.act_gear[u] = kGear;
-    m.act_ctrlrange[u][0] = -1.0; m.act_ctrlrange[u][1] = 1.0;
+    m.act_ctrlrange[u][0] = -MJC_CTRLRANGE; m.act_ctrlrange[u][1] = MJC_CTRLRANGE;
   }
   m.npair = 0;
   for (int b1 = 0; b1 < NB; ++b1)
@@ -887,7 +933,12 @@ int upload_model() {
 }
 
 // ---- kernels -------------------------------------------------------------------------------------------------------------------
-constexpr int kObs = NQ - 1 + NV, kInfo = 6;  // info rows: x_position, z_distance_from_origin, x_velocity, reward_forward, reward_ctrl, reward_survive
+#if defined(MJC_ROBOT_INVPEND)
+constexpr int kObs = NQ + NV;  // inverted_pendulum_v5.py:185-186: qpos | qvel, nothing skipped or clipped
+#else
+constexpr int kObs = NQ - 1 + NV;
+#endif
+constexpr int kInfo = 6;  // info rows: x_position, z_distance_from_origin, x_velocity, reward_forward, reward_ctrl, reward_survive
 struct HopperArgs {
   int64_t n, env_offset;
   int32_t max_steps, mode, rng_mode, lanes, frame_skip, terminate_when_unhealthy;
@@ -909,11 +960,18 @@ struct HopperArgs {
   const uint8_t* __restrict__ mask;
 };
 
+#if defined(MJC_ROBOT_INVPEND)
+__device__ void write_obs(const HData& d, double* __restrict__ obs) {  // inverted_pendulum_v5.py:185-186
+  for (int i = 0; i < NQ; ++i) obs[i] = d.qpos[i];
+  for (int i = 0; i < NV; ++i) obs[NQ + i] = d.qvel[i];
+}
+#else
 __device__ void write_obs(const HData& d, double* __restrict__ obs) {  // hopper_v5.py:253-261
   int o = 0;
   for (int i = 1; i < NQ; ++i) obs[o++] = d.qpos[i];
   for (int i = 0; i < NV; ++i) { const double v = d.qvel[i]; obs[o++] = v < -10.0 ? -10.0 : (v > 10.0 ? 10.0 : v); }
 }
+#endif
 __device__ bool is_healthy(const HopperArgs& a, const HData& d) {
   const double z = d.qpos[1], angle = d.qpos[2];
   bool ok = true;
@@ -949,9 +1007,13 @@ __device__ void env_reset(const HopperArgs& a, int64_t i, HData& d, PDraws& D, d
   for (int k = 0; k < NV; ++k) d.qvel[k] = 0.0 + (-c + (c - -c) * D.next());
   mj_forward(m, d);
   write_obs(d, obs);
+#if defined(MJC_ROBOT_INVPEND)
+  for (int k = 0; k < kInfo; ++k) a.info[k * a.n + i] = 0.0;  // MujocoEnv._get_reset_info: {}
+#else
   for (int k = 2; k < kInfo; ++k) a.info[k * a.n + i] = 0.0;
   a.info[0 * a.n + i] = d.qpos[0];                    // _get_reset_info, hopper_v5.py:339-343
   a.info[1 * a.n + i] = d.qpos[1] - m.qpos0[1];
+#endif
 }
 
 __device__ void load_state(const HopperArgs& a, int64_t i, HData& d) {
@@ -1012,9 +1074,20 @@ __global__ void __launch_bounds__(kHopperBlock) hopper_step_kernel(const HopperA
     return;
   }
   load_state(a, i, d);
-  const double x_before = d.qpos[0];  // hopper_v5.py:272
+  const int64_t n = a.n;
   const ActT* act = reinterpret_cast<const ActT*>(a.actions) + i * NU;
   for (int u = 0; u < NU; ++u) d.ctrl[u] = (double)act[u];
+#if defined(MJC_ROBOT_INVPEND)
+  for (int k = 0; k < a.frame_skip; ++k) mj_step_rk4(m, d);  // do_simulation, inverted_pendulum_v5.py:148
+  write_obs(d, obs);
+  bool finite = true;
+  for (int k = 0; k < kObs; ++k) finite = finite && isfinite(obs[k]);
+  const bool term = !finite || fabs(obs[1]) > 0.2;  // inverted_pendulum_v5.py:152-156
+  const double reward = term ? 0.0 : 1.0;           // int(not terminated)
+  for (int k = 0; k < kInfo - 1; ++k) a.info[k * n + i] = 0.0;
+  a.info[5 * n + i] = reward;                       // info["reward_survive"]
+#else
+  const double x_before = d.qpos[0];  // hopper_v5.py:272
   // control_cost (hopper_v5.py:226-228) squares and sums the ACTION as passed; for float32 actions NumPy 2 keeps the
   // product with the Python float weight in float32 (NEP 50): one rounding per operation, left to right
   ActT sq = (ActT)0;
@@ -1029,13 +1102,13 @@ __global__ void __launch_bounds__(kHopperBlock) hopper_step_kernel(const HopperA
   const double forward_reward = a.w_forward * xv, healthy_reward = healthy ? a.healthy_reward : 0.0;
   const double reward = (forward_reward + healthy_reward) - ctrl_cost;  // hopper_v5.py:305-312
   const bool term = !healthy && a.terminate_when_unhealthy;
-  const int64_t n = a.n;
   a.info[0 * n + i] = x_after;
   a.info[1 * n + i] = d.qpos[1] - m.qpos0[1];
   a.info[2 * n + i] = xv;
   a.info[3 * n + i] = forward_reward;
   a.info[4 * n + i] = -ctrl_cost;
   a.info[5 * n + i] = healthy_reward;
+#endif
   const int32_t elapsed = ctrl_elapsed(c) + 1;
   const bool trunc = a.max_steps > 0 && elapsed >= a.max_steps;
   a.reward[i] = reward;

@@ -29,6 +29,14 @@ class _MjPlanarVectorEnv(B200VectorEnv):
     discrete_actions = False
     soa_output_keys = ("info",)
     robot, xml, NQ, NU = "hopper", "hopper.xml", 6, 3
+    TIMESTEP, ACT_HIGH = 0.002, 1.0
+    INFO_ROWS = {k: i for i, k in enumerate(INFO_KEYS)}  # key -> row of the kernel's info[6][n]
+    RESET_KEYS, STEP_KEYS = INFO_KEYS[:2], INFO_KEYS[2:]  # _get_reset_info keys / keys only step() reports
+
+    @classmethod
+    def _obs_layout(cls):
+        """(observation size, observation_structure): qpos[1:] | clip(qvel) for the locomotion robots (hopper_v5.py:241-246)."""
+        return 2 * cls.NQ - 1, {"skipped_qpos": 1, "qpos": cls.NQ - 1, "qvel": cls.NQ}
 
     def __init__(self, num_envs, max_episode_steps, xml_file, frame_skip, forward_reward_weight, ctrl_cost_weight,
                  healthy_reward, terminate_when_unhealthy, healthy_state_range, healthy_z_range, healthy_angle_range,
@@ -38,15 +46,15 @@ class _MjPlanarVectorEnv(B200VectorEnv):
         if not exclude_current_positions_from_observation:
             raise NotImplementedError("only the default observation layout (x position excluded) is implemented")
         nq, nu = self.NQ, self.NU
-        self.obs_size = 2 * nq - 1
+        self.obs_size, structure = self._obs_layout()
         obs_space = Box(low=-np.inf, high=np.inf, shape=(self.obs_size,), dtype=np.float64)  # hopper_v5.py:237-239
-        act_space = Box(low=-1.0, high=1.0, shape=(nu,), dtype=np.float32)                   # ctrlrange, mujoco_env.py:105-110
+        act_space = Box(low=-self.ACT_HIGH, high=self.ACT_HIGH, shape=(nu,), dtype=np.float32)  # ctrlrange, mujoco_env.py:105-110
         super().__init__(num_envs, obs_space, act_space, max_episode_steps=max_episode_steps, render_mode=render_mode,
                          **engine_kwargs)
         n, dev = self.num_envs, self.device
         self.frame_skip = int(frame_skip)
-        self.dt = 0.002 * self.frame_skip  # mujoco_env.py:189-191
-        self.observation_structure = {"skipped_qpos": 1, "qpos": nq - 1, "qvel": nq}  # hopper_v5.py:241-246
+        self.dt = self.TIMESTEP * self.frame_skip  # mujoco_env.py:189-191
+        self.observation_structure = structure
         self._cfg = _lib.MjPlanarCfg(
             reset_noise_scale=float(reset_noise_scale), forward_reward_weight=float(forward_reward_weight),
             ctrl_cost_weight=float(ctrl_cost_weight), healthy_reward=float(healthy_reward),
@@ -122,7 +130,7 @@ class _MjPlanarVectorEnv(B200VectorEnv):
         n = self.num_envs
         if mask is None:
             mask = np.ones(n, dtype=np.bool_) if isinstance(raw, np.ndarray) else torch.ones(n, dtype=torch.bool, device=self.device)
-        return {k2: v for k in keys for k2, v in ((k, raw[INFO_KEYS.index(k)]), ("_" + k, mask))}
+        return {k2: v for k in keys for k2, v in ((k, raw[self.INFO_ROWS[k]]), ("_" + k, mask))}
 
     def _same_kind(self, x, like):
         if isinstance(x, np.ndarray) == isinstance(like, np.ndarray):
@@ -136,7 +144,7 @@ class _MjPlanarVectorEnv(B200VectorEnv):
         elif self._last_done is not None:
             self._last_done = self._same_kind(self._last_done, mask) & ~mask
         self._info_sid = -1
-        return self._info_dict(out, mask, INFO_KEYS[:2])
+        return self._info_dict(out, mask, self.RESET_KEYS)
 
     def _step_info(self, out):
         """Step info; lanes on their NEXT_STEP reset call (or, in SAME_STEP mode, lanes that just ended an episode) report
@@ -145,13 +153,13 @@ class _MjPlanarVectorEnv(B200VectorEnv):
         sid = int(self._batch.call_counter)
         if sid != self._info_sid:
             self._info_sid, self._info_prev = sid, self._last_done
-        info = self._info_dict(out, None, INFO_KEYS[:2])
+        info = self._info_dict(out, None, self.RESET_KEYS)
         step_mask = None
         if self.autoreset_mode == AutoresetMode.NEXT_STEP and self._info_prev is not None:
             step_mask = ~self._same_kind(self._info_prev, done)
         elif self.autoreset_mode == AutoresetMode.SAME_STEP:
             step_mask = ~done
-        info.update(self._info_dict(out, step_mask, INFO_KEYS[2:]))
+        info.update(self._info_dict(out, step_mask, self.STEP_KEYS))
         self._last_done = done.copy() if isinstance(done, np.ndarray) else done
         if self.autoreset_mode == AutoresetMode.SAME_STEP:
             info.update({"final_obs": out["final_obs"], "_final_obs": done})
@@ -173,6 +181,14 @@ class HopperVectorEnv(_MjPlanarVectorEnv):
     """N Hopper-v5 envs (hopper_v5.py:163-178 for the keyword arguments)."""
 
     robot, xml, NQ, NU = "hopper", "hopper.xml", 6, 3
+    TIMESTEP, ACT_HIGH = 0.002, 1.0
+    INFO_ROWS = {k: i for i, k in enumerate(INFO_KEYS)}  # key -> row of the kernel's info[6][n]
+    RESET_KEYS, STEP_KEYS = INFO_KEYS[:2], INFO_KEYS[2:]  # _get_reset_info keys / keys only step() reports
+
+    @classmethod
+    def _obs_layout(cls):
+        """(observation size, observation_structure): qpos[1:] | clip(qvel) for the locomotion robots (hopper_v5.py:241-246)."""
+        return 2 * cls.NQ - 1, {"skipped_qpos": 1, "qpos": cls.NQ - 1, "qvel": cls.NQ}
 
     def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 1000, xml_file: str = "hopper.xml",
                  frame_skip: int = 4, forward_reward_weight: float = 1.0, ctrl_cost_weight: float = 1e-3,
@@ -198,3 +214,24 @@ class Walker2dVectorEnv(_MjPlanarVectorEnv):
         super().__init__(num_envs, max_episode_steps, xml_file, frame_skip, forward_reward_weight, ctrl_cost_weight,
                          healthy_reward, terminate_when_unhealthy, (-np.inf, np.inf), healthy_z_range, healthy_angle_range,
                          reset_noise_scale, exclude_current_positions_from_observation, render_mode, engine_kwargs)
+
+
+class InvertedPendulumVectorEnv(_MjPlanarVectorEnv):
+    """N InvertedPendulum-v5 envs (inverted_pendulum_v5.py:110-116 for the keyword arguments): observation ``(N, 4) float64``
+    = qpos | qvel, action ``(N, 1) float32`` in [-3, 3], reward 1.0 while the pole is within 0.2 rad (else 0.0 and terminated),
+    info ``reward_survive``; reset info is empty."""
+
+    robot, xml, NQ, NU = "inverted_pendulum", "inverted_pendulum.xml", 2, 1
+    TIMESTEP, ACT_HIGH = 0.02, 3.0
+    INFO_ROWS = {"reward_survive": 5}
+    RESET_KEYS, STEP_KEYS = (), ("reward_survive",)
+    metadata = {"render_modes": [], "render_fps": 25, "autoreset_mode": AutoresetMode.NEXT_STEP}
+
+    @classmethod
+    def _obs_layout(cls):
+        return cls.NQ + cls.NQ, {"qpos": cls.NQ, "qvel": cls.NQ}  # inverted_pendulum_v5.py:140-143
+
+    def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 1000, xml_file: str = "inverted_pendulum.xml",
+                 frame_skip: int = 2, reset_noise_scale: float = 0.01, render_mode: str | None = None, **engine_kwargs):
+        super().__init__(num_envs, max_episode_steps, xml_file, frame_skip, 0.0, 0.0, 0.0, True, (-np.inf, np.inf),
+                         (-np.inf, np.inf), (-np.inf, np.inf), reset_noise_scale, True, render_mode, engine_kwargs)

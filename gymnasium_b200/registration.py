@@ -47,6 +47,8 @@ ENVS = {
     "Hopper-v5": ("gymnasium_b200.envs.hopper:HopperVectorEnv", "gymnasium.envs.mujoco.hopper_v5:HopperEnv", 1000, 3800.0, {}),
     "Walker2d-v5": ("gymnasium_b200.envs.hopper:Walker2dVectorEnv", "gymnasium.envs.mujoco.walker2d_v5:Walker2dEnv", 1000,
                     None, {}),
+    "InvertedPendulum-v5": ("gymnasium_b200.envs.hopper:InvertedPendulumVectorEnv",
+                            "gymnasium.envs.mujoco.inverted_pendulum_v5:InvertedPendulumEnv", 1000, 950.0, {}),
 }
 NAMESPACE = "B200"
 

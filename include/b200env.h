@@ -408,6 +408,16 @@ int b2e_walker2d_reset(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2
 int b2e_walker2d_step(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st, const void* actions,
                       double* obs, double* reward, uint8_t* terminated, uint8_t* truncated, double* info, double* final_obs,
                       void* stream);
+/* InvertedPendulum-v5: gymnasium/envs/mujoco/inverted_pendulum_v5.py:147-186, assets/inverted_pendulum.xml on the same
+ * kernels.  nq = nv = 2 (slider, hinge), nu = 1 (ctrlrange +-3, gear 100), timestep 0.02; cfg uses reset_noise_scale (0.01),
+ * frame_skip (2) and lanes_per_warp only.  obs float64 [n][4] = qpos | qvel; reward 1.0 while |angle| <= 0.2 and the state is
+ * finite, else 0.0 and terminated; info row 5 = reward_survive (rows 0-4 zero); nbody = 3. */
+int b2e_inverted_pendulum_model_info(double* body_mass, double* misc, double* invweight);
+int b2e_inverted_pendulum_reset(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st,
+                                const uint8_t* mask, double* obs, double* info, void* stream);
+int b2e_inverted_pendulum_step(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st,
+                               const void* actions, double* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
+                               double* info, double* final_obs, void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,8 +47,18 @@
 #define MAXCON 8
 #define MAXEFC 32
 #define API(name) w2_##name
+#elif defined(ROBOT_INVPEND)
+#define NB 3
+#define NQ 2
+#define NV 2
+#define NU 1
+#define NJ 2
+#define NG 2
+#define MAXCON 2
+#define MAXEFC 4
+#define API(name) ip_##name
 #else
-#error "define ROBOT_HOPPER or ROBOT_WALKER2D before including mjc_planar.h"
+#error "define ROBOT_HOPPER, ROBOT_WALKER2D or ROBOT_INVPEND before including mjc_planar.h"
 #endif
 #define MINVAL 1e-15
 #define PI 3.14159265358979323846
@@ -250,6 +260,27 @@ static const gdef_t GEOM_DEF[NG] = {
 static const adef_t ACT_DEF[NU] = {{3, 200.0}, {4, 200.0}, {5, 200.0}};
 #define OPT_MARGIN 0.001
 #define OPT_SOLIMP_CONTACT {0.8, 0.8, 0.01, 0.5, 2.0}
+#elif defined(ROBOT_INVPEND)
+/* inverted_pendulum.xml: defaults joint armature 0 damping 1 limited (:4), geom contype 0 (:5: nothing collides), motor
+ * ctrlrange -3 3 (:7); RK4, timestep 0.02 (:9); the rail (a world geom, :13) takes part in nothing and is left out.  Slide
+ * ranges are lengths, hinge ranges degrees.  The pole's capsule is given by fromto (:19): see build_model. */
+static const char* BODY_NAMES[NB] = {"world", "cart", "pole"};
+static const bdef_t BODY_DEF[NB] = {{0, {0, 0, 0}}, {0, {0, 0, 0}}, {1, {0, 0, 0}}};
+static const jdef_t JOINT_DEF[NJ] = {
+    {2, 1, {0, 0, 0}, {1, 0, 0}, 1, -1, 1, 0, 1, 0},   /* slider */
+    {3, 2, {0, 0, 0}, {0, 1, 0}, 1, -90, 90, 0, 1, 0}, /* hinge */
+};
+#define POLE_FROMTO {0, 0, 0, 0.001, 0, 0.6}
+static const gdef_t GEOM_DEF[NG] = {
+    {G_CAPSULE, 1, {0, 0, 0}, {0.707, 0, 0.707, 0}, 0.1, 0.1, 1.0, 3, 0, 1}, /* cart */
+    {G_CAPSULE, 2, {0, 0, 0}, {1, 0, 0, 0}, 0.049, 0.3, 1.0, 3, 0, 1},        /* cpole: pos / quat / half length from fromto */
+};
+static const adef_t ACT_DEF[NU] = {{0, 100.0}};
+#define OPT_MARGIN 0.0
+#define OPT_SOLIMP_CONTACT {0.9, 0.95, 0.001, 0.5, 2.0}
+#define OPT_TIMESTEP 0.02
+#define OPT_CTRLRANGE 3.0
+#define FRAME_SKIP 2
 #else
 /* walker2d_v5.xml: defaults joint armature 0.01 damping .1 limited (:10), geom condim 3 contype 1 conaffinity 0 friction .7
  * (:11: the robot's geoms collide with the floor only); floor conaffinity 1 (:16); RK4, timestep 0.002 (:13) */
@@ -284,12 +315,18 @@ static const adef_t ACT_DEF[NU] = {{3, 100.0}, {4, 100.0}, {5, 100.0}, {6, 100.0
 #define OPT_SOLIMP_CONTACT {0.9, 0.95, 0.001, 0.5, 2.0}
 #endif
 
+#ifndef OPT_TIMESTEP
+#define OPT_TIMESTEP 0.002
+#define OPT_CTRLRANGE 1.0
+#define FRAME_SKIP 4
+#endif
+
 static void forward_position(const model_t* m, data_t* d);
 static void solve_M(const model_t* m, const data_t* d, double* x);
 
 static void build_model(model_t* m) {
   memset(m, 0, sizeof(*m));
-  m->timestep = 0.002; m->gravity[2] = -9.81; m->margin = OPT_MARGIN; m->tolerance = 1e-8; m->iterations = 100;
+  m->timestep = OPT_TIMESTEP; m->gravity[2] = -9.81; m->margin = OPT_MARGIN; m->tolerance = 1e-8; m->iterations = 100;
   m->solref[0] = 0.02; m->solref[1] = 1.0;
   m->solimp[0] = 0.9; m->solimp[1] = 0.95; m->solimp[2] = 0.001; m->solimp[3] = 0.5; m->solimp[4] = 2.0;
   {
@@ -309,7 +346,8 @@ static void build_model(model_t* m) {
     cp3(m->jnt_axis[j], J->axis);
     normalize3(m->jnt_axis[j]);
     m->jnt_limited[j] = J->limited;
-    m->jnt_range[j][0] = J->lo * DEG; m->jnt_range[j][1] = J->hi * DEG;
+    const double unit = J->type == 3 ? DEG : 1.0; /* compiler angle="degree" applies to hinges only */
+    m->jnt_range[j][0] = J->lo * unit; m->jnt_range[j][1] = J->hi * unit;
     m->jnt_stiffness[j] = 0.0;
     m->dof_armature[j] = J->armature; m->dof_damping[j] = J->damping;
     m->qpos0[j] = J->ref;
@@ -336,15 +374,30 @@ static void build_model(model_t* m) {
     m->geom_type[g] = G->type; m->geom_body[g] = G->body; m->geom_condim[g] = G->condim;
     m->geom_contype[g] = G->contype; m->geom_conaffinity[g] = G->conaffinity;
     m->geom_friction[g] = G->friction;
-    double I[3] = {0, 0, 0}, q[4] = {G->quat[0], G->quat[1], G->quat[2], G->quat[3]};
+    double I[3] = {0, 0, 0}, q[4] = {G->quat[0], G->quat[1], G->quat[2], G->quat[3]}, gpos[3], ghalf = G->half;
+    cp3(gpos, G->pos);
+#if defined(ROBOT_INVPEND)
+    if (g == 1) { /* capsule from `fromto` (user_objects.cc mjCGeom::Compile / mjuu_z2quat): centre = midpoint, half length =
+                     |to - from| / 2, frame = the rotation taking z onto the segment about z x segment */
+      const double ft[6] = POLE_FROMTO;
+      double vec[3] = {ft[3] - ft[0], ft[4] - ft[1], ft[5] - ft[2]}, z[3] = {0, 0, 1}, axis[3];
+      for (int k = 0; k < 3; ++k) gpos[k] = 0.5 * (ft[k] + ft[3 + k]);
+      ghalf = 0.5 * normalize3(vec);
+      cross3(axis, z, vec);
+      const double sn = norm3(axis);
+      if (sn < 1e-10) { axis[0] = 1; axis[1] = 0; axis[2] = 0; } else { axis[0] /= sn; axis[1] /= sn; axis[2] /= sn; }
+      const double ang = atan2(sn, vec[2]);
+      q[0] = cos(0.5 * ang); q[1] = axis[0] * sin(0.5 * ang); q[2] = axis[1] * sin(0.5 * ang); q[3] = axis[2] * sin(0.5 * ang);
+    }
+#endif
     quat_normalize(q);
     quat2mat(m->geom_mat[g], q);
-    cp3(m->geom_pos[g], G->pos);
+    cp3(m->geom_pos[g], gpos);
     gmass[g] = 0;
     if (G->type == G_PLANE) {
       m->geom_rbound[g] = 0;
     } else {
-      double r = G->r, half = G->half, h = 2.0 * half;
+      double r = G->r, half = ghalf, h = 2.0 * half;
       m->geom_size[g][0] = r; m->geom_size[g][1] = half;
       m->geom_rbound[g] = r + half;
       double ms = 1000.0 * (4.0 / 3.0) * PI * r * r * r, mc = 1000.0 * PI * r * r * h;
@@ -364,8 +417,9 @@ static void build_model(model_t* m) {
     m->body_mass[b] = bm[b];
     for (int k = 0; k < 3; ++k) m->body_ipos[b][k] = bcom[b][k] / bm[b];
   }
-  for (int g = 1; g < NG; ++g) { /* parallel-axis accumulation about the body com */
+  for (int g = 0; g < NG; ++g) { /* parallel-axis accumulation about the body com */
     int b = GEOM_DEF[g].body;
+    if (b == 0) continue; /* world geoms (the floor) carry no inertia */
     double dv[3] = {m->geom_pos[g][0] - m->body_ipos[b][0], m->geom_pos[g][1] - m->body_ipos[b][1],
                     m->geom_pos[g][2] - m->body_ipos[b][2]};
     double d2 = dot3(dv, dv);
@@ -377,7 +431,7 @@ static void build_model(model_t* m) {
   for (int b = NB - 1; b >= 1; --b) m->subtree_mass[m->parent[b]] += m->subtree_mass[b];
   for (int u = 0; u < NU; ++u) {
     m->act_dof[u] = m->jnt_dofadr[ACT_DEF[u].joint]; m->act_gear[u] = ACT_DEF[u].gear;
-    m->act_ctrlrange[u][0] = -1.0; m->act_ctrlrange[u][1] = 1.0;
+    m->act_ctrlrange[u][0] = -OPT_CTRLRANGE; m->act_ctrlrange[u][1] = OPT_CTRLRANGE;
   }
   /* collision pairs: different bodies, not parent-child (unless the parent is the world), ordered by (body, body, geom) */
   m->npair = 0;
@@ -947,8 +1001,12 @@ static void mj_step_rk4(const model_t* m, data_t* d) {
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* environment (hopper_v5.py / walker2d_v5.py); info rows: x_position, z_distance_from_origin, x_velocity, reward_forward,
  * reward_ctrl, reward_survive */
+#if defined(ROBOT_INVPEND)
+#define OBS (NQ + NV) /* inverted_pendulum_v5.py:185-186: qpos | qvel, nothing skipped or clipped */
+#else
 #define OBS (NQ - 1 + NV)
-#define NINFO 6
+#endif
+#define NINFO 6 /* InvertedPendulum uses row 5 (reward_survive) only */
 typedef struct {
   data_t d;
   pcg64_t rng;
@@ -961,6 +1019,39 @@ typedef struct {
   int *elapsed, *autoreset;
 } pl_vec_t;
 
+#if defined(ROBOT_INVPEND)
+static void get_obs(const data_t* d, double* obs) { /* inverted_pendulum_v5.py:185-186 */
+  for (int i = 0; i < NQ; ++i) obs[i] = d->qpos[i];
+  for (int i = 0; i < NV; ++i) obs[NQ + i] = d->qvel[i];
+}
+static void env_reset(pl_vec_t* v, int i, double* obs, double* info) { /* inverted_pendulum_v5.py:168-183 */
+  const model_t* m = &v->model;
+  henv_t* e = &v->env[i];
+  pcg64_t rng = e->rng;
+  memset(&e->d, 0, sizeof(e->d)); /* mj_resetData */
+  e->rng = rng;
+  data_t* d = &e->d;
+  const double c = v->reset_noise_scale;
+  for (int k = 0; k < NQ; ++k) d->qpos[k] = m->qpos0[k] + (-c + (c - -c) * pcg64_double(&e->rng));
+  for (int k = 0; k < NV; ++k) d->qvel[k] = 0.0 + (-c + (c - -c) * pcg64_double(&e->rng));
+  mj_forward(m, d); /* set_state */
+  get_obs(d, obs);
+  memset(info, 0, NINFO * sizeof(double)); /* MujocoEnv._get_reset_info: {} */
+}
+static void env_step(pl_vec_t* v, int i, const float* action, double* obs, double* reward, int* terminated, double* info) {
+  const model_t* m = &v->model;
+  data_t* d = &v->env[i].d;
+  for (int u = 0; u < NU; ++u) d->ctrl[u] = (double)action[u];
+  for (int k = 0; k < FRAME_SKIP; ++k) mj_step_rk4(m, d);
+  get_obs(d, obs);
+  int finite = 1;
+  for (int k = 0; k < OBS; ++k) finite = finite && isfinite(obs[k]);
+  *terminated = !finite || fabs(obs[1]) > 0.2; /* inverted_pendulum_v5.py:152-156 */
+  *reward = *terminated ? 0.0 : 1.0;            /* int(not terminated) */
+  memset(info, 0, NINFO * sizeof(double));
+  info[5] = *reward;                            /* info["reward_survive"] */
+}
+#else
 static void get_obs(const data_t* d, double* obs) { /* hopper_v5.py:253-261 */
   int o = 0;
   for (int i = 1; i < NQ; ++i) obs[o++] = d->qpos[i];
@@ -1015,6 +1106,7 @@ static void env_step(pl_vec_t* v, int i, const float* action, double* obs, doubl
   info[0] = x_after; info[1] = d->qpos[1] - m->qpos0[1]; info[2] = xv;
   info[3] = forward_reward; info[4] = -ctrl_cost; info[5] = healthy_reward;
 }
+#endif
 
 pl_vec_t* API(create)(int n, int max_episode_steps, double reset_noise_scale) {
   pl_vec_t* v = (pl_vec_t*)calloc(1, sizeof(pl_vec_t));

@@ -11,7 +11,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 INFO_KEYS = ["x_position", "z_distance_from_origin", "x_velocity", "reward_forward", "reward_ctrl", "reward_survive"]
 # robot -> (library, symbol prefix, nbody, nq = nv, nu)
-ROBOTS = {"hopper": ("libhopper_oracle.so", "hp_", 5, 6, 3), "walker2d": ("libwalker2d_oracle.so", "w2_", 8, 9, 6)}
+ROBOTS = {"hopper": ("libhopper_oracle.so", "hp_", 5, 6, 3), "walker2d": ("libwalker2d_oracle.so", "w2_", 8, 9, 6),
+          "inverted_pendulum": ("libinverted_pendulum_oracle.so", "ip_", 3, 2, 1)}
+OBS_SIZE = {"inverted_pendulum": 4}  # default: 2 nq - 1 (qpos[1:] | qvel)
 _libs = {}
 
 
@@ -44,7 +46,7 @@ class OraclePlanar:
     def __init__(self, num_envs, max_episode_steps=1000, reset_noise_scale=5e-3):
         self.num_envs = n = int(num_envs)
         _, _, self.nb, self.nq, self.nu = ROBOTS[self.robot]
-        self.nv, self.obs_size = self.nq, 2 * self.nq - 1
+        self.nv, self.obs_size = self.nq, OBS_SIZE.get(self.robot, 2 * self.nq - 1)
         self._f = lib(self.robot)
         self._h = self._f["create"](n, int(max_episode_steps or 0), float(reset_noise_scale))
         self._obs = np.zeros((n, self.obs_size), dtype=np.float64)

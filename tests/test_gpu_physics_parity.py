@@ -292,6 +292,44 @@ def test_planar_robots_match_oracle_bit_exact(robot, n, T, dtype):
     assert not env.buffer_overflow()
 
 
+@pytest.mark.parametrize("n,T,dtype", [(512, 160, np.float32), (16384, 60, np.float32), (64, 40, np.float64)])
+def test_inverted_pendulum_matches_oracle_bit_exact(n, T, dtype):
+    """InvertedPendulum-v5 on the planar kernels against oracle/inverted_pendulum.c (itself pinned to the cart-pole equations
+    of motion, tests/test_oracle_hopper.py): observations, rewards, flags and reward_survive, across autoresets."""
+    from oracle.inverted_pendulum import OracleInvertedPendulum
+
+    seed = 5
+    rs = np.random.default_rng(9)
+    idx = np.arange(n) if n <= 512 else np.sort(rs.choice(n, size=256, replace=False))
+    env = make("InvertedPendulum-v5", n)
+    ora = OracleInvertedPendulum(len(idx))
+    o1, i1 = env.reset(seed=seed)
+    o2, _ = ora.reset(seed=[seed + int(i) for i in idx])
+    assert o1.shape == (n, 4) and o1.dtype == np.float64 and i1 == {}
+    assert env.single_action_space.shape == (1,) and float(env.single_action_space.high[0]) == 3.0
+    np.testing.assert_array_equal(o1[idx], o2)
+    resets = np.zeros(len(idx), dtype=np.int64)
+    prev_done = np.zeros(n, dtype=bool)
+    for t in range(T):
+        a = rs.uniform(-3.5, 3.5, size=(n, 1)).astype(dtype)  # beyond the control range on purpose: clamped like ctrllimited
+        x = env.step(a)
+        y = ora.step(a[idx].astype(np.float32))
+        if dtype == np.float64 and (a[idx].astype(np.float32).astype(np.float64) != a[idx]).any():
+            np.testing.assert_allclose(x[0][idx], y[0], rtol=0, atol=1e-4)  # float64 actions drive a slightly different run
+            break
+        np.testing.assert_array_equal(x[0][idx], y[0], err_msg=f"obs differ at step {t}")
+        np.testing.assert_array_equal(x[1][idx], y[1], err_msg=f"reward differs at step {t}")
+        np.testing.assert_array_equal(x[2][idx], y[2])
+        np.testing.assert_array_equal(x[3][idx], y[3])
+        np.testing.assert_array_equal(x[4]["reward_survive"][idx][~prev_done[idx]], y[4]["reward_survive"][~prev_done[idx]])
+        np.testing.assert_array_equal(x[4]["_reward_survive"], ~prev_done)  # lanes on their reset call report no step keys
+        prev_done = x[2] | x[3]
+        resets += y[2] | y[3]
+    if dtype == np.float32:
+        assert (resets >= 1).mean() > 0.9  # random pushes drop the pole within ~15 steps
+    assert not env.buffer_overflow()
+
+
 def test_hopper_sharding_and_api():
     import torch
 

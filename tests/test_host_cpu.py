@@ -115,6 +115,21 @@ def test_humanoid_compiled_model_matches_oracle_compile():
     np.testing.assert_allclose(mass, known, rtol=2e-8)
 
 
+def test_inverted_pendulum_compiled_model_matches_oracle_compile():
+    """Host side of csrc/inverted_pendulum.cu (capsule-from-fromto, slide range in metres, ctrlrange 3) against the oracle's
+    compile of inverted_pendulum.xml, bit for bit, and against the closed-form capsule masses."""
+    from oracle.inverted_pendulum import OracleInvertedPendulum
+
+    lib = _lib.load()
+    mass = np.zeros(3); misc = np.zeros(8); inv = np.zeros(3 * 2 + 2)
+    assert lib.b2e_inverted_pendulum_model_info(mass.ctypes.data, misc.ctypes.data, inv.ctypes.data) == 0
+    om, omisc, oinv = OracleInvertedPendulum(1).model_info()
+    np.testing.assert_array_equal(mass, om)
+    np.testing.assert_array_equal(misc[:3], omisc[:3])
+    np.testing.assert_array_equal(inv, oinv)
+    np.testing.assert_allclose(mass, [0.0, 10.471975511965978, 5.018591641363305], rtol=1e-13)  # rho (4/3 pi r^3 + pi r^2 h)
+
+
 def test_packed_cliffwalking_and_taxi_tables_equal_reference_P():
     from gymnasium_b200.envs.toy_text import pack_cliffwalking, pack_taxi
     from oracle.toy_text import build_cliff, build_taxi, taxi_action_mask

@@ -143,3 +143,75 @@ def test_walker2d_model_free_fall_and_rewards():
         nterm += int(te.sum())
         prev = te | tr
     assert nterm > n // 2
+
+
+# InvertedPendulum-v5 on the same core (oracle/inverted_pendulum.c -> mjc_planar.h)
+def _capsule(r, half, rho=1000.0):
+    h = 2 * half
+    ms, mc = rho * 4 / 3 * np.pi * r ** 3, rho * np.pi * r * r * h
+    return ms + mc, mc * (3 * r * r + h * h) / 12 + ms * (0.4 * r * r + 0.25 * h * h + 0.375 * r * h)
+
+
+def test_inverted_pendulum_matches_the_cart_pole_equations_of_motion():
+    """Analytic pin of the multibody core (kinematics, composite inertia, bias forces, factorisation, damping, actuation,
+    RK4): the cart-pole Lagrangian for inverted_pendulum.xml -- cart 10.47 kg on a damped slider, pole = capsule r 0.049
+    from (0,0,0) to (0.001,0,0.6) on a damped hinge, motor gear 100 -- integrated here with an independent RK4 at the
+    model's timestep must give the oracle's observations."""
+    from oracle.inverted_pendulum import OracleInvertedPendulum
+
+    env = OracleInvertedPendulum(1, max_episode_steps=0)
+    mass, misc, _ = env.model_info()
+    m_cart, _ = _capsule(0.1, 0.1)
+    length = np.hypot(0.001, 0.6)
+    m_pole, i_pole = _capsule(0.049, length / 2)
+    np.testing.assert_allclose(mass, [0.0, m_cart, m_pole], rtol=1e-13)
+    assert misc[1] == 0  # contype 0: no collision pairs
+    com = np.array([0.0005, 0.3])
+    l, phi0, g = np.hypot(*com), np.arctan2(com[0], com[1]), 9.81
+
+    def f(y, force):
+        x, th, xd, thd = y
+        a = th + phi0
+        M = np.array([[m_cart + m_pole, m_pole * l * np.cos(a)], [m_pole * l * np.cos(a), i_pole + m_pole * l * l]])
+        rhs = np.array([force - 1.0 * xd + m_pole * l * np.sin(a) * thd * thd, -1.0 * thd + m_pole * g * l * np.sin(a)])
+        return np.concatenate([[xd, thd], np.linalg.solve(M, rhs)])
+
+    def rk4(y, force, h=0.02):
+        k1 = f(y, force); k2 = f(y + 0.5 * h * k1, force); k3 = f(y + 0.5 * h * k2, force); k4 = f(y + h * k3, force)
+        return y + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+
+    obs, info = env.reset(seed=3)
+    assert info == {} or all(len(v) == 1 for v in info.values())
+    assert obs.shape == (1, 4) and np.abs(obs).max() <= 0.01  # init_qpos = init_qvel = 0, noise 0.01
+    y, rs, worst, terminated = obs[0].copy(), np.random.default_rng(0), 0.0, False
+    for t in range(60):
+        a = rs.uniform(-1.5, 1.5, size=(1, 1)).astype(np.float32)
+        o, r, te, tr, info = env.step(a)
+        if terminated:  # NEXT_STEP: this call was the reset
+            assert r[0] == 0.0 and np.abs(o).max() <= 0.01
+            y, terminated = o[0].copy(), False
+            continue
+        for _ in range(2):  # frame_skip
+            y = rk4(y, 100.0 * float(a[0, 0]))
+        worst = max(worst, np.abs(o[0] - y).max())
+        assert te[0] == (abs(y[1]) > 0.2) and r[0] == (0.0 if te[0] else 1.0) and info["reward_survive"][0] == r[0]
+        terminated = bool(te[0])
+    assert worst < 1e-12, worst
+
+
+def test_inverted_pendulum_slider_limit_and_ctrl_clamp():
+    from oracle.inverted_pendulum import OracleInvertedPendulum
+
+    env = OracleInvertedPendulum(1, max_episode_steps=0)
+    env.reset(seed=0)
+    env.set_state(0, [0.99, 0.0], [1.5, 0.0])  # the cart runs into the +1 end of the rail
+    xs = []
+    for _ in range(8):
+        o = env.step(np.array([[0.0]], dtype=np.float32))[0]
+        xs.append(o[0, 0])
+    assert max(xs) < 1.05 and env.debug(0)[3][1] >= 0  # the soft limit holds the cart near the range
+    env.set_state(0, [0.0, 0.0], [0.0, 0.0])
+    a1 = env.step(np.array([[3.0]], dtype=np.float32))[0].copy()
+    env.set_state(0, [0.0, 0.0], [0.0, 0.0])
+    a2 = env.step(np.array([[30.0]], dtype=np.float32))[0]
+    np.testing.assert_array_equal(a1, a2)  # ctrlrange -3 3 with ctrllimited: the force saturates at gear * 3
