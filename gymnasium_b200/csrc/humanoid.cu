@@ -1267,8 +1267,10 @@ extern "C" int b2e_humanoid_step(const b2e_batch* b, const b2e_humanoid_cfg* cfg
   cudaStream_t s = (cudaStream_t)stream;
   if (use_warp_impl(cfg)) {
     const int W = cfg->envs_per_cta > 0 ? cfg->envs_per_cta : kWarpEnvsPerCta;
-    a.cta_sync = W > 1 && !(cfg->schedule & 1);
-    if (!a.cta_sync || (cfg->schedule & 2)) a.order = nullptr;  // grouping only matters to warps that wait for each other
+    // schedule bits (tuning knobs, results never change): 1 = no CTA barrier, 2 = no work grouping, 4 = barrier once per
+    // mj_step instead of before every mj_forward, 8 = no barrier but keep the grouping
+    a.cta_sync = (W > 1 && !(cfg->schedule & (1 | 8))) ? ((cfg->schedule & 4) ? 2 : 1) : 0;
+    if ((!a.cta_sync && !(cfg->schedule & 8)) || (cfg->schedule & 2)) a.order = nullptr;  // grouping matters to warps that wait for each other
     const bool f64 = b->action_dtype == B2E_ACT_F64;
     if (b->action_dtype != B2E_ACT_F32 && !f64) {
       set_error("b2e_humanoid_step: action_dtype %d is not a float dtype", b->action_dtype);

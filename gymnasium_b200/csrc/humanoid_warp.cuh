@@ -784,7 +784,8 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t slot = (int64_t)blockIdx.x * W + warp, n = a.n;
-  const bool cta_sync = W > 1 && a.cta_sync, live = slot < n;
+  const int cta_sync = W > 1 ? a.cta_sync : 0;  // 1: barrier before every mj_forward, 2: once per mj_step
+  const bool live = slot < n;
   const int64_t i = !live ? 0 : a.order ? a.order[slot] : slot;  // envs of similar cost share a CTA (they wait for each other)
   WS& w = reinterpret_cast<WS*>(w_smem + sizeof(WModel))[warp];
   const int32_t c = live ? a.ctrl[i] : 0;
@@ -809,7 +810,7 @@ __global__ void __launch_bounds__(32 * W) humanoid_step_warp_kernel(const Humano
   for (int k = 0; k < a.frame_skip; ++k) {  // mj_step x frame_skip (mujoco_env.py:150)
 #pragma unroll 1
     for (int st = 0; st < 4; ++st) {
-      if (cta_sync) __syncthreads();
+      if (cta_sync == 1 || (cta_sync == 2 && st == 0)) __syncthreads();
       if (stepping) w_rk4_stage(wm, w, lane, st);
     }
     if (stepping) w_rk4_finish(wm, w, lane);

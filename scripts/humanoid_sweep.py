@@ -34,7 +34,8 @@ for impl, per_cta, schedule in configs:
     sig = (out[0].double().sum().item(), out[1].sum().item(), int(out[2].sum().item()))
     same = "" if ref is None else ("same" if sig == ref else f"DIFFERENT {sig} vs {ref}")
     ref = ref or sig
-    label = (f"warp envs/CTA={per_cta} barrier={'n' if schedule & 1 or per_cta == 1 else 'y'} "
-             f"grouped={'n' if schedule & 3 or per_cta == 1 else 'y'}") if impl == "warp" else "thread"
+    barrier = "n" if (schedule & 9 or per_cta == 1) else ("per-step" if schedule & 4 else "y")
+    grouped = "n" if (per_cta == 1 or schedule & 2 or (schedule & 1 and not schedule & 8)) else "y"
+    label = f"warp envs/CTA={per_cta} barrier={barrier} grouped={grouped}" if impl == "warp" else "thread"
     print(f"Humanoid n={n} {label:46s}: {dt*1e3:8.2f} ms/step  {n/dt:.3e} steps/s  {same}", flush=True)
     del e
