@@ -73,14 +73,14 @@ class LunarLanderCfg(C.Structure):
     """``b2e_lunarlander_cfg``."""
 
     _fields_ = [("gravity", c_double), ("enable_wind", c_i32), ("continuous", c_i32), ("lanes_per_warp", c_i32),
-                ("grouping", c_i32)]
+                ("grouping", c_i32), ("wind_power", c_double), ("turbulence_power", c_double)]
 
 
 class LunarLanderState(C.Structure):
     """``b2e_lunarlander_state`` (device pointers)."""
 
     _fields_ = [(k, c_void_p) for k in ("bodies", "joints", "terrain", "fat", "contacts", "flags", "prev_shaping",
-                                        "ctrl", "rng", "work", "order")]
+                                        "ctrl", "rng", "work", "order", "wind", "u32buf")]
 
 
 class HumanoidCfg(C.Structure):

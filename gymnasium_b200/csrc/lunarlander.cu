@@ -187,7 +187,9 @@ struct Lander {
   Contact ct[kMaxContacts];
   int nct;
   int awake, game_over, leg_contact[2], overflow;
-  V2 force;  // lander only (reset's ApplyForceToCenter)
+  V2 force;      // lander only (reset's ApplyForceToCenter, the wind)
+  float torque;  // lander only (turbulence: ApplyTorque)
+  int32_t wind_idx, torque_idx;  // enable_wind: offsets into the wind / turbulence pattern (lunar_lander.py:401-403)
   double prev_shaping;
 };
 
@@ -679,7 +681,7 @@ __device__ __noinline__ void solve_island(Lander& L, float h, float dt_ratio, fl
     b.a0 = b.a;
     const V2 force = i == 0 ? L.force : mk(0.0f, 0.0f);
     v = v + h * ((1.0f * g) + (M.inv_mass[i] * force));
-    w += h * M.inv_I[i] * 0.0f;
+    w += h * M.inv_I[i] * (i == 0 ? L.torque : 0.0f);
     v = (1.0f / (1.0f + h * 0.0f)) * v;
     w *= 1.0f / (1.0f + h * 0.0f);
     P[i].c = b.c; P[i].a = b.a; Vv[i].v = v; Vv[i].w = w;
@@ -1677,6 +1679,7 @@ DI void world_step(Lander& L, float dt, float dt_ratio, float gravity, bool firs
   }
   if (L.awake) solve_toi(L, dt);  // m_continuousPhysics; a sleeping island has no active body
   L.force = mk(0.0f, 0.0f);  // ClearForces
+  L.torque = 0.0f;
 }
 
 // ---- kernel arguments / global layout -------------------------------------------------------------------------------------
@@ -1685,6 +1688,10 @@ struct LanderArgs {
   int32_t max_steps, mode, rng_mode, lanes;
   uint64_t philox_seed, call_counter;
   float gravity;
+  int32_t continuous, enable_wind;
+  double wind_power, turbulence_power;
+  int32_t* __restrict__ wind;        // [2][n] wind_idx, torque_idx (enable_wind)
+  int64_t* __restrict__ u32buf;      // [n] PCG64's one-word 32-bit buffer: bit 32 = valid (enable_wind, numpy RNG)
   float* __restrict__ bodies;        // [21][n]
   float* __restrict__ joints;        // [8][n]
   float* __restrict__ terrain;       // [11][n] smooth_y
@@ -1744,6 +1751,9 @@ DI void load_state(const LanderArgs& a, int64_t i, Lander& L) {
   L.nct = (f >> 8) & 15;
   L.overflow = (f >> 12) & 1;
   L.force = mk(0.0f, 0.0f);
+  L.torque = 0.0f;
+  L.wind_idx = a.enable_wind ? a.wind[i] : 0;
+  L.torque_idx = a.enable_wind ? a.wind[n + i] : 0;
   L.prev_shaping = a.prev_shaping[i];
   for (int k = 0; k < L.nct; ++k) {
     const uint32_t* w = a.contacts + (int64_t)k * kSlotWords * n + i;
@@ -1799,6 +1809,10 @@ DI void store_state(const LanderArgs& a, int64_t i, const Lander& L) {
     a.fat[(4 * d + 3) * n + i] = L.fat[d].hi.y;
   }
   a.prev_shaping[i] = L.prev_shaping;
+  if (a.enable_wind) {
+    a.wind[i] = L.wind_idx;
+    a.wind[n + i] = L.torque_idx;
+  }
   for (int k = 0; k < L.nct; ++k) {
     uint32_t* w = a.contacts + (int64_t)k * kSlotWords * n + i;
     const Contact& c = L.ct[k];
@@ -1834,10 +1848,40 @@ struct Draws {
     return u;
   }
   DI double uniform(double lo, double hi) { return lo + (hi - lo) * next(); }
+  // Generator.integers(low, high) for a range below 2^32: Lemire's multiply-and-reject on PCG64's buffered 32-bit words
+  // (numpy: buffered_bounded_lemire_uint32 over pcg64_next32; oracle/np_rng.py bounded_uint32) -- low half of a fresh
+  // 64-bit draw first, the high half on the next call
+  bool has32;
+  uint32_t word;
+  DI uint32_t next32() {
+    if (has32) {
+      has32 = false;
+      return word;
+    }
+    const uint64_t x = g.next_u64();
+    has32 = true;
+    word = (uint32_t)(x >> 32);
+    return (uint32_t)x;
+  }
+  DI int64_t integers(int64_t low, int64_t high) {
+    const uint32_t rng = (uint32_t)(high - low - 1), rng_excl = rng + 1u;
+    if (!numpy) return low + (int64_t)(next() * (double)rng_excl);  // Philox mode: not a parity mode
+    uint64_t m = (uint64_t)next32() * rng_excl;
+    uint32_t leftover = (uint32_t)m;
+    if (leftover < rng_excl) {
+      const uint32_t threshold = (0xFFFFFFFFu - rng) % rng_excl;
+      while (leftover < threshold) {
+        m = (uint64_t)next32() * rng_excl;
+        leftover = (uint32_t)m;
+      }
+    }
+    return low + (int64_t)(m >> 32);
+  }
 };
 
 // LunarLander.reset up to (not including) the embedded step(0): lunar_lander.py:321-445
-__device__ __noinline__ void env_reset_state(Lander& L, Draws& D, float* terrain_out, int64_t n, int64_t i) {
+__device__ __noinline__ void env_reset_state(Lander& L, Draws& D, float* terrain_out, int64_t n, int64_t i,
+                                             bool enable_wind) {
   const Model& M = g_model;
   double height[12];
   for (int k = 0; k < 12; ++k) height[k] = D.uniform(0.0, kH / 2);
@@ -1851,6 +1895,12 @@ __device__ __noinline__ void env_reset_state(Lander& L, Draws& D, float* terrain
   const double fx = D.uniform(-kInitialRandom, kInitialRandom);
   const double fy = D.uniform(-kInitialRandom, kInitialRandom);
   L.force = mk((float)fx, (float)fy);
+  L.torque = 0.0f;
+  L.wind_idx = L.torque_idx = 0;
+  if (enable_wind) {  // lunar_lander.py:401-403
+    L.wind_idx = (int32_t)D.integers(-9999, 9999);
+    L.torque_idx = (int32_t)D.integers(-9999, 9999);
+  }
 #pragma unroll
   for (int b = 0; b < kND; ++b) {
     Body& B = L.b[b];
@@ -1880,11 +1930,68 @@ struct StepOut {
   bool terminated;
 };
 
-// LunarLander.step (discrete actions, no wind): lunar_lander.py:471-665
-__device__ __noinline__ void env_step(Lander& L, Draws& D, int action, float gravity, bool first_step, bool has_prev,
-                                      StepOut& out) {
+// tanh in double from a fixed sequence of IEEE operations (the same one as oracle/lunar_lander.c: det_tanh)
+DI double det_tanh(double x) {
+  const double ax = fabs(x);
+  double r;
+  if (ax < 1e-3) {
+    r = ax * (1.0 - (ax * ax) * (1.0 / 3.0));
+  } else if (ax > 20.0) {
+    r = 1.0;
+  } else {
+    const double t = 2.0 * ax;
+    const double k = rint(t * 1.44269504088896338700e+00);
+    const double y = (t - k * 6.93147180369123816490e-01) - k * 1.90821492927058770002e-10;
+    double p = 1.0 / 6227020800.0;
+    p = p * y + 1.0 / 479001600.0;
+    p = p * y + 1.0 / 39916800.0;
+    p = p * y + 1.0 / 3628800.0;
+    p = p * y + 1.0 / 362880.0;
+    p = p * y + 1.0 / 40320.0;
+    p = p * y + 1.0 / 5040.0;
+    p = p * y + 1.0 / 720.0;
+    p = p * y + 1.0 / 120.0;
+    p = p * y + 1.0 / 24.0;
+    p = p * y + 1.0 / 6.0;
+    p = p * y + 0.5;
+    p = p * y + 1.0;
+    p = p * y + 1.0;
+    const double e = p * (double)(1ull << (int)k);  // 0 <= k <= 58
+    r = (e - 1.0) / (e + 1.0);
+  }
+  return x < 0 ? -r : r;
+}
+
+struct EnvCfg {
+  float gravity;
+  bool continuous, enable_wind;
+  double wind_power, turbulence_power;
+};
+
+// LunarLander.step: lunar_lander.py:471-665.  `action` for the discrete env; (c0, c1) = the continuous action already
+// clipped to [-1, 1] in its own precision and widened (np.clip(action, -1, +1).astype(np.float64), :510)
+__device__ __noinline__ void env_step(Lander& L, Draws& D, int action, double a0, double a1, const EnvCfg& cfg,
+                                      bool first_step, bool has_prev, StepOut& out) {
   const Model& M = g_model;
+  const float gravity = cfg.gravity;
   Body& lander = L.b[0];
+  if (cfg.enable_wind && !(L.leg_contact[0] || L.leg_contact[1])) {  // lunar_lander.py:476-506
+    constexpr double kPi = 3.141592653589793;
+    double s1, s2, unused;
+    det_sincos(0.02 * (double)L.wind_idx, &s1, &unused);
+    det_sincos((kPi * 0.01) * (double)L.wind_idx, &s2, &unused);
+    const double wind_mag = det_tanh(s1 + s2) * cfg.wind_power;
+    L.wind_idx += 1;
+    if (!L.awake) L.awake = 1;  // ApplyForceToCenter(..., wake=True)
+    L.force = L.force + mk((float)wind_mag, 0.0f);
+    det_sincos(0.02 * (double)L.torque_idx, &s1, &unused);
+    det_sincos((kPi * 0.01) * (double)L.torque_idx, &s2, &unused);
+    const double torque_mag = det_tanh(s1 + s2) * cfg.turbulence_power;
+    L.torque_idx += 1;
+    L.torque += (float)torque_mag;  // ApplyTorque
+  }
+  const bool fire_main = cfg.continuous ? (a0 > 0.0) : (action == 2);
+  const bool fire_side = cfg.continuous ? (fabs(a1) > 0.5) : (action == 1 || action == 3);
   double tip0, tip1;
   det_sincos((double)lander.a, &tip0, &tip1);
   const double side0 = -tip1, side1 = tip0;
@@ -1892,8 +1999,8 @@ __device__ __noinline__ void env_step(Lander& L, Draws& D, int action, float gra
   disp[0] = D.uniform(-1.0, +1.0) / kScale;
   disp[1] = D.uniform(-1.0, +1.0) / kScale;
   double m_power = 0.0, s_power = 0.0;
-  if (action == 2) {
-    m_power = 1.0;
+  if (fire_main) {
+    m_power = cfg.continuous ? (fmin(fmax(a0, 0.0), 1.0) + 1.0) * 0.5 : 1.0;  // 0.5..1.0
     const double ox = tip0 * (kMainEngineY / kScale + 2 * disp[0]) + side0 * disp[1];
     const double oy = -tip1 * (kMainEngineY / kScale + 2 * disp[0]) - side1 * disp[1];
     const double px = (double)lander.xf.p.x + ox, py = (double)lander.xf.p.y + oy;
@@ -1903,9 +2010,9 @@ __device__ __noinline__ void env_step(Lander& L, Draws& D, int action, float gra
     lander.v = lander.v + M.inv_mass[0] * imp;
     lander.w += M.inv_I[0] * cross(pt - lander.c, imp);
   }
-  if (action == 1 || action == 3) {
-    const double direction = action - 2;
-    s_power = 1.0;
+  if (fire_side) {
+    const double direction = cfg.continuous ? (a1 > 0 ? 1.0 : -1.0) : (double)(action - 2);  // np.sign(action[1])
+    s_power = cfg.continuous ? fmin(fmax(fabs(a1), 0.5), 1.0) : 1.0;
     const double ox = tip0 * disp[0] + side0 * (3 * disp[1] + direction * kSideEngineAway / kScale);
     const double oy = -tip1 * disp[0] - side1 * (3 * disp[1] + direction * kSideEngineAway / kScale);
     const double px = (double)lander.xf.p.x + ox - tip0 * 17 / kScale;
@@ -1959,7 +2066,43 @@ DI Draws make_draws(const LanderArgs& a, int64_t i, uint32_t stream_base) {
   D.env = (uint64_t)(a.env_offset + i);
   D.counter = a.call_counter;
   D.k = stream_base;
+  D.has32 = false;
+  D.word = 0;
+  if (D.numpy && a.enable_wind) {
+    const int64_t b = a.u32buf[i];
+    D.has32 = (b >> 32) & 1;
+    D.word = (uint32_t)b;
+  }
   return D;
+}
+DI void store_draws(const LanderArgs& a, int64_t i, const Draws& D) {
+  if (!D.numpy) return;
+  pcg64_store_state(a.rng, i, D.g);
+  if (a.enable_wind) a.u32buf[i] = (int64_t)D.word | ((int64_t)(D.has32 ? 1 : 0) << 32);
+}
+DI EnvCfg env_cfg(const LanderArgs& a) {
+  EnvCfg c;
+  c.gravity = a.gravity;
+  c.continuous = a.continuous != 0;
+  c.enable_wind = a.enable_wind != 0;
+  c.wind_power = a.wind_power;
+  c.turbulence_power = a.turbulence_power;
+  return c;
+}
+// the action of env i: an integer in 0..3, or (continuous) two floats clipped to [-1, 1] in their own precision and widened
+template <typename ActT>
+DI void load_lander_action(const LanderArgs& a, int64_t i, int& action, double& a0, double& a1) {
+  action = 0;
+  a0 = a1 = 0.0;
+  if constexpr (std::is_floating_point<ActT>::value) {
+    const ActT* p = reinterpret_cast<const ActT*>(a.actions) + 2 * i;
+    const ActT c0 = p[0] < (ActT)-1 ? (ActT)-1 : (p[0] > (ActT)1 ? (ActT)1 : p[0]);
+    const ActT c1 = p[1] < (ActT)-1 ? (ActT)-1 : (p[1] > (ActT)1 ? (ActT)1 : p[1]);
+    a0 = (double)c0;
+    a1 = (double)c1;
+  } else {
+    action = min(max(load_action<ActT>(a.actions, i), 0), 3);
+  }
 }
 
 DI void write_obs(float* __restrict__ obs, int64_t i, const StepOut& o) {
@@ -2022,10 +2165,11 @@ __global__ void __launch_bounds__(kLanderBlock) lunarlander_reset_kernel(const L
   L.overflow = 0;
   L.prev_shaping = 0.0;
   Draws D = make_draws(a, i, 0);
-  env_reset_state(L, D, a.terrain, a.n, i);
+  const EnvCfg cfg = env_cfg(a);
+  env_reset_state(L, D, a.terrain, a.n, i, cfg.enable_wind);
   StepOut o;
-  env_step(L, D, 0, a.gravity, true, false, o);  // return self.step(0)[0] (lunar_lander.py:447)
-  if (D.numpy) pcg64_store_state(a.rng, i, D.g);
+  env_step(L, D, 0, 0.0, 0.0, cfg, true, false, o);  // return self.step(0 / [0, 0])[0] (lunar_lander.py:447)
+  store_draws(a, i, D);
   store_state(a, i, L);
   a.ctrl[i] = 0;
   if (a.work) a.work[i] = lander_key(L, false);
@@ -2045,21 +2189,24 @@ __global__ void __launch_bounds__(kLanderBlock) lunarlander_step_kernel(const La
     if (i < 0 || i >= a.n) return;
   }
   const int32_t c = a.ctrl[i];
-  int action = load_action<ActT>(a.actions, i);
-  action = min(max(action, 0), 3);
+  int action;
+  double a0, a1;
+  load_lander_action<ActT>(a, i, action, a0, a1);
   Lander L;
   Draws D = make_draws(a, i, 0);
+  const EnvCfg cfg = env_cfg(a);
   StepOut o;
   const bool is_reset = a.mode == B2E_AUTORESET_NEXT_STEP && ctrl_pending(c);
   if (is_reset) {
     L.overflow = 0;
     L.prev_shaping = 0.0;
-    env_reset_state(L, D, a.terrain, a.n, i);
+    env_reset_state(L, D, a.terrain, a.n, i, cfg.enable_wind);
     action = 0;
+    a0 = a1 = 0.0;
   } else {
     load_state(a, i, L);
   }
-  env_step(L, D, action, a.gravity, is_reset, !is_reset, o);
+  env_step(L, D, action, a0, a1, cfg, is_reset, !is_reset, o);
   int32_t cn;
   if (is_reset) {  // sync_vector_env.py:279-284
     a.reward[i] = 0.0;
@@ -2080,13 +2227,13 @@ __global__ void __launch_bounds__(kLanderBlock) lunarlander_step_kernel(const La
         write_obs(a.final_obs, i, o);
         L.overflow = 0;
         L.prev_shaping = 0.0;
-        env_reset_state(L, D, a.terrain, a.n, i);
-        env_step(L, D, 0, a.gravity, true, false, o);
+        env_reset_state(L, D, a.terrain, a.n, i, cfg.enable_wind);
+        env_step(L, D, 0, 0.0, 0.0, cfg, true, false, o);
         cn = 0;
       }
     }
   }
-  if (D.numpy) pcg64_store_state(a.rng, i, D.g);
+  store_draws(a, i, D);
   store_state(a, i, L);
   a.ctrl[i] = cn;
   if (a.work) a.work[i] = lander_key(L, ctrl_pending(cn));
@@ -2241,11 +2388,17 @@ int fill(const b2e_batch* b, const b2e_lunarlander_cfg* cfg, const b2e_lunarland
     set_error("%s: null pointer in cfg/state", fn);
     return B2E_EINVAL;
   }
-  if (cfg->enable_wind || cfg->continuous) {
-    set_error("%s: enable_wind / continuous actions are not implemented", fn);
+  if (cfg->enable_wind && (!st->wind || (b->rng_mode == B2E_RNG_NUMPY && !st->u32buf))) {
+    set_error("%s: enable_wind needs state.wind (and state.u32buf with the numpy RNG)", fn);
     return B2E_EINVAL;
   }
   a = LanderArgs{};
+  a.continuous = cfg->continuous != 0;
+  a.enable_wind = cfg->enable_wind != 0;
+  a.wind_power = cfg->wind_power;
+  a.turbulence_power = cfg->turbulence_power;
+  a.wind = st->wind;
+  a.u32buf = st->u32buf;
   a.n = b->n;
   a.env_offset = b->env_offset;
   a.max_steps = b->max_episode_steps;
@@ -2312,6 +2465,14 @@ extern "C" int b2e_lunarlander_step(const b2e_batch* b, const b2e_lunarlander_cf
   const unsigned grid = a.order ? (unsigned)((a.slots + kLanderBlock - 1) / kLanderBlock) : sparse_grid(b->n, a.lanes, kLanderBlock);
   cudaStream_t s = (cudaStream_t)stream;
   if (a.order) lunarlander_group_kernel<<<1, 1024, 0, s>>>(a.work, a.order, a.n, a.slots, lander_group_lanes(cfg->grouping));
+  if (cfg->continuous) {  // actions [n][2] float32 / float64 in [-1, 1] (clipped in-kernel like the reference, :510)
+    switch (b->action_dtype) {
+      case B2E_ACT_F32: lunarlander_step_kernel<float><<<grid, kLanderBlock, 0, s>>>(a); break;
+      case B2E_ACT_F64: lunarlander_step_kernel<double><<<grid, kLanderBlock, 0, s>>>(a); break;
+      default: set_error("b2e_lunarlander_step: continuous=1 needs float32 / float64 actions, got dtype %d", b->action_dtype); return B2E_EINVAL;
+    }
+    return cuda_status(cudaGetLastError(), "b2e_lunarlander_step");
+  }
   switch (b->action_dtype) {
     case B2E_ACT_I64: lunarlander_step_kernel<int64_t><<<grid, kLanderBlock, 0, s>>>(a); break;
     case B2E_ACT_I32: lunarlander_step_kernel<int32_t><<<grid, kLanderBlock, 0, s>>>(a); break;

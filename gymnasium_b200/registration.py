@@ -42,6 +42,8 @@ ENVS = {
     "Taxi-v4": ("gymnasium_b200.envs.toy_text:TaxiVectorEnv", "gymnasium.envs.toy_text.taxi:TaxiEnv", 200, 8, {}),
     "LunarLander-v3": ("gymnasium_b200.envs.lunar_lander:LunarLanderVectorEnv",
                        "gymnasium.envs.box2d.lunar_lander:LunarLander", 1000, 200, {}),
+    "LunarLanderContinuous-v3": ("gymnasium_b200.envs.lunar_lander:LunarLanderVectorEnv",
+                                 "gymnasium.envs.box2d.lunar_lander:LunarLander", 1000, 200, {"continuous": True}),
     "Humanoid-v5": ("gymnasium_b200.envs.humanoid:HumanoidVectorEnv",
                     "gymnasium.envs.mujoco.humanoid_v5:HumanoidEnv", 1000, None, {}),
     "Hopper-v5": ("gymnasium_b200.envs.hopper:HopperVectorEnv", "gymnasium.envs.mujoco.hopper_v5:HopperEnv", 1000, 3800.0, {}),

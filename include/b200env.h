@@ -270,7 +270,8 @@ int b2e_classic_step(const b2e_batch* b, const b2e_classic_cfg* cfg, const void*
                      uint8_t* terminated, uint8_t* truncated, float* final_obs, void* stream);
 
 /* ---- LunarLander-v3: gymnasium/envs/box2d/lunar_lander.py:321-665 (+ the Box2D 2.3.x subset world.Step needs) -------
- * Discrete actions (0 nop, 1 left, 2 main, 3 right), no wind.  Per-env state, struct-of-arrays over n envs (device):
+ * Discrete actions (0 nop, 1 left, 2 main, 3 right) or continuous=1 (two throttles), optional wind.  Per-env state,
+ * struct-of-arrays over n envs (device):
  *   bodies  : float32 [21][n]  for b in (lander, legs[0], legs[1]): c.x, c.y, angle, v.x, v.y, w, sleepTime
  *   joints  : float32 [8][n]   for each revolute joint: impulse.x, .y, .z, motorImpulse
  *   terrain : float32 [11][n]  smooth_y of the 11 terrain chunks
@@ -282,11 +283,13 @@ int b2e_classic_step(const b2e_batch* b, const b2e_classic_cfg* cfg, const void*
  */
 typedef struct b2e_lunarlander_cfg {
   double gravity;        /* LunarLander(gravity=-10.0) */
-  int32_t enable_wind;   /* must be 0 */
-  int32_t continuous;    /* must be 0 */
+  int32_t enable_wind;   /* lunar_lander.py:476-506: wind force / turbulence torque while no leg touches the ground */
+  int32_t continuous;    /* lunar_lander.py:509-616: actions float [n][2] = (main throttle, lateral throttle) in [-1, 1] */
   int32_t lanes_per_warp; /* envs mapped to each warp (1..32); 0 = library default. Fewer lanes = less divergence */
   int32_t grouping;       /* h > 0: envs in free flight share dense warps, envs near the ground get sparse warps of h lanes (clamped to 4..32)
                              (needs work/order; scheduling only); 0 = off */
+  double wind_power;       /* 15.0 */
+  double turbulence_power; /* 1.5 */
 } b2e_lunarlander_cfg;
 
 typedef struct b2e_lunarlander_state {
@@ -302,6 +305,9 @@ typedef struct b2e_lunarlander_state {
   int32_t* work;   /* [n] optional (may be NULL with order): scheduling key of every env after its last step */
   int32_t* order;  /* [9 * n + 64] optional scratch: env index (or -1) of every thread slot of a grouped launch
                       (scheduling only: results do not depend on it) */
+  int32_t* wind;   /* [2][n] wind_idx, torque_idx: offsets into the wind pattern, drawn at reset (enable_wind; else NULL) */
+  int64_t* u32buf; /* [n] PCG64's one-word 32-bit buffer (bit 32 = valid) that np_random.integers leaves behind
+                      (enable_wind with the numpy RNG; else NULL).  Zero it whenever the streams are re-seeded. */
 } b2e_lunarlander_state;
 
 int b2e_lunarlander_state_words(void);

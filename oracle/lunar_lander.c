@@ -31,7 +31,7 @@
  * numpy Generator(PCG64(SeedSequence(seed))) -- gymnasium/utils/seeding.py:39-41 (see oracle/np_rng.py for the pinned
  * Python restatement; this is the same algorithm in C) */
 typedef unsigned __int128 u128;
-typedef struct { u128 state, inc; int seeded; } pcg64_t;
+typedef struct { u128 state, inc; int seeded; int has32; uint32_t word; /* pcg64_next32's one-word buffer */ } pcg64_t;
 
 static void pcg64_seed(pcg64_t* g, uint64_t seed) {
   const uint32_t INIT_A = 0x43b0d7e5u, MULT_A = 0x931e8875u, INIT_B = 0x8b51f9ddu, MULT_B = 0x58f38dedu;
@@ -56,6 +56,7 @@ static void pcg64_seed(pcg64_t* g, uint64_t seed) {
   g->state += initstate;
   g->state = g->state * mult + g->inc;
   g->seeded = 1;
+  g->has32 = 0; g->word = 0; /* a fresh Generator starts with an empty 32-bit buffer */
 }
 static double pcg64_double(pcg64_t* g) {
   const u128 mult = ((u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
@@ -66,6 +67,32 @@ static double pcg64_double(pcg64_t* g) {
   return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 static double pcg64_uniform(pcg64_t* g, double lo, double hi) { return lo + (hi - lo) * pcg64_double(g); }
+static uint64_t pcg64_next64(pcg64_t* g) {
+  const u128 mult = ((u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+  g->state = g->state * mult + g->inc;
+  uint64_t hi = (uint64_t)(g->state >> 64), lo = (uint64_t)g->state, x = hi ^ lo;
+  unsigned rot = (unsigned)(hi >> 58);
+  return (x >> rot) | (x << ((64 - rot) & 63));
+}
+/* pcg64_next32 (numpy/random/src/pcg64/pcg64.h): low half of a fresh 64-bit draw first, the high half on the next call */
+static uint32_t pcg64_next32(pcg64_t* g) {
+  if (g->has32) { g->has32 = 0; return g->word; }
+  uint64_t x = pcg64_next64(g);
+  g->has32 = 1; g->word = (uint32_t)(x >> 32);
+  return (uint32_t)x;
+}
+/* Generator.integers(low, high) for a range below 2^32: buffered_bounded_lemire_uint32 (numpy/random/src/distributions/
+ * distributions.c), pinned against numpy in oracle/np_rng.py (bounded_uint32) */
+static int64_t pcg64_integers(pcg64_t* g, int64_t low, int64_t high) {
+  const uint32_t rng = (uint32_t)(high - low - 1), rng_excl = rng + 1u;
+  uint64_t m = (uint64_t)pcg64_next32(g) * rng_excl;
+  uint32_t leftover = (uint32_t)m;
+  if (leftover < rng_excl) {
+    const uint32_t threshold = (0xFFFFFFFFu - rng) % rng_excl;
+    while (leftover < threshold) { m = (uint64_t)pcg64_next32(g) * rng_excl; leftover = (uint32_t)m; }
+  }
+  return low + (int64_t)(m >> 32);
+}
 
 /* ------------------------------------------------------------------------------------------------------------------
  * b2Math */
@@ -120,6 +147,39 @@ static inline rot_t rot_set(float a) {
   det_sincos((double)a, &s, &c);
   rot_t r = {(float)s, (float)c};
   return r;
+}
+/* tanh in double from a fixed sequence of IEEE operations (the CUDA engine runs the same one): exp by Cody-Waite reduction
+ * with ln 2 in two pieces + a degree-13 Taylor polynomial, tanh = (e^2|x| - 1) / (e^2|x| + 1); accurate to ~2e-16 for the
+ * |x| <= 2 the wind function feeds it, i.e. its float rounding equals libm's except on ~1e-8 of inputs. */
+static inline double det_tanh(double x) {
+  const double ax = fabs(x);
+  double r;
+  if (ax < 1e-3) {
+    r = ax * (1.0 - (ax * ax) * (1.0 / 3.0));
+  } else if (ax > 20.0) {
+    r = 1.0;
+  } else {
+    const double t = 2.0 * ax;
+    const double k = rint(t * 1.44269504088896338700e+00);
+    const double y = (t - k * 6.93147180369123816490e-01) - k * 1.90821492927058770002e-10;
+    double p = 1.0 / 6227020800.0;
+    p = p * y + 1.0 / 479001600.0;
+    p = p * y + 1.0 / 39916800.0;
+    p = p * y + 1.0 / 3628800.0;
+    p = p * y + 1.0 / 362880.0;
+    p = p * y + 1.0 / 40320.0;
+    p = p * y + 1.0 / 5040.0;
+    p = p * y + 1.0 / 720.0;
+    p = p * y + 1.0 / 120.0;
+    p = p * y + 1.0 / 24.0;
+    p = p * y + 1.0 / 6.0;
+    p = p * y + 0.5;
+    p = p * y + 1.0;
+    p = p * y + 1.0;
+    const double e = p * (double)(1ull << (int)k); /* 0 <= k <= 58 */
+    r = (e - 1.0) / (e + 1.0);
+  }
+  return x < 0 ? -r : r;
 }
 static inline v2 rmul(rot_t q, v2 v) { return V(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
 static inline v2 rmulT(rot_t q, v2 v) { return V(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
@@ -225,6 +285,11 @@ typedef struct {
                                       many b2TimeOfImpact did NOT answer alpha = 1 (must stay 0: the skip is exact) */
   double prev_shaping, helipad_y;
   float gravity;
+  /* LunarLander(continuous, enable_wind, wind_power, turbulence_power): configuration (kept across resets) and the wind
+   * pattern offsets drawn at every reset (lunar_lander.py:401-403) */
+  int continuous, enable_wind;
+  double wind_power, turbulence_power;
+  int64_t wind_idx, torque_idx;
   pcg64_t rng;
 } lander_t;
 
@@ -1622,6 +1687,7 @@ static void world_step(lander_t* L, float dt, int vel_iters, int pos_iters) {
 
 /* ------------------------------------------------------------------------------------------------------------------
  * environment (lunar_lander.py) */
+#define PI_D 3.141592653589793 /* math.pi */
 #define FPS 50
 #define SCALE 30.0
 #define MAIN_ENGINE_POWER 13.0
@@ -1646,14 +1712,17 @@ static void apply_linear_impulse(body_t* b, v2 impulse, v2 point) {
 
 typedef struct { double obs[8]; double reward; int terminated; } step_out_t;
 
-static void env_step(lander_t* L, int action, step_out_t* out);
+static void env_step(lander_t* L, int action, const float* caction, step_out_t* out);
 
 /* LunarLander.reset (lunar_lander.py:321-447); the RNG stream continues unless the caller re-seeded it */
 static void env_reset(lander_t* L, float gravity, step_out_t* out) {
   pcg64_t rng = L->rng;
+  const int continuous = L->continuous, enable_wind = L->enable_wind;
+  const double wind_power = L->wind_power, turbulence_power = L->turbulence_power;
   memset(L, 0, sizeof(*L));
   L->rng = rng;
   L->gravity = gravity;
+  L->continuous = continuous; L->enable_wind = enable_wind; L->wind_power = wind_power; L->turbulence_power = turbulence_power;
   const double W = VIEWPORT_W / SCALE, H = VIEWPORT_H / SCALE;
   enum { CHUNKS = 11 };
   double height[CHUNKS + 1], chunk_x[CHUNKS], smooth_y[CHUNKS];
@@ -1687,6 +1756,10 @@ static void env_reset(lander_t* L, float gravity, step_out_t* out) {
   double fx = pcg64_uniform(&L->rng, -INITIAL_RANDOM, INITIAL_RANDOM);
   double fy = pcg64_uniform(&L->rng, -INITIAL_RANDOM, INITIAL_RANDOM);
   L->b[1].force = vadd(L->b[1].force, V((float)fx, (float)fy));
+  if (L->enable_wind) { /* lunar_lander.py:401-403: two bounded integers from the env's stream */
+    L->wind_idx = pcg64_integers(&L->rng, -9999, 9999);
+    L->torque_idx = pcg64_integers(&L->rng, -9999, 9999);
+  }
   for (int k = 0; k < 2; ++k) {
     int i = k == 0 ? -1 : +1;
     poly_set_box(&L->poly[1 + k], (float)(LEG_W / SCALE), (float)(LEG_H / SCALE));
@@ -1708,12 +1781,35 @@ static void env_reset(lander_t* L, float gravity, step_out_t* out) {
   L->b[0].xf.q.c = 1.0f;
   for (int d = 0; d < NDYN; ++d) L->poly_fat[d] = fatten(poly_aabb(&L->poly[d], L->b[1 + d].xf));
   L->new_fixture = 1;
-  env_step(L, 0, out); /* return self.step(0)[0] */
+  const float zero2[2] = {0.0f, 0.0f};
+  env_step(L, 0, zero2, out); /* return self.step(np.array([0, 0]) if self.continuous else 0)[0] */
 }
 
-/* LunarLander.step, discrete actions (lunar_lander.py:471-665), wind disabled */
-static void env_step(lander_t* L, int action, step_out_t* out) {
+/* LunarLander.step (lunar_lander.py:471-665): `action` for the discrete env, `caction` (float32 [2]) for continuous=True */
+static void env_step(lander_t* L, int action, const float* caction, step_out_t* out) {
   body_t* lander = &L->b[1];
+  if (L->enable_wind && !(L->leg_contact[0] || L->leg_contact[1])) { /* lunar_lander.py:476-506 */
+    double s1, s2, c_unused;
+    det_sincos(0.02 * (double)L->wind_idx, &s1, &c_unused);
+    det_sincos((PI_D * 0.01) * (double)L->wind_idx, &s2, &c_unused);
+    const double wind_mag = det_tanh(s1 + s2) * L->wind_power;
+    L->wind_idx += 1;
+    if (!lander->awake) set_awake(lander, 1); /* ApplyForceToCenter(..., wake=True) */
+    lander->force = vadd(lander->force, V((float)wind_mag, 0.0f));
+    det_sincos(0.02 * (double)L->torque_idx, &s1, &c_unused);
+    det_sincos((PI_D * 0.01) * (double)L->torque_idx, &s2, &c_unused);
+    const double torque_mag = det_tanh(s1 + s2) * L->turbulence_power;
+    L->torque_idx += 1;
+    lander->torque += (float)torque_mag; /* ApplyTorque */
+  }
+  /* continuous: action = np.clip(action, -1, +1).astype(np.float64) (clipped in float32, then widened) */
+  double a0 = 0.0, a1 = 0.0;
+  if (L->continuous) {
+    const float c0 = fminf(fmaxf(caction[0], -1.0f), 1.0f), c1 = fminf(fmaxf(caction[1], -1.0f), 1.0f);
+    a0 = (double)c0; a1 = (double)c1;
+  }
+  const int fire_main = L->continuous ? (a0 > 0.0) : (action == 2);
+  const int fire_side = L->continuous ? (fabs(a1) > 0.5) : (action == 1 || action == 3);
   double tip0, tip1; /* tip = (math.sin(angle), math.cos(angle)) */
   det_sincos((double)lander->a, &tip0, &tip1);
   const double side0 = -tip1, side1 = tip0;
@@ -1721,17 +1817,17 @@ static void env_step(lander_t* L, int action, step_out_t* out) {
   dispersion[0] = pcg64_uniform(&L->rng, -1.0, +1.0) / SCALE;
   dispersion[1] = pcg64_uniform(&L->rng, -1.0, +1.0) / SCALE;
   double m_power = 0.0, s_power = 0.0;
-  if (action == 2) {
-    m_power = 1.0;
+  if (fire_main) {
+    m_power = L->continuous ? (fmin(fmax(a0, 0.0), 1.0) + 1.0) * 0.5 : 1.0; /* 0.5..1.0 */
     double ox = tip0 * (MAIN_ENGINE_Y_LOCATION / SCALE + 2 * dispersion[0]) + side0 * dispersion[1];
     double oy = -tip1 * (MAIN_ENGINE_Y_LOCATION / SCALE + 2 * dispersion[0]) - side1 * dispersion[1];
     double px = (double)lander->xf.p.x + ox, py = (double)lander->xf.p.y + oy;
     apply_linear_impulse(lander, V((float)(-ox * MAIN_ENGINE_POWER * m_power), (float)(-oy * MAIN_ENGINE_POWER * m_power)),
                          V((float)px, (float)py));
   }
-  if (action == 1 || action == 3) {
-    double direction = action - 2;
-    s_power = 1.0;
+  if (fire_side) {
+    double direction = L->continuous ? (a1 > 0 ? 1.0 : -1.0) : (double)(action - 2); /* np.sign(action[1]) */
+    s_power = L->continuous ? fmin(fmax(fabs(a1), 0.5), 1.0) : 1.0;
     double ox = tip0 * dispersion[0] + side0 * (3 * dispersion[1] + direction * SIDE_ENGINE_AWAY / SCALE);
     double oy = -tip1 * dispersion[0] - side1 * (3 * dispersion[1] + direction * SIDE_ENGINE_AWAY / SCALE);
     double px = (double)lander->xf.p.x + ox - tip0 * 17 / SCALE;
@@ -1778,9 +1874,17 @@ ll_vec_t* ll_create(int n, int max_episode_steps, double gravity) {
   ll_vec_t* v = (ll_vec_t*)calloc(1, sizeof(ll_vec_t));
   v->n = n; v->max_episode_steps = max_episode_steps; v->gravity = (float)gravity;
   v->env = (lander_t*)calloc((size_t)n, sizeof(lander_t));
+  for (int i = 0; i < n; ++i) { v->env[i].wind_power = 15.0; v->env[i].turbulence_power = 1.5; }
   v->elapsed = (int*)calloc((size_t)n, sizeof(int));
   v->autoreset = (int*)calloc((size_t)n, sizeof(int));
   return v;
+}
+/* LunarLander(continuous=..., enable_wind=..., wind_power=..., turbulence_power=...); call before the first reset */
+void ll_configure(ll_vec_t* v, int continuous, int enable_wind, double wind_power, double turbulence_power) {
+  for (int i = 0; i < v->n; ++i) {
+    lander_t* L = &v->env[i];
+    L->continuous = continuous; L->enable_wind = enable_wind; L->wind_power = wind_power; L->turbulence_power = turbulence_power;
+  }
 }
 void ll_destroy(ll_vec_t* v) {
   if (!v) return;
@@ -1799,7 +1903,10 @@ void ll_reset(ll_vec_t* v, const uint64_t* seeds, const uint8_t* mask, float* ob
     v->elapsed[i] = 0; v->autoreset[i] = 0;
   }
 }
-void ll_step(ll_vec_t* v, const int64_t* actions, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated) {
+/* actions: int64 [n] (discrete) or, for continuous=True, float32 [n][2] */
+void ll_step(ll_vec_t* v, const void* actions_, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated) {
+  const int64_t* actions = (const int64_t*)actions_;
+  const float* cactions = (const float*)actions_;
   for (int i = 0; i < v->n; ++i) {
     step_out_t o;
     if (v->autoreset[i]) {
@@ -1809,7 +1916,8 @@ void ll_step(ll_vec_t* v, const int64_t* actions, float* obs, double* reward, ui
       v->elapsed[i] = 0; v->autoreset[i] = 0;
       continue;
     }
-    env_step(&v->env[i], (int)actions[i], &o);
+    if (v->env[i].continuous) env_step(&v->env[i], 0, cactions + 2 * i, &o);
+    else env_step(&v->env[i], (int)actions[i], cactions, &o);
     write_obs(obs + 8 * i, &o);
     reward[i] = o.reward;
     terminated[i] = (uint8_t)o.terminated;
@@ -1831,6 +1939,9 @@ void ll_debug_state(const ll_vec_t* v, int i, float* bodies, float* misc) {
   int nc = 0, nt = 0;
   for (int k = 0; k < NPAIR; ++k) { nc += L->contact[k].exists; nt += L->contact[k].touching; }
   misc[6] = (float)nc; misc[7] = (float)nt;
+}
+void ll_wind_state(const ll_vec_t* v, int i, int64_t* out /* [2]: wind_idx, torque_idx */) {
+  out[0] = v->env[i].wind_idx; out[1] = v->env[i].torque_idx;
 }
 void ll_toi_stats(const ll_vec_t* v, int i, long* out /* [2]: b2TimeOfImpact calls, solid TOI events since reset */) {
   out[0] = v->env[i].toi_calls; out[1] = v->env[i].toi_events;

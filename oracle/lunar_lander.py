@@ -28,6 +28,8 @@ def lib():
         l.ll_debug_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         l.ll_terrain.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.ll_toi_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        l.ll_configure.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        l.ll_wind_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.ll_toi_shortcut_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.ll_toi_probe.restype = C.c_int
         l.ll_toi_probe.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
@@ -38,9 +40,12 @@ def lib():
 class OracleLunarLander:
     """SyncVectorEnv(LunarLander-v3 x N) semantics: seed+i PCG64 streams, NEXT_STEP autoreset, TimeLimit 1000."""
 
-    def __init__(self, num_envs, max_episode_steps=1000, gravity=-10.0):
+    def __init__(self, num_envs, max_episode_steps=1000, gravity=-10.0, continuous=False, enable_wind=False, wind_power=15.0,
+                 turbulence_power=1.5):
         self.num_envs = int(num_envs)
+        self.continuous = bool(continuous)
         self._h = lib().ll_create(self.num_envs, int(max_episode_steps or 0), float(gravity))
+        lib().ll_configure(self._h, int(self.continuous), int(bool(enable_wind)), float(wind_power), float(turbulence_power))
         self._obs = np.zeros((self.num_envs, 8), dtype=np.float32)
 
     def __del__(self):
@@ -63,9 +68,13 @@ class OracleLunarLander:
 
     def step(self, actions):
         n = self.num_envs
-        a = np.ascontiguousarray(actions, dtype=np.int64)
-        assert a.shape == (n,)
-        assert ((a >= 0) & (a < 4)).all(), f"invalid action in {a!r}"
+        if self.continuous:
+            a = np.ascontiguousarray(actions, dtype=np.float32)
+            assert a.shape == (n, 2)
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.int64)
+            assert a.shape == (n,)
+            assert ((a >= 0) & (a < 4)).all(), f"invalid action in {a!r}"
         reward = np.zeros(n, dtype=np.float64)
         term = np.zeros(n, dtype=np.uint8)
         trunc = np.zeros(n, dtype=np.uint8)
@@ -86,6 +95,12 @@ class OracleLunarLander:
         misc = np.zeros(8, dtype=np.float32)
         lib().ll_debug_state(self._h, i, bodies.ctypes.data, misc.ctypes.data)
         return bodies, misc
+
+    def wind_state(self, i=0):
+        """(wind_idx, torque_idx) of env i."""
+        out = (C.c_int64 * 2)()
+        lib().ll_wind_state(self._h, i, out)
+        return int(out[0]), int(out[1])
 
     def toi_stats(self, i=0):
         """(b2TimeOfImpact evaluations, solid TOI events) of env i since its last reset."""

@@ -48,6 +48,68 @@ def test_lunarlander_config_size_sampled_lanes_match_oracle():
     assert not env.contact_overflow()
 
 
+@pytest.mark.parametrize("continuous,wind,n,T", [(True, True, 2048, 230), (True, False, 512, 200), (False, True, 512, 200)])
+def test_lunarlander_continuous_and_wind_match_oracle_bit_exact(continuous, wind, n, T):
+    """LunarLander(continuous=..., enable_wind=...) (lunar_lander.py:476-616, :401-403) against oracle/lunar_lander.c: throttled
+    engines, fuel costs, the wind / turbulence pattern with its np_random.integers offsets, across autoresets."""
+    from oracle.lunar_lander import OracleLunarLander
+
+    seed = 41
+    rs = np.random.default_rng(6)
+    idx = np.arange(n) if n <= 512 else np.sort(rs.choice(n, size=256, replace=False))
+    kw = dict(continuous=continuous, enable_wind=wind, wind_power=12.0, turbulence_power=1.0)
+    env = make("LunarLander-v3", n, **kw)
+    ora = OracleLunarLander(len(idx), **kw)
+    o1, _ = env.reset(seed=seed)
+    o2, _ = ora.reset(seed=[seed + int(i) for i in idx])
+    np.testing.assert_array_equal(o1[idx], o2)
+    if continuous:
+        assert env.single_action_space.shape == (2,) and env.single_action_space.dtype == np.float32
+    if wind:
+        np.testing.assert_array_equal(env.wind_state().cpu().numpy()[idx], [ora.wind_state(i) for i in range(len(idx))])
+    resets = np.zeros(len(idx), dtype=np.int64)
+    for t in range(T):
+        a = rs.uniform(-1.3, 1.3, size=(n, 2)).astype(np.float32) if continuous else rs.integers(0, 4, n)
+        x, y = env.step(a), ora.step(a[idx])
+        np.testing.assert_array_equal(x[0][idx], y[0], err_msg=f"obs differ at step {t}")
+        np.testing.assert_array_equal(x[1][idx], y[1], err_msg=f"reward differs at step {t}")
+        np.testing.assert_array_equal(x[2][idx], y[2])
+        np.testing.assert_array_equal(x[3][idx], y[3])
+        resets += y[2] | y[3]
+    assert (resets >= 1).mean() > 0.9  # the wind pattern was re-drawn and the 32-bit buffer carried across resets
+    if wind:
+        np.testing.assert_array_equal(env.wind_state().cpu().numpy()[idx], [ora.wind_state(i) for i in range(len(idx))])
+    assert not env.contact_overflow()
+    # a masked re-seed starts those lanes' streams (and their 32-bit buffers) afresh
+    mask = np.zeros(n, dtype=bool)
+    mask[idx[: len(idx) // 2]] = True
+    o3, _ = env.reset(seed=seed + 1000, options={"reset_mask": mask})
+    sub = np.zeros(len(idx), dtype=bool)
+    sub[: len(idx) // 2] = True
+    o4, _ = ora.reset(seed=[seed + 1000 + int(i) for i in idx], options={"reset_mask": sub})
+    np.testing.assert_array_equal(o3[idx][sub], o4[sub])
+    for t in range(30):
+        a = rs.uniform(-1.3, 1.3, size=(n, 2)).astype(np.float32) if continuous else rs.integers(0, 4, n)
+        x, y = env.step(a), ora.step(a[idx])
+        np.testing.assert_array_equal(x[0][idx], y[0], err_msg=f"obs differ at step {t} after the masked re-seed")
+        np.testing.assert_array_equal(x[1][idx], y[1])
+
+
+def test_lunarlander_continuous_id_and_float64_actions():
+    env = make("LunarLanderContinuous-v3", 64)
+    assert env.continuous and env.single_action_space.shape == (2,)
+    ref = make("LunarLander-v3", 64, continuous=True)
+    np.testing.assert_array_equal(env.reset(seed=2)[0], ref.reset(seed=2)[0])
+    rs = np.random.default_rng(0)
+    for _ in range(40):
+        a = rs.uniform(-1, 1, size=(64, 2)).astype(np.float32)
+        x, y = env.step(a.astype(np.float64)), ref.step(a)  # float32-representable float64 actions: identical run
+        for k in range(4):
+            np.testing.assert_array_equal(x[k], y[k])
+    with pytest.raises(ValueError):
+        env.step(np.zeros(64, dtype=np.int64))
+
+
 def test_humanoid_config_size_sampled_lanes_match_oracle():
     """BASELINE configs[4]: 8192 envs per GPU.  256 sampled global indices vs oracle/humanoid.c, bit-exact, through autoresets."""
     from oracle.humanoid import OracleHumanoid

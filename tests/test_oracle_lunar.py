@@ -146,3 +146,99 @@ def test_toi_clearly_separated_shortcut_never_changes_a_result():
             calls, covered, wrong = calls + d[:, 0].sum(), covered + d[:, 1].sum(), wrong + d[:, 2].sum()
     assert wrong == 0
     assert calls > 2000 and covered > 0.25 * calls, (calls, covered)
+
+
+def _lander_masses():
+    poly = np.array([(-14, 17), (-17, 0), (-17, -10), (17, -10), (17, 0), (14, 17)], dtype=np.float64) / 30.0
+    x, y = poly[:, 0], poly[:, 1]
+    area = 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+    return np.array([5.0 * area, 1.0 * (2 * 2 / 30.0) * (2 * 8 / 30.0), 1.0 * (2 * 2 / 30.0) * (2 * 8 / 30.0)])
+
+
+def test_wind_and_continuous_free_flight_known_answer():
+    """LunarLander(continuous=True, enable_wind=True), engines off: before any contact the external forces on (lander + legs)
+    are gravity, the initial random force and the wind, F_wind = tanh(sin(0.02 i) + sin(pi 0.01 i)) * 15 with i drawn by
+    np_random.integers(-9999, 9999) at reset and advanced once per step (lunar_lander.py:401-403, :476-490).  The total
+    momentum then has a closed form; the draws come from numpy itself and the wind from Python's math module."""
+    import math
+
+    n, seed, h, g = 16, 77, 1.0 / 50.0, -10.0
+    env = OracleLunarLander(n, continuous=True, enable_wind=True, wind_power=15.0, turbulence_power=1.5)
+    env.reset(seed=seed)
+    masses = _lander_masses()
+    F, idx = np.zeros((n, 2)), np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        gen = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed + i)))
+        gen.uniform(0, 400 / 30.0 / 2, size=(12,))
+        F[i] = [gen.uniform(-1000.0, 1000.0), gen.uniform(-1000.0, 1000.0)]
+        idx[i] = gen.integers(-9999, 9999)
+        t_idx = int(gen.integers(-9999, 9999))
+        assert env.wind_state(i) == (int(idx[i]) + 1, t_idx + 1)  # reset() ends with one step
+
+    def wind(i):
+        return math.tanh(math.sin(0.02 * i) + math.sin(math.pi * 0.01 * i)) * 15.0
+
+    def momentum():
+        b = np.stack([env.debug_state(i)[0] for i in range(n)]).astype(np.float64)  # (n, 3, 7)
+        return (masses[None, :, None] * b[:, :, 3:5]).sum(axis=1)
+
+    px = h * F[:, 0] + h * np.array([wind(int(i)) for i in idx])
+    py = h * F[:, 1] + masses.sum() * h * g
+    p = momentum()
+    np.testing.assert_allclose(p[:, 0], px, rtol=5e-5, atol=5e-4)
+    np.testing.assert_allclose(p[:, 1], py, rtol=5e-5, atol=5e-4)
+    a = np.zeros((n, 2), dtype=np.float32)
+    a[:, 1] = 0.5  # |a1| == 0.5 is NOT above the side-engine threshold; a0 == 0 is not above the main-engine one
+    for k in range(1, 22):
+        o, r, te, tr, _ = env.step(a)
+        assert not te.any() and (o[:, 6:8] == 0).all()
+        px = px + h * np.array([wind(int(i) + k) for i in idx])
+        py = py + masses.sum() * h * g
+        p = momentum()
+        np.testing.assert_allclose(p[:, 0], px, rtol=1e-4, atol=1e-3, err_msg=f"step {k}")
+        np.testing.assert_allclose(p[:, 1], py, rtol=1e-4, atol=1e-3, err_msg=f"step {k}")
+
+
+def test_continuous_actions_throttle_and_fuel_cost():
+    """continuous=True (lunar_lander.py:509-616): the main engine fires for a0 > 0 with power (clip(a0, 0, 1) + 1) / 2, the
+    side engines for |a1| > 0.5 with power clip(|a1|, 0.5, 1); fuel costs 0.30 / 0.03 per unit power; actions are clipped to
+    [-1, 1] first.  Two copies of the same env that differ only in one throttle differ in reward by the fuel term plus the
+    shaping change of the extra impulse; an action beyond the box equals its clipped value exactly."""
+    def run(act, steps=3):
+        env = OracleLunarLander(1, continuous=True)
+        env.reset(seed=5)
+        out = [env.step(np.array([act], dtype=np.float32)) for _ in range(steps)]
+        return out, env.debug_state(0)[0]
+
+    idle, b_idle = run([0.0, 0.0])
+    clipped, b_c = run([1.0, -1.0])
+    beyond, b_b = run([7.5, -3.0])
+    np.testing.assert_array_equal(clipped[-1][0], beyond[-1][0])
+    np.testing.assert_array_equal(b_c, b_b)
+    assert all(x[1][0] == y[1][0] for x, y in zip(clipped, beyond))
+    # below the thresholds nothing fires: identical to idling
+    quiet, b_q = run([-0.3, 0.5])
+    np.testing.assert_array_equal(quiet[-1][0], idle[-1][0])
+    np.testing.assert_array_equal(b_q, b_idle)
+    # the main engine pushes the lander up relative to idling, more so at full throttle than at the minimum 50 %
+    half, b_h = run([1e-6, 0.0])
+    full, b_f = run([1.0, 0.0])
+    assert b_idle[0, 4] < b_h[0, 4] < b_f[0, 4]
+    gain_half, gain_full = b_h[0, 4] - b_idle[0, 4], b_f[0, 4] - b_idle[0, 4]
+    assert 1.7 < gain_full / gain_half < 2.3  # power 1.0 against 0.5 (dispersion draws are the same in both runs)
+    # the side engine turns the lander, in opposite directions for opposite signs
+    left, b_l = run([0.0, -1.0])
+    right, b_r = run([0.0, 1.0])
+    assert (b_l[0, 5] - b_idle[0, 5]) * (b_r[0, 5] - b_idle[0, 5]) < 0
+
+
+def test_discrete_env_is_unchanged_by_the_wind_and_continuous_code():
+    a = OracleLunarLander(4)
+    b = OracleLunarLander(4, continuous=False, enable_wind=False, wind_power=3.0, turbulence_power=0.2)
+    np.testing.assert_array_equal(a.reset(seed=9)[0], b.reset(seed=9)[0])
+    rs = np.random.default_rng(1)
+    for _ in range(120):
+        act = rs.integers(0, 4, 4)
+        x, y = a.step(act), b.step(act)
+        for k in range(4):
+            np.testing.assert_array_equal(x[k], y[k])
