@@ -139,3 +139,40 @@ def test_hostbatch_world2_lands_rows_key_major_and_throttles():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[-1] for r in res), res
+
+
+def test_call_recorder_encodes_a_step_as_machine_words():
+    """HostBatchPipeline's fast path replays a family's step from C: every argument of a recorded C-ABI call must be one
+    machine word (pointer, integer, byref struct); anything else (a float by value) makes the family non-replayable."""
+    import ctypes as C
+
+    from gymnasium_b200.distributed import _CallRecorder
+
+    class Cfg(C.Structure):
+        _fields_ = [("a", C.c_double), ("b", C.c_int32)]
+
+    seen = []
+    proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+    def impl(p0, p1, n, s):
+        seen.append((p0, p1, n, s))
+        return 0
+
+    class FakeLib:
+        b2e_fake_step = proto(impl)
+        other = staticmethod(lambda: 7)
+
+    lib = FakeLib()
+    rec = _CallRecorder(lib)
+    cfg, buf = Cfg(1.5, 3), (C.c_uint8 * 16)()
+    assert rec.b2e_fake_step(C.byref(cfg), C.cast(buf, C.c_void_p), -1, None) == 0
+    assert seen == []  # recording does not launch
+    assert rec.other() == 7  # non-ABI attributes pass through
+    (fn, words), = rec.calls
+    assert fn == C.cast(lib.b2e_fake_step, C.c_void_p).value
+    assert words == [C.addressof(cfg), C.addressof(buf), (1 << 64) - 1, 0]
+    # replaying the words through the function pointer reaches the implementation with the same arguments
+    replay = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64)(fn)
+    assert replay(*words) == 0 and seen[0][0] == C.addressof(cfg) and seen[0][2] == -1 and seen[0][3] is None
+    with pytest.raises(TypeError):
+        rec.b2e_fake_step(C.byref(cfg), 0.25, 1, None)
