@@ -428,8 +428,10 @@ def test_lunarlander_api():
     assert env.observation_space.shape == (6, 8) and env.action_space.shape == (6,)
     o, r, te, tr, _ = env.step(torch.zeros(6, dtype=torch.int64, device="cuda"))
     assert r.dtype == torch.float64 and te.dtype == torch.bool
-    with pytest.raises(NotImplementedError):
-        make("LunarLander-v3", 2, continuous=True)
+    cont = make("LunarLander-v3", 2, continuous=True)  # lunar_lander.py:298-305
+    assert cont.single_action_space.shape == (2,) and cont.action_space.shape == (2, 2)
+    with pytest.raises(AssertionError):  # lunar_lander.py:232-234
+        make("LunarLander-v3", 2, gravity=-13.0)
     # determinism + sharding invariance
     a = make("LunarLander-v3", 64)
     b = [make("LunarLander-v3", 32, env_offset=0), make("LunarLander-v3", 32, env_offset=32)]
