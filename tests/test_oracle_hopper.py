@@ -215,3 +215,29 @@ def test_inverted_pendulum_slider_limit_and_ctrl_clamp():
     env.set_state(0, [0.0, 0.0], [0.0, 0.0])
     a2 = env.step(np.array([[30.0]], dtype=np.float32))[0]
     np.testing.assert_array_equal(a1, a2)  # ctrlrange -3 3 with ctrllimited: the force saturates at gear * 3
+
+
+def test_model_sizes_follow_the_reference_structural_pins():
+    """tests/envs/mujoco/test_mujoco_v5.py:516-640 lists nq / nv / nu / nbody / njnt / ngeom of every v5 model.  The oracles
+    (and the kernels, whose host-side compile is compared with the oracles' bit for bit in tests/test_host_cpu.py) carry:
+    Hopper 6/6/3/5/6/5, Walker2d 9/9/6/8/9/8, InvertedPendulum 2/2/1/3/2 and 2 of its 3 geoms (the rail, a world geom with
+    contype 0, takes part in nothing and is not modelled)."""
+    import oracle.hopper as hp
+    import oracle.inverted_pendulum as ip
+    import oracle.walker2d as w2
+    from oracle.mjc_planar import ROBOTS
+
+    assert (hp.NQ, hp.NV, hp.NU, hp.NB, hp.OBS) == (6, 6, 3, 5, 11)
+    assert (w2.NQ, w2.NV, w2.NU, w2.NB, w2.OBS) == (9, 9, 6, 8, 17)
+    assert (ip.NQ, ip.NV, ip.NU, ip.NB, ip.OBS) == (2, 2, 1, 3, 4)
+    for robot, (_, _, nb, nq, nu) in ROBOTS.items():
+        env = {"hopper": hp.OracleHopper, "walker2d": w2.OracleWalker2d, "inverted_pendulum": ip.OracleInvertedPendulum}[robot](1)
+        obs, _ = env.reset(seed=0)
+        mass, misc, inv = env.model_info()
+        assert len(mass) == nb and mass[0] == 0 and (mass[1:] > 0).all()
+        assert obs.shape[1] == env.obs_size and len(inv) == 2 * nb + nq
+        qpos, qvel, qacc, counts, xipos = env.debug(0)
+        assert qpos.shape == (nq,) and qvel.shape == (nq,) and xipos.shape == (nb, 3)
+        a = np.zeros((1, nu), dtype=np.float32)
+        o, r, te, tr, info = env.step(a)
+        assert o.shape == obs.shape and np.isfinite(o).all()
