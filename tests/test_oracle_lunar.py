@@ -242,3 +242,55 @@ def test_discrete_env_is_unchanged_by_the_wind_and_continuous_code():
         x, y = a.step(act), b.step(act)
         for k in range(4):
             np.testing.assert_array_equal(x[k], y[k])
+
+
+def test_turbulence_changes_the_angular_momentum_by_the_applied_torque():
+    """enable_wind=True in free flight: per step the angular momentum of (lander + legs) about their common mass centre changes
+    by h (r x F_wind + tau) with r = lander centre - mass centre, F_wind and tau the reference's wind / turbulence pattern
+    (lunar_lander.py:476-506) evaluated with Python's math -- gravity has no moment about the mass centre and the joint
+    impulses are internal.  Holds step by step under Box2D's semi-implicit Euler (positions move along the NEW velocities,
+    which changes no cross product); checks ApplyTorque -> integration, which the momentum test cannot see."""
+    import math
+
+    n, h = 8, 1.0 / 50.0
+    env = OracleLunarLander(n, continuous=True, enable_wind=True, wind_power=15.0, turbulence_power=2.0)
+    env.reset(seed=5)
+    _, misc = env.debug_state(0)
+    m = np.array([misc[0], misc[2], misc[2]], dtype=np.float64)
+    inertia = np.array([misc[1], misc[3], misc[3]], dtype=np.float64)
+    lc = np.array([[misc[4], misc[5]], [0, 0], [0, 0]], dtype=np.float64)  # local centres of mass (legs: box centres)
+
+    def state():
+        b = np.stack([env.debug_state(i)[0] for i in range(n)]).astype(np.float64)  # (n, 3, 7): origin x y, angle, v, w
+        p, a, v, w = b[:, :, 0:2], b[:, :, 2], b[:, :, 3:5], b[:, :, 5]
+        c = p + np.stack([np.cos(a) * lc[None, :, 0] - np.sin(a) * lc[None, :, 1],
+                          np.sin(a) * lc[None, :, 0] + np.cos(a) * lc[None, :, 1]], axis=-1)
+        return c, v, w
+
+    def l_com(c, v, w):
+        big_m = m.sum()
+        cm, vm = (m[None, :, None] * c).sum(1) / big_m, (m[None, :, None] * v).sum(1) / big_m
+        r, u = c - cm[:, None, :], v - vm[:, None, :]
+        return (m[None, :] * (r[:, :, 0] * u[:, :, 1] - r[:, :, 1] * u[:, :, 0])).sum(1) + (inertia[None, :] * w).sum(1), cm
+
+    def pattern(i, power):
+        return math.tanh(math.sin(0.02 * i) + math.sin(math.pi * 0.01 * i)) * power
+
+    idx = np.array([env.wind_state(i) for i in range(n)])  # the indices the NEXT step uses
+    c, v, w = state()
+    l0, cm = l_com(c, v, w)
+    a = np.zeros((n, 2), dtype=np.float32)
+    signal = 0.0
+    for k in range(20):
+        o, r, te, tr, _ = env.step(a)
+        assert not te.any() and (o[:, 6:8] == 0).all()
+        force = np.array([pattern(int(idx[i, 0]) + k, 15.0) for i in range(n)])
+        torque = np.array([pattern(int(idx[i, 1]) + k, 2.0) for i in range(n)])
+        arm = c[:, 0, :] - cm
+        expect = h * (-arm[:, 1] * force + torque)  # (r x (F, 0))_z = -r_y F
+        c, v, w = state()
+        l1, cm1 = l_com(c, v, w)
+        np.testing.assert_allclose(l1 - l0, expect, rtol=0, atol=2e-4, err_msg=f"step {k}")
+        signal = max(signal, np.abs(expect).max())
+        l0, cm = l1, cm1
+    assert signal > 0.02  # the check resolves the turbulence term (h * 2.0 * tanh(...) ~ 0.04) 100x above its tolerance
