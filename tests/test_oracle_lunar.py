@@ -294,3 +294,130 @@ def test_turbulence_changes_the_angular_momentum_by_the_applied_torque():
         signal = max(signal, np.abs(expect).max())
         l0, cm = l1, cm1
     assert signal > 0.02  # the check resolves the turbulence term (h * 2.0 * tanh(...) ~ 0.04) 100x above its tolerance
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_engine_impulses_change_the_momentum_as_the_reference_formulas_say(continuous):
+    """Free flight with the engines firing: every step the total momentum of (lander + legs) changes by the engine impulses of
+    lunar_lander.py:536-616 plus h M g.  The impulses are recomputed here from the reference's expressions -- tip / side from
+    the lander angle, the two dispersion draws from numpy's own stream in the reference's order (12 terrain heights, fx, fy,
+    then 2 per step, including the step inside reset), MAIN_ENGINE_POWER 13, SIDE_ENGINE_POWER 0.6, the continuous throttle
+    rules -- not from oracle/lunar_lander.c."""
+    import math
+
+    n, seed, h, g, scale = 12, 31, 1.0 / 50.0, -10.0, 30.0
+    env = OracleLunarLander(n, continuous=continuous)
+    env.reset(seed=seed)
+    masses = _lander_masses()
+    gens = []
+    for i in range(n):
+        gen = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed + i)))
+        gen.uniform(0, 400 / 30.0 / 2, size=(12,))
+        gen.uniform(-1000.0, 1000.0), gen.uniform(-1000.0, 1000.0)
+        gen.uniform(-1.0, 1.0), gen.uniform(-1.0, 1.0)  # the dispersion draws of reset()'s own step
+        gens.append(gen)
+
+    def bodies():
+        return np.stack([env.debug_state(i)[0] for i in range(n)]).astype(np.float64)
+
+    def momentum(b):
+        return (masses[None, :, None] * b[:, :, 3:5]).sum(axis=1)
+
+    rs = np.random.default_rng(4)
+    b = bodies()
+    p = momentum(b)
+    fired_main = fired_side = 0
+    for k in range(18):
+        if continuous:
+            act = rs.uniform(-1.0, 1.0, size=(n, 2)).astype(np.float32)
+        else:
+            act = rs.integers(0, 4, n)
+        expect = np.zeros((n, 2))
+        for i in range(n):
+            angle = float(b[i, 0, 2])
+            tip, side = (math.sin(angle), math.cos(angle)), (-math.cos(angle), math.sin(angle))
+            d = [gens[i].uniform(-1.0, +1.0) / scale for _ in range(2)]
+            a = np.clip(act[i], -1, +1).astype(np.float64) if continuous else int(act[i])
+            if (continuous and a[0] > 0.0) or (not continuous and a == 2):
+                m_power = (np.clip(a[0], 0.0, 1.0) + 1.0) * 0.5 if continuous else 1.0
+                ox = tip[0] * (4 / scale + 2 * d[0]) + side[0] * d[1]  # MAIN_ENGINE_Y_LOCATION = 4
+                oy = -tip[1] * (4 / scale + 2 * d[0]) - side[1] * d[1]
+                expect[i] += [-ox * 13.0 * m_power, -oy * 13.0 * m_power]
+                fired_main += 1
+            if (continuous and abs(a[1]) > 0.5) or (not continuous and a in (1, 3)):
+                direction = np.sign(a[1]) if continuous else a - 2
+                s_power = np.clip(abs(a[1]), 0.5, 1.0) if continuous else 1.0
+                ox = tip[0] * d[0] + side[0] * (3 * d[1] + direction * 12 / scale)  # SIDE_ENGINE_AWAY = 12
+                oy = -tip[1] * d[0] - side[1] * (3 * d[1] + direction * 12 / scale)
+                expect[i] += [-ox * 0.6 * s_power, -oy * 0.6 * s_power]
+                fired_side += 1
+        expect[:, 1] += masses.sum() * h * g
+        o, r, te, tr, _ = env.step(act)
+        assert not te.any() and (o[:, 6:8] == 0).all()
+        b = bodies()
+        p1 = momentum(b)
+        np.testing.assert_allclose(p1 - p, expect, rtol=0, atol=3e-4, err_msg=f"step {k}")
+        p = p1
+    assert fired_main > 30 and fired_side > 30
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_observation_and_reward_follow_the_reference_expressions_exactly(continuous):
+    """lunar_lander.py:620-662 re-evaluated in Python from the body states the oracle exposes (position, velocity, angle,
+    angular velocity as float32, like pybox2d hands them out): the 8 observation entries, the shaping reward, the fuel costs
+    (0.30 / 0.03 per unit power), -100 on a crash or when |x| >= 1, +100 when the lander sleeps.  Exact equality: both sides
+    are the same IEEE double expressions."""
+    n = 24
+    env = OracleLunarLander(n, continuous=continuous, max_episode_steps=0)
+    obs, _ = env.reset(seed=13)
+    w, hgt, scale, fps, leg_down = 600, 400, 30.0, 50, 18
+    helipad_y = hgt / scale / 4
+
+    def state(i, legs):
+        b = env.debug_state(i)[0]
+        px, py, ang, vx, vy, om = (float(b[0, k]) for k in range(6))
+        return [(px - w / scale / 2) / (w / scale / 2), (py - (helipad_y + leg_down / scale)) / (hgt / scale / 2),
+                vx * (w / scale / 2) / fps, vy * (hgt / scale / 2) / fps, ang, 20.0 * om / fps, legs[0], legs[1]]
+
+    def shaping(s):
+        return (-100 * np.sqrt(s[0] * s[0] + s[1] * s[1]) - 100 * np.sqrt(s[2] * s[2] + s[3] * s[3]) - 100 * abs(s[4])
+                + 10 * s[6] + 10 * s[7])
+
+    prev = [shaping(state(i, [float(obs[i, 6]), float(obs[i, 7])])) for i in range(n)]
+    for i in range(n):
+        np.testing.assert_array_equal(obs[i], np.array(state(i, obs[i, 6:8].astype(np.float64)), dtype=np.float32))
+    rs = np.random.default_rng(2)
+    pending = np.zeros(n, dtype=bool)
+    ended = 0
+    for t in range(400):
+        act = rs.uniform(-1, 1, size=(n, 2)).astype(np.float32) if continuous else rs.integers(0, 4, n)
+        o, r, te, tr, _ = env.step(act)
+        for i in range(n):
+            legs = [float(o[i, 6]), float(o[i, 7])]
+            s = state(i, legs)
+            np.testing.assert_array_equal(o[i], np.array(s, dtype=np.float32), err_msg=f"obs of env {i} at step {t}")
+            if pending[i]:  # this call was the env's reset: reward 0, and the shaping memory restarts
+                assert r[i] == 0.0 and not te[i]
+                prev[i] = shaping(s)
+                continue
+            if continuous:
+                a = np.clip(act[i], -1, +1).astype(np.float64)
+                m_power = (np.clip(a[0], 0.0, 1.0) + 1.0) * 0.5 if a[0] > 0.0 else 0.0
+                s_power = np.clip(np.abs(a[1]), 0.5, 1.0) if np.abs(a[1]) > 0.5 else 0.0
+            else:
+                m_power, s_power = (1.0 if act[i] == 2 else 0.0), (1.0 if act[i] in (1, 3) else 0.0)
+            sh = shaping(s)
+            reward = sh - prev[i]
+            prev[i] = sh
+            reward -= m_power * 0.30
+            reward -= s_power * 0.03
+            if te[i]:
+                assert r[i] in (-100.0, 100.0)
+                awake = env.debug_state(i)[0][0, 6] != 0
+                assert r[i] == (-100.0 if awake else 100.0)
+                ended += 1
+            else:
+                assert abs(s[0]) < 1.0
+                assert r[i] == reward, (t, i, r[i], reward)
+        pending = te | tr
+    assert ended > n  # every env crashed or landed at least once on average
