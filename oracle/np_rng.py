@@ -70,6 +70,24 @@ def seed_sequence_state(seed: int, n_words: int = 8) -> list[int]:
     return out
 
 
+ZIGGURAT_NOR_R = 3.6541528853610087963519472518
+ZIGGURAT_NOR_INV_R = 0.27366123732975827203338247596
+_ZIG = None
+
+
+def _ziggurat_tables():
+    """(wi, ki, fi) as Python lists: wi_double / ki_double / fi_double of numpy's ziggurat_constants.h."""
+    global _ZIG
+    if _ZIG is None:
+        import os
+
+        import numpy as np
+
+        t = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "ziggurat_normal.npz"))
+        _ZIG = ([float(v) for v in t["wi"]], [int(v) for v in t["ki"]], [float(v) for v in t["fi"]])
+    return _ZIG
+
+
 class PCG64:
     """numpy's PCG64 (XSL-RR 128/64) bit generator seeded from a SeedSequence."""
 
@@ -112,6 +130,34 @@ class PCG64:
         x = self.next_uint64()
         self.has_uint32, self.uinteger = True, x >> 32
         return x & M32
+
+    def standard_normal(self) -> float:
+        """``Generator.standard_normal()`` / ``normal()``: the 256-strip ziggurat of numpy/random/src/distributions/
+        distributions.c (random_standard_normal) over this bit generator's 64-bit words -- 8 bits pick the strip, 1 bit the
+        sign, 52 bits the abscissa; 99.3 % of the draws return on the first comparison, the wedges take one more uniform, the
+        tail two per trial.  Tables: oracle/data/ziggurat_normal.npz (numpy's own doubles, see extract_ziggurat.py)."""
+        import math
+
+        wi, ki, fi = _ziggurat_tables()
+        while True:
+            r = self.next_uint64()
+            idx = r & 0xFF
+            r >>= 8
+            sign = r & 1
+            rabs = (r >> 1) & 0x000FFFFFFFFFFFFF
+            x = rabs * wi[idx]
+            if sign:
+                x = -x
+            if rabs < ki[idx]:
+                return x
+            if idx == 0:
+                while True:
+                    xx = -ZIGGURAT_NOR_INV_R * math.log1p(-self.next_double())
+                    yy = -math.log1p(-self.next_double())
+                    if yy + yy > xx * xx:
+                        return -(ZIGGURAT_NOR_R + xx) if (rabs >> 8) & 1 else ZIGGURAT_NOR_R + xx
+            elif (fi[idx - 1] - fi[idx]) * self.next_double() + fi[idx] < math.exp(-0.5 * x * x):
+                return x
 
     def bounded_uint32(self, n_excl: int) -> int:
         """Uniform integer in ``[0, n_excl)`` for ``1 <= n_excl <= 2**32``: Lemire's multiply-and-reject on buffered

@@ -26,3 +26,29 @@ def test_known_answer_seed42():
     p = PCG64(42)
     got = [p.uniform(-0.05, 0.05) for _ in range(4)]
     assert got == [0.027395604855596334, -0.006112156024794771, 0.03585979199113824, 0.019736802905936393]
+
+
+def test_standard_normal_ziggurat_matches_numpy_bit_for_bit():
+    """Generator.standard_normal (what HalfCheetah / Ant / InvertedDoublePendulum reset_model draw their velocity noise from):
+    the ziggurat restatement returns numpy's doubles exactly -- fast path, wedges and tail -- and leaves the stream where
+    numpy leaves it."""
+    from oracle.np_rng import PCG64
+
+    wedge_or_tail = 0
+    for seed in (0, 7, 2 ** 40 + 7):
+        gen = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        ref = gen.standard_normal(60000)
+        mine = PCG64(seed)
+        before = mine.state
+        got = np.array([mine.standard_normal() for _ in range(60000)])
+        np.testing.assert_array_equal(got, ref)
+        assert mine.next_double() == gen.random()
+        # more than one 64-bit word per sample on average: the slow paths were exercised
+        steps = 0
+        probe = PCG64(seed)
+        assert probe.state == before
+        while probe.state != mine.state and steps < 70000:
+            probe.next_uint64()
+            steps += 1
+        wedge_or_tail += steps - 60001
+    assert wedge_or_tail > 500 and np.abs(got).max() > 3.7  # beyond r = 3.654: the tail sampler ran
