@@ -183,6 +183,9 @@ SIGNATURES = {
     "b2e_walker2d_model_info": (C.c_int, [P, P, P]),
     "b2e_walker2d_reset": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P]),
     "b2e_walker2d_step": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P, P, P, P, P]),
+    "b2e_half_cheetah_model_info": (C.c_int, [P, P, P]),
+    "b2e_half_cheetah_reset": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P]),
+    "b2e_half_cheetah_step": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P, P, P, P, P]),
     "b2e_inverted_pendulum_model_info": (C.c_int, [P, P, P]),
     "b2e_inverted_pendulum_reset": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P]),
     "b2e_inverted_pendulum_step": (C.c_int, [_BP, C.POINTER(MjPlanarCfg), C.POINTER(MjPlanarState), P, P, P, P, P, P, P, P]),

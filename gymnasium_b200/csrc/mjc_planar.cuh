@@ -30,11 +30,14 @@
 #elif defined(MJC_ROBOT_WALKER2D)
 #define MJC_API(name) b2e_walker2d_##name
 #define MJC_NAME "walker2d"
+#elif defined(MJC_ROBOT_HALFCHEETAH)
+#define MJC_API(name) b2e_half_cheetah_##name
+#define MJC_NAME "half_cheetah"
 #elif defined(MJC_ROBOT_INVPEND)
 #define MJC_API(name) b2e_inverted_pendulum_##name
 #define MJC_NAME "inverted_pendulum"
 #else
-#error "define MJC_ROBOT_HOPPER, MJC_ROBOT_WALKER2D or MJC_ROBOT_INVPEND before including mjc_planar.cuh"
+#error "define MJC_ROBOT_HOPPER, MJC_ROBOT_WALKER2D, MJC_ROBOT_HALFCHEETAH or MJC_ROBOT_INVPEND before including mjc_planar.cuh"
 #endif
 #define MJC_STR2(x) #x
 #define MJC_STR(x) MJC_STR2(x)
@@ -46,6 +49,8 @@ namespace {
 
 #if defined(MJC_ROBOT_HOPPER)
 constexpr int NB = 5, NQ = 6, NV = 6, NU = 3, NJ = 6, NG = 5, MAXCON = 8, MAXEFC = 16, MAXPAIR = 16;
+#elif defined(MJC_ROBOT_HALFCHEETAH)
+constexpr int NB = 8, NQ = 9, NV = 9, NU = 6, NJ = 9, NG = 9, MAXCON = 12, MAXEFC = 56, MAXPAIR = 16;
 #elif defined(MJC_ROBOT_INVPEND)
 constexpr int NB = 3, NQ = 2, NV = 2, NU = 1, NJ = 2, NG = 2, MAXCON = 2, MAXEFC = 4, MAXPAIR = 2;
 #else
@@ -670,6 +675,40 @@ HD void mj_step_rk4(const HModel& m, HData& d) {
   integrate_pos(d.qpos, dXv, h);
   for (int k = 0; k < NV; ++k) d.qacc_warmstart[k] = d.qacc[k];
 }
+// mj_Euler (engine_forward.c: mj_EulerSkip + mj_advance): semi-implicit Euler with the joint damping treated implicitly --
+// qacc' = (M + h diag(B))^-1 (qfrc_smooth + qfrc_constraint); qvel += h qacc'; qpos += h qvel (the NEW velocity);
+// qacc_warmstart = the forward dynamics' qacc
+HD void mj_step_euler(const HModel& m, HData& d) {
+  const double h = m.timestep;
+  mj_forward(m, d);
+  double qacc[NV];
+  bool damped = false;
+  for (int i = 0; i < NV; ++i) damped = damped || m.dof_damping[i] > 0;
+  if (!damped) {
+    for (int i = 0; i < NV; ++i) qacc[i] = d.qacc[i];
+  } else {
+    double H[NV][NV], Hinv[NV];
+    for (int i = 0; i < NV; ++i) for (int j = 0; j < NV; ++j) H[i][j] = d.qM[i][j];
+    for (int i = 0; i < NV; ++i) H[i][i] += h * m.dof_damping[i];
+    for (int k = NV - 1; k >= 0; --k) {  // mj_factorI: the same L^T D L as crb_and_factor
+      for (int i = m.dof_parent[k]; i >= 0; i = m.dof_parent[i]) {
+        const double tmp = H[k][i] / H[k][k];
+        for (int j = i; j >= 0; j = m.dof_parent[j]) H[i][j] -= H[k][j] * tmp;
+        H[k][i] = tmp;
+      }
+      Hinv[k] = 1.0 / H[k][k];
+    }
+    for (int i = 0; i < NV; ++i) qacc[i] = d.qfrc_smooth[i] + d.qfrc_constraint[i];
+    for (int i = NV - 1; i >= 0; --i)  // mj_solveLD
+      for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) qacc[j] -= H[i][j] * qacc[i];
+    for (int i = 0; i < NV; ++i) qacc[i] *= Hinv[i];
+    for (int i = 0; i < NV; ++i)
+      for (int j = m.dof_parent[i]; j >= 0; j = m.dof_parent[j]) qacc[i] -= H[i][j] * qacc[j];
+  }
+  for (int k = 0; k < NV; ++k) d.qvel[k] += h * qacc[k];
+  integrate_pos(d.qpos, d.qvel, h);
+  for (int k = 0; k < NV; ++k) d.qacc_warmstart[k] = d.qacc[k];  // mj_advance
+}
 // ---- models (hopper.xml / walker2d_v5.xml re-typed as data) + compile --------------------------------------------------------
 struct BDef { int parent; double pos[3]; };
 struct JDef { int type, body; double pos[3], axis[3]; int limited; double lo, hi, armature, damping, ref; };
@@ -698,6 +737,51 @@ const GDef GEOM[NG] = {
 const int ACT_JOINT[NU] = {3, 4, 5};
 constexpr double kGear = 200.0, kMargin = 0.001;
 const double kSolimpContact[5] = {0.8, 0.8, 0.01, 0.5, 2.0};
+#elif defined(MJC_ROBOT_HALFCHEETAH)
+// half_cheetah.xml: compiler angle="radian" settotalmass="14" (:35); defaults joint armature .1 damping .01 limited solimplimit
+// 0 .8 .03 solreflimit .02 1 stiffness 8 (:37; every hinge overrides damping / stiffness), geom conaffinity 0 condim 3 contype 1
+// friction .4 solimp 0 .8 .01 solref .02 1 (:38: the robot collides with the floor only); option timestep 0.01, integrator left
+// at its default = Euler (:42); root joints: armature 0 damping 0 stiffness 0 (:55-57); motors gear 120 90 60 120 60 30 (:88-93)
+const BDef BODY[NB] = {{0, {0, 0, 0}}, {0, {0, 0, 0.7}},
+                       {1, {-0.5, 0, 0}}, {2, {0.16, 0, -0.25}}, {3, {-0.28, 0, -0.14}},
+                       {1, {0.5, 0, 0}}, {5, {-0.14, 0, -0.24}}, {6, {0.13, 0, -0.18}}};
+const JDef JOINT[NJ] = {  // ranges in radians
+    {2, 1, {0, 0, 0}, {1, 0, 0}, 0, 0, 0, 0, 0, 0},             // rootx
+    {2, 1, {0, 0, 0}, {0, 0, 1}, 0, 0, 0, 0, 0, 0},             // rootz
+    {3, 1, {0, 0, 0}, {0, 1, 0}, 0, 0, 0, 0, 0, 0},             // rooty
+    {3, 2, {0, 0, 0}, {0, 1, 0}, 1, -0.52, 1.05, 0.1, 6, 0},     // bthigh
+    {3, 3, {0, 0, 0}, {0, 1, 0}, 1, -0.785, 0.785, 0.1, 4.5, 0}, // bshin
+    {3, 4, {0, 0, 0}, {0, 1, 0}, 1, -0.4, 0.785, 0.1, 3, 0},     // bfoot
+    {3, 5, {0, 0, 0}, {0, 1, 0}, 1, -1, 0.7, 0.1, 4.5, 0},       // fthigh
+    {3, 6, {0, 0, 0}, {0, 1, 0}, 1, -1.2, 0.87, 0.1, 3, 0},      // fshin
+    {3, 7, {0, 0, 0}, {0, 1, 0}, 1, -0.5, 0.5, 0.1, 1.5, 0},     // ffoot
+};
+const double JOINT_STIFFNESS[NJ] = {0, 0, 0, 240, 180, 120, 180, 120, 60};
+const GDef GEOM[NG] = {
+    {G_PLANE, 0, {0, 0, 0}, {1, 0, 0, 0}, 0, 0, 0.4, 3, 1, 1},
+    {G_CAPSULE, 1, {0, 0, 0}, {1, 0, 0, 0}, 0.046, 0.5, 0.4, 3, 1, 0},           // torso: fromto -.5 0 0 .5 0 0
+    {G_CAPSULE, 1, {0.6, 0, 0.1}, {1, 0, 0, 0}, 0.046, 0.15, 0.4, 3, 1, 0},      // head: axisangle 0 1 0 .87
+    {G_CAPSULE, 2, {0.1, 0, -0.13}, {1, 0, 0, 0}, 0.046, 0.145, 0.4, 3, 1, 0},   // bthigh: -3.8
+    {G_CAPSULE, 3, {-0.14, 0, -0.07}, {1, 0, 0, 0}, 0.046, 0.15, 0.4, 3, 1, 0},  // bshin: -2.03
+    {G_CAPSULE, 4, {0.03, 0, -0.097}, {1, 0, 0, 0}, 0.046, 0.094, 0.4, 3, 1, 0}, // bfoot: -.27
+    {G_CAPSULE, 5, {-0.07, 0, -0.12}, {1, 0, 0, 0}, 0.046, 0.133, 0.4, 3, 1, 0}, // fthigh: .52
+    {G_CAPSULE, 6, {0.065, 0, -0.09}, {1, 0, 0, 0}, 0.046, 0.106, 0.4, 3, 1, 0}, // fshin: -.6
+    {G_CAPSULE, 7, {0.045, 0, -0.07}, {1, 0, 0, 0}, 0.046, 0.07, 0.4, 3, 1, 0},  // ffoot: -.6
+};
+// orientation / placement spec per geom: kind 0 = the quat above, 1 = axisangle about +y with angle a[0], 2 = fromto a[0..5]
+struct GSpec { int kind; double a[6]; };
+const GSpec GEOM_SPEC[NG] = {
+    {0, {0}}, {2, {-0.5, 0, 0, 0.5, 0, 0}}, {1, {0.87}}, {1, {-3.8}}, {1, {-2.03}}, {1, {-0.27}}, {1, {0.52}}, {1, {-0.6}}, {1, {-0.6}}};
+const int ACT_JOINT[NU] = {3, 4, 5, 6, 7, 8};
+const double ACT_GEAR[NU] = {120.0, 90.0, 60.0, 120.0, 60.0, 30.0};
+constexpr double kGear = 0.0, kMargin = 0.0;  // kGear unused: per-actuator gears above
+const double kSolimpContact[5] = {0.0, 0.8, 0.01, 0.5, 2.0};
+const double kSolimpLimit[5] = {0.0, 0.8, 0.03, 0.5, 2.0};
+#define MJC_TIMESTEP 0.01
+#define MJC_CTRLRANGE 1.0
+#define MJC_ANGLE_RADIAN 1
+#define MJC_TOTALMASS 14.0
+#define MJC_EULER 1
 #elif defined(MJC_ROBOT_INVPEND)
 // inverted_pendulum.xml: defaults joint armature 0 damping 1 limited (:4), geom contype 0 (:5: nothing collides), motor
 // ctrlrange -3 3 gear 100 (:7, :27); RK4, timestep 0.02 (:9); the rail (a world geom, :13) takes part in nothing and is left
@@ -763,6 +847,14 @@ void build_model(HModel& m) {
   m.solref[0] = 0.02; m.solref[1] = 1.0;
   m.solimp[0] = 0.9; m.solimp[1] = 0.95; m.solimp[2] = 0.001; m.solimp[3] = 0.5; m.solimp[4] = 2.0;
   for (int k = 0; k < 5; ++k) m.solimp_contact[k] = kSolimpContact[k];
+#if defined(MJC_ROBOT_HALFCHEETAH)
+  for (int k = 0; k < 5; ++k) m.solimp[k] = kSolimpLimit[k];
+#endif
+  // getsolparam (engine_core_constraint.c): dmin and dmax are clipped to [mjMINIMP, mjMAXIMP] = [0.0001, 0.9999]
+  for (int k = 0; k < 2; ++k) {
+    m.solimp[k] = m.solimp[k] < 0.0001 ? 0.0001 : (m.solimp[k] > 0.9999 ? 0.9999 : m.solimp[k]);
+    m.solimp_contact[k] = m.solimp_contact[k] < 0.0001 ? 0.0001 : (m.solimp_contact[k] > 0.9999 ? 0.9999 : m.solimp_contact[k]);
+  }
   for (int b = 0; b < NB; ++b) {
     m.parent[b] = BODY[b].parent;
     cp3(m.body_pos[b], BODY[b].pos);
@@ -776,9 +868,17 @@ void build_model(HModel& m) {
     cp3(m.jnt_axis[j], J.axis);
     normalize3(m.jnt_axis[j]);
     m.jnt_limited[j] = J.limited;
+#if defined(MJC_ANGLE_RADIAN)
+    const double unit = 1.0;                       // compiler angle="radian"
+#else
     const double unit = J.type == 3 ? DEG : 1.0;  // compiler angle="degree" applies to hinges only
+#endif
     m.jnt_range[j][0] = J.lo * unit; m.jnt_range[j][1] = J.hi * unit;
+#if defined(MJC_ROBOT_HALFCHEETAH)
+    m.jnt_stiffness[j] = JOINT_STIFFNESS[j];
+#else
     m.jnt_stiffness[j] = 0.0;
+#endif
     m.dof_armature[j] = J.armature; m.dof_damping[j] = J.damping;
     m.qpos0[j] = J.ref;
   }
@@ -808,6 +908,22 @@ void build_model(HModel& m) {
     if (g == 1) {  // capsule from `fromto`: centre = midpoint, half length = |to - from| / 2, frame = the rotation taking z
                    // onto the segment about z x segment (user_objects.cc mjCGeom::Compile / mjuu_z2quat)
       const double* ft = kPoleFromTo;
+      double vec[3] = {ft[3] - ft[0], ft[4] - ft[1], ft[5] - ft[2]}, z[3] = {0, 0, 1}, axis[3];
+      for (int k = 0; k < 3; ++k) gpos[k] = 0.5 * (ft[k] + ft[3 + k]);
+      ghalf = 0.5 * normalize3(vec);
+      cross3(axis, z, vec);
+      const double sn = norm3(axis);
+      if (sn < 1e-10) { axis[0] = 1; axis[1] = 0; axis[2] = 0; } else { axis[0] /= sn; axis[1] /= sn; axis[2] /= sn; }
+      const double ang = atan2(sn, vec[2]);
+      q[0] = cos(0.5 * ang); q[1] = axis[0] * sin(0.5 * ang); q[2] = axis[1] * sin(0.5 * ang); q[3] = axis[2] * sin(0.5 * ang);
+    }
+#endif
+#if defined(MJC_ROBOT_HALFCHEETAH)
+    if (GEOM_SPEC[g].kind == 1) {  // axisangle="0 1 0 a" (radians): quat = (cos a/2, 0, sin a/2, 0)
+      const double ang = GEOM_SPEC[g].a[0];
+      q[0] = cos(0.5 * ang); q[1] = 0; q[2] = sin(0.5 * ang); q[3] = 0;
+    } else if (GEOM_SPEC[g].kind == 2) {  // fromto: as for the inverted pendulum's pole
+      const double* ft = GEOM_SPEC[g].a;
       double vec[3] = {ft[3] - ft[0], ft[4] - ft[1], ft[5] - ft[2]}, z[3] = {0, 0, 1}, axis[3];
       for (int k = 0; k < 3; ++k) gpos[k] = 0.5 * (ft[k] + ft[3 + k]);
       ghalf = 0.5 * normalize3(vec);
@@ -855,10 +971,25 @@ void build_model(HModel& m) {
       for (int j = 0; j < 3; ++j)
         m.body_inertia[b][3 * i + j] += gI[g][3 * i + j] + gmass[g] * ((i == j ? d2 : 0.0) - dv[i] * dv[j]);
   }
+#if defined(MJC_TOTALMASS)
+  {  // compiler settotalmass: every body's mass and inertia scaled so that the masses add up to it (user_model.cc)
+    double total = 0;
+    for (int b = 1; b < NB; ++b) total += m.body_mass[b];
+    const double scale = MJC_TOTALMASS / total;
+    for (int b = 1; b < NB; ++b) {
+      m.body_mass[b] *= scale;
+      for (int k = 0; k < 9; ++k) m.body_inertia[b][k] *= scale;
+    }
+  }
+#endif
   for (int b = NB - 1; b >= 0; --b) m.subtree_mass[b] = m.body_mass[b];
   for (int b = NB - 1; b >= 1; --b) m.subtree_mass[m.parent[b]] += m.subtree_mass[b];
   for (int u = 0; u < NU; ++u) {
+#if defined(MJC_ROBOT_HALFCHEETAH)
+    m.act_dof[u] = m.jnt_dofadr[ACT_JOINT[u]]; m.act_gear[u] = ACT_GEAR[u];
+#else
     m.act_dof[u] = m.jnt_dofadr[ACT_JOINT[u]]; m.act_gear[u] = kGear;
+#endif
     m.act_ctrlrange[u][0] = -MJC_CTRLRANGE; m.act_ctrlrange[u][1] = MJC_CTRLRANGE;
   }
   m.npair = 0;
@@ -935,6 +1066,8 @@ int upload_model() {
 // ---- kernels -------------------------------------------------------------------------------------------------------------------
 #if defined(MJC_ROBOT_INVPEND)
 constexpr int kObs = NQ + NV;  // inverted_pendulum_v5.py:185-186: qpos | qvel, nothing skipped or clipped
+#elif defined(MJC_ROBOT_HALFCHEETAH)
+constexpr int kObs = NQ - 1 + NV;  // half_cheetah_v5.py:251-259: qpos[1:] | qvel, nothing clipped
 #else
 constexpr int kObs = NQ - 1 + NV;
 #endif
@@ -965,6 +1098,12 @@ __device__ void write_obs(const HData& d, double* __restrict__ obs) {  // invert
   for (int i = 0; i < NQ; ++i) obs[i] = d.qpos[i];
   for (int i = 0; i < NV; ++i) obs[NQ + i] = d.qvel[i];
 }
+#elif defined(MJC_ROBOT_HALFCHEETAH)
+__device__ void write_obs(const HData& d, double* __restrict__ obs) {  // half_cheetah_v5.py:251-259
+  int o = 0;
+  for (int i = 1; i < NQ; ++i) obs[o++] = d.qpos[i];
+  for (int i = 0; i < NV; ++i) obs[o++] = d.qvel[i];
+}
 #else
 __device__ void write_obs(const HData& d, double* __restrict__ obs) {  // hopper_v5.py:253-261
   int o = 0;
@@ -982,6 +1121,55 @@ __device__ bool is_healthy(const HopperArgs& a, const HData& d) {
   return ok && (a.z_min < z && z < a.z_max) && (a.angle_min < angle && angle < a.angle_max);
 }
 
+#if defined(MJC_ROBOT_HALFCHEETAH)
+// Generator.standard_normal: numpy/random/src/distributions/distributions.c random_standard_normal (256-strip ziggurat over the
+// 64-bit words of the env's PCG64 stream; tables = numpy's own doubles).  The two slow paths use exp / log from fixed IEEE
+// sequences shared with oracle/mjc_planar.h (det_exp, det_log).
+#define B2E_ZIG_QUAL __device__
+#include "ziggurat_tables.inc"
+__device__ inline double det_exp(double y) {  // y <= 0 here
+  const double k = rint(y * 1.44269504088896338700e+00);
+  const double r = (y - k * 6.93147180369123816490e-01) - k * 1.90821492927058770002e-10;
+  double p = 1.0 / 6227020800.0;
+  p = p * r + 1.0 / 479001600.0;
+  p = p * r + 1.0 / 39916800.0;
+  p = p * r + 1.0 / 3628800.0;
+  p = p * r + 1.0 / 362880.0;
+  p = p * r + 1.0 / 40320.0;
+  p = p * r + 1.0 / 5040.0;
+  p = p * r + 1.0 / 720.0;
+  p = p * r + 1.0 / 120.0;
+  p = p * r + 1.0 / 24.0;
+  p = p * r + 1.0 / 6.0;
+  p = p * r + 0.5;
+  p = p * r + 1.0;
+  p = p * r + 1.0;
+  const int ik = (int)k;
+  return ik >= 0 ? p * (double)(1ull << ik) : (ik > -63 ? p / (double)(1ull << -ik) : 0.0);
+}
+__device__ inline double det_log(double y) {  // y in (0, 1]
+  uint64_t bits = (uint64_t)__double_as_longlong(y);
+  int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  bits = (bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+  double mant = __longlong_as_double((long long)bits);  // [1, 2)
+  if (mant > 1.41421356237309514547) { mant *= 0.5; e += 1; }
+  const double s = (mant - 1.0) / (mant + 1.0), z = s * s;
+  double p = 1.0 / 23.0;
+  p = p * z + 1.0 / 21.0;
+  p = p * z + 1.0 / 19.0;
+  p = p * z + 1.0 / 17.0;
+  p = p * z + 1.0 / 15.0;
+  p = p * z + 1.0 / 13.0;
+  p = p * z + 1.0 / 11.0;
+  p = p * z + 1.0 / 9.0;
+  p = p * z + 1.0 / 7.0;
+  p = p * z + 1.0 / 5.0;
+  p = p * z + 1.0 / 3.0;
+  p = p * z + 1.0;
+  return (double)e * 6.93147180369123816490e-01 + ((double)e * 1.90821492927058770002e-10 + 2.0 * s * p);
+}
+#endif
+
 // uniform draws for reset noise: numpy stream or Philox
 struct PDraws {
   Pcg64 g;
@@ -995,6 +1183,34 @@ struct PDraws {
     ++k;
     return u;
   }
+#if defined(MJC_ROBOT_HALFCHEETAH)
+  __device__ double normal() {
+    if (!numpy) {  // Philox mode is not a parity mode: Box-Muller on two counter-based uniforms
+      const double u1 = 1.0 - next(), u2 = next();
+      return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+    const double nor_r = 3.6541528853610087963519472518, nor_inv_r = 0.27366123732975827203338247596;
+    for (;;) {
+      uint64_t r = g.next_u64();
+      const int idx = (int)(r & 0xff);
+      r >>= 8;
+      const int sign = (int)(r & 0x1);
+      const uint64_t rabs = (r >> 1) & 0x000fffffffffffffull;
+      double x = (double)rabs * zig_wi[idx];
+      if (sign) x = -x;
+      if (rabs < zig_ki[idx]) return x;
+      if (idx == 0) {
+        for (;;) {
+          const double xx = -nor_inv_r * det_log(1.0 - g.next_double());
+          const double yy = -det_log(1.0 - g.next_double());
+          if (yy + yy > xx * xx) return ((rabs >> 8) & 0x1) ? -(nor_r + xx) : nor_r + xx;
+        }
+      } else if ((zig_fi[idx - 1] - zig_fi[idx]) * g.next_double() + zig_fi[idx] < det_exp(-0.5 * x * x)) {
+        return x;
+      }
+    }
+  }
+#endif
 };
 
 // MujocoEnv.reset + HopperEnv.reset_model (mujoco_env.py:172-187, hopper_v5.py:322-337)
@@ -1004,11 +1220,18 @@ __device__ void env_reset(const HopperArgs& a, int64_t i, HData& d, PDraws& D, d
   for (int u = 0; u < NU; ++u) d.ctrl[u] = 0;
   const double c = a.noise;
   for (int k = 0; k < NQ; ++k) d.qpos[k] = m.qpos0[k] + (-c + (c - -c) * D.next());
+#if defined(MJC_ROBOT_HALFCHEETAH)
+  for (int k = 0; k < NV; ++k) d.qvel[k] = 0.0 + c * D.normal();  // half_cheetah_v5.py:268-271
+#else
   for (int k = 0; k < NV; ++k) d.qvel[k] = 0.0 + (-c + (c - -c) * D.next());
+#endif
   mj_forward(m, d);
   write_obs(d, obs);
 #if defined(MJC_ROBOT_INVPEND)
   for (int k = 0; k < kInfo; ++k) a.info[k * a.n + i] = 0.0;  // MujocoEnv._get_reset_info: {}
+#elif defined(MJC_ROBOT_HALFCHEETAH)
+  for (int k = 1; k < kInfo; ++k) a.info[k * a.n + i] = 0.0;
+  a.info[0 * a.n + i] = d.qpos[0];                    // _get_reset_info: x_position (half_cheetah_v5.py:278-281)
 #else
   for (int k = 2; k < kInfo; ++k) a.info[k * a.n + i] = 0.0;
   a.info[0 * a.n + i] = d.qpos[0];                    // _get_reset_info, hopper_v5.py:339-343
@@ -1086,6 +1309,25 @@ __global__ void __launch_bounds__(kHopperBlock) hopper_step_kernel(const HopperA
   const double reward = term ? 0.0 : 1.0;           // int(not terminated)
   for (int k = 0; k < kInfo - 1; ++k) a.info[k * n + i] = 0.0;
   a.info[5 * n + i] = reward;                       // info["reward_survive"]
+#elif defined(MJC_ROBOT_HALFCHEETAH)
+  const double x_before = d.qpos[0];  // half_cheetah_v5.py:225
+  ActT sq = (ActT)0;  // control_cost on the action as passed (float32: NumPy 2 keeps weight * sum in float32, NEP 50)
+  for (int u = 0; u < NU; ++u) sq += act[u] * act[u];
+  const double ctrl_cost = (double)((ActT)a.w_ctrl * sq);
+  for (int k = 0; k < a.frame_skip; ++k) mj_step_euler(m, d);  // mj_step(nstep=frame_skip), integrator Euler
+  const double x_after = d.qpos[0];
+  const double dt = m.timestep * a.frame_skip;
+  const double xv = (x_after - x_before) / dt;
+  write_obs(d, obs);
+  const double forward_reward = a.w_forward * xv;
+  const double reward = forward_reward - ctrl_cost;  // half_cheetah_v5.py:239-243
+  const bool term = false;                           // never terminates
+  a.info[0 * n + i] = x_after;
+  a.info[1 * n + i] = 0.0;
+  a.info[2 * n + i] = xv;
+  a.info[3 * n + i] = forward_reward;
+  a.info[4 * n + i] = -ctrl_cost;
+  a.info[5 * n + i] = 0.0;
 #else
   const double x_before = d.qpos[0];  // hopper_v5.py:272
   // control_cost (hopper_v5.py:226-228) squares and sums the ACTION as passed; for float32 actions NumPy 2 keeps the

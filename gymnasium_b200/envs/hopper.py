@@ -235,3 +235,24 @@ class InvertedPendulumVectorEnv(_MjPlanarVectorEnv):
                  frame_skip: int = 2, reset_noise_scale: float = 0.01, render_mode: str | None = None, **engine_kwargs):
         super().__init__(num_envs, max_episode_steps, xml_file, frame_skip, 0.0, 0.0, 0.0, True, (-np.inf, np.inf),
                          (-np.inf, np.inf), (-np.inf, np.inf), reset_noise_scale, True, render_mode, engine_kwargs)
+
+
+class HalfCheetahVectorEnv(_MjPlanarVectorEnv):
+    """N HalfCheetah-v5 envs (half_cheetah_v5.py:153-162 for the keyword arguments): observation ``(N, 17) float64`` =
+    qpos[1:] | qvel (not clipped), action ``(N, 6) float32`` in [-1, 1], reward = forward_reward_weight * x_velocity -
+    ctrl_cost_weight * sum(action^2); never terminates (TimeLimit 1000); reset noise: uniform on qpos, ``reset_noise_scale *
+    standard_normal`` on qvel (numpy's ziggurat, restated on the device)."""
+
+    robot, xml, NQ, NU = "half_cheetah", "half_cheetah.xml", 9, 6
+    TIMESTEP, ACT_HIGH = 0.01, 1.0
+    INFO_ROWS = {"x_position": 0, "x_velocity": 2, "reward_forward": 3, "reward_ctrl": 4}
+    RESET_KEYS, STEP_KEYS = ("x_position",), ("x_velocity", "reward_forward", "reward_ctrl")
+    metadata = {"render_modes": [], "render_fps": 20, "autoreset_mode": AutoresetMode.NEXT_STEP}
+
+    def __init__(self, num_envs: int = 1, max_episode_steps: int | None = 1000, xml_file: str = "half_cheetah.xml",
+                 frame_skip: int = 5, forward_reward_weight: float = 1.0, ctrl_cost_weight: float = 0.1,
+                 reset_noise_scale: float = 0.1, exclude_current_positions_from_observation: bool = True,
+                 render_mode: str | None = None, **engine_kwargs):
+        super().__init__(num_envs, max_episode_steps, xml_file, frame_skip, forward_reward_weight, ctrl_cost_weight, 0.0, False,
+                         (-np.inf, np.inf), (-np.inf, np.inf), (-np.inf, np.inf), reset_noise_scale,
+                         exclude_current_positions_from_observation, render_mode, engine_kwargs)

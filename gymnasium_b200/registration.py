@@ -49,6 +49,8 @@ ENVS = {
     "Hopper-v5": ("gymnasium_b200.envs.hopper:HopperVectorEnv", "gymnasium.envs.mujoco.hopper_v5:HopperEnv", 1000, 3800.0, {}),
     "Walker2d-v5": ("gymnasium_b200.envs.hopper:Walker2dVectorEnv", "gymnasium.envs.mujoco.walker2d_v5:Walker2dEnv", 1000,
                     None, {}),
+    "HalfCheetah-v5": ("gymnasium_b200.envs.hopper:HalfCheetahVectorEnv",
+                       "gymnasium.envs.mujoco.half_cheetah_v5:HalfCheetahEnv", 1000, 4800.0, {}),
     "InvertedPendulum-v5": ("gymnasium_b200.envs.hopper:InvertedPendulumVectorEnv",
                             "gymnasium.envs.mujoco.inverted_pendulum_v5:InvertedPendulumEnv", 1000, 950.0, {}),
 }

@@ -414,6 +414,17 @@ int b2e_walker2d_reset(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2
 int b2e_walker2d_step(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st, const void* actions,
                       double* obs, double* reward, uint8_t* terminated, uint8_t* truncated, double* info, double* final_obs,
                       void* stream);
+/* HalfCheetah-v5: gymnasium/envs/mujoco/half_cheetah_v5.py:220-281, assets/half_cheetah.xml on the same kernels (Euler
+ * integrator with implicit joint damping, joint springs, settotalmass 14, per-actuator gears).  nq = nv = 9, nu = 6; cfg uses
+ * reset_noise_scale (0.1: uniform on qpos, 0.1 * standard_normal on qvel -- numpy's ziggurat over the env's PCG64 stream),
+ * forward_reward_weight (1.0), ctrl_cost_weight (0.1), frame_skip (5), lanes_per_warp.  obs float64 [n][17] = qpos[1:] | qvel;
+ * never terminates; info rows 0 x_position, 2 x_velocity, 3 reward_forward, 4 reward_ctrl; nbody = 8. */
+int b2e_half_cheetah_model_info(double* body_mass, double* misc, double* invweight);
+int b2e_half_cheetah_reset(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st, const uint8_t* mask,
+                           double* obs, double* info, void* stream);
+int b2e_half_cheetah_step(const b2e_batch* b, const b2e_mjplanar_cfg* cfg, const b2e_mjplanar_state* st, const void* actions,
+                          double* obs, double* reward, uint8_t* terminated, uint8_t* truncated, double* info, double* final_obs,
+                          void* stream);
 /* InvertedPendulum-v5: gymnasium/envs/mujoco/inverted_pendulum_v5.py:147-186, assets/inverted_pendulum.xml on the same
  * kernels.  nq = nv = 2 (slider, hinge), nu = 1 (ctrlrange +-3, gear 100), timestep 0.02; cfg uses reset_noise_scale (0.01),
  * frame_skip (2) and lanes_per_warp only.  obs float64 [n][4] = qpos | qvel; reward 1.0 while |angle| <= 0.2 and the state is

@@ -47,6 +47,16 @@
 #define MAXCON 8
 #define MAXEFC 32
 #define API(name) w2_##name
+#elif defined(ROBOT_HALFCHEETAH)
+#define NB 8
+#define NQ 9
+#define NV 9
+#define NU 6
+#define NJ 9
+#define NG 9
+#define MAXCON 12
+#define MAXEFC 56
+#define API(name) hc_##name
 #elif defined(ROBOT_INVPEND)
 #define NB 3
 #define NQ 2
@@ -58,7 +68,7 @@
 #define MAXEFC 4
 #define API(name) ip_##name
 #else
-#error "define ROBOT_HOPPER, ROBOT_WALKER2D or ROBOT_INVPEND before including mjc_planar.h"
+#error "define ROBOT_HOPPER, ROBOT_WALKER2D, ROBOT_HALFCHEETAH or ROBOT_INVPEND before including mjc_planar.h"
 #endif
 #define MINVAL 1e-15
 #define PI 3.14159265358979323846
@@ -260,6 +270,56 @@ static const gdef_t GEOM_DEF[NG] = {
 static const adef_t ACT_DEF[NU] = {{3, 200.0}, {4, 200.0}, {5, 200.0}};
 #define OPT_MARGIN 0.001
 #define OPT_SOLIMP_CONTACT {0.8, 0.8, 0.01, 0.5, 2.0}
+#elif defined(ROBOT_HALFCHEETAH)
+/* half_cheetah.xml: compiler angle="radian" settotalmass="14" (:35); defaults joint armature .1 damping .01 limited
+ * solimplimit 0 .8 .03 solreflimit .02 1 stiffness 8 (:37; every hinge overrides damping / stiffness), geom conaffinity 0
+ * condim 3 contype 1 friction .4 solimp 0 .8 .01 solref .02 1 (:38: the robot collides with the floor only); option
+ * timestep 0.01, integrator left at its default = Euler (:42); the root joints carry armature 0 damping 0 stiffness 0 (:55-57);
+ * motors gear 120 90 60 120 60 30, ctrlrange -1 1 (:88-93) */
+static const char* BODY_NAMES[NB] = {"world", "torso", "bthigh", "bshin", "bfoot", "fthigh", "fshin", "ffoot"};
+static const bdef_t BODY_DEF[NB] = {
+    {0, {0, 0, 0}}, {0, {0, 0, 0.7}},
+    {1, {-0.5, 0, 0}}, {2, {0.16, 0, -0.25}}, {3, {-0.28, 0, -0.14}},
+    {1, {0.5, 0, 0}}, {5, {-0.14, 0, -0.24}}, {6, {0.13, 0, -0.18}}};
+/* ranges in radians */
+static const jdef_t JOINT_DEF[NJ] = {
+    {2, 1, {0, 0, 0}, {1, 0, 0}, 0, 0, 0, 0, 0, 0},          /* rootx */
+    {2, 1, {0, 0, 0}, {0, 0, 1}, 0, 0, 0, 0, 0, 0},          /* rootz */
+    {3, 1, {0, 0, 0}, {0, 1, 0}, 0, 0, 0, 0, 0, 0},          /* rooty */
+    {3, 2, {0, 0, 0}, {0, 1, 0}, 1, -0.52, 1.05, 0.1, 6, 0},   /* bthigh */
+    {3, 3, {0, 0, 0}, {0, 1, 0}, 1, -0.785, 0.785, 0.1, 4.5, 0}, /* bshin */
+    {3, 4, {0, 0, 0}, {0, 1, 0}, 1, -0.4, 0.785, 0.1, 3, 0},   /* bfoot */
+    {3, 5, {0, 0, 0}, {0, 1, 0}, 1, -1, 0.7, 0.1, 4.5, 0},     /* fthigh */
+    {3, 6, {0, 0, 0}, {0, 1, 0}, 1, -1.2, 0.87, 0.1, 3, 0},    /* fshin */
+    {3, 7, {0, 0, 0}, {0, 1, 0}, 1, -0.5, 0.5, 0.1, 1.5, 0},   /* ffoot */
+};
+static const double JOINT_STIFFNESS[NJ] = {0, 0, 0, 240, 180, 120, 180, 120, 60};
+/* geoms: the floor, then torso (fromto), head, and one capsule per leg segment given by pos + axisangle about y (radians) */
+static const gdef_t GEOM_DEF[NG] = {
+    {G_PLANE, 0, {0, 0, 0}, {1, 0, 0, 0}, 0, 0, 0.4, 3, 1, 1},
+    {G_CAPSULE, 1, {0, 0, 0}, {1, 0, 0, 0}, 0.046, 0.5, 0.4, 3, 1, 0},          /* torso: fromto -.5 0 0 .5 0 0 */
+    {G_CAPSULE, 1, {0.6, 0, 0.1}, {1, 0, 0, 0}, 0.046, 0.15, 0.4, 3, 1, 0},     /* head: axisangle 0 1 0 .87 */
+    {G_CAPSULE, 2, {0.1, 0, -0.13}, {1, 0, 0, 0}, 0.046, 0.145, 0.4, 3, 1, 0},  /* bthigh: -3.8 */
+    {G_CAPSULE, 3, {-0.14, 0, -0.07}, {1, 0, 0, 0}, 0.046, 0.15, 0.4, 3, 1, 0}, /* bshin: -2.03 */
+    {G_CAPSULE, 4, {0.03, 0, -0.097}, {1, 0, 0, 0}, 0.046, 0.094, 0.4, 3, 1, 0}, /* bfoot: -.27 */
+    {G_CAPSULE, 5, {-0.07, 0, -0.12}, {1, 0, 0, 0}, 0.046, 0.133, 0.4, 3, 1, 0}, /* fthigh: .52 */
+    {G_CAPSULE, 6, {0.065, 0, -0.09}, {1, 0, 0, 0}, 0.046, 0.106, 0.4, 3, 1, 0}, /* fshin: -.6 */
+    {G_CAPSULE, 7, {0.045, 0, -0.07}, {1, 0, 0, 0}, 0.046, 0.07, 0.4, 3, 1, 0},  /* ffoot: -.6 */
+};
+/* orientation / placement spec per geom: kind 0 = the quat above, 1 = axisangle about +y with angle a[0], 2 = fromto a[0..5] */
+typedef struct { int kind; double a[6]; } gspec_t;
+static const gspec_t GEOM_SPEC[NG] = {
+    {0, {0}}, {2, {-0.5, 0, 0, 0.5, 0, 0}}, {1, {0.87}}, {1, {-3.8}}, {1, {-2.03}}, {1, {-0.27}}, {1, {0.52}}, {1, {-0.6}}, {1, {-0.6}}};
+static const adef_t ACT_DEF[NU] = {{3, 120.0}, {4, 90.0}, {5, 60.0}, {6, 120.0}, {7, 60.0}, {8, 30.0}};
+#define OPT_MARGIN 0.0
+#define OPT_SOLIMP_CONTACT {0.0, 0.8, 0.01, 0.5, 2.0}
+#define OPT_SOLIMP_LIMIT {0.0, 0.8, 0.03, 0.5, 2.0}
+#define OPT_TIMESTEP 0.01
+#define OPT_CTRLRANGE 1.0
+#define FRAME_SKIP 5
+#define OPT_ANGLE_RADIAN 1
+#define OPT_TOTALMASS 14.0
+#define OPT_EULER 1
 #elif defined(ROBOT_INVPEND)
 /* inverted_pendulum.xml: defaults joint armature 0 damping 1 limited (:4), geom contype 0 (:5: nothing collides), motor
  * ctrlrange -3 3 (:7); RK4, timestep 0.02 (:9); the rail (a world geom, :13) takes part in nothing and is left out.  Slide
@@ -332,6 +392,15 @@ static void build_model(model_t* m) {
   {
     const double sc[5] = OPT_SOLIMP_CONTACT;
     memcpy(m->solimp_contact, sc, sizeof(sc));
+#if defined(OPT_SOLIMP_LIMIT)
+    const double sl[5] = OPT_SOLIMP_LIMIT;
+    memcpy(m->solimp, sl, sizeof(sl));
+#endif
+    /* getsolparam (engine_core_constraint.c): dmin and dmax are clipped to [mjMINIMP, mjMAXIMP] = [0.0001, 0.9999] */
+    for (int k = 0; k < 2; ++k) {
+      m->solimp[k] = m->solimp[k] < 0.0001 ? 0.0001 : (m->solimp[k] > 0.9999 ? 0.9999 : m->solimp[k]);
+      m->solimp_contact[k] = m->solimp_contact[k] < 0.0001 ? 0.0001 : (m->solimp_contact[k] > 0.9999 ? 0.9999 : m->solimp_contact[k]);
+    }
   }
   for (int b = 0; b < NB; ++b) {
     m->parent[b] = BODY_DEF[b].parent;
@@ -346,9 +415,17 @@ static void build_model(model_t* m) {
     cp3(m->jnt_axis[j], J->axis);
     normalize3(m->jnt_axis[j]);
     m->jnt_limited[j] = J->limited;
+#if defined(OPT_ANGLE_RADIAN)
+    const double unit = 1.0;                      /* compiler angle="radian" */
+#else
     const double unit = J->type == 3 ? DEG : 1.0; /* compiler angle="degree" applies to hinges only */
+#endif
     m->jnt_range[j][0] = J->lo * unit; m->jnt_range[j][1] = J->hi * unit;
+#if defined(ROBOT_HALFCHEETAH)
+    m->jnt_stiffness[j] = JOINT_STIFFNESS[j];
+#else
     m->jnt_stiffness[j] = 0.0;
+#endif
     m->dof_armature[j] = J->armature; m->dof_damping[j] = J->damping;
     m->qpos0[j] = J->ref;
   }
@@ -380,6 +457,22 @@ static void build_model(model_t* m) {
     if (g == 1) { /* capsule from `fromto` (user_objects.cc mjCGeom::Compile / mjuu_z2quat): centre = midpoint, half length =
                      |to - from| / 2, frame = the rotation taking z onto the segment about z x segment */
       const double ft[6] = POLE_FROMTO;
+      double vec[3] = {ft[3] - ft[0], ft[4] - ft[1], ft[5] - ft[2]}, z[3] = {0, 0, 1}, axis[3];
+      for (int k = 0; k < 3; ++k) gpos[k] = 0.5 * (ft[k] + ft[3 + k]);
+      ghalf = 0.5 * normalize3(vec);
+      cross3(axis, z, vec);
+      const double sn = norm3(axis);
+      if (sn < 1e-10) { axis[0] = 1; axis[1] = 0; axis[2] = 0; } else { axis[0] /= sn; axis[1] /= sn; axis[2] /= sn; }
+      const double ang = atan2(sn, vec[2]);
+      q[0] = cos(0.5 * ang); q[1] = axis[0] * sin(0.5 * ang); q[2] = axis[1] * sin(0.5 * ang); q[3] = axis[2] * sin(0.5 * ang);
+    }
+#endif
+#if defined(ROBOT_HALFCHEETAH)
+    if (GEOM_SPEC[g].kind == 1) { /* axisangle="0 1 0 a" (radians): quat = (cos a/2, 0, sin a/2, 0) */
+      const double ang = GEOM_SPEC[g].a[0];
+      q[0] = cos(0.5 * ang); q[1] = 0; q[2] = sin(0.5 * ang); q[3] = 0;
+    } else if (GEOM_SPEC[g].kind == 2) { /* fromto: as for the inverted pendulum's pole */
+      const double* ft = GEOM_SPEC[g].a;
       double vec[3] = {ft[3] - ft[0], ft[4] - ft[1], ft[5] - ft[2]}, z[3] = {0, 0, 1}, axis[3];
       for (int k = 0; k < 3; ++k) gpos[k] = 0.5 * (ft[k] + ft[3 + k]);
       ghalf = 0.5 * normalize3(vec);
@@ -427,6 +520,17 @@ static void build_model(model_t* m) {
       for (int j = 0; j < 3; ++j)
         m->body_inertia[b][3 * i + j] += gI[g][3 * i + j] + gmass[g] * ((i == j ? d2 : 0.0) - dv[i] * dv[j]);
   }
+#if defined(OPT_TOTALMASS)
+  { /* compiler settotalmass: every body's mass and inertia scaled so that the masses add up to it (user_model.cc) */
+    double total = 0;
+    for (int b = 1; b < NB; ++b) total += m->body_mass[b];
+    const double scale = OPT_TOTALMASS / total;
+    for (int b = 1; b < NB; ++b) {
+      m->body_mass[b] *= scale;
+      for (int k = 0; k < 9; ++k) m->body_inertia[b][k] *= scale;
+    }
+  }
+#endif
   for (int b = NB - 1; b >= 0; --b) m->subtree_mass[b] = m->body_mass[b];
   for (int b = NB - 1; b >= 1; --b) m->subtree_mass[m->parent[b]] += m->subtree_mass[b];
   for (int u = 0; u < NU; ++u) {
@@ -969,6 +1073,7 @@ static void mj_forward(const model_t* m, data_t* d) {
 static void integrate_pos(double* qpos, const double* vel, double h) {
   for (int i = 0; i < NV; ++i) qpos[i] += h * vel[i]; /* slide and hinge joints only */
 }
+#if !defined(OPT_EULER)
 static void mj_step_rk4(const model_t* m, data_t* d) {
   mj_forward(m, d);
   const double h = m->timestep;
@@ -998,6 +1103,47 @@ static void mj_step_rk4(const model_t* m, data_t* d) {
   d->time = time0 + h;
   memcpy(d->qacc_warmstart, d->qacc, sizeof(d->qacc)); /* mj_advance */
 }
+#endif
+#if defined(OPT_EULER)
+/* mj_Euler (engine_forward.c: mj_EulerSkip + mj_advance): semi-implicit Euler with the joint damping treated implicitly --
+ * qacc' = (M + h diag(B))^-1 (qfrc_smooth + qfrc_constraint); qvel += h qacc'; qpos += h qvel (the NEW velocity);
+ * qacc_warmstart = the forward dynamics' qacc */
+static void mj_step_euler(const model_t* m, data_t* d) {
+  const double h = m->timestep;
+  mj_forward(m, d);
+  double qacc[NV];
+  int damped = 0;
+  for (int i = 0; i < NV; ++i) damped = damped || m->dof_damping[i] > 0;
+  if (!damped) {
+    memcpy(qacc, d->qacc, sizeof(qacc));
+  } else {
+    double H[NV][NV], Hinv[NV];
+    memcpy(H, d->qM, sizeof(H));
+    for (int i = 0; i < NV; ++i) H[i][i] += h * m->dof_damping[i];
+    for (int k = NV - 1; k >= 0; --k) { /* mj_factorI: the same L^T D L as crb_and_factor */
+      for (int i = m->dof_parent[k]; i >= 0; i = m->dof_parent[i]) {
+        double tmp = H[k][i] / H[k][k];
+        for (int j = i; j >= 0; j = m->dof_parent[j]) H[i][j] -= H[k][j] * tmp;
+        H[k][i] = tmp;
+      }
+      Hinv[k] = 1.0 / H[k][k];
+    }
+    for (int i = 0; i < NV; ++i) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
+    for (int i = NV - 1; i >= 0; --i) /* mj_solveLD */
+      for (int j = m->dof_parent[i]; j >= 0; j = m->dof_parent[j]) qacc[j] -= H[i][j] * qacc[i];
+    for (int i = 0; i < NV; ++i) qacc[i] *= Hinv[i];
+    for (int i = 0; i < NV; ++i)
+      for (int j = m->dof_parent[i]; j >= 0; j = m->dof_parent[j]) qacc[i] -= H[i][j] * qacc[j];
+  }
+  for (int k = 0; k < NV; ++k) d->qvel[k] += h * qacc[k];
+  integrate_pos(d->qpos, d->qvel, h);
+  d->time += h;
+  memcpy(d->qacc_warmstart, d->qacc, sizeof(d->qacc)); /* mj_advance */
+}
+#define MJ_STEP mj_step_euler
+#else
+#define MJ_STEP mj_step_rk4
+#endif
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* environment (hopper_v5.py / walker2d_v5.py); info rows: x_position, z_distance_from_origin, x_velocity, reward_forward,
  * reward_ctrl, reward_survive */
@@ -1051,6 +1197,125 @@ static void env_step(pl_vec_t* v, int i, const float* action, double* obs, doubl
   memset(info, 0, NINFO * sizeof(double));
   info[5] = *reward;                            /* info["reward_survive"] */
 }
+#elif defined(ROBOT_HALFCHEETAH)
+#include "ziggurat_tables.h"
+/* exp and log from fixed sequences of IEEE operations (the CUDA engine runs the same ones), for the two slow paths of the
+ * ziggurat: accurate to ~2e-16, so a wedge decision differs from libm's only when the two sides agree to 1e-15, and a tail
+ * sample (0.03 % of the draws) can differ from numpy's by one ulp. */
+static inline double det_exp(double y) { /* y <= 0 here */
+  const double k = rint(y * 1.44269504088896338700e+00);
+  const double r = (y - k * 6.93147180369123816490e-01) - k * 1.90821492927058770002e-10;
+  double p = 1.0 / 6227020800.0;
+  p = p * r + 1.0 / 479001600.0;
+  p = p * r + 1.0 / 39916800.0;
+  p = p * r + 1.0 / 3628800.0;
+  p = p * r + 1.0 / 362880.0;
+  p = p * r + 1.0 / 40320.0;
+  p = p * r + 1.0 / 5040.0;
+  p = p * r + 1.0 / 720.0;
+  p = p * r + 1.0 / 120.0;
+  p = p * r + 1.0 / 24.0;
+  p = p * r + 1.0 / 6.0;
+  p = p * r + 0.5;
+  p = p * r + 1.0;
+  p = p * r + 1.0;
+  const int ik = (int)k;
+  return ik >= 0 ? p * (double)(1ull << ik) : (ik > -63 ? p / (double)(1ull << -ik) : 0.0);
+}
+static inline double det_log(double y) { /* y in (0, 1] */
+  uint64_t bits;
+  memcpy(&bits, &y, 8);
+  int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  bits = (bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+  double mant;
+  memcpy(&mant, &bits, 8); /* [1, 2) */
+  if (mant > 1.41421356237309514547) { mant *= 0.5; e += 1; }
+  const double s = (mant - 1.0) / (mant + 1.0), z = s * s;
+  double p = 1.0 / 23.0;
+  p = p * z + 1.0 / 21.0;
+  p = p * z + 1.0 / 19.0;
+  p = p * z + 1.0 / 17.0;
+  p = p * z + 1.0 / 15.0;
+  p = p * z + 1.0 / 13.0;
+  p = p * z + 1.0 / 11.0;
+  p = p * z + 1.0 / 9.0;
+  p = p * z + 1.0 / 7.0;
+  p = p * z + 1.0 / 5.0;
+  p = p * z + 1.0 / 3.0;
+  p = p * z + 1.0;
+  return (double)e * 6.93147180369123816490e-01 + ((double)e * 1.90821492927058770002e-10 + 2.0 * s * p);
+}
+/* Generator.standard_normal: numpy/random/src/distributions/distributions.c random_standard_normal (ziggurat, 256 strips);
+ * pinned against numpy in oracle/np_rng.py (PCG64.standard_normal) */
+static uint64_t pcg64_u64(pcg64_t* g) {
+  const u128 mult = ((u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+  g->state = g->state * mult + g->inc;
+  uint64_t hi = (uint64_t)(g->state >> 64), lo = (uint64_t)g->state, x = hi ^ lo;
+  unsigned rot = (unsigned)(hi >> 58);
+  return (x >> rot) | (x << ((64 - rot) & 63));
+}
+static double pcg64_standard_normal(pcg64_t* g) {
+  const double nor_r = 3.6541528853610087963519472518, nor_inv_r = 0.27366123732975827203338247596;
+  for (;;) {
+    uint64_t r = pcg64_u64(g);
+    const int idx = (int)(r & 0xff);
+    r >>= 8;
+    const int sign = (int)(r & 0x1);
+    const uint64_t rabs = (r >> 1) & 0x000fffffffffffffull;
+    double x = (double)rabs * zig_wi[idx];
+    if (sign) x = -x;
+    if (rabs < zig_ki[idx]) return x;
+    if (idx == 0) {
+      for (;;) {
+        const double xx = -nor_inv_r * det_log(1.0 - pcg64_double(g));
+        const double yy = -det_log(1.0 - pcg64_double(g));
+        if (yy + yy > xx * xx) return ((rabs >> 8) & 0x1) ? -(nor_r + xx) : nor_r + xx;
+      }
+    } else if ((zig_fi[idx - 1] - zig_fi[idx]) * pcg64_double(g) + zig_fi[idx] < det_exp(-0.5 * x * x)) {
+      return x;
+    }
+  }
+}
+static void get_obs(const data_t* d, double* obs) { /* half_cheetah_v5.py:251-259: qpos[1:] | qvel, nothing clipped */
+  int o = 0;
+  for (int i = 1; i < NQ; ++i) obs[o++] = d->qpos[i];
+  for (int i = 0; i < NV; ++i) obs[o++] = d->qvel[i];
+}
+static void env_reset(pl_vec_t* v, int i, double* obs, double* info) { /* half_cheetah_v5.py:261-276 */
+  const model_t* m = &v->model;
+  henv_t* e = &v->env[i];
+  pcg64_t rng = e->rng;
+  memset(&e->d, 0, sizeof(e->d)); /* mj_resetData */
+  e->rng = rng;
+  data_t* d = &e->d;
+  const double c = v->reset_noise_scale;
+  for (int k = 0; k < NQ; ++k) d->qpos[k] = m->qpos0[k] + (-c + (c - -c) * pcg64_double(&e->rng));
+  for (int k = 0; k < NV; ++k) d->qvel[k] = 0.0 + c * pcg64_standard_normal(&e->rng);
+  mj_forward(m, d); /* set_state */
+  get_obs(d, obs);
+  memset(info, 0, NINFO * sizeof(double));
+  info[0] = d->qpos[0]; /* _get_reset_info: x_position */
+}
+static void env_step(pl_vec_t* v, int i, const float* action, double* obs, double* reward, int* terminated, double* info) {
+  const model_t* m = &v->model;
+  data_t* d = &v->env[i].d;
+  const double x_before = d->qpos[0];
+  for (int u = 0; u < NU; ++u) d->ctrl[u] = (double)action[u];
+  for (int k = 0; k < FRAME_SKIP; ++k) MJ_STEP(m, d);
+  const double x_after = d->qpos[0];
+  const double dt = m->timestep * FRAME_SKIP;
+  const double xv = (x_after - x_before) / dt;
+  get_obs(d, obs);
+  const double forward_reward = 1.0 * xv;
+  float sq = 0.0f; /* control_cost squares and sums the float32 action; NumPy 2 keeps weight * sum in float32 (NEP 50) */
+  for (int u = 0; u < NU; ++u) sq += action[u] * action[u];
+  const float ctrl_cost32 = (float)0.1 * sq;
+  const double ctrl_cost = (double)ctrl_cost32;
+  *reward = forward_reward - ctrl_cost; /* half_cheetah_v5.py:239-243 */
+  *terminated = 0;                      /* never terminates */
+  memset(info, 0, NINFO * sizeof(double));
+  info[0] = x_after; info[2] = xv; info[3] = forward_reward; info[4] = -ctrl_cost;
+}
 #else
 static void get_obs(const data_t* d, double* obs) { /* hopper_v5.py:253-261 */
   int o = 0;
@@ -1088,7 +1353,7 @@ static void env_step(pl_vec_t* v, int i, const float* action, double* obs, doubl
   data_t* d = &v->env[i].d;
   const double x_before = d->qpos[0];
   for (int u = 0; u < NU; ++u) d->ctrl[u] = (double)action[u];
-  for (int k = 0; k < 4; ++k) mj_step_rk4(m, d); /* frame_skip 4 */
+  for (int k = 0; k < FRAME_SKIP; ++k) MJ_STEP(m, d); /* frame_skip 4 */
   const double x_after = d->qpos[0];
   const double dt = m->timestep * 4;
   const double xv = (x_after - x_before) / dt;

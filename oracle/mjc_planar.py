@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 INFO_KEYS = ["x_position", "z_distance_from_origin", "x_velocity", "reward_forward", "reward_ctrl", "reward_survive"]
 # robot -> (library, symbol prefix, nbody, nq = nv, nu)
 ROBOTS = {"hopper": ("libhopper_oracle.so", "hp_", 5, 6, 3), "walker2d": ("libwalker2d_oracle.so", "w2_", 8, 9, 6),
-          "inverted_pendulum": ("libinverted_pendulum_oracle.so", "ip_", 3, 2, 1)}
+          "inverted_pendulum": ("libinverted_pendulum_oracle.so", "ip_", 3, 2, 1),
+          "half_cheetah": ("libhalf_cheetah_oracle.so", "hc_", 8, 9, 6)}
 OBS_SIZE = {"inverted_pendulum": 4}  # default: 2 nq - 1 (qpos[1:] | qvel)
 _libs = {}
 

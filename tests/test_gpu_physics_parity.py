@@ -392,6 +392,43 @@ def test_inverted_pendulum_matches_oracle_bit_exact(n, T, dtype):
     assert not env.buffer_overflow()
 
 
+@pytest.mark.parametrize("n,T,limit", [(512, 110, 35), (8192, 50, 20)])
+def test_half_cheetah_matches_oracle_bit_exact(n, T, limit):
+    """HalfCheetah-v5 on the planar kernels (Euler integrator with implicit joint damping, joint springs, standard_normal reset
+    noise from numpy's ziggurat) against oracle/half_cheetah.c: observations, rewards, flags and info, across TimeLimit
+    autoresets (the env never terminates)."""
+    from oracle.half_cheetah import OracleHalfCheetah
+
+    seed = 17
+    rs = np.random.default_rng(21)
+    idx = np.arange(n) if n <= 512 else np.sort(rs.choice(n, size=256, replace=False))
+    env = make("HalfCheetah-v5", n, max_episode_steps=limit)
+    ora = OracleHalfCheetah(len(idx), max_episode_steps=limit)
+    o1, i1 = env.reset(seed=seed)
+    o2, i2 = ora.reset(seed=[seed + int(i) for i in idx])
+    assert o1.shape == (n, 17) and o1.dtype == np.float64 and env.single_action_space.shape == (6,)
+    np.testing.assert_array_equal(o1[idx], o2)
+    np.testing.assert_array_equal(i1["x_position"][idx], i2["x_position"])
+    for i in idx[:16]:  # reset_model's draws are numpy's: uniform(-0.1, 0.1, 9), then 0.1 * standard_normal(9)
+        gen = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed + int(i))))
+        qpos = gen.uniform(low=-0.1, high=0.1, size=9)
+        np.testing.assert_array_equal(o1[i], np.concatenate([qpos[1:], 0.1 * gen.standard_normal(9)]))
+    truncs = 0
+    for t in range(T):
+        a = rs.uniform(-1.0, 1.0, size=(n, 6)).astype(np.float32)
+        x, y = env.step(a), ora.step(a[idx])
+        np.testing.assert_array_equal(x[0][idx], y[0], err_msg=f"obs differ at step {t}")
+        np.testing.assert_array_equal(x[1][idx], y[1], err_msg=f"reward differs at step {t}")
+        assert not x[2].any()
+        np.testing.assert_array_equal(x[3][idx], y[3])
+        live = x[4]["_x_velocity"][idx]
+        for k in ("x_velocity", "reward_forward", "reward_ctrl"):
+            np.testing.assert_array_equal(x[4][k][idx][live], y[4][k][live], err_msg=k)
+        assert (x[1][x[4]["_x_velocity"]] == (x[4]["reward_forward"] + x[4]["reward_ctrl"])[x[4]["_x_velocity"]]).all()
+        truncs += int(y[3].sum())
+    assert truncs >= 2 * len(idx) and not env.buffer_overflow()
+
+
 def test_hopper_sharding_and_api():
     import torch
 

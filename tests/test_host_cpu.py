@@ -130,6 +130,21 @@ def test_inverted_pendulum_compiled_model_matches_oracle_compile():
     np.testing.assert_allclose(mass, [0.0, 10.471975511965978, 5.018591641363305], rtol=1e-13)  # rho (4/3 pi r^3 + pi r^2 h)
 
 
+def test_half_cheetah_compiled_model_matches_oracle_compile():
+    """Host side of csrc/half_cheetah.cu (axisangle / fromto capsules, settotalmass, radian ranges, per-joint springs and
+    per-actuator gears) against the oracle's compile of half_cheetah.xml, bit for bit."""
+    from oracle.half_cheetah import OracleHalfCheetah
+
+    lib = _lib.load()
+    mass = np.zeros(8); misc = np.zeros(8); inv = np.zeros(8 * 2 + 9)
+    assert lib.b2e_half_cheetah_model_info(mass.ctypes.data, misc.ctypes.data, inv.ctypes.data) == 0
+    om, omisc, oinv = OracleHalfCheetah(1).model_info()
+    np.testing.assert_array_equal(mass, om)
+    np.testing.assert_array_equal(misc[:3], omisc[:3])
+    np.testing.assert_array_equal(inv, oinv)
+    assert abs(mass.sum() - 14.0) < 1e-12
+
+
 def test_packed_cliffwalking_and_taxi_tables_equal_reference_P():
     from gymnasium_b200.envs.toy_text import pack_cliffwalking, pack_taxi
     from oracle.toy_text import build_cliff, build_taxi, taxi_action_mask

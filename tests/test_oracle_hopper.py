@@ -220,8 +220,9 @@ def test_inverted_pendulum_slider_limit_and_ctrl_clamp():
 def test_model_sizes_follow_the_reference_structural_pins():
     """tests/envs/mujoco/test_mujoco_v5.py:516-640 lists nq / nv / nu / nbody / njnt / ngeom of every v5 model.  The oracles
     (and the kernels, whose host-side compile is compared with the oracles' bit for bit in tests/test_host_cpu.py) carry:
-    Hopper 6/6/3/5/6/5, Walker2d 9/9/6/8/9/8, InvertedPendulum 2/2/1/3/2 and 2 of its 3 geoms (the rail, a world geom with
+    Hopper 6/6/3/5/6/5, Walker2d 9/9/6/8/9/8, HalfCheetah 9/9/6/8/9/9, InvertedPendulum 2/2/1/3/2 and 2 of its 3 geoms (the rail, a world geom with
     contype 0, takes part in nothing and is not modelled)."""
+    import oracle.half_cheetah as hc
     import oracle.hopper as hp
     import oracle.inverted_pendulum as ip
     import oracle.walker2d as w2
@@ -230,8 +231,10 @@ def test_model_sizes_follow_the_reference_structural_pins():
     assert (hp.NQ, hp.NV, hp.NU, hp.NB, hp.OBS) == (6, 6, 3, 5, 11)
     assert (w2.NQ, w2.NV, w2.NU, w2.NB, w2.OBS) == (9, 9, 6, 8, 17)
     assert (ip.NQ, ip.NV, ip.NU, ip.NB, ip.OBS) == (2, 2, 1, 3, 4)
+    assert (hc.NQ, hc.NV, hc.NU, hc.NB, hc.OBS) == (9, 9, 6, 8, 17)  # HalfCheetah: nbody 8, njnt 9, ngeom 9
     for robot, (_, _, nb, nq, nu) in ROBOTS.items():
-        env = {"hopper": hp.OracleHopper, "walker2d": w2.OracleWalker2d, "inverted_pendulum": ip.OracleInvertedPendulum}[robot](1)
+        env = {"hopper": hp.OracleHopper, "walker2d": w2.OracleWalker2d, "inverted_pendulum": ip.OracleInvertedPendulum,
+               "half_cheetah": hc.OracleHalfCheetah}[robot](1)
         obs, _ = env.reset(seed=0)
         mass, misc, inv = env.model_info()
         assert len(mass) == nb and mass[0] == 0 and (mass[1:] > 0).all()
@@ -241,3 +244,55 @@ def test_model_sizes_follow_the_reference_structural_pins():
         a = np.zeros((1, nu), dtype=np.float32)
         o, r, te, tr, info = env.step(a)
         assert o.shape == obs.shape and np.isfinite(o).all()
+
+
+# HalfCheetah-v5 on the same core (oracle/half_cheetah.c -> mjc_planar.h): Euler integrator with implicit joint damping, joint
+# springs, settotalmass, axisangle / fromto geoms, standard_normal reset noise
+def test_half_cheetah_masses_match_mujoco_and_reset_noise_matches_numpy():
+    from oracle.half_cheetah import OracleHalfCheetah
+
+    n, seed = 400, 123
+    env = OracleHalfCheetah(n)
+    mass, misc, _ = env.model_info()
+    # mjModel.body_mass of the stock half_cheetah.xml (inertiafromgeom, then settotalmass = 14)
+    known = [0.0, 6.25020921, 1.54351464, 1.5874477, 1.09539749, 1.43807531, 1.20083682, 0.88451883]
+    np.testing.assert_allclose(mass, known, rtol=1e-8)  # the literature values carry 8 decimals
+    assert abs(mass.sum() - 14.0) < 1e-12 and misc[1] == 8  # 8 capsules against the floor, nothing else collides
+    obs, info = env.reset(seed=seed)
+    assert obs.shape == (n, 17) and set(info) == {"x_position", "x_velocity", "reward_forward", "reward_ctrl"}
+    for i in range(n):  # half_cheetah_v5.py:261-276: uniform(-0.1, 0.1, nq) then 0.1 * standard_normal(nv)
+        gen = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed + i)))
+        qpos = gen.uniform(low=-0.1, high=0.1, size=9)
+        qvel = 0.1 * gen.standard_normal(9)
+        np.testing.assert_array_equal(obs[i], np.concatenate([qpos[1:], qvel]))
+        assert info["x_position"][i] == qpos[0]
+
+
+def test_half_cheetah_free_fall_reward_identity_and_time_limit():
+    from oracle.half_cheetah import OracleHalfCheetah
+
+    env = OracleHalfCheetah(1, reset_noise_scale=0.0, max_episode_steps=7)
+    obs, _ = env.reset(seed=0)
+    assert (obs == 0).all()  # qpos0 = 0 (the torso's height 0.7 is the body position, rootz itself starts at 0)
+    h, g = 0.01, 9.81
+    zero = np.zeros((1, 6), dtype=np.float32)
+    for step in (1, 2):  # 10 simulation steps before a foot reaches the floor: semi-implicit Euler, z_k = -g h^2 k (k + 1) / 2
+        o, r, te, tr, info = env.step(zero)
+        k = 5 * step
+        np.testing.assert_allclose(o[0, 0], -g * h * h * k * (k + 1) / 2, rtol=1e-12)
+        np.testing.assert_allclose(o[0, 9], -g * h * k, rtol=1e-12)  # qvel of rootz
+        assert np.abs(o[0, 1:8]).max() < 1e-12 and env.debug(0)[3][0] == 0  # nothing bends, no contact yet
+    rs = np.random.default_rng(3)
+    env.reset(seed=1)
+    for t in range(7):
+        a = rs.uniform(-1, 1, size=(1, 6)).astype(np.float32)
+        x0 = env.debug(0)[0][0]
+        o, r, te, tr, info = env.step(a)
+        x1 = env.debug(0)[0][0]
+        assert not te[0] and tr[0] == (t == 6)  # never terminates; TimeLimit truncates
+        assert info["x_velocity"][0] == (x1 - x0) / 0.05 and info["x_position"][0] == x1
+        ctrl = np.float32(0.1) * np.sum(np.square(a[0]))  # float32, as NumPy 2 evaluates it for float32 actions
+        assert info["reward_ctrl"][0] == -float(ctrl) and info["reward_forward"][0] == 1.0 * info["x_velocity"][0]
+        assert r[0] == info["reward_forward"][0] + info["reward_ctrl"][0]  # half_cheetah_v5.py:243
+    o, r, te, tr, info = env.step(zero)  # NEXT_STEP: the reset call
+    assert r[0] == 0.0 and not te[0] and not tr[0] and np.abs(o[0, :8]).max() <= 0.1 + 1e-12
