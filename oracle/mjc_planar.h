@@ -66,7 +66,11 @@
 #define NG 2
 #define MAXCON 2
 #define MAXEFC 4
+#if defined(OPT_EULER) /* test-only instance: the same model under mj_Euler (oracle/inverted_pendulum_euler.c) */
+#define API(name) ipe_##name
+#else
 #define API(name) ip_##name
+#endif
 #else
 #error "define ROBOT_HOPPER, ROBOT_WALKER2D, ROBOT_HALFCHEETAH or ROBOT_INVPEND before including mjc_planar.h"
 #endif
@@ -1188,7 +1192,7 @@ static void env_step(pl_vec_t* v, int i, const float* action, double* obs, doubl
   const model_t* m = &v->model;
   data_t* d = &v->env[i].d;
   for (int u = 0; u < NU; ++u) d->ctrl[u] = (double)action[u];
-  for (int k = 0; k < FRAME_SKIP; ++k) mj_step_rk4(m, d);
+  for (int k = 0; k < FRAME_SKIP; ++k) MJ_STEP(m, d);
   get_obs(d, obs);
   int finite = 1;
   for (int k = 0; k < OBS; ++k) finite = finite && isfinite(obs[k]);

@@ -13,8 +13,10 @@ INFO_KEYS = ["x_position", "z_distance_from_origin", "x_velocity", "reward_forwa
 # robot -> (library, symbol prefix, nbody, nq = nv, nu)
 ROBOTS = {"hopper": ("libhopper_oracle.so", "hp_", 5, 6, 3), "walker2d": ("libwalker2d_oracle.so", "w2_", 8, 9, 6),
           "inverted_pendulum": ("libinverted_pendulum_oracle.so", "ip_", 3, 2, 1),
-          "half_cheetah": ("libhalf_cheetah_oracle.so", "hc_", 8, 9, 6)}
-OBS_SIZE = {"inverted_pendulum": 4}  # default: 2 nq - 1 (qpos[1:] | qvel)
+          "half_cheetah": ("libhalf_cheetah_oracle.so", "hc_", 8, 9, 6),
+          # test-only: the inverted pendulum under mj_Euler (checks the integrator HalfCheetah uses against physics)
+          "inverted_pendulum_euler": ("libinverted_pendulum_euler_oracle.so", "ipe_", 3, 2, 1)}
+OBS_SIZE = {"inverted_pendulum": 4, "inverted_pendulum_euler": 4}  # default: 2 nq - 1 (qpos[1:] | qvel)
 _libs = {}
 
 

@@ -296,3 +296,50 @@ def test_half_cheetah_free_fall_reward_identity_and_time_limit():
         assert r[0] == info["reward_forward"][0] + info["reward_ctrl"][0]  # half_cheetah_v5.py:243
     o, r, te, tr, info = env.step(zero)  # NEXT_STEP: the reset call
     assert r[0] == 0.0 and not te[0] and not tr[0] and np.abs(o[0, :8]).max() <= 0.1 + 1e-12
+
+
+def test_euler_integrator_with_implicit_damping_matches_the_cart_pole_equations():
+    """mj_Euler as HalfCheetah-v5 runs it -- qvel += h (M + h B)^-1 (qfrc_smooth + qfrc_constraint), qpos += h qvel_new -- on a
+    model whose equations of motion are known: a TEST-ONLY instance of the planar core compiles inverted_pendulum.xml with the
+    Euler integrator (oracle/inverted_pendulum_euler.c); the same scheme written out for the cart-pole Lagrangian must give
+    the same trajectory."""
+    from oracle.mjc_planar import OraclePlanar
+
+    class EulerPendulum(OraclePlanar):
+        robot = "inverted_pendulum_euler"
+
+    env = EulerPendulum(1, max_episode_steps=0, reset_noise_scale=0.01)
+    m_cart, _ = _capsule(0.1, 0.1)
+    m_pole, i_pole = _capsule(0.049, np.hypot(0.001, 0.6) / 2)
+    com = np.array([0.0005, 0.3])
+    l, phi0, g, h, damping = np.hypot(*com), np.arctan2(com[0], com[1]), 9.81, 0.02, np.array([1.0, 1.0])
+
+    def step(y, force):
+        x, th, xd, thd = y
+        a = th + phi0
+        M = np.array([[m_cart + m_pole, m_pole * l * np.cos(a)], [m_pole * l * np.cos(a), i_pole + m_pole * l * l]])
+        smooth = np.array([force - damping[0] * xd + m_pole * l * np.sin(a) * thd * thd,
+                           -damping[1] * thd + m_pole * g * l * np.sin(a)])
+        v = np.array([xd, thd]) + h * np.linalg.solve(M + h * np.diag(damping), smooth)
+        return np.concatenate([np.array([x, th]) + h * v, v])
+
+    obs, _ = env.reset(seed=4)
+    y, rs, worst = obs[0].copy(), np.random.default_rng(1), 0.0
+    for _ in range(9):
+        a = rs.uniform(-1, 1, size=(1, 1)).astype(np.float32)
+        o, r, te, tr, _ = env.step(a)
+        for _ in range(2):
+            y = step(y, 100.0 * float(a[0, 0]))
+        worst = max(worst, np.abs(o[0] - y).max())
+        if te[0]:
+            break
+    assert worst < 1e-13, worst
+    # and it is NOT what RK4 gives: the two integrators separate by far more than the tolerance above
+    from oracle.inverted_pendulum import OracleInvertedPendulum
+
+    rk = OracleInvertedPendulum(1, max_episode_steps=0)
+    np.testing.assert_array_equal(rk.reset(seed=4)[0], obs)
+    o_rk = rk.step(np.array([[0.7]], dtype=np.float32))[0]
+    env.reset(seed=4)
+    o_eu = env.step(np.array([[0.7]], dtype=np.float32))[0]
+    assert np.abs(o_rk - o_eu).max() > 1e-4
