@@ -233,6 +233,8 @@ def test_model_sizes_follow_the_reference_structural_pins():
     assert (ip.NQ, ip.NV, ip.NU, ip.NB, ip.OBS) == (2, 2, 1, 3, 4)
     assert (hc.NQ, hc.NV, hc.NU, hc.NB, hc.OBS) == (9, 9, 6, 8, 17)  # HalfCheetah: nbody 8, njnt 9, ngeom 9
     for robot, (_, _, nb, nq, nu) in ROBOTS.items():
+        if robot.endswith("_euler"):  # test-only instance (see test_euler_integrator_...)
+            continue
         env = {"hopper": hp.OracleHopper, "walker2d": w2.OracleWalker2d, "inverted_pendulum": ip.OracleInvertedPendulum,
                "half_cheetah": hc.OracleHalfCheetah}[robot](1)
         obs, _ = env.reset(seed=0)
