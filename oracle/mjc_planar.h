@@ -1430,4 +1430,20 @@ void API(set_state)(pl_vec_t* v, int i, const double* qpos, const double* qvel) 
   memcpy(d->qpos, qpos, sizeof(d->qpos)); memcpy(d->qvel, qvel, sizeof(d->qvel));
   mj_forward(&v->model, d);
 }
+/* contact forces of the last forward evaluation: per contact the normal force (pyramidal cone: the sum of its four rows) and
+ * the contact frame's normal; returns ncon */
+int API(contact_forces)(const pl_vec_t* v, int i, double* normal_force /*MAXCON*/, double* normal /*MAXCON*3*/) {
+  const data_t* d = &v->env[i].d;
+  for (int c = 0; c < d->ncon; ++c) {
+    const contact_t* con = &d->con[c];
+    double f = 0;
+    if (con->efc_adr >= 0) {
+      if (con->dim == 1) f = d->efc_force[con->efc_adr];
+      else for (int k = 0; k < 4; ++k) f += d->efc_force[con->efc_adr + k];
+    }
+    normal_force[c] = f;
+    for (int k = 0; k < 3; ++k) normal[3 * c + k] = con->frame[k];
+  }
+  return d->ncon;
+}
 const char* API(body_name)(int b) { return BODY_NAMES[b]; }

@@ -37,7 +37,9 @@ def lib(robot):
         f("model_info").argtypes = [C.c_void_p] * 4
         f("debug").argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         f("set_state").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        _libs[robot] = {n: f(n) for n in ("create", "destroy", "reset", "step", "model_info", "debug", "set_state")}
+        f("contact_forces").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        f("contact_forces").restype = C.c_int
+        _libs[robot] = {n: f(n) for n in ("create", "destroy", "reset", "step", "model_info", "debug", "set_state", "contact_forces")}
     return _libs[robot]
 
 
@@ -107,6 +109,12 @@ class OraclePlanar:
         xipos = np.zeros((self.nb, 3))
         self._f["debug"](self._h, i, qpos.ctypes.data, qvel.ctypes.data, qacc.ctypes.data, counts.ctypes.data, xipos.ctypes.data)
         return qpos, qvel, qacc, counts, xipos
+
+    def contact_forces(self, i=0):
+        """(normal force per contact, contact normals) of env i's last forward evaluation."""
+        f = np.zeros(64); nrm = np.zeros((64, 3))
+        n = self._f["contact_forces"](self._h, i, f.ctypes.data, nrm.ctypes.data)
+        return f[:n].copy(), nrm[:n].copy()
 
     def set_state(self, i, qpos, qvel):
         qpos = np.ascontiguousarray(qpos, dtype=np.float64); qvel = np.ascontiguousarray(qvel, dtype=np.float64)

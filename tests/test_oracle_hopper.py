@@ -345,3 +345,24 @@ def test_euler_integrator_with_implicit_damping_matches_the_cart_pole_equations(
     env.reset(seed=4)
     o_eu = env.step(np.array([[0.7]], dtype=np.float32))[0]
     assert np.abs(o_rk - o_eu).max() > 1e-4
+
+
+def test_half_cheetah_at_rest_is_carried_by_its_contacts():
+    """Statics of the contact pipeline (collision, pyramidal friction cone rows, contact Jacobians, the constraint solver): with
+    zero control the cheetah settles on the floor, and whatever the soft-constraint parameters, a body at rest is carried by
+    its contacts -- the normal forces (each the sum of its four cone rows) add up to M g, on floor normals (0, 0, 1)."""
+    from oracle.half_cheetah import OracleHalfCheetah
+
+    env = OracleHalfCheetah(1, reset_noise_scale=0.0, max_episode_steps=0)
+    env.reset(seed=0)
+    zero = np.zeros((1, 6), dtype=np.float32)
+    for _ in range(400):
+        o, r, te, tr, _ = env.step(zero)
+        assert not te[0] and not tr[0]
+    qpos, qvel, qacc, counts, _ = env.debug(0)
+    force, normal = env.contact_forces(0)
+    weight = env.model_info()[0].sum() * 9.81
+    assert len(force) >= 2 and (force > 0).all() and np.abs(qvel).max() < 1e-4 and np.abs(qacc).max() < 1e-2
+    np.testing.assert_array_equal(normal, np.tile([0.0, 0.0, 1.0], (len(force), 1)))
+    np.testing.assert_allclose(force.sum(), weight, rtol=1e-5)
+    assert counts[1] == 4 * len(force)  # condim 3: four pyramid rows per contact, no joint at its limit
