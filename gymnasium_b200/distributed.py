@@ -1,9 +1,13 @@
 """Sharding a vector env across the GPUs of one box (one process per GPU, ``torch.distributed``).
 
 Sub-envs are independent (no cross-env term anywhere on the path), so the global index range is cut into contiguous
-shards, each rank steps its own shard with no exchange, and the only collective is an optional gather of the step
-outputs into a single batch (NCCL over NVLink on GPUs; gloo on CPU in the tests).  Seeds use the GLOBAL env index
-(``seed + env_offset + i``) so results do not depend on the number of ranks.
+shards and each rank steps its own shard with no exchange.  Seeds use the GLOBAL env index (``seed + env_offset + i``) so
+results do not depend on the number of ranks.  Two ways to one batch of step outputs:
+
+* :class:`BatchGather` -- on the device, one NCCL gather / all-gather per tensor (NVLink; gloo on CPU in the tests);
+* :class:`HostBatch` + :class:`HostBatchPipeline` -- on the host, what ``AsyncVectorEnv`` hands out: every rank maps ONE
+  shared page-locked buffer and lands its rows there over its own PCIe link, `depth` steps in flight (a landing kernel
+  stores the rows and publishes a per-rank sequence word; the consumer releases slots through an acknowledgement word).
 """
 from __future__ import annotations
 
